@@ -1,0 +1,294 @@
+/*
+ * bridge_b200.h -- C ABI of the B200-native hot path of mschauer/Bridge.jl.
+ *
+ * One shared library (libbridge_b200.so, hand-written CUDA for sm_100a) replaces
+ * the reference's single-threaded Julia loops for:
+ *   sample!(W, Wiener)                         src/wiener.jl:24-58
+ *   solve!(EulerMaruyama(), Y, u, W, P)        src/euler.jl:135-152, src/sde!.jl:21-53
+ *   GuidedBridge / PartialBridge / PartialBridgeνH constructors (backward ODEs)
+ *                                              src/guip.jl:172-180, src/partialbridge.jl:1-22,
+ *                                              src/partialbridgenuH.jl:1-55,84-103, src/lyap.jl:2-6
+ *   solve!(Euler(), Y, u, W, P°)               src/euler.jl:246-268
+ *   llikelihood(LeftRule(), X, P°; skip)       src/partialbridgenuH.jl:171-189, src/guip.jl:429-446,
+ *                                              src/partialbridge.jl:67-87
+ *   innovations!(EulerMaruyama(), W, Y, P)     src/euler.jl:357-376
+ *   the pCN / Metropolis-Hastings path update  test/partialbridgenuH.jl:155-198 (script code)
+ *
+ * The reference has no FFI of its own (it is pure Julia; extension is by multiple
+ * dispatch).  These entry points are what a `ccall` shim adds methods for; the
+ * shim itself is julia/BridgeB200.jl and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - All floating point data is IEEE double.  Indices are 0-based in this ABI
+ *     (the Julia shim converts).  Small matrices are ROW-major.
+ *   - Host path layout is the reference's: one path = N consecutive states, a
+ *     state = d consecutive doubles (Vector{SVector{d,Float64}} / VSamplePath's
+ *     d x N column-major Matrix have exactly this byte layout).  An ensemble of
+ *     np chains x S segments is [np][S][N][d].
+ *   - Every function returns 0 (BB_OK) or a negative bb_status; no exception or
+ *     longjmp crosses the ABI.  bb_strerror maps codes to the reference's own
+ *     error strings where the reference has one.
+ *   - Pointers are caller-owned unless returned by a *_create function.
+ *   - One CUDA stream per bb_ctx; calls on one ctx are not re-entrant; different
+ *     contexts are independent (one ctx per GPU / per host task).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns BB_ERR_NODEVICE.
+ */
+#ifndef BRIDGE_B200_H
+#define BRIDGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+#define BB_MAXD 4   /* largest state dimension of the registry models */
+#define BB_NPAR 32  /* doubles in a model parameter block */
+
+/* ------------------------------------------------------------------ status */
+typedef enum {
+  BB_OK = 0,
+  BB_ERR_LENGTH = -1,      /* "Y and W differ in length."            src/euler.jl:137,251,361 */
+  BB_ERR_TIMEAXIS = -2,    /* "Time axis mismatch between bridge P and driving W."  src/euler.jl:248 */
+  BB_ERR_STARTPOINT = -3,  /* "Starting point has wrong length."     src/sde!.jl:30 */
+  BB_ERR_DIM = -4,         /* DimensionMismatch("length(tt) != size(yy, 2)")  src/types.jl:127 */
+  BB_ERR_ASSERT_M = -5,    /* AssertionError: m == length(v)         src/partialbridgenuH.jl:3 */
+  BB_ERR_MODEL = -6,       /* unknown model id / model-ensemble dimension mismatch */
+  BB_ERR_ARG = -7,         /* NULL pointer, negative size, bad enum */
+  BB_ERR_CUDA = -8,        /* a CUDA runtime call failed; see bb_last_cuda_error */
+  BB_ERR_NOMEM = -9,       /* device allocation failed */
+  BB_ERR_NODEVICE = -10,   /* no CUDA device: the library has no CPU path */
+  BB_ERR_UNSUPPORTED = -11,/* combination not instantiated (model x guide x dims) */
+  BB_ERR_SINGULAR = -12    /* singular matrix in a backward solve / update */
+} bb_status;
+
+const char* bb_strerror(int status);
+const char* bb_last_cuda_error(void);
+int bb_abi_version(void);
+
+/* ------------------------------------------------------------------ models
+ * Target processes: the reference's user-defined b(t,x,P), sigma(t,x,P) are Julia
+ * closures and cannot run on the device, so the device has a closed registry.
+ * par[] layouts:
+ *   WIENER    d=d'∈{1,2,3}; b=0, sigma=I                    src/wiener.jl:143-167
+ *   OU        d=d'=1; par={beta, sigma}; b=-beta*x           docs/src/manual.md:44-46
+ *   LINPRO    d=d'∈{1,2,3}; par={B[d*d], mu[d], sigma[d*d]}; b=B(x-mu)   src/linpro.jl:78-87
+ *   FHN_DIAG  d=d'=2; par={eps,s,gamma,beta,sigma1,sigma2}   src/Models.jl:18-19
+ *   FHN_HYPO  d=2,d'=1; par={eps,s,gamma,beta,sigma}; sigma=(0,sigma)'
+ *                                       project_partialbridge/partialbridge_fitzhugh.jl:44-45
+ *   INTDIFF   d=2,d'=1; par={gamma}; b=(x2, -(x2+sin x2)+1/2), sigma=(0,gamma)'
+ *                                       test/partialbridge.jl:25-27
+ *   NCLAR3    d=3,d'=1; par={alpha,omega,sigma}; b=(x2,x3,-alpha sin(omega x3))
+ *                                       project_partialbridge/partialbridge_nclar.jl:58-60
+ *   LORENZ    d=d'=3; par={th1,th2,th3, s1,s2,s3}; sigma=diag(s)  src/Models.jl:38-55, test/euler.jl:49-50
+ */
+typedef enum {
+  BB_MODEL_WIENER = 0,
+  BB_MODEL_OU = 1,
+  BB_MODEL_LINPRO = 2,
+  BB_MODEL_FHN_DIAG = 3,
+  BB_MODEL_FHN_HYPO = 4,
+  BB_MODEL_INTDIFF = 5,
+  BB_MODEL_NCLAR3 = 6,
+  BB_MODEL_LORENZ = 7,
+  BB_MODEL_COUNT = 8
+} bb_model_id;
+
+typedef struct {
+  int32_t id;       /* bb_model_id */
+  int32_t d;        /* state dimension */
+  int32_t dprime;   /* dimension of the driving Wiener process */
+  int32_t reserved;
+  double par[BB_NPAR];
+} bb_model;
+
+/* ------------------------------------------------------------------ auxiliary process
+ * The linear auxiliary process  dX~ = (B~(t) X~ + beta~(t)) dt + sigma~(t) dW  of a guided
+ * proposal (Bridge.B(t,Pt), Bridge.β(t,Pt), Bridge.a(t,Pt); src/linpro.jl:78-86,
+ * project_partialbridge/partialbridge_fitzhugh.jl:99-116).  It is passed as VALUES, never
+ * as code: either one constant triple, or the values at the three Ralston stage times of
+ * every grid interval (the shim evaluates the user's closures there).
+ *   interval i (0 <= i < N-1) is [tt[i], tt[i+1]]; the backward step over it starts at
+ *   t = tt[i+1] with h = tt[i]-tt[i+1] < 0 and evaluates at t, t+h/2, t+3h/4
+ *   (src/ode.jl:44-49,92-95)  ->  stage k of interval i is entry 3*i+k.
+ */
+typedef struct {
+  int32_t d;
+  int32_t is_const;     /* 1: single value each; 0: staged arrays */
+  const double* B;      /* [d*d]  or [(N-1)*3][d*d] */
+  const double* beta;   /* [d]    or [(N-1)*3][d]   */
+  const double* a;      /* [d*d]  or [(N-1)*3][d*d] */
+  const double* a_left; /* staged only: a~(tt[i]) per interval, [(N-1)][d*d] (Lyapunov step, src/lyap.jl:5) */
+} bb_aux;
+
+/* ------------------------------------------------------------------ opaque handles */
+typedef struct bb_ctx bb_ctx;     /* device + stream */
+typedef struct bb_ens bb_ens;     /* device-resident ensemble of chains */
+typedef struct bb_guide bb_guide; /* device-resident guiding tables of one segment */
+
+/* ------------------------------------------------------------------ context */
+int bb_ctx_create(int device, bb_ctx** out);
+int bb_ctx_destroy(bb_ctx* ctx);
+int bb_ctx_synchronize(bb_ctx* ctx);
+/* adopt an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int bb_ctx_set_stream(bb_ctx* ctx, void* cuda_stream);
+void* bb_ctx_get_stream(bb_ctx* ctx);
+/* data-movement backend of the chain kernel */
+enum { BB_BACKEND_AUTO = 0, BB_BACKEND_LSU = 1, BB_BACKEND_TMA = 2 };
+int bb_ctx_set_backend(bb_ctx* ctx, int backend);
+int bb_ctx_get_backend(bb_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t bb_ctx_launch_count(bb_ctx* ctx);
+/* elapsed device time (ms) of the most recent compute call, measured with CUDA
+ * events on the context's stream; valid after bb_ctx_synchronize */
+int bb_ctx_set_timing(bb_ctx* ctx, int enabled);
+double bb_ctx_last_kernel_ms(bb_ctx* ctx);
+
+/* ------------------------------------------------------------------ ensemble
+ * P chains, each a concatenation of S segments of N grid points (N-1 Euler steps);
+ * segment s+1 starts at the end point of segment s (bolus3.jl:187-192).  S=1 is the
+ * plain ensemble of independent paths.  Replaces P*S reference SamplePath pairs (W, X)
+ * (src/types.jl:71-76) and, with BB_ENS_DOUBLE_BUFFER, their proposal copies (Wo, Xo)
+ * (test/partialbridgenuH.jl:168-170).
+ */
+enum {
+  BB_ENS_DOUBLE_BUFFER = 1u, /* allocate proposal buffers (needed by bb_pcn_step) */
+  BB_ENS_NO_X = 2u           /* do not allocate X (paths are never stored) */
+};
+int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32_t d, int32_t dprime,
+                  uint32_t flags, bb_ens** out);
+int bb_ens_destroy(bb_ens* ens);
+/* chain ids used for the random streams are  chain_offset + local index  (multi-GPU sharding) */
+int bb_ens_set_chain_offset(bb_ens* ens, int64_t chain_offset);
+/* time grid of segment seg; n must equal N (else BB_ERR_LENGTH) */
+int bb_ens_set_grid(bb_ens* ens, int32_t seg, const double* tt, int32_t n);
+int bb_ens_get_grid(bb_ens* ens, int32_t seg, double* tt, int32_t n);
+/* starting points: u is [d] (broadcast != 0) or [P][d] */
+int bb_ens_set_start(bb_ens* ens, const double* u, int32_t n_u, int32_t broadcast);
+
+enum { BB_W = 0, BB_X = 1 };       /* which array */
+enum { BB_CUR = 0, BB_PROP = 1 };  /* current state of each chain, or its last proposal */
+/* host layout [np][S][N][k], k = dprime (W) or d (X); chains p0 .. p0+np-1 */
+int bb_ens_upload(bb_ens* ens, int what, int which, int64_t p0, int64_t np, const double* host);
+int bb_ens_download(bb_ens* ens, int what, int which, int64_t p0, int64_t np, double* host);
+
+enum {
+  BB_F_LL = 0,       /* double[P]  log-likelihood of the current path (sum over segments) */
+  BB_F_LL_PROP = 1,  /* double[P]  log-likelihood of the last proposal */
+  BB_F_LOGU = 2,     /* double[P]  log(U) drawn for the last accept test */
+  BB_F_XEND = 3,     /* double[P][d] end point yy[N] of the last solve (current) */
+  BB_F_XEND_PROP = 4 /* double[P][d] end point of the last proposal */
+};
+int bb_ens_get_f64(bb_ens* ens, int field, int64_t p0, int64_t np, double* host);
+int bb_ens_set_ll(bb_ens* ens, int64_t p0, int64_t np, const double* host);
+/* uint8[P]: 1 if the last bb_pcn_step accepted the chain's proposal */
+int bb_ens_get_accepted(bb_ens* ens, int64_t p0, int64_t np, uint8_t* host);
+/* number of accepted proposals since creation / last reset, summed over this ensemble's chains */
+int bb_ens_get_acc(bb_ens* ens, int64_t* acc);
+int bb_ens_reset_acc(bb_ens* ens);
+/* device address of the int64 acceptance counter (for an NCCL all-reduce issued by the host) */
+void* bb_ens_acc_device_ptr(bb_ens* ens);
+int64_t bb_ens_bytes(bb_ens* ens); /* device bytes held */
+
+/* ------------------------------------------------------------------ a4: sample!(W, Wiener{T}())
+ * W_cur[row][0] is kept (y1 = W.yy[1], src/wiener.jl:50-51); W[j] = W[j-1] + sqrt(tt[j]-tt[j-1]) xi.
+ * xi ~ N(0,1): Philox4x32-10 keyed by seed, counter (pair index, stream, global row id), Box-Muller
+ * in double.  `stream` separates independent draws with the same seed (e.g. MCMC iteration).
+ */
+int bb_wiener_sample(bb_ens* ens, uint64_t seed, uint32_t stream);
+
+/* ------------------------------------------------------------------ a5/a6: solve!(EulerMaruyama(), X, u, W, P)
+ * X_cur <- Euler-Maruyama solution driven by W_cur from the ensemble's starting points; segment
+ * s+1 continues from the end point of segment s.  src/euler.jl:135-152.
+ */
+int bb_euler(bb_ens* ens, const bb_model* model);
+/* fused sample! + solve! (W and X are both written, W is never read) */
+int bb_sample_euler(bb_ens* ens, const bb_model* model, uint64_t seed, uint32_t stream);
+
+/* ------------------------------------------------------------------ guiding tables
+ * Values on the time grid of one segment, as the reference's proposal structs hold them
+ * (src/partialbridgenuH.jl:122-130, src/guip.jl:165-170, src/partialbridge.jl:33-41), plus
+ * the auxiliary drift B~(tt[i]), beta~(tt[i]) that llikelihood evaluates (b~ = B~ x + beta~).
+ */
+typedef enum {
+  BB_GUIDE_NUH = 1,  /* PartialBridgeνH: r = H[i](nu[i]-x)                 partialbridgenuH.jl:157-161 */
+  BB_GUIDE_HV = 2,   /* GuidedBridge:    r = H♢[i] \ (V[i]-x)               guip.jl:192-194 */
+  BB_GUIDE_LMMU = 3  /* PartialBridge:   r = L[i]'M[i](v-mu[i]-L[i]x)       partialbridge.jl:53-58 */
+} bb_guide_kind;
+
+/*  kind   A                 b               Mm            v
+ *  NUH    H   [N][d][d]     nu [N][d]       NULL          NULL
+ *  HV     H♢  [N][d][d]     V  [N][d]       NULL          NULL
+ *  LMMU   L   [N][m][d]     mu [N][m]       M [N][m][m]   v [m]
+ *  Bt, betat: [d*d],[d] if aux_const != 0, else [N][d*d],[N][d].
+ */
+int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                    const double* A, const double* b, const double* Mm, const double* v,
+                    const double* Bt, const double* betat, int32_t aux_const, bb_guide** out);
+int bb_guide_destroy(bb_guide* g);
+
+/* ------------------------------------------------------------------ a7-a10: backward ODEs (constructors)
+ * All run on the device (one thread per system; they are O(N d^3), once per segment).
+ */
+/* updateνH⁺C(L, Σ, v, ϵ)  src/partialbridgenuH.jl:1-17.  L [m][d], Sigma [m][m], v [m]. */
+int bb_update_nuHC(bb_ctx* ctx, int32_t d, int32_t m, const double* L, const double* Sigma,
+                   const double* v, double eps, double* nu, double* Hplus, double* C);
+/* observation update of (ν, H⁺) between segments (partialbridge_bolus3.jl:128-137):
+ * Z = I - H⁺L'(Σ + LH⁺L')⁻¹L;  ν <- Z H⁺L'Σ⁻¹v + Zν;  H⁺ <- Z H⁺   (in place) */
+int bb_gpupdate_nuH(bb_ctx* ctx, int32_t d, int32_t m, double* nu, double* Hplus,
+                    const double* L, const double* Sigma, const double* v);
+/* Bridge.gpupdate(H♢, V, L, Σ, v)  src/guip.jl:221-243 (in place; handles H♢ = Inf diag) */
+int bb_gpupdate_HV(bb_ctx* ctx, int32_t d, int32_t m, double* Hdia, double* V,
+                   const double* L, const double* Sigma, const double* v);
+
+enum { BB_ODE_R3 = 0, BB_ODE_LYAP = 1 };
+/* partialbridgeodeνH!(R3()/Lyap(), tt, νt, Ht, Pt, (ν, H⁺, C))  src/partialbridgenuH.jl:21-55,86-103.
+ * in : nu_end [d], Hplus_end [d][d], C0
+ * out: nu [N][d], H [N][d][d];  nu_left [d], Hplus_left [d][d], C  at tt[0] (for chaining). */
+int bb_backward_nuH(bb_ctx* ctx, int32_t method, int32_t N, int32_t d, const double* tt,
+                    const bb_aux* aux, const double* nu_end, const double* Hplus_end, double C0,
+                    double* nu, double* H, double* nu_left, double* Hplus_left, double* C);
+/* partialbridgeodeHνH!(R3(), tt, Ft, Ht, Pt, (F, H, C))  src/partialbridgenuH.jl:64-81 */
+int bb_backward_FH(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const bb_aux* aux,
+                   const double* F_end, const double* H_end, double C0,
+                   double* F, double* H, double* C);
+/* gpHinv!/gpV! of the GuidedBridge constructor  src/guip.jl:172-180, src/gode.jl:2-3,13,21.
+ * in: v [d], hdia_end [d][d] (NULL = zero);  out: Hdia [N][d][d], V [N][d] */
+int bb_backward_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const bb_aux* aux,
+                   const double* v, const double* hdia_end, double* Hdia, double* V);
+/* partialbridgeode!(R3(), t, L, Σ, Lt, Mt, μt, P)  src/partialbridge.jl:1-22.
+ * out: Lt [N][m][d], Mt [N][m][m] (= inv(M⁺)), mut [N][m] */
+int bb_backward_LMmu(bb_ctx* ctx, int32_t N, int32_t d, int32_t m, const double* tt,
+                     const bb_aux* aux, const double* L, const double* Sigma,
+                     double* Lt, double* Mt, double* mut);
+
+/* ------------------------------------------------------------------ a11-a13: guided Euler + Girsanov ll
+ * solve!(Euler(), X, u, W, P°) fused with llikelihood(LeftRule(), X, P°; skip):
+ * X_cur <- guided Euler path driven by W_cur, ll_cur <- sum over segments of the log-likelihood,
+ * xend <- yy[N] of the last segment.  guides: one table per segment.  src/euler.jl:246-268.
+ */
+enum { BB_RUN_STORE_X = 1u, BB_RUN_NO_LL = 2u };
+int bb_guided_euler_ll(bb_ens* ens, const bb_model* model, bb_guide* const* guides,
+                       int32_t skip, uint32_t flags);
+/* llikelihood(LeftRule(), X, P°; skip) on the stored X_cur -> ll_cur  (second-pass form) */
+int bb_llikelihood(bb_ens* ens, const bb_model* model, bb_guide* const* guides, int32_t skip);
+/* innovations!(EulerMaruyama(), W, X, P): W_cur <- sigma^{-1}-increments of X_cur  src/euler.jl:357-376.
+ * guides == NULL: unguided drift.  Needs an invertible sigma (d' = d). */
+int bb_innovations(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
+
+/* ------------------------------------------------------------------ a15: one pCN / MH iteration for every chain
+ * W2 ~ Wiener;  W° = rho W + sqrt(1-rho^2) W2 (cumulative values);  X° = guided Euler(W°);
+ * ll° = llikelihood(X°);  accept iff log(U) <= ll° - ll;  on accept the chain's buffers swap
+ * roles (no copy), ll <- ll°, acc += 1.   test/partialbridgenuH.jl:176-191.
+ * All S segments of a chain are updated jointly with one accept (bolus3.jl:300-355 with
+ * ind = all segments and a fixed starting point).  flags: BB_RUN_STORE_X keeps X°.
+ */
+int bb_pcn_step(bb_ens* ens, const bb_model* model, bb_guide* const* guides, double rho,
+                uint64_t seed, uint32_t iter, int32_t skip, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIDGE_B200_H */

@@ -1,0 +1,290 @@
+"""ctypes binding of the CPU oracle (oracle/bridge_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+Two builds are exposed:
+    load("ref")  reference arithmetic (no FMA contraction; what Julia computes)
+    load("fma")  identical algorithm in the CUDA kernels' rounding order
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BB_NPAR = 32
+
+# model ids (include/bridge_b200.h)
+WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ = range(8)
+GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
+ODE_R3, ODE_LYAP = 0, 1
+
+
+class Model(C.Structure):
+    _fields_ = [("id", C.c_int32), ("d", C.c_int32), ("dprime", C.c_int32),
+                ("reserved", C.c_int32), ("par", C.c_double * BB_NPAR)]
+
+
+class Aux(C.Structure):
+    _fields_ = [("d", C.c_int32), ("is_const", C.c_int32), ("B", C.c_void_p),
+                ("beta", C.c_void_p), ("a", C.c_void_p), ("a_left", C.c_void_p)]
+
+
+class Guide(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("N", C.c_int32), ("d", C.c_int32), ("m", C.c_int32),
+                ("tt", C.c_void_p), ("A", C.c_void_p), ("b", C.c_void_p), ("Mm", C.c_void_p),
+                ("v", C.c_void_p), ("Bt", C.c_void_p), ("betat", C.c_void_p),
+                ("aux_const", C.c_int32)]
+
+
+def build(force: bool = False) -> None:
+    """Compile both oracle builds with the committed Makefile."""
+    args = ["make", "-C", _HERE]
+    if force:
+        args.append("-B")
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_model(mid: int, d: int, dprime: int, par=()) -> Model:
+    m = Model()
+    m.id, m.d, m.dprime, m.reserved = mid, d, dprime, 0
+    par = np.asarray(par, dtype=np.float64).ravel()
+    assert par.size <= BB_NPAR
+    for i, v in enumerate(par):
+        m.par[i] = float(v)
+    return m
+
+
+def linpro_model(B, mu, sigma) -> Model:
+    B = np.atleast_2d(_f64(B))
+    d = B.shape[0]
+    par = np.concatenate([B.ravel(), _f64(mu).ravel(), np.atleast_2d(_f64(sigma)).ravel()])
+    return make_model(LINPRO, d, d, par)
+
+
+class AuxHolder:
+    """Keeps the numpy arrays behind a bb_aux alive."""
+
+    def __init__(self, d, B, beta, a, a_left=None, is_const=True):
+        self.d = d
+        self.B, self.beta, self.a = _f64(B), _f64(beta), _f64(a)
+        self.a_left = None if a_left is None else _f64(a_left)
+        self.c = Aux(d, 1 if is_const else 0, _p(self.B), _p(self.beta), _p(self.a),
+                     _p(self.a_left))
+
+
+def const_aux(B, beta, a) -> AuxHolder:
+    B = np.atleast_2d(_f64(B))
+    return AuxHolder(B.shape[0], B, np.atleast_1d(_f64(beta)), np.atleast_2d(_f64(a)))
+
+
+def staged_aux(tt, Bf, betaf, af) -> AuxHolder:
+    """Evaluate callables B(t), beta(t), a(t) at the Ralston stage times of every interval."""
+    tt = _f64(tt)
+    N = tt.size
+    d = np.atleast_2d(Bf(tt[0])).shape[0]
+    Bs = np.empty((N - 1, 3, d, d)); bs = np.empty((N - 1, 3, d)); As = np.empty((N - 1, 3, d, d))
+    al = np.empty((N - 1, d, d))
+    for i in range(N - 1):
+        t, h = tt[i + 1], tt[i] - tt[i + 1]
+        for k, c in enumerate((0.0, 0.5, 0.75)):
+            s = t + c * h
+            Bs[i, k] = Bf(s); bs[i, k] = betaf(s); As[i, k] = af(s)
+        al[i] = af(tt[i])
+    return AuxHolder(d, Bs, bs, As, al, is_const=False)
+
+
+class GuideHolder:
+    def __init__(self, kind, tt, A, b, Mm=None, v=None, Bt=None, betat=None, aux_const=True, m=0):
+        self.tt = _f64(tt)
+        self.A, self.b = _f64(A), _f64(b)
+        self.Mm = None if Mm is None else _f64(Mm)
+        self.v = None if v is None else _f64(v)
+        self.Bt, self.betat = _f64(Bt), _f64(betat)
+        N = self.tt.size
+        d = self.Bt.shape[-1]
+        self.kind, self.N, self.d, self.m = kind, N, d, m
+        self.c = Guide(kind, N, d, m, _p(self.tt), _p(self.A), _p(self.b), _p(self.Mm),
+                       _p(self.v), _p(self.Bt), _p(self.betat), 1 if aux_const else 0)
+
+
+class Oracle:
+    def __init__(self, variant: str = "ref"):
+        path = os.path.join(_HERE, f"liboracle_{variant}.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = L = C.CDLL(path)
+        self.variant = variant
+        L.bbo_logpdfnormal.restype = C.c_double
+        L.bbo_normal.restype = C.c_double
+        L.bbo_accept_logu.restype = C.c_double
+        L.bbo_llikelihood.restype = C.c_double
+        L.bbo_pcn_propose.restype = C.c_double
+        L.bbo_pcn_bench.restype = C.c_longlong
+        assert L.bbo_gpu_order() == (1 if variant == "fma" else 0)
+
+    # ---- rng
+    def philox(self, ctr, key):
+        ctr = np.asarray(ctr, dtype=np.uint32); key = np.asarray(key, dtype=np.uint32)
+        out = np.zeros(4, dtype=np.uint32)
+        self.lib.bbo_philox4x32_10(_p(ctr), _p(key), _p(out))
+        return out
+
+    def normal(self, seed, stream, row, n):
+        return self.lib.bbo_normal(C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(row),
+                                   C.c_uint64(n))
+
+    def accept_logu(self, seed, stream, chain):
+        return self.lib.bbo_accept_logu(C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(chain))
+
+    def logpdfnormal(self, x, Sigma):
+        x = np.atleast_1d(_f64(x)); S = np.atleast_2d(_f64(Sigma))
+        return self.lib.bbo_logpdfnormal(x.size, _p(x), _p(S))
+
+    # ---- paths
+    def wiener_sample(self, tt, dprime, seed, stream, row, y1=None):
+        tt = _f64(tt)
+        W = np.zeros((tt.size, dprime))
+        if y1 is not None:
+            W[0] = y1
+        self.lib.bbo_wiener_sample(tt.size, dprime, _p(tt), C.c_uint64(seed), C.c_uint32(stream),
+                                   C.c_uint64(row), _p(W))
+        return W
+
+    def euler(self, model, tt, u, W):
+        tt = _f64(tt); W = _f64(W).reshape(tt.size, model.dprime); u = np.atleast_1d(_f64(u))
+        X = np.zeros((tt.size, model.d))
+        self.lib.bbo_euler(C.byref(model), tt.size, _p(tt), _p(u), _p(W), _p(X))
+        return X
+
+    def guided_euler(self, model, guide: GuideHolder, u, W, store=True):
+        W = _f64(W).reshape(guide.N, model.dprime); u = np.atleast_1d(_f64(u))
+        X = np.zeros((guide.N, model.d)) if store else None
+        xend = np.zeros(model.d)
+        self.lib.bbo_guided_euler(C.byref(model), C.byref(guide.c), _p(u), _p(W), _p(X), _p(xend))
+        return X, xend
+
+    def llikelihood(self, model, guide: GuideHolder, X, skip=0):
+        X = _f64(X).reshape(guide.N, model.d)
+        return self.lib.bbo_llikelihood(C.byref(model), C.byref(guide.c), _p(X), C.c_int(skip))
+
+    def innovations(self, model, guide, tt, X):
+        tt = _f64(tt); X = _f64(X).reshape(tt.size, model.d)
+        W = np.zeros((tt.size, model.d))
+        rc = self.lib.bbo_innovations(C.byref(model), None if guide is None else C.byref(guide.c),
+                                      tt.size, _p(tt), _p(X), _p(W))
+        assert rc == 0, rc
+        return W
+
+    # ---- constructors
+    def update_nuHC(self, L, Sigma, v, eps):
+        L = np.atleast_2d(_f64(L)); m, d = L.shape
+        Sigma = np.atleast_2d(_f64(Sigma)); v = np.atleast_1d(_f64(v))
+        nu = np.zeros(d); Hp = np.zeros((d, d)); Cc = C.c_double(0)
+        rc = self.lib.bbo_update_nuHC(d, m, _p(L), _p(Sigma), _p(v), C.c_double(eps), _p(nu),
+                                      _p(Hp), C.byref(Cc))
+        assert rc == 0, rc
+        return nu, Hp, Cc.value
+
+    def update_FHC(self, L, Sigma, v, F, H, eps=0.0, C0=0.0):
+        L = np.atleast_2d(_f64(L)); m, d = L.shape
+        Sigma = np.atleast_2d(_f64(Sigma)); v = np.atleast_1d(_f64(v))
+        F = _f64(F).copy(); H = _f64(H).copy(); Cc = C.c_double(C0)
+        rc = self.lib.bbo_update_FHC(d, m, _p(L), _p(Sigma), _p(v), _p(F), _p(H), C.c_double(eps),
+                                     C.byref(Cc))
+        assert rc == 0, rc
+        return F, H, Cc.value
+
+    def gpupdate_nuH(self, nu, Hplus, L, Sigma, v):
+        L = np.atleast_2d(_f64(L)); m, d = L.shape
+        nu = _f64(nu).copy(); Hp = _f64(Hplus).copy()
+        Sigma = np.atleast_2d(_f64(Sigma)); v = np.atleast_1d(_f64(v))
+        rc = self.lib.bbo_gpupdate_nuH(d, m, _p(nu), _p(Hp), _p(L), _p(Sigma), _p(v))
+        assert rc == 0, rc
+        return nu, Hp
+
+    def gpupdate_HV(self, Hdia, V, L, Sigma, v):
+        V2, H2 = self.gpupdate_nuH(V, Hdia, L, Sigma, v)
+        return H2, V2
+
+    def backward_nuH(self, method, tt, aux: AuxHolder, nu_end, Hplus_end, C0=0.0):
+        tt = _f64(tt); N, d = tt.size, aux.d
+        nu_end = np.atleast_1d(_f64(nu_end)); Hp = np.atleast_2d(_f64(Hplus_end))
+        nu = np.zeros((N, d)); H = np.zeros((N, d, d))
+        nul = np.zeros(d); Hl = np.zeros((d, d)); Cc = C.c_double(0)
+        rc = self.lib.bbo_backward_nuH(method, N, d, _p(tt), C.byref(aux.c), _p(nu_end), _p(Hp),
+                                       C.c_double(C0), _p(nu), _p(H), _p(nul), _p(Hl), C.byref(Cc))
+        assert rc == 0, rc
+        return nu, H, nul, Hl, Cc.value
+
+    def backward_FH(self, tt, aux, F_end, H_end, C0=0.0):
+        tt = _f64(tt); N, d = tt.size, aux.d
+        F_end = np.atleast_1d(_f64(F_end)); H_end = np.atleast_2d(_f64(H_end))
+        F = np.zeros((N, d)); H = np.zeros((N, d, d)); Cc = C.c_double(0)
+        rc = self.lib.bbo_backward_FH(N, d, _p(tt), C.byref(aux.c), _p(F_end), _p(H_end),
+                                      C.c_double(C0), _p(F), _p(H), C.byref(Cc))
+        assert rc == 0, rc
+        return F, H, Cc.value
+
+    def backward_HV(self, tt, aux, v, hdia_end=None):
+        tt = _f64(tt); N, d = tt.size, aux.d
+        v = np.atleast_1d(_f64(v))
+        he = None if hdia_end is None else np.atleast_2d(_f64(hdia_end))
+        Hd = np.zeros((N, d, d)); V = np.zeros((N, d))
+        rc = self.lib.bbo_backward_HV(N, d, _p(tt), C.byref(aux.c), _p(v), _p(he), _p(Hd), _p(V))
+        assert rc == 0, rc
+        return Hd, V
+
+    def backward_LMmu(self, tt, aux, L, Sigma):
+        tt = _f64(tt); N, d = tt.size, aux.d
+        L = np.atleast_2d(_f64(L)); m = L.shape[0]; Sigma = np.atleast_2d(_f64(Sigma))
+        Lt = np.zeros((N, m, d)); Mt = np.zeros((N, m, m)); mut = np.zeros((N, m))
+        rc = self.lib.bbo_backward_LMmu(N, d, m, _p(tt), C.byref(aux.c), _p(L), _p(Sigma), _p(Lt),
+                                        _p(Mt), _p(mut))
+        assert rc == 0, rc
+        return Lt, Mt, mut
+
+    # ---- pCN
+    def pcn_propose(self, model, guides, u, Wc, rho, seed, it, chain, skip=0):
+        S = len(guides); N = guides[0].N
+        garr = (C.POINTER(Guide) * S)(*[C.pointer(g.c) for g in guides])
+        Wc = _f64(Wc).reshape(S, N, model.dprime); u = np.atleast_1d(_f64(u))
+        Wo = np.zeros_like(Wc); Xo = np.zeros((S, N, model.d)); xend = np.zeros(model.d)
+        logu = C.c_double(0)
+        ll = self.lib.bbo_pcn_propose(C.byref(model), garr, S, _p(u), _p(Wc), C.c_double(rho),
+                                      C.c_uint64(seed), C.c_uint32(it), C.c_uint64(chain),
+                                      C.c_int(skip), _p(Wo), _p(Xo), _p(xend), C.byref(logu))
+        return ll, logu.value, Wo, Xo, xend
+
+    def pcn_bench(self, model, guides, P, u, rho, seed, iters, skip=0, nthreads=0):
+        S = len(guides)
+        garr = (C.POINTER(Guide) * S)(*[C.pointer(g.c) for g in guides])
+        u = np.atleast_1d(_f64(u)); secs = C.c_double(0); ll = np.zeros(P)
+        acc = self.lib.bbo_pcn_bench(C.byref(model), garr, S, C.c_longlong(P), _p(u),
+                                     C.c_double(rho), C.c_uint64(seed), C.c_int(iters),
+                                     C.c_int(skip), C.c_int(nthreads), C.byref(secs), _p(ll))
+        return acc, secs.value, ll
+
+    def max_threads(self):
+        return self.lib.bbo_max_threads()
+
+
+_cache = {}
+
+
+def load(variant: str = "ref") -> Oracle:
+    if variant not in _cache:
+        _cache[variant] = Oracle(variant)
+    return _cache[variant]

@@ -1,0 +1,433 @@
+"""Pins the CPU oracle (oracle/bridge_oracle.c) to the reference's own golden vector and
+known-answer tests.  CPU only.
+
+Each test names the reference test / doc it restates.  Seeded Julia streams cannot be
+reproduced (no Julia here), so only seed-free assertions are restated; where the
+reference test is statistical, the same statistic is computed with Philox noise.
+"""
+import numpy as np
+import pytest
+from scipy.linalg import expm, solve_continuous_lyapunov
+
+from oracle import oracle as O
+
+
+# --------------------------------------------------------------------------- RNG
+def test_philox_known_answers(oracle_ref):
+    """Random123 kat_vectors for philox4x32-10 (Salmon et al., SC'11)."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        got = oracle_ref.philox(ctr, key)
+        assert [int(x) for x in got] == want
+
+
+def test_normals_are_standard(oracle_ref):
+    z = np.array([oracle_ref.normal(7, 3, 11, n) for n in range(40000)])
+    assert abs(z.mean()) < 4 / np.sqrt(z.size)
+    assert abs(z.var() - 1) < 0.03
+    assert abs((z ** 3).mean()) < 0.05 and abs((z ** 4).mean() - 3) < 0.15
+    # pairs are (sin, cos) of the same radius: uncorrelated
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 0.03
+    # distinct rows / streams give distinct numbers
+    assert oracle_ref.normal(7, 3, 11, 0) != oracle_ref.normal(7, 3, 12, 0)
+    assert oracle_ref.normal(7, 3, 11, 0) != oracle_ref.normal(7, 4, 11, 0)
+
+
+def test_wiener_sample_recurrence(oracle_ref):
+    """src/wiener.jl:50-58: yy[1] kept, yy[i] = yy[i-1] + sqrt(dt_i) * randn, component-minor."""
+    tt = np.array([0.0, 0.1, 0.25, 0.7, 1.0])
+    W = oracle_ref.wiener_sample(tt, 2, seed=5, stream=1, row=9, y1=[0.5, -1.0])
+    assert np.array_equal(W[0], [0.5, -1.0])
+    for j in range(1, 5):
+        for k in range(2):
+            xi = oracle_ref.normal(5, 1, 9, j * 2 + k)
+            assert W[j, k] == W[j - 1, k] + np.sqrt(tt[j] - tt[j - 1]) * xi
+
+
+# --------------------------------------------------------------------------- Euler-Maruyama
+GOLD_TT = np.array([0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0])
+GOLD_W = np.array([0.0, 0.0940107, 0.214935, 0.0259463, 0.0226432, -0.24268, -0.144298,
+                   0.581472, -0.135443, 0.0321464, 0.168574])
+GOLD_X = np.array([0.1, -0.00598928, 0.126914, -0.315902, 0.312599, -0.577923, 0.676305,
+                   0.0494658, -0.766381, 0.933971, -0.797544])
+
+
+def test_docs_golden_vector(oracle_ref, oracle_fma):
+    """docs/src/manual.md:59-63,73-77: solve(Euler(), 0.1, W, OrnsteinUhlenbeck(20.0, 1.0)).
+    W and X are printed with 6 significant digits; the stiff recurrence (1-20*0.1 = -1)
+    carries the print error of W without damping, hence 1e-5 absolute."""
+    P = O.make_model(O.OU, 1, 1, [20.0, 1.0])
+    for orc in (oracle_ref, oracle_fma):
+        X = orc.euler(P, GOLD_TT, [0.1], GOLD_W)[:, 0]
+        assert np.max(np.abs(X - GOLD_X)) < 1e-5
+
+
+def test_euler_matches_independent_loop(oracle_ref):
+    """test/euler.jl:63-68 (three Euler code paths agree to eps()) restated as: the C oracle
+    agrees to the last bit with a direct numpy transcription of src/euler.jl:144-151 on Lorenz d=3."""
+    n = 500
+    tt = np.linspace(0.0, 1.0, n + 1)
+    P = O.make_model(O.LORENZ, 3, 3, [10.0, 28.0, 8 / 3, 3.0, 3.0, 3.0])
+    W = oracle_ref.wiener_sample(tt, 3, 1, 0, 0)
+    X = oracle_ref.euler(P, tt, [1.0, 0.0, 0.0], W)
+    y = np.array([1.0, 0.0, 0.0])
+    for i in range(n):
+        assert np.array_equal(X[i], y)
+        b = np.array([10.0 * (y[1] - y[0]), y[0] * (28.0 - y[2]) - y[1], y[0] * y[1] - (8 / 3) * y[2]])
+        y = y + b * (tt[i + 1] - tt[i]) + 3.0 * (W[i + 1] - W[i])
+    assert np.array_equal(X[n], y)
+
+
+def test_wiener_as_process_reproduces_w(oracle_ref):
+    """BASELINE config 2: P = Wiener() (b=0, sigma=I) gives X = u + W."""
+    tt = np.linspace(0, 1, 101)
+    W = oracle_ref.wiener_sample(tt, 1, 2, 0, 5)
+    X = oracle_ref.euler(O.make_model(O.WIENER, 1, 1), tt, [0.0], W)
+    assert np.allclose(X, W, rtol=0, atol=1e-14)
+
+
+# --------------------------------------------------------------------------- LinPro closed forms
+def linpro_closed(B, a, mu):
+    lam = solve_continuous_lyapunov(B, -a)  # B lam + lam B' + a = 0   (src/linpro.jl:74)
+    lam = 0.5 * (lam + lam.T)
+
+    def Hinv(t, T):  # inverse of src/linpro.jl:122-125
+        phim = expm(-(T - t) * B)
+        return phim @ lam @ phim.T - lam
+
+    def V(t, T, v):  # src/linpro.jl:127-130
+        return expm(-(T - t) * B) @ (v - mu) + mu
+
+    return lam, Hinv, V
+
+
+B2 = np.array([[-1.0, 0.1], [-0.2, -1.0]])
+SIG2 = 2 * np.array([[-0.212887, 0.0687025], [0.193157, 0.388997]])
+A2 = SIG2 @ SIG2.T
+
+
+def test_linprobridge_r3_vs_closed_form(oracle_ref):
+    """test/linprobridge.jl:22-25: R3 backward solution of _dHinv and V on tt=0:2/10000:2 equals
+    the matrix-exponential closed forms to 1e-8."""
+    n, T = 10000, 2.0
+    tt = np.arange(n + 1) * (T / n)
+    mu = np.zeros(2)
+    v = np.array([0.5, 0.0])
+    aux = O.const_aux(B2, -B2 @ mu, A2)
+    Hd, Vt = oracle_ref.backward_HV(tt, aux, v)
+    _, Hinv, Vcf = linpro_closed(B2, A2, mu)
+    assert np.linalg.norm(np.linalg.inv(Hd[0]) - np.linalg.inv(Hinv(0.0, T))) < 1e-8
+    assert np.linalg.norm(Hd[0] - Hinv(0.0, T)) < 1e-8
+    assert np.linalg.norm(Vt[0] - Vcf(0.0, T, v)) < 1e-8
+
+
+def test_linpro_n150(oracle_ref):
+    """test/linpro.jl:38-53: gpHinv!/gpV! at N=150 on [0.5, 2]: |K[1] H - I| and |V[1] - V_cf| < 10/150^3."""
+    n2 = 150
+    t, T = 0.5, 2.0
+    tt = np.linspace(t, T, n2)
+    mu = 0.1 * np.array([0.2, 0.3])
+    v = np.array([0.5, 0.0])
+    aux = O.const_aux(B2, -B2 @ mu, A2)
+    K, Vt = oracle_ref.backward_HV(tt, aux, v)
+    _, Hinv, Vcf = linpro_closed(B2, A2, mu)
+    H_cf = np.linalg.inv(Hinv(t, T))
+    assert np.linalg.norm(K[0] @ H_cf - np.eye(2)) < 10 / n2 ** 3
+    assert np.linalg.norm(Vt[0] - Vcf(t, T, v)) < 10 / n2 ** 3
+
+
+def test_vhk_1d(oracle_ref):
+    """test/VHK.jl:29-30: GuidedBridge.H♢, V vs closed form to 1e-5 (n=200, T=2, LinPro(-0.8, 0.2, sqrt(0.7))).
+    Session check values: max|H♢-1/H| = 5.87e-6, max|V-V_cf| = 1.7e-8."""
+    n, T = 200, 2.0
+    tt = np.linspace(0, T, n)
+    beta, mu, a, v = 0.8, 0.2, 0.7, 0.1
+    B = np.array([[-beta]])
+    aux = O.const_aux(B, -B @ np.array([mu]), [[a]])
+    Hd, Vt = oracle_ref.backward_HV(tt, aux, [v])
+    lam = a / (2 * beta)
+    Hcf = np.array([np.exp(2 * beta * (T - t)) * lam - lam for t in tt])  # phim*lam*phim' - lam
+    Vcf = np.array([np.exp(beta * (T - t)) * (v - mu) + mu for t in tt])
+    eH = np.max(np.abs(Hd[:, 0, 0] - Hcf))
+    eV = np.max(np.abs(Vt[:, 0] - Vcf))
+    assert eH < 1e-5 and eV < 1e-5
+    assert abs(eH - 5.87e-6) < 0.05e-6
+    assert abs(eV - 1.7e-8) < 0.1e-8
+
+
+# --------------------------------------------------------------------------- partial bridges (test/partialparam.jl)
+T_PB = 1.5
+TT_PB = np.arange(1501) * (1 / 1000)
+X0_PB = np.array([2.0, 1.0])
+L_PB = np.array([[1.0, 0.0]])
+SIG_PB = np.array([[0.1]])
+V_PB = np.array([2.5])
+GAMMA = 0.7
+EPS_PB = 1e-5
+AUX_PB = dict(B=np.array([[0.0, 1.0], [0.0, -1.0]]), beta=np.array([0.0, 0.5]),
+              a=np.array([[0.0, 0.0], [0.0, GAMMA ** 2]]))
+
+
+def test_partialbridge_finite_differences(oracle_ref):
+    """test/partialbridge.jl:73-74 (j = 10, 1-based)."""
+    aux = O.const_aux(**AUX_PB)
+    Lt, Mt, mut = oracle_ref.backward_LMmu(TT_PB, aux, L_PB, SIG_PB)
+    j, dt = 9, 1 / 1000  # 0-based index of Julia's j=10
+    lhs = (mut[j + 1] - mut[j]) / dt
+    assert np.linalg.norm(lhs - (-Lt[j + 1] @ AUX_PB["beta"])) < 0.01
+    lhs = (np.linalg.inv(Mt[j + 1]) - np.linalg.inv(Mt[j])) / dt
+    assert np.linalg.norm(lhs - (-Lt[j + 1] @ AUX_PB["a"] @ Lt[j + 1].T)) < 0.01
+    assert np.array_equal(Lt[-1], L_PB) and np.allclose(Mt[-1], np.linalg.inv(SIG_PB))
+
+
+def test_partialbridgenuH_consistency(oracle_ref):
+    """test/partialbridgenuH.jl:108-127 (lines 243-262 of the file): ν/H vs F/H parametrisation and
+    the LP ~ LP2 tie to the Gaussian transition density, with the session-derived check values."""
+    aux = O.const_aux(**AUX_PB)
+    nuT, HpT, C_ = oracle_ref.update_nuHC(L_PB, SIG_PB, V_PB, EPS_PB)
+    F0, H0, C0 = oracle_ref.update_FHC(L_PB, SIG_PB, V_PB, np.zeros(2), np.zeros((2, 2)), EPS_PB)
+    assert np.isclose(C0, C_)                       # @test C ≈ C_
+    assert np.allclose(F0, H0 @ nuT)                # @test F ≈ H*ν
+    assert np.allclose(HpT, np.linalg.inv(H0))      # @test H⁺ ≈ inv(H)
+
+    nu, H, _, _, C = oracle_ref.backward_nuH(O.ODE_R3, TT_PB, aux, nuT, HpT, C_)
+    Ft, Ht, C2 = oracle_ref.backward_FH(TT_PB, aux, F0, H0, C0)
+    assert abs(C2 - C) < 0.03
+    relH = max(np.linalg.norm(Ht[i] - H[i]) for i in range(len(TT_PB))) / np.linalg.norm(Ht.reshape(len(TT_PB), -1), axis=1).max()
+    # reference: maximum(norm.(Ht .- Po2.H)./norm(Ht)) with norm(Ht) the norm of the vector of matrices
+    normHt = np.sqrt(sum(np.linalg.norm(Ht[i]) ** 2 for i in range(len(TT_PB))))
+    relH = max(np.linalg.norm(Ht[i] - H[i]) for i in range(len(TT_PB))) / normHt
+    assert relH < 1e-5
+    dF = max(np.linalg.norm(H[i] @ nu[i] - Ft[i]) for i in range(len(TT_PB)))
+    assert dF < 0.015
+
+    # LP from the (L, M, mu) backward solve: test/partialbridge.jl:87
+    Lt, Mt, mut = oracle_ref.backward_LMmu(TT_PB, aux, L_PB, SIG_PB)
+    mean = mut[0][0] + (Lt[0] @ X0_PB)[0]
+    std = Mt[0][0, 0] ** -0.5
+    LP = -0.5 * ((V_PB[0] - mean) / std) ** 2 - np.log(std) - 0.5 * np.log(2 * np.pi)
+    LP2 = -0.5 * (X0_PB @ H[0] @ X0_PB - 2 * X0_PB @ H[0] @ nu[0]) - C
+    assert abs(LP - LP2) < 0.01
+    # session-derived anchors
+    assert abs(LP - (-0.99293614)) < 1e-6
+    assert abs(LP2 - (-0.98368522)) < 1e-6
+    assert abs(C - 7.78123371) < 1e-6
+    assert abs(abs(C - C2) - 0.02452) < 1e-4
+    assert abs(dF - 0.01105) < 1e-4
+    assert abs(np.linalg.cond(H[0]) - 1.6857e7) / 1.6857e7 < 1e-3
+
+
+def test_lyap_step_preserves_psd(oracle_ref):
+    """test/lyap.jl:9-24: the Lyapunov backward step keeps H⁺ positive definite (d=20, t=2:0.01:5)."""
+    d = 20
+    tt = np.arange(2.0, 5.0 + 1e-12, 0.01)
+    rng = np.random.default_rng(4)
+    # the reference draws a fresh random B, sigma at EVERY call of B(t,P), sigma(t,P)
+    N = tt.size
+    Bs = rng.random((N - 1, 3, d, d))
+    sig = rng.random((N - 1, 3, d, 10))
+    As = np.einsum("iskl,isml->iskm", sig, sig)
+    sl = rng.random((N - 1, d, 10))
+    al = np.einsum("ikl,iml->ikm", sl, sl)
+    aux = O.AuxHolder(d, Bs, np.zeros((N - 1, 3, d)), As, al, is_const=False)
+    nu, H, _, Hl, _ = oracle_ref.backward_nuH(O.ODE_LYAP, tt, aux, np.zeros(d), np.eye(d))
+    for i in range(N):
+        Hp = np.linalg.inv(H[i])
+        Hp = 0.5 * (Hp + Hp.T)
+        assert np.all(np.linalg.eigvalsh(Hp) > 0)
+
+
+def test_lyap_agrees_with_r3(oracle_ref):
+    """The two backward schemes of src/partialbridgenuH.jl (R3 :21-55, Lyap :86-103) solve the same ODE."""
+    aux = O.const_aux(**AUX_PB)
+    nuT, HpT, C_ = oracle_ref.update_nuHC(L_PB, SIG_PB, V_PB, 1e-3)
+    nu1, H1, _, Hl1, C1 = oracle_ref.backward_nuH(O.ODE_R3, TT_PB, aux, nuT, HpT, C_)
+    nu2, H2, _, Hl2, C2 = oracle_ref.backward_nuH(O.ODE_LYAP, TT_PB, aux, nuT, HpT, C_)
+    assert np.max(np.abs(nu1 - nu2)) < 1e-12
+    assert np.linalg.norm(Hl1 - Hl2) / np.linalg.norm(Hl1) < 1e-5
+    assert abs(C1 - C2) < 5e-3
+
+
+def test_gpupdate_matches_direct_formula(oracle_ref):
+    """src/guip.jl:221-243 / bolus3.jl:128-137 against numpy."""
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((3, 3)); Hp = A @ A.T + np.eye(3)
+    nu = rng.standard_normal(3)
+    L = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.5]]); Sig = np.diag([0.1, 0.2]); v = np.array([0.3, -0.2])
+    nu2, Hp2 = oracle_ref.gpupdate_nuH(nu, Hp, L, Sig, v)
+    Z = np.eye(3) - Hp @ L.T @ np.linalg.inv(Sig + L @ Hp @ L.T) @ L
+    assert np.allclose(Hp2, Z @ Hp, rtol=1e-12, atol=1e-14)
+    assert np.allclose(nu2, Z @ Hp @ L.T @ np.linalg.inv(Sig) @ v + Z @ nu, rtol=1e-12, atol=1e-14)
+    # Kalman form: posterior precision = prior precision + L' Sig^-1 L
+    assert np.allclose(np.linalg.inv(Hp2), np.linalg.inv(Hp) + L.T @ np.linalg.inv(Sig) @ L)
+    # infinite prior variance branch
+    Hinf = np.diag([np.inf] * 2)
+    nu3, Hp3 = oracle_ref.gpupdate_nuH(np.zeros(2), Hinf, np.eye(2), 0.5 * np.eye(2), np.array([1.0, 2.0]))
+    assert np.allclose(Hp3, 0.5 * np.eye(2)) and np.allclose(nu3, [1.0, 2.0])
+
+
+# --------------------------------------------------------------------------- forward guided path + ll
+def nuH_guide(orc, tt, eps=EPS_PB):
+    aux = O.const_aux(**AUX_PB)
+    nuT, HpT, C_ = orc.update_nuHC(L_PB, SIG_PB, V_PB, eps)
+    nu, H, _, _, C = orc.backward_nuH(O.ODE_R3, tt, aux, nuT, HpT, C_)
+    return O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=AUX_PB["B"], betat=AUX_PB["beta"])
+
+
+def test_guided_euler_and_ll_match_numpy(oracle_ref):
+    """src/euler.jl:262-267 with the drift of src/partialbridgenuH.jl:157-159 and the sum of :171-189."""
+    tt = TT_PB[:301]
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    G = nuH_guide(oracle_ref, tt)
+    W = oracle_ref.wiener_sample(tt, 1, 11, 0, 0)
+    X, xend = oracle_ref.guided_euler(P, G, X0_PB, W)
+    ll = oracle_ref.llikelihood(P, G, X)
+    y = X0_PB.copy(); som = 0.0
+    a = AUX_PB["a"]
+    for i in range(len(tt) - 1):
+        assert np.allclose(X[i], y, rtol=1e-13, atol=1e-13)
+        b = np.array([y[1], -(y[1] + np.sin(y[1])) + 0.5])
+        r = G.A[i] @ (G.b[i] - y)
+        bt = AUX_PB["B"] @ y + AUX_PB["beta"]
+        dt = tt[i + 1] - tt[i]
+        som += np.dot(b - bt, r) * dt
+        y = y + (b + a @ r) * dt + np.array([0.0, GAMMA]) * (W[i + 1, 0] - W[i, 0])
+    assert np.allclose(xend, y, rtol=1e-12, atol=1e-12)
+    assert abs(ll - som) < 1e-9 * max(1.0, abs(som))
+    # skip drops the last terms
+    assert oracle_ref.llikelihood(P, G, X, skip=5) != ll
+
+
+def test_guided_bridge_hits_observation(oracle_ref):
+    """With a small observation variance the guided path ends near L x = v (the point of the construction)."""
+    tt = TT_PB
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    aux = O.const_aux(**AUX_PB)
+    nuT, HpT, C_ = oracle_ref.update_nuHC(L_PB, np.array([[1e-6]]), V_PB, 1e-3)
+    nu, H, _, _, _ = oracle_ref.backward_nuH(O.ODE_R3, tt, aux, nuT, HpT, C_)
+    G = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=AUX_PB["B"], betat=AUX_PB["beta"])
+    ends = []
+    for row in range(20):
+        W = oracle_ref.wiener_sample(tt, 1, 3, 0, row)
+        ends.append(oracle_ref.guided_euler(P, G, X0_PB, W)[1][0])
+    assert np.max(np.abs(np.array(ends) - V_PB[0])) < 0.05
+
+
+def test_partialbridge_and_nuH_proposals_agree(oracle_ref):
+    """PartialBridge (L,M,mu) and PartialBridgeνH describe the same guided drift when eps -> 0
+    (test/partialbridgenuH.jl:276 `norm(Xo1.yy - Xo2.yy) < sqrt(eps())` is for the in-place twin;
+    here the (L,M,mu) and (nu,H) forms are compared, tolerance set by eps=1e-5 regularisation)."""
+    tt = TT_PB
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    aux = O.const_aux(**AUX_PB)
+    Lt, Mt, mut = oracle_ref.backward_LMmu(tt, aux, L_PB, SIG_PB)
+    G1 = O.GuideHolder(O.GUIDE_LMMU, tt, Lt, mut, Mm=Mt, v=V_PB, Bt=AUX_PB["B"], betat=AUX_PB["beta"], m=1)
+    G2 = nuH_guide(oracle_ref, tt)
+    W = oracle_ref.wiener_sample(tt, 1, 1, 0, 0)
+    X1, _ = oracle_ref.guided_euler(P, G1, X0_PB, W)
+    X2, _ = oracle_ref.guided_euler(P, G2, X0_PB, W)
+    assert np.max(np.abs(X1 - X2)) < 2e-3
+    ll1 = oracle_ref.llikelihood(P, G1, X1); ll2 = oracle_ref.llikelihood(P, G2, X2)
+    assert abs(ll1 - ll2) < 2e-3 * max(1.0, abs(ll1))
+
+
+def test_guidedbridge_importance_weights_unbiased(oracle_ref):
+    """test/guip.jl:245-274 (GuidedBridge z-score): E[exp(ll) p~/p] = 1.  Target and auxiliary are
+    both LinPro so that p and p~ are closed-form Gaussians; a fine tau-warped grid keeps the
+    discretisation bias (SURVEY 8c caveat) below the Monte-Carlo error."""
+    T, n, m = 2.0, 1000, 3000
+    s = np.linspace(0, T, n)
+    tt = s * (2 - s / T)
+    a, u, v = 0.7, 0.5, 0.1
+    Bt_, mu_t = -0.8, 0.2      # auxiliary LinPro(-0.8, 0.2, sqrt(a))
+    Bp_, mu_p = -0.3, -0.1     # target
+    P = O.linpro_model([[Bp_]], [mu_p], [[np.sqrt(a)]])
+    aux = O.const_aux([[Bt_]], [-Bt_ * mu_t], [[a]])
+    Hd, Vt = oracle_ref.backward_HV(tt, aux, [v])
+    G = O.GuideHolder(O.GUIDE_HV, tt, Hd, Vt, Bt=[[Bt_]], betat=[-Bt_ * mu_t])
+
+    def logp(B, mu):
+        mean = np.exp(B * T) * (u - mu) + mu
+        var = a / (2 * -B) * (1 - np.exp(2 * B * T))
+        return -0.5 * (v - mean) ** 2 / var - 0.5 * np.log(2 * np.pi * var)
+
+    w = np.empty(m)
+    for k in range(m):
+        W = oracle_ref.wiener_sample(tt, 1, 99, 0, k)
+        X, xend = oracle_ref.guided_euler(P, G, [u], W)
+        assert xend[0] == v  # endpoint(y, P::GuidedBridge) = V[end] when H♢[end] = 0  (src/euler.jl:241-242)
+        w[k] = np.exp(oracle_ref.llikelihood(P, G, X) + logp(Bt_, mu_t) - logp(Bp_, mu_p))
+    z = abs(w.mean() - 1) * np.sqrt(m) / w.std()
+    assert z < 3.5, (w.mean(), z)
+
+
+# --------------------------------------------------------------------------- pCN
+def test_pcn_smoke_acceptance(oracle_ref):
+    """test/partialbridge.jl:133 `1 < acc < iterations` on the partialparam setup (rho = 0.9)."""
+    tt = TT_PB
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    G = nuH_guide(oracle_ref, tt)
+    iters = 300
+    W = oracle_ref.wiener_sample(tt, 1, 1, 12345, 0)
+    X, _ = oracle_ref.guided_euler(P, G, X0_PB, W)
+    ll = oracle_ref.llikelihood(P, G, X)
+    acc = 0
+    for it in range(iters):
+        llo, logu, Wo, Xo, _ = oracle_ref.pcn_propose(P, [G], X0_PB, W, 0.9, 1, it, 0)
+        # the proposal is rho*W + sqrt(1-rho^2)*W2 with a fresh W2 (test/partialbridgenuH.jl:313-314)
+        if it == 0:
+            W2 = oracle_ref.wiener_sample(tt, 1, 1, 0, 0)
+            assert np.allclose(Wo[0], 0.9 * W + np.sqrt(1 - 0.81) * W2, rtol=0, atol=1e-14)
+        if logu <= llo - ll:
+            W, ll, acc = Wo[0], llo, acc + 1
+    assert 1 < acc < iters
+
+
+def test_pcn_bench_driver_matches_stepwise(oracle_ref):
+    """The OpenMP baseline driver is the same algorithm as the single-chain entry point."""
+    tt = TT_PB[:201]
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    G = nuH_guide(oracle_ref, tt)
+    acc, secs, ll = oracle_ref.pcn_bench(P, [G], 4, X0_PB, 0.9, 7, 5, nthreads=2)
+    # replay chain 2 by hand
+    c = 2
+    W = oracle_ref.wiener_sample(tt, 1, 7, 0xFFFFFFFE, c)
+    X, _ = oracle_ref.guided_euler(P, G, X0_PB, W)
+    l = oracle_ref.llikelihood(P, G, X)
+    for it in range(5):
+        llo, logu, Wo, _, _ = oracle_ref.pcn_propose(P, [G], X0_PB, W, 0.9, 7, it, c)
+        if logu <= llo - l:
+            W, l = Wo[0], llo
+    assert l == ll[c]
+    assert 0 <= acc <= 20 and secs >= 0
+
+
+# --------------------------------------------------------------------------- the two oracle builds
+def test_ref_and_fma_builds_agree_to_rounding(oracle_ref, oracle_fma):
+    """Contraction sensitivity of the FHN hypoelliptic bridge: reference arithmetic vs the kernels'
+    FMA order on identical W.  This is the gap the GPU-vs-reference tolerance has to cover."""
+    T = 0.5
+    s = np.linspace(0, T, 501)
+    tt = s * (2 - s / T)
+    P = O.make_model(O.FHN_HYPO, 2, 1, [0.1, 0.0, 1.5, 0.8, 0.3])
+    v = -1.0
+    Bt = np.array([[10.0, -10.0], [1.5, -1.0]]); bet = np.array([0.0 - v ** 3 / 0.1, 0.8])
+    at = np.array([[0.0, 0.0], [0.0, 0.09]])
+    aux = O.const_aux(Bt, bet, at)
+    out = []
+    for orc in (oracle_ref, oracle_fma):
+        nuT, HpT, C_ = orc.update_nuHC([[1.0, 0.0]], [[1e-10]], [v], 1e-3)
+        nu, H, _, _, _ = orc.backward_nuH(O.ODE_R3, tt, aux, nuT, HpT, C_)
+        G = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=Bt, betat=bet)
+        W = oracle_ref.wiener_sample(tt, 1, 4, 0, 0)
+        X, _ = orc.guided_euler(P, G, [-0.5, -0.6], W)
+        out.append((X, orc.llikelihood(P, G, X)))
+    (X1, l1), (X2, l2) = out
+    assert np.max(np.abs(X1 - X2)) < 1e-9 * (1 + np.max(np.abs(X1)))
+    assert abs(l1 - l2) < 1e-6 * abs(l1) + 1e-9
+    assert abs(X1[-1, 0] - v) < 1e-3
