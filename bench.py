@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- guided-bridge path-steps/s of the pCN sampler (BASELINE.json config 4) on N B200s.
+
+A "step" is ONE pCN / Metropolis-Hastings iteration of every chain on every rank: fresh Wiener noise,
+W° = ρW + sqrt(1-ρ²)W2, guided Euler through 4 chained FitzHugh-Nagumo bridge segments (N = 1001 each),
+Girsanov log-likelihood, accept/reject -- one fused kernel launch per rank, plus (N > 1) one NCCL
+all-reduce of the acceptance counter.  path-step = one Euler step of one chain incl. its ll increment.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--chains P_per_gpu]
+
+Weak scaling: every rank owns --chains chains (default 250 000 = BASELINE config 4 in full on each GPU;
+48 GB of path state per GPU, far beyond the 126 MB L2, so no cache flush is needed between steps).
+--impl reference times the CPU restatement of the reference loop (oracle/, OpenMP over chains on all host
+cores); the reference itself is Julia and cannot run in this image.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEGMENTS, NGRID = 4, 1001
+ALG_BYTES_PER_STEP = 32  # mode M with X° kept: read W 8 d' + write W° 8 d' + write X° 8 d  (d' = 1, d = 2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=250000, help="chains per GPU")
+    ap.add_argument("--n", type=int, default=NGRID, help="grid points per segment")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample we have
+            for ts, ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def oracle_workload(n):
+    """The same workload for the CPU restatement: tables from the oracle's own backward chain."""
+    from oracle import oracle as O
+    O.build()
+    orc = O.load("fast")  # -O3 -march=native build of the same restatement
+    par = (0.1, 0.0, 1.5, 0.8, 0.3)
+    obs_t, obs_v = (0.5, 1.0, 1.5, 2.0), (-1.0, -0.5, 0.5, 1.1)
+
+    def tau(t0, t1):
+        s = np.linspace(0.0, t1 - t0, n)
+        return t0 + s * (2.0 - s / (t1 - t0))
+
+    grids = [tau(a, b) for a, b in zip((0.0,) + obs_t[:-1], obs_t)]
+    L = np.array([[1.0, 0.0]]); Sg = np.array([[1e-10]])
+    nu = np.zeros(2); Hp = np.eye(2) / 1e-3
+    nu, Hp = orc.gpupdate_nuH(nu, Hp, L, Sg, [obs_v[-1]])
+    guides = [None] * 4
+    for i in range(3, -1, -1):
+        v = obs_v[i]
+        Bt = np.array([[10.0, -10.0], [1.5, -1.0]]); bt = np.array([0.0 - v ** 3 / 0.1, 0.8])
+        at = np.array([[0.0, 0.0], [0.0, 0.09]])
+        nut, Ht, nu, Hp, _ = orc.backward_nuH(O.ODE_LYAP, grids[i], O.const_aux(Bt, bt, at), nu, Hp, 0.0)
+        guides[i] = O.GuideHolder(O.GUIDE_NUH, grids[i], Ht, nut, Bt=Bt, betat=bt)
+        if i > 0:
+            nu, Hp = orc.gpupdate_nuH(nu, Hp, L, Sg, [obs_v[i - 1]])
+    model = O.make_model(O.FHN_HYPO, 2, 1, par)
+    return orc, model, guides, np.array([-0.5, -0.6])
+
+
+def cpu_run(n, seconds, iters=None, chains=None):
+    """Times the oracle's OpenMP pCN driver on a bounded sample; returns (steps/s, cores, sample text)."""
+    orc, model, guides, x0 = oracle_workload(n)
+    cores = orc.max_threads()
+    steps_per_chain_iter = SEGMENTS * (n - 1)
+    if chains is None:
+        pc = max(64, 8 * cores)
+        _, secs, _ = orc.pcn_bench(model, guides, pc, x0, 0.99, 4, 2, nthreads=cores)
+        rate = pc * 2 * steps_per_chain_iter / max(secs, 1e-6)
+        iters = 4
+        chains = int(max(8 * cores, min(200000, rate * seconds / (iters * steps_per_chain_iter))))
+        chains = max(cores, chains - chains % cores)
+    acc, secs, _ = orc.pcn_bench(model, guides, chains, x0, 0.99, 4, iters, nthreads=cores)
+    value = chains * iters * steps_per_chain_iter / secs
+    sample = (f"{chains} chains x {SEGMENTS} segments x {n - 1} steps x {iters} pCN iterations "
+              f"({chains * iters * steps_per_chain_iter:.3g} path-steps, {secs:.2f} s)")
+    return value, cores, sample, secs, chains, iters
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = []
+    per_step_budget = max(0.5, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    value, cores, sample, secs, chains, iters = cpu_run(args.n, per_step_budget)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_run(args.n, 0, iters, chains)
+    tot_steps, tot_secs = 0.0, 0.0
+    for _ in range(args.steps):
+        v, _, _, s, c, it = cpu_run(args.n, 0, iters, chains)
+        tot_steps += c * it * SEGMENTS * (args.n - 1); tot_secs += s
+        t_all.append(s)
+    value = tot_steps / tot_secs
+    line = {
+        "impl": "reference", "metric": "guided_bridge_path_steps_per_s", "value": value, "unit": "path-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[3]: FitzHugh-Nagumo PartialBridgeνH pCN, 4 segments x N=1001, rho=0.99",
+                   "per_step_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C restatement of the Julia loop (oracle/bridge_oracle.c), OpenMP over chains; "
+                                 "Julia itself is not installed in this image"},
+        "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, p, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 3}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import bridge_jl_b200 as B
+    import bridge_jl_b200.configs as cfg
+
+    ctx = B.Context(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # kernels run on torch's current stream: torch events time them
+
+    n, P = args.n, args.chains
+    Pm, guides, x0, rho = cfg.fhn_config4(n, ctx=ctx)
+    S = len(guides)
+    ens = B.PathEnsemble(P, S, n, 2, 1, double_buffer=True, store_x=True, ctx=ctx, chain_offset=rank * P)
+    for s, g in enumerate(guides):
+        ens.set_grid(s, g.tt)
+    ens.set_start(x0)
+    seed = 4
+    ens.sample_(seed, 0xFFFFFFFE)
+    ens.guided_euler_ll_(Pm, guides)
+    acc_t = torch.as_tensor(_DevArray(ens.acc_device_ptr, 1, "<i8"), device=torch.device("cuda", local))
+    acc_sum = torch.zeros(1, dtype=torch.int64, device=acc_t.device)
+
+    def step(it):
+        ens.pcn_step_(Pm, guides, rho, seed, it)
+        if world > 1:  # the one collective of the path: the acceptance statistic
+            acc_sum.copy_(acc_t)
+            dist.all_reduce(acc_sum)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = 0
+    for _ in range(max(3, args.warmup)):
+        step(it); it += 1
+    steps_per_iter_rank = P * S * (n - 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    launches0 = ctx.launch_count
+    acc0 = ens.acc
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    t0 = time.time()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        ev[2 + 2 * k].record(stream)
+        ens.pcn_step_(Pm, guides, rho, seed, it)
+        ev[3 + 2 * k].record(stream)
+        if world > 1:
+            acc_sum.copy_(acc_t)
+            dist.all_reduce(acc_sum)
+        it += 1
+    ev[1].record(stream)
+    barrier()
+    t1 = time.time()
+    launches = ctx.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[1])
+    kern_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps)]
+    clocks = sampler.stop(t0, t1)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=acc_t.device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    value = world * steps_per_iter_rank * args.steps / (total_ms * 1e-3)
+    acc_rate = (ens.acc - acc0) / (P * args.steps)  # this rank's acceptance rate over the timed steps
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = float(np.mean(kern_ms))
+    achieved = steps_per_iter_rank * ALG_BYTES_PER_STEP / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "bb_chain_kernel<MFhnHypo, NUH, aux const, pCN>",
+                "kernel_ms": k_ms, "alg_bytes_per_path_step": ALG_BYTES_PER_STEP,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"}
+
+    # ---- end to end through host buffers: the reference loop keeps W, X in host memory
+    e2e = None
+    if not args.no_e2e:
+        hostW = torch.empty((P, S, n, 1), dtype=torch.float64, pin_memory=True).numpy()
+        hostWo = torch.empty((P, S, n, 1), dtype=torch.float64, pin_memory=True).numpy()
+        hostXo = torch.empty((P, S, n, 2), dtype=torch.float64, pin_memory=True).numpy()
+        ens.download(B.W, out=hostW)
+
+        def e2e_step(itn):
+            ens.upload(B.W, hostW)                       # H2D: the chain state the host owns
+            ens.pcn_step_(Pm, guides, rho, seed, itn)
+            ens.download(B.W, which=B.PROP, out=hostWo)  # D2H: proposal W°, X°
+            ens.download(B.X, which=B.PROP, out=hostXo)
+            return ens.ll_prop, ens.accepted, ens.acc    # D2H: ll°, accept flags, counter
+
+        e2e_step(it); it += 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.e2e_steps):
+            e2e_step(it); it += 1
+        e1.record(stream)
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=acc_t.device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * steps_per_iter_rank * args.e2e_steps / (float(ems.item()) * 1e-3),
+               "unit": "path-steps/s", "h2d_bytes_per_step": int(hostW.nbytes),
+               "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
+               "steps": args.e2e_steps,
+               "what": "per step: upload W (pinned host) -> bb_pcn_step -> download W°, X°, ll°, accept flags"}
+        # device-resident ensemble API: per step only the guide tables go up and ll°/flags/acc come back
+        barrier()
+        e0.record(stream)
+        for _ in range(args.e2e_steps * 4):
+            Pm2, guides2, _, _ = cfg.fhn_config4(n, ctx=ctx)  # backward ODEs + table upload every step
+            ens.pcn_step_(Pm2, guides2, rho, seed, it); it += 1
+            _ = ens.ll_prop, ens.accepted, ens.acc
+        e1.record(stream)
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=acc_t.device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e["resident"] = {"value": world * steps_per_iter_rank * args.e2e_steps * 4 / (float(ems.item()) * 1e-3),
+                           "unit": "path-steps/s", "d2h_bytes_per_step": P * 9 + 8,
+                           "what": "chain state stays in HBM (PathEnsemble); per step: rebuild + upload the 4 guide "
+                                   "tables, bb_pcn_step, read back ll°, accept flags, acc"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample, _, _, _ = cpu_run(n, args.cpu_seconds)
+        cpu = {"value": v, "unit": "path-steps/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "guided_bridge_path_steps_per_s", "value": value, "unit": "path-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[3]: FitzHugh-Nagumo (hypoelliptic, d=2, d'=1) PartialBridgeνH pCN, "
+                                   "4 segments x N=1001 (tau-warped), rho=0.99, X° stored",
+                       "chains_per_gpu": P, "segments": S, "grid_points": n,
+                       "path_steps_per_step": world * steps_per_iter_rank,
+                       "state_bytes_per_gpu": ens.nbytes, "l2": "working set >> 126 MB L2: no flush needed",
+                       "parallelism": f"chains sharded over {world} GPU(s), all-reduce of acc only"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "acc_rate": acc_rate,
+        }
+        print(json.dumps(line), flush=True)
+    ens.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,820 @@
+"""Host-side mirror of the Bridge.jl interface for the accelerated path.
+
+Names, argument order and error behaviour follow the reference (mschauer/Bridge.jl @ b09488fe):
+
+    ContinuousTimeProcess{T}, b, σ, a            src/types.jl:23,32-33, src/Bridge.jl:105-106
+    SamplePath, VSamplePath, samplepath           src/types.jl:71-81,123-130
+    sample, sample!                               src/wiener.jl:11-58
+    solve, solve!(::EulerMaruyama / ::Euler, …)   src/euler.jl:117-118,135-152,246-268
+    bridge!                                       src/deprecated.jl:16-17, project/partialbridge.jl:63
+    llikelihood(::LeftRule, X, P°; skip)          src/partialbridgenuH.jl:171, guip.jl:429, partialbridge.jl:67
+    innovations!                                  src/euler.jl:357-376
+    GuidedBridge, PartialBridge, PartialBridgeνH, partialbridgeνH, gpupdate
+                                                  src/guip.jl:165-243, partialbridge.jl:33-51, partialbridgenuH.jl:122-155
+
+Julia's `f!` is spelled `f_` here.  Every numeric result comes from libbridge_b200.so (CUDA, sm_100a)
+through the C ABI in _cabi.py; this module only converts between the reference's containers and the
+ABI's buffers.  `PathEnsemble` is the device-resident container a many-chain sampler uses instead of
+one SamplePath pair per chain.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi as K
+from ._cabi import BridgeError, check, f64, lib, ptr
+
+# ----------------------------------------------------------------------------------------------- context
+
+
+class Context:
+    """One CUDA device + stream (bb_ctx)."""
+
+    def __init__(self, device: Optional[int] = None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        check(lib.bb_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        self._small = {}
+
+    def synchronize(self):
+        check(lib.bb_ctx_synchronize(self.h))
+
+    def set_stream(self, cuda_stream: int):
+        check(lib.bb_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_timing(self, on: bool):
+        check(lib.bb_ctx_set_timing(self.h, 1 if on else 0))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return lib.bb_ctx_last_kernel_ms(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return lib.bb_ctx_launch_count(self.h)
+
+    def close(self):
+        for e in self._small.values():
+            e.close()
+        self._small = {}
+        if self.h:
+            lib.bb_ctx_destroy(self.h)
+            self.h = None
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+# ----------------------------------------------------------------------------------------------- solver tags
+class SDESolver:
+    pass
+
+
+class EulerMaruyama(SDESolver):  # src/euler.jl:17-21
+    pass
+
+
+Euler = EulerMaruyama  # src/euler.jl:23
+
+
+class LeftRule:  # src/ode.jl:8
+    pass
+
+
+class R3:  # src/ode.jl:26
+    pass
+
+
+class Lyap:  # src/partialbridgenuH.jl:84
+    pass
+
+
+# ----------------------------------------------------------------------------------------------- processes
+class ContinuousTimeProcess:
+    """Base of the target processes the device registry knows (src/types.jl:23).  Subclasses give
+    the registry id and parameter block, plus host evaluations of b, σ, a for inspection."""
+
+    model_id = -1
+    d = 1
+    dprime = 1
+
+    def par(self) -> Sequence[float]:
+        raise NotImplementedError
+
+    def cmodel(self) -> K.Model:
+        m = K.Model()
+        m.id, m.d, m.dprime, m.reserved = self.model_id, self.d, self.dprime, 0
+        for i, v in enumerate(np.asarray(self.par(), dtype=np.float64).ravel()):
+            m.par[i] = float(v)
+        return m
+
+    # host-side coefficient protocol (Bridge.b/σ/a); not used by the solvers
+    def b(self, t, x):
+        raise NotImplementedError
+
+    def σ(self, t, x):
+        raise NotImplementedError
+
+    def a(self, t, x=None):
+        s = np.atleast_2d(self.σ(t, x))
+        return s @ s.T  # fallback a = σσ'  src/types.jl:32
+
+    sigma = σ
+    constdiff = True
+
+
+class Wiener(ContinuousTimeProcess):  # src/wiener.jl
+    model_id = K.WIENER
+
+    def __init__(self, d: int = 1):
+        self.d = self.dprime = d
+
+    def par(self):
+        return []
+
+    def b(self, t, x):
+        return np.zeros(self.d)
+
+    def σ(self, t, x=None):
+        return np.eye(self.d)
+
+
+class OrnsteinUhlenbeck(ContinuousTimeProcess):  # docs/src/manual.md:44-46
+    model_id = K.OU
+
+    def __init__(self, β: float, σ: float):
+        self.β, self.σ_ = float(β), float(σ)
+
+    def par(self):
+        return [self.β, self.σ_]
+
+    def b(self, t, x):
+        return -self.β * np.asarray(x)
+
+    def σ(self, t, x=None):
+        return np.array([[self.σ_]])
+
+
+class LinPro(ContinuousTimeProcess):  # src/linpro.jl:65-87
+    model_id = K.LINPRO
+    is_const = True
+
+    def __init__(self, B, μ, σ):
+        self.Bm = np.atleast_2d(f64(B))
+        self.d = self.dprime = self.Bm.shape[0]
+        self.μ = np.atleast_1d(f64(μ))
+        self.σm = np.atleast_2d(f64(σ))
+        if self.σm.shape == (1, 1) and self.d > 1:
+            self.σm = self.σm[0, 0] * np.eye(self.d)
+
+    def par(self):
+        return np.concatenate([self.Bm.ravel(), self.μ.ravel(), self.σm.ravel()])
+
+    def b(self, t, x):
+        return self.Bm @ (np.asarray(x) - self.μ)
+
+    def σ(self, t, x=None):
+        return self.σm
+
+    # auxiliary-process protocol  src/linpro.jl:81-86
+    def B(self, t):
+        return self.Bm
+
+    def β(self, t):
+        return -self.Bm @ self.μ
+
+    def a(self, t, x=None):
+        return self.σm @ self.σm.T
+
+
+class FitzHughNagumo(ContinuousTimeProcess):  # src/Models.jl:9-20 (diagonal noise)
+    model_id = K.FHN_DIAG
+    d = dprime = 2
+
+    def __init__(self, ϵ, s, γ, β, σ1, σ2):
+        self.p = [float(v) for v in (ϵ, s, γ, β, σ1, σ2)]
+
+    def par(self):
+        return self.p
+
+    def b(self, t, x):
+        ϵ, s, γ, β = self.p[:4]
+        return np.array([(x[0] - x[0] ** 3 - x[1] + s) / ϵ, γ * x[0] - x[1] + β])
+
+    def σ(self, t, x=None):
+        return np.diag(self.p[4:6])
+
+
+class FitzhughDiffusion(ContinuousTimeProcess):  # project_partialbridge/partialbridge_fitzhugh.jl:36-46
+    model_id = K.FHN_HYPO
+    d, dprime = 2, 1
+
+    def __init__(self, ϵ, s, γ, β, σ):
+        self.p = [float(v) for v in (ϵ, s, γ, β, σ)]
+
+    def par(self):
+        return self.p
+
+    def b(self, t, x):
+        ϵ, s, γ, β = self.p[:4]
+        return np.array([(x[0] - x[1] - x[0] ** 3 + s) / ϵ, γ * x[0] - x[1] + β])
+
+    def σ(self, t, x=None):
+        return np.array([[0.0], [self.p[4]]])
+
+
+class IntegratedDiffusion(ContinuousTimeProcess):  # test/partialbridge.jl:18-28
+    model_id = K.INTDIFF
+    d, dprime = 2, 1
+
+    def __init__(self, γ):
+        self.γ = float(γ)
+
+    def par(self):
+        return [self.γ]
+
+    def b(self, t, x):
+        return np.array([x[1], -(x[1] + np.sin(x[1])) + 0.5])
+
+    def σ(self, t, x=None):
+        return np.array([[0.0], [self.γ]])
+
+
+class NclarDiffusion(ContinuousTimeProcess):  # project_partialbridge/partialbridge_nclar.jl:50-60
+    model_id = K.NCLAR3
+    d, dprime = 3, 1
+
+    def __init__(self, α, ω, σ):
+        self.p = [float(α), float(ω), float(σ)]
+
+    def par(self):
+        return self.p
+
+    def b(self, t, x):
+        return np.array([x[1], x[2], -self.p[0] * np.sin(self.p[1] * x[2])])
+
+    def σ(self, t, x=None):
+        return np.array([[0.0], [0.0], [self.p[2]]])
+
+
+class Lorenz(ContinuousTimeProcess):  # src/Models.jl:38-55
+    model_id = K.LORENZ
+    d = dprime = 3
+
+    def __init__(self, θ, σ):
+        σ = np.atleast_1d(f64(σ))
+        if σ.size == 1:
+            σ = np.repeat(σ, 3)
+        self.p = [float(v) for v in list(θ) + list(σ)]
+
+    def par(self):
+        return self.p
+
+    def b(self, t, x):
+        θ = self.p
+        return np.array([θ[0] * (x[1] - x[0]), x[0] * (θ[1] - x[2]) - x[1], x[0] * x[1] - θ[2] * x[2]])
+
+    def σ(self, t, x=None):
+        return np.diag(self.p[3:6])
+
+
+class LinearAux:
+    """An auxiliary process given by B(t), β(t), a(t) (constants or callables), the protocol the
+    guided proposals use (Bridge.B, Bridge.β, Bridge.a; partialbridge_fitzhugh.jl:99-116)."""
+
+    def __init__(self, B, β, a):
+        self._B, self._β, self._a = B, β, a
+        self.is_const = not (callable(B) or callable(β) or callable(a))
+        B0 = np.atleast_2d(f64(B(0.0) if callable(B) else B))
+        self.d = B0.shape[0]
+
+    def B(self, t):
+        return np.atleast_2d(f64(self._B(t) if callable(self._B) else self._B))
+
+    def β(self, t):
+        return np.atleast_1d(f64(self._β(t) if callable(self._β) else self._β))
+
+    def a(self, t, x=None):
+        return np.atleast_2d(f64(self._a(t) if callable(self._a) else self._a))
+
+
+class _AuxC:
+    """bb_aux for a backward solve on grid tt (keeps the arrays alive)."""
+
+    def __init__(self, Pt, tt):
+        d = np.atleast_2d(Pt.B(tt[0])).shape[0]
+        self.d = d
+        if getattr(Pt, "is_const", False):
+            self.B, self.beta, self.a = f64(Pt.B(tt[0])), f64(Pt.β(tt[0])), f64(Pt.a(tt[0]))
+            self.al = None
+            const = 1
+        else:
+            N = len(tt)
+            self.B = np.empty((N - 1, 3, d, d)); self.beta = np.empty((N - 1, 3, d))
+            self.a = np.empty((N - 1, 3, d, d)); self.al = np.empty((N - 1, d, d))
+            for i in range(N - 1):
+                t, h = tt[i + 1], tt[i] - tt[i + 1]
+                for k, c in enumerate((0.0, 0.5, 0.75)):  # stage times of src/ode.jl:44-49
+                    s = t + c * h
+                    self.B[i, k] = Pt.B(s); self.beta[i, k] = Pt.β(s); self.a[i, k] = Pt.a(s)
+                self.al[i] = Pt.a(tt[i])
+            const = 0
+        self.c = K.Aux(d, const, ptr(self.B), ptr(self.beta), ptr(self.a), ptr(self.al))
+
+
+def _aux_on_grid(Pt, tt):
+    """B̃(tt[i]), β̃(tt[i]) for llikelihood (b̃ = B̃x+β̃, src/partialbridgenuH.jl:176)."""
+    if getattr(Pt, "is_const", False):
+        return f64(Pt.B(tt[0])), f64(Pt.β(tt[0])), 1
+    Bt = np.stack([np.atleast_2d(Pt.B(t)) for t in tt])
+    bt = np.stack([np.atleast_1d(Pt.β(t)) for t in tt])
+    return f64(Bt), f64(bt), 0
+
+
+# ----------------------------------------------------------------------------------------------- sample paths
+class SamplePath:
+    """tt::Vector{Float64}, yy::Vector{T}  (src/types.jl:71-76); yy is [N] (T=Float64) or [N, d]."""
+
+    def __init__(self, tt, yy):
+        self.tt = f64(tt)
+        self.yy = np.array(yy, dtype=np.float64)
+        if self.yy.shape[0] != self.tt.shape[0]:
+            raise BridgeError(K.ERR_DIM, lib.bb_strerror(K.ERR_DIM).decode())
+
+    def __len__(self):
+        return len(self.tt)
+
+    def copy(self):
+        return SamplePath(self.tt.copy(), self.yy.copy())
+
+    @property
+    def dim(self):
+        return 1 if self.yy.ndim == 1 else self.yy.shape[1]
+
+    def _as2d(self):
+        return self.yy.reshape(len(self.tt), -1)
+
+
+class VSamplePath(SamplePath):
+    """yy::Matrix of size d x N (src/types.jl:123-130); stored here as [N, d] views of the same data."""
+
+    def __init__(self, tt, yy):
+        yy = np.asarray(yy, dtype=np.float64)
+        if yy.ndim != 2 or yy.shape[1] != len(tt):
+            raise BridgeError(K.ERR_DIM, lib.bb_strerror(K.ERR_DIM).decode())
+        super().__init__(tt, yy.T.copy())
+
+
+def samplepath(tt, v) -> SamplePath:  # src/types.jl:78-81 (aliases tt)
+    tt = f64(tt)
+    v = np.asarray(v, dtype=np.float64)
+    yy = np.zeros((len(tt),) + v.shape)
+    yy[...] = v
+    sp = SamplePath.__new__(SamplePath)
+    sp.tt, sp.yy = tt, yy
+    return sp
+
+
+# ----------------------------------------------------------------------------------------------- ensemble
+class PathEnsemble:
+    """P chains x S segments x N grid points resident in HBM (bb_ens)."""
+
+    def __init__(self, P: int, S: int, N: int, d: int, dprime: int, double_buffer: bool = True,
+                 store_x: bool = True, ctx: Optional[Context] = None, chain_offset: int = 0):
+        self.ctx = ctx or default_context()
+        self.P, self.S, self.N, self.d, self.dprime = P, S, N, d, dprime
+        flags = (K.ENS_DOUBLE_BUFFER if double_buffer else 0) | (0 if store_x else K.ENS_NO_X)
+        h = C.c_void_p()
+        check(lib.bb_ens_create(self.ctx.h, P, S, N, d, dprime, flags, C.byref(h)))
+        self.h = h
+        self.has_x = store_x
+        if chain_offset:
+            check(lib.bb_ens_set_chain_offset(self.h, chain_offset))
+
+    def close(self):
+        if self.h:
+            lib.bb_ens_destroy(self.h)
+            self.h = None
+
+    # ---- configuration
+    def set_grid(self, seg: int, tt):
+        tt = f64(tt)
+        check(lib.bb_ens_set_grid(self.h, seg, ptr(tt), len(tt)))
+
+    def set_start(self, u):
+        u = f64(u)
+        if u.ndim <= 1 and u.size == self.d:
+            check(lib.bb_ens_set_start(self.h, ptr(u), u.size, 1))
+        else:
+            check(lib.bb_ens_set_start(self.h, ptr(u), u.size, 0))
+
+    # ---- data movement; host layout [np][S][N][k]
+    def upload(self, what, arr, which=K.CUR, p0=0):
+        k = self.dprime if what == K.W else self.d
+        arr = f64(arr).reshape(-1, self.S, self.N, k)
+        check(lib.bb_ens_upload(self.h, what, which, p0, arr.shape[0], ptr(arr)))
+
+    def download(self, what, which=K.CUR, p0=0, np_=None, out=None):
+        k = self.dprime if what == K.W else self.d
+        n = self.P - p0 if np_ is None else np_
+        if out is None:
+            out = np.empty((n, self.S, self.N, k))
+        check(lib.bb_ens_download(self.h, what, which, p0, n, ptr(out)))
+        return out
+
+    def _f(self, field, width=1):
+        out = np.empty((self.P, width) if width > 1 else self.P)
+        check(lib.bb_ens_get_f64(self.h, field, 0, self.P, ptr(out)))
+        return out
+
+    @property
+    def ll(self):
+        return self._f(K.F_LL)
+
+    @property
+    def ll_prop(self):
+        return self._f(K.F_LL_PROP)
+
+    @property
+    def logu(self):
+        return self._f(K.F_LOGU)
+
+    @property
+    def xend(self):
+        return self._f(K.F_XEND, self.d).reshape(self.P, self.d)
+
+    @property
+    def xend_prop(self):
+        return self._f(K.F_XEND_PROP, self.d).reshape(self.P, self.d)
+
+    def set_ll(self, ll):
+        ll = f64(ll)
+        check(lib.bb_ens_set_ll(self.h, 0, ll.size, ptr(ll)))
+
+    @property
+    def accepted(self):
+        out = np.empty(self.P, dtype=np.uint8)
+        check(lib.bb_ens_get_accepted(self.h, 0, self.P, ptr(out)))
+        return out
+
+    @property
+    def acc(self) -> int:
+        v = C.c_int64(0)
+        check(lib.bb_ens_get_acc(self.h, C.byref(v)))
+        return v.value
+
+    def reset_acc(self):
+        check(lib.bb_ens_reset_acc(self.h))
+
+    @property
+    def acc_device_ptr(self) -> int:
+        return lib.bb_ens_acc_device_ptr(self.h)
+
+    @property
+    def nbytes(self) -> int:
+        return lib.bb_ens_bytes(self.h)
+
+    # ---- compute
+    @staticmethod
+    def _garr(guides):
+        hs = [g._guide if hasattr(g, "_guide") else g for g in guides]
+        return (C.c_void_p * len(hs))(*[h.value if isinstance(h, C.c_void_p) else h for h in hs])
+
+    def sample_(self, seed: int, stream: int = 0):
+        """sample!(W, Wiener()) for every chain and segment."""
+        check(lib.bb_wiener_sample(self.h, seed, stream))
+
+    def euler_(self, P: ContinuousTimeProcess):
+        m = P.cmodel()
+        check(lib.bb_euler(self.h, C.byref(m)))
+
+    def sample_euler_(self, P: ContinuousTimeProcess, seed: int, stream: int = 0):
+        m = P.cmodel()
+        check(lib.bb_sample_euler(self.h, C.byref(m), seed, stream))
+
+    def guided_euler_ll_(self, P, guides, skip: int = 0, store_x: bool = True, ll: bool = True):
+        m = P.cmodel()
+        flags = (K.RUN_STORE_X if store_x else 0) | (0 if ll else K.RUN_NO_LL)
+        check(lib.bb_guided_euler_ll(self.h, C.byref(m), self._garr(guides), skip, flags))
+
+    def llikelihood_(self, P, guides, skip: int = 0):
+        m = P.cmodel()
+        check(lib.bb_llikelihood(self.h, C.byref(m), self._garr(guides), skip))
+
+    def innovations_(self, P, guides=None):
+        m = P.cmodel()
+        check(lib.bb_innovations(self.h, C.byref(m), None if guides is None else self._garr(guides)))
+
+    def pcn_step_(self, P, guides, ρ: float, seed: int, it: int, skip: int = 0, store_x: bool = True):
+        """One pCN / Metropolis-Hastings update of every chain (test/partialbridgenuH.jl:176-191)."""
+        m = P.cmodel()
+        check(lib.bb_pcn_step(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip,
+                              K.RUN_STORE_X if store_x else 0))
+
+
+def _small_ens(ctx: Context, S, N, d, dp, double_buffer=False) -> PathEnsemble:
+    key = (S, N, d, dp, double_buffer)
+    e = ctx._small.get(key)
+    if e is None:
+        e = PathEnsemble(1, S, N, d, dp, double_buffer=double_buffer, ctx=ctx)
+        ctx._small[key] = e
+    return e
+
+
+# ----------------------------------------------------------------------------------------------- guided proposals
+class _Proposal:
+    kind = 0
+    m = 0
+
+    def _make_guide(self, A, b, Mm=None, v=None):
+        Bt, bt, const = _aux_on_grid(self.Pt, self.tt)
+        h = C.c_void_p()
+        A, b = f64(A), f64(b)
+        Mm = None if Mm is None else f64(Mm)
+        v = None if v is None else f64(v)
+        check(lib.bb_guide_create(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt), ptr(A),
+                                  ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, C.byref(h)))
+        self._guide = h
+
+    def __del__(self):
+        g = getattr(self, "_guide", None)
+        if g and self.ctx.h:
+            lib.bb_guide_destroy(g)
+            self._guide = None
+
+
+class GuideTables(_Proposal):
+    """A guided proposal from tables the caller already holds (values on the grid `tt`, layouts of
+    bb_guide_create): kind NUH (A=H, b=ν), HV (A=H♢, b=V) or LMMU (A=L, b=μ, Mm=M, v)."""
+
+    def __init__(self, kind, tt, P, A, b, Bt, betat, Mm=None, v=None, aux_const=True, m=0, ctx=None):
+        self.ctx = ctx or default_context()
+        self.kind, self.m = kind, m
+        self.tt, self.Target, self.Pt = f64(tt), P, None
+        h = C.c_void_p()
+        A, b, Bt, betat = f64(A), f64(b), f64(Bt), f64(betat)
+        Mm = None if Mm is None else f64(Mm)
+        v = None if v is None else f64(v)
+        check(lib.bb_guide_create(self.ctx.h, kind, len(self.tt), P.d, m, ptr(self.tt), ptr(A), ptr(b), ptr(Mm),
+                                  ptr(v), ptr(Bt), ptr(betat), 1 if aux_const else 0, C.byref(h)))
+        self._guide = h
+
+
+def _update_nuHC(ctx, L, Σ, v, ϵ):
+    L = np.atleast_2d(f64(L)); m, d = L.shape
+    Σ = np.atleast_2d(f64(Σ)); v = np.atleast_1d(f64(v))
+    if v.size != m:
+        raise BridgeError(K.ERR_ASSERT_M, lib.bb_strerror(K.ERR_ASSERT_M).decode())
+    ν = np.zeros(d); Hp = np.zeros((d, d)); Cc = C.c_double(0)
+    check(lib.bb_update_nuHC(ctx.h, d, m, ptr(L), ptr(Σ), ptr(v), float(ϵ), ptr(ν), ptr(Hp), C.byref(Cc)))
+    return ν, Hp, Cc.value
+
+
+def _backward_nuH(ctx, method, tt, Pt, νend, Hendp, C0=0.0):
+    tt = f64(tt); aux = _AuxC(Pt, tt); N, d = len(tt), aux.d
+    νend = np.atleast_1d(f64(νend)); Hendp = np.atleast_2d(f64(Hendp))
+    ν = np.zeros((N, d)); H = np.zeros((N, d, d)); νl = np.zeros(d); Hl = np.zeros((d, d)); Cc = C.c_double(0)
+    check(lib.bb_backward_nuH(ctx.h, method, N, d, ptr(tt), C.byref(aux.c), ptr(νend), ptr(Hendp), float(C0),
+                              ptr(ν), ptr(H), ptr(νl), ptr(Hl), C.byref(Cc)))
+    return ν, H, νl, Hl, Cc.value
+
+
+class PartialBridgeνH(_Proposal):
+    """PartialBridgeνH(tt, P, Pt, L, v, ϵ, Σ)  src/partialbridgenuH.jl:134-145; fields Target, Pt, tt, ν, H, C."""
+    kind = K.GUIDE_NUH
+
+    def __init__(self, tt, P, Pt, L=None, v=None, ϵ=None, Σ=None, *, _tables=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        if _tables is not None:
+            self.ν, self.H, self.C = _tables
+        else:
+            L = np.atleast_2d(f64(L))
+            if Σ is None:
+                Σ = np.zeros((L.shape[0], L.shape[0]))
+            νT, HpT, C0 = _update_nuHC(self.ctx, L, Σ, v, ϵ)
+            self.ν, self.H, _, _, self.C = _backward_nuH(self.ctx, K.ODE_R3, self.tt, Pt, νT, HpT, C0)
+        self._make_guide(self.H, self.ν)
+
+
+PartialBridgenuH = PartialBridgeνH
+
+
+def partialbridgeνH(tt, P, Pt, νend, Hendp, ctx=None):
+    """Bridge.partialbridgeνH(tt, P, Pt, νend, Hend⁺) -> (P°, ν, H⁺, C)  src/partialbridgenuH.jl:148-155
+    (Lyapunov backward step; the unbound C of the reference is taken as 0.0)."""
+    ctx = ctx or default_context()
+    ν, H, νl, Hl, Cc = _backward_nuH(ctx, K.ODE_LYAP, tt, Pt, νend, Hendp, 0.0)
+    return PartialBridgeνH(tt, P, Pt, _tables=(ν, H, Cc), ctx=ctx), νl, Hl, Cc
+
+
+partialbridgenuH = partialbridgeνH
+
+
+class GuidedBridge(_Proposal):
+    """GuidedBridge(tt, P, Pt, v[, h♢])  src/guip.jl:172-180; fields Target, Pt, tt, H♢, V."""
+    kind = K.GUIDE_HV
+
+    def __init__(self, tt, P, Pt, v, hdia=None, *, ctx=None):
+        self.ctx = ctx or default_context()
+        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        aux = _AuxC(Pt, self.tt); N, d = len(self.tt), aux.d
+        v = np.atleast_1d(f64(v))
+        he = None if hdia is None else np.atleast_2d(f64(hdia))
+        self.Hdia = np.zeros((N, d, d)); self.V = np.zeros((N, d))
+        check(lib.bb_backward_HV(self.ctx.h, N, d, ptr(self.tt), C.byref(aux.c), ptr(v), ptr(he), ptr(self.Hdia),
+                                 ptr(self.V)))
+        self._make_guide(self.Hdia, self.V)
+
+
+class PartialBridge(_Proposal):
+    """PartialBridge(tt, P, Pt, L, v[, Σ])  src/partialbridge.jl:42-50; fields Target, Pt, tt, v, L, M, μ."""
+    kind = K.GUIDE_LMMU
+
+    def __init__(self, tt, P, Pt, L, v, Σ=None, *, ctx=None):
+        self.ctx = ctx or default_context()
+        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        L = np.atleast_2d(f64(L)); m, d = L.shape
+        self.m = m
+        self.v = np.atleast_1d(f64(v))
+        if self.v.size != m:
+            raise BridgeError(K.ERR_ASSERT_M, lib.bb_strerror(K.ERR_ASSERT_M).decode())
+        Σ = np.zeros((m, m)) if Σ is None else np.atleast_2d(f64(Σ))
+        aux = _AuxC(Pt, self.tt); N = len(self.tt)
+        self.L = np.zeros((N, m, d)); self.M = np.zeros((N, m, m)); self.μ = np.zeros((N, m))
+        check(lib.bb_backward_LMmu(self.ctx.h, N, d, m, ptr(self.tt), C.byref(aux.c), ptr(L), ptr(Σ), ptr(self.L),
+                                   ptr(self.M), ptr(self.μ)))
+        self._make_guide(self.L, self.μ, self.M, self.v)
+
+
+def gpupdate(*args, ctx=None):
+    """Bridge.gpupdate(H♢, V, L, Σ, v) / gpupdate(P°, L, Σ, v) -> (H♢', V')  src/guip.jl:221-243."""
+    ctx = ctx or default_context()
+    if len(args) == 4:
+        Po, L, Σ, v = args
+        Hd, V = Po.Hdia[0], Po.V[0]
+    else:
+        Hd, V, L, Σ, v = args
+    L = np.atleast_2d(f64(L)); m, d = L.shape
+    Hd = np.atleast_2d(f64(Hd)).copy(); V = np.atleast_1d(f64(V)).copy()
+    Σ = np.atleast_2d(f64(Σ)); v = np.atleast_1d(f64(v))
+    check(lib.bb_gpupdate_HV(ctx.h, d, m, ptr(Hd), ptr(V), ptr(L), ptr(Σ), ptr(v)))
+    return Hd, V
+
+
+def gpupdate_νH(ν, Hp, L, Σ, v, ctx=None):
+    """Observation update of (ν, H⁺) between segments (partialbridge_bolus3.jl:128-137)."""
+    ctx = ctx or default_context()
+    L = np.atleast_2d(f64(L)); m, d = L.shape
+    ν = np.atleast_1d(f64(ν)).copy(); Hp = np.atleast_2d(f64(Hp)).copy()
+    Σ = np.atleast_2d(f64(Σ)); v = np.atleast_1d(f64(v))
+    check(lib.bb_gpupdate_nuH(ctx.h, d, m, ptr(ν), ptr(Hp), ptr(L), ptr(Σ), ptr(v)))
+    return ν, Hp
+
+
+# ----------------------------------------------------------------------------------------------- reference calls
+class _Rng:
+    seed = 0
+    stream = 0
+
+
+def seed_(s: int):
+    """Random.seed!(s): seeds the Philox streams used by sample / sample!."""
+    _Rng.seed, _Rng.stream = int(s), 0
+
+
+def sample_(W: SamplePath, P: Wiener, y1=None, ctx=None) -> SamplePath:
+    """sample!(W, Wiener{T}(), y1 = W.yy[1])  src/wiener.jl:50-58."""
+    ctx = ctx or default_context()
+    N, dp = len(W), W.dim
+    e = _small_ens(ctx, 1, N, dp, dp)
+    w = W._as2d().copy()
+    if y1 is not None:
+        w[0] = y1
+    e.set_grid(0, W.tt)
+    e.upload(K.W, w)
+    e.sample_(_Rng.seed, _Rng.stream)
+    _Rng.stream += 1
+    out = e.download(K.W)
+    W.yy[...] = out.reshape(W.yy.shape)
+    return W
+
+
+def sample(tt, P: Wiener, y1=None, ctx=None) -> SamplePath:
+    """sample(tt, Wiener{T}()[, y1])  src/wiener.jl:11-21."""
+    d = P.d
+    yy = np.zeros(len(tt)) if d == 1 else np.zeros((len(tt), d))
+    return sample_(SamplePath(tt, yy), P, y1, ctx)
+
+
+def _is_proposal(P):
+    return isinstance(P, _Proposal)
+
+
+def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
+    """solve!(::EulerMaruyama, Y, u, W, P) -> Y                     src/euler.jl:135-152
+    solve!(::Euler, Y, u, W, P°) -> Y.yy[N] (the end point)       src/euler.jl:247-268"""
+    ctx = ctx or default_context()
+    if not isinstance(method, EulerMaruyama):
+        raise NotImplementedError("only EulerMaruyama()/Euler() is on the accelerated path")
+    guided = _is_proposal(P)
+    target = P.Target if guided else P
+    if guided and W.tt is P.tt:
+        raise BridgeError(K.ERR_TIMEAXIS, lib.bb_strerror(K.ERR_TIMEAXIS).decode())  # src/euler.jl:248
+    N = len(W)
+    if len(Y) != N or (guided and N != len(P.tt)):
+        raise BridgeError(K.ERR_LENGTH, lib.bb_strerror(K.ERR_LENGTH).decode())  # src/euler.jl:137,251
+    u = np.atleast_1d(f64(u))
+    if u.size != target.d:
+        raise BridgeError(K.ERR_STARTPOINT, lib.bb_strerror(K.ERR_STARTPOINT).decode())
+    e = _small_ens(ctx, 1, N, target.d, target.dprime)
+    e.set_start(u)
+    e.upload(K.W, W._as2d())
+    if guided:
+        e.guided_euler_ll_(target, [P], store_x=True, ll=False)
+        Y.tt[...] = P.tt  # tt[:] = P.tt  src/euler.jl:256
+    else:
+        e.set_grid(0, W.tt)
+        e.euler_(target)
+        Y.tt[...] = W.tt
+    X = e.download(K.X)
+    Y.yy[...] = X.reshape(Y.yy.shape)
+    if guided:
+        return Y.yy[-1].copy()
+    return Y
+
+
+def solve(method: SDESolver, u, W: SamplePath, P, ctx=None) -> SamplePath:
+    """solve(::SDESolver, u, W, P) -> SamplePath  src/euler.jl:117-118, :246."""
+    target = P.Target if _is_proposal(P) else P
+    d = target.d
+    yy = np.zeros(len(W)) if (d == 1 and np.ndim(u) == 0) else np.zeros((len(W), d))
+    Y = SamplePath(W.tt.copy(), yy)
+    solve_(method, Y, u, W, P, ctx)
+    return Y
+
+
+def bridge_(*args, ctx=None):
+    """bridge!(Y, W, P) (src/deprecated.jl:16-17) and the older 4-argument bridge!(X, x0, W, P°)
+    (project/partialbridge.jl:63) = solve!(Euler(), X, x0, W, P°)."""
+    if len(args) == 4:
+        X, x0, W, Po = args
+        return solve_(Euler(), X, x0, W, Po, ctx)
+    Y, W, Po = args
+    return solve_(Euler(), Y, Y.yy[0], W, Po, ctx)
+
+
+def llikelihood(rule: LeftRule, X: SamplePath, Po, skip: int = 0, ctx=None) -> float:
+    """llikelihood(::LeftRule, X, P°; skip = 0) -> Float64."""
+    ctx = ctx or default_context()
+    target = Po.Target
+    N = len(X)
+    if N != len(Po.tt):
+        raise BridgeError(K.ERR_LENGTH, lib.bb_strerror(K.ERR_LENGTH).decode())
+    e = _small_ens(ctx, 1, N, target.d, target.dprime)
+    e.upload(K.X, X._as2d())
+    e.llikelihood_(target, [Po], skip)
+    return float(e.ll[0])
+
+
+def innovations_(method: SDESolver, W: SamplePath, Y: SamplePath, P, ctx=None) -> SamplePath:
+    """innovations!(::EulerMaruyama, W, Y, P) -> W  src/euler.jl:358-376."""
+    ctx = ctx or default_context()
+    guided = _is_proposal(P)
+    target = P.Target if guided else P
+    N = len(Y)
+    if len(W) != N:
+        raise BridgeError(K.ERR_LENGTH, lib.bb_strerror(K.ERR_LENGTH).decode())
+    e = _small_ens(ctx, 1, N, target.d, target.dprime)
+    e.upload(K.X, Y._as2d())
+    if not guided:
+        e.set_grid(0, Y.tt)
+    e.innovations_(target, [P] if guided else None)
+    W.tt[...] = Y.tt
+    W.yy[...] = e.download(K.W).reshape(W.yy.shape)
+    return W
+
+
+def pcn_(ens: PathEnsemble, P, guides, ρ: float, iterations: int, seed: int, first_iter: int = 0,
+         skip: int = 0, store_x: bool = True, callback: Optional[Callable] = None) -> int:
+    """The sampler loop of test/partialbridgenuH.jl:176-195 for all chains of `ens`: `iterations`
+    pCN updates; returns the number of accepted proposals (summed over chains)."""
+    for it in range(first_iter, first_iter + iterations):
+        ens.pcn_step_(P, guides, ρ, seed, it, skip, store_x)
+        if callback is not None:
+            callback(it, ens)
+    return ens.acc

@@ -1,0 +1,767 @@
+/*
+ * bb_api.cu -- the C ABI of include/bridge_b200.h: contexts, ensembles, guiding tables and the
+ * launches of the path kernel (bb_chain.cuh).  Host code only prepares tables and launches; there
+ * is no CPU implementation of any compute entry point (BB_ERR_NODEVICE without a GPU).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "bb_host.h"
+
+/* ------------------------------------------------------------------------------------------------ errors */
+static thread_local char g_cuda_err[512] = "";
+void bb_set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
+}
+extern "C" const char* bb_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int bb_abi_version(void) { return BB_ABI_VERSION; }
+extern "C" const char* bb_strerror(int status) {
+  switch (status) {
+    case BB_OK: return "ok";
+    case BB_ERR_LENGTH: return "Y and W differ in length.";
+    case BB_ERR_TIMEAXIS: return "Time axis mismatch between bridge P and driving W.";
+    case BB_ERR_STARTPOINT: return "Starting point has wrong length.";
+    case BB_ERR_DIM: return "DimensionMismatch(\"length(tt) != size(yy, 2)\")";
+    case BB_ERR_ASSERT_M: return "AssertionError: m == length(v)";
+    case BB_ERR_MODEL: return "unknown model id, or model and ensemble dimensions differ";
+    case BB_ERR_ARG: return "invalid argument";
+    case BB_ERR_CUDA: return "CUDA runtime error (see bb_last_cuda_error)";
+    case BB_ERR_NOMEM: return "device memory allocation failed";
+    case BB_ERR_NODEVICE: return "no CUDA device: libbridge_b200 has no CPU path";
+    case BB_ERR_UNSUPPORTED: return "combination of model, guide and dimensions is not instantiated";
+    case BB_ERR_SINGULAR: return "singular matrix";
+    default: return "unknown status";
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ context */
+extern "C" int bb_ctx_create(int device, bb_ctx** out) {
+  if (!out) return BB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    if (e != cudaSuccess) bb_set_cuda_error(e, "cudaGetDeviceCount");
+    return BB_ERR_NODEVICE;
+  }
+  if (device < 0 || device >= n) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(device));
+  bb_ctx* c = new (std::nothrow) bb_ctx();
+  if (!c) return BB_ERR_NOMEM;
+  c->device = device;
+  BB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  BB_CUDA(cudaEventCreate(&c->ev0));
+  BB_CUDA(cudaEventCreate(&c->ev1));
+  BB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  *out = c;
+  return BB_OK;
+}
+extern "C" int bb_ctx_destroy(bb_ctx* c) {
+  if (!c) return BB_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->stage) cudaFree(c->stage);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+  return BB_OK;
+}
+extern "C" int bb_ctx_synchronize(bb_ctx* c) {
+  if (!c) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(c->device));
+  BB_CUDA(cudaStreamSynchronize(c->stream));
+  return BB_OK;
+}
+extern "C" int bb_ctx_set_stream(bb_ctx* c, void* s) {
+  if (!c) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(c->device));
+  BB_CUDA(cudaStreamSynchronize(c->stream));
+  if (s) {
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+  } else if (!c->own_stream) {
+    BB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return BB_OK;
+}
+extern "C" void* bb_ctx_get_stream(bb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int bb_ctx_set_backend(bb_ctx* c, int b) {
+  if (!c || b < BB_BACKEND_AUTO || b > BB_BACKEND_TMA) return BB_ERR_ARG;
+  c->backend = b;
+  return BB_OK;
+}
+extern "C" int bb_ctx_get_backend(bb_ctx* c) { return c ? c->backend : BB_ERR_ARG; }
+extern "C" int64_t bb_ctx_launch_count(bb_ctx* c) { return c ? c->launches : -1; }
+extern "C" int bb_ctx_set_timing(bb_ctx* c, int on) {
+  if (!c) return BB_ERR_ARG;
+  c->timing = on != 0;
+  c->ev_valid = false;
+  return BB_OK;
+}
+extern "C" double bb_ctx_last_kernel_ms(bb_ctx* c) {
+  if (!c || !c->ev_valid) return -1.0;
+  cudaSetDevice(c->device);
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+void bb_time_begin(bb_ctx* c) {
+  if (c->timing) cudaEventRecord(c->ev0, c->stream);
+}
+void bb_time_end(bb_ctx* c) {
+  if (c->timing) {
+    cudaEventRecord(c->ev1, c->stream);
+    c->ev_valid = true;
+  }
+}
+
+static int ctx_stage(bb_ctx* c, size_t bytes) {
+  if (c->stage_bytes >= bytes) return BB_OK;
+  if (c->stage) {
+    BB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+  }
+  BB_CUDA(cudaMalloc(&c->stage, bytes));
+  c->stage_bytes = bytes;
+  return BB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ host algebra
+ * (oracle operation order: plain products/sums, closed-form inverses for d <= 3, Gauss-Jordan above) */
+int bb_h_inv(int d, const double* A, double* Ai) {
+  if (d == 1) {
+    if (A[0] == 0.0) return -1;
+    Ai[0] = 1.0 / A[0];
+    return 0;
+  }
+  if (d == 2) {
+    double det = A[0] * A[3] - A[1] * A[2];
+    if (det == 0.0) return -1;
+    double id = 1.0 / det;
+    double r0 = A[3] * id, r1 = -A[1] * id, r2 = -A[2] * id, r3 = A[0] * id;
+    Ai[0] = r0; Ai[1] = r1; Ai[2] = r2; Ai[3] = r3;
+    return 0;
+  }
+  if (d == 3) {
+    double c00 = A[4] * A[8] - A[5] * A[7];
+    double c01 = A[5] * A[6] - A[3] * A[8];
+    double c02 = A[3] * A[7] - A[4] * A[6];
+    double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    if (det == 0.0) return -1;
+    double id = 1.0 / det;
+    double T[9];
+    T[0] = c00 * id;
+    T[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+    T[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    T[3] = c01 * id;
+    T[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+    T[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    T[6] = c02 * id;
+    T[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+    T[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    memcpy(Ai, T, sizeof(T));
+    return 0;
+  }
+  if (d > BB_MAXD) return -1;
+  double M[BB_MAXD][2 * BB_MAXD];
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++) {
+      M[i][j] = A[i * d + j];
+      M[i][d + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < d; c++) {
+    int p = c;
+    for (int i = c + 1; i < d; i++)
+      if (fabs(M[i][c]) > fabs(M[p][c])) p = i;
+    if (M[p][c] == 0.0) return -1;
+    if (p != c)
+      for (int j = 0; j < 2 * d; j++) {
+        double t = M[c][j]; M[c][j] = M[p][j]; M[p][j] = t;
+      }
+    double ip = 1.0 / M[c][c];
+    for (int j = 0; j < 2 * d; j++) M[c][j] *= ip;
+    for (int i = 0; i < d; i++)
+      if (i != c) {
+        double f = M[i][c];
+        if (f != 0.0)
+          for (int j = 0; j < 2 * d; j++) M[i][j] -= f * M[c][j];
+      }
+  }
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++) Ai[i * d + j] = M[i][d + j];
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ models */
+static bool model_shape_ok(const bb_model* m) {
+  const int d = m->d, dp = m->dprime;
+  switch (m->id) {
+    case BB_MODEL_WIENER: return d == dp && d >= 1 && d <= 3;
+    case BB_MODEL_OU: return d == 1 && dp == 1;
+    case BB_MODEL_LINPRO: return d == dp && d >= 1 && d <= 3;
+    case BB_MODEL_FHN_DIAG: return d == 2 && dp == 2;
+    case BB_MODEL_FHN_HYPO: return d == 2 && dp == 1;
+    case BB_MODEL_INTDIFF: return d == 2 && dp == 1;
+    case BB_MODEL_NCLAR3: return d == 3 && dp == 1;
+    case BB_MODEL_LORENZ: return d == 3 && dp == 3;
+    default: return false;
+  }
+}
+/* sigma as a dense d x d' matrix (oracle model_sigma) */
+static void model_sigma_host(const bb_model* P, double* S) {
+  const int d = P->d, dp = P->dprime;
+  const double* p = P->par;
+  memset(S, 0, sizeof(double) * d * dp);
+  switch (P->id) {
+    case BB_MODEL_WIENER: for (int i = 0; i < d; i++) S[i * dp + i] = 1.0; break;
+    case BB_MODEL_OU: S[0] = p[1]; break;
+    case BB_MODEL_LINPRO: memcpy(S, p + d * d + d, sizeof(double) * d * d); break;
+    case BB_MODEL_FHN_DIAG: S[0] = p[4]; S[3] = p[5]; break;
+    case BB_MODEL_FHN_HYPO: S[1] = p[4]; break;
+    case BB_MODEL_INTDIFF: S[1] = p[0]; break;
+    case BB_MODEL_NCLAR3: S[2] = p[2]; break;
+    case BB_MODEL_LORENZ: S[0] = p[3]; S[4] = p[4]; S[8] = p[5]; break;
+  }
+}
+void bb_prepare_model(const bb_model* m, bb_model_dev* o) {
+  memset(o, 0, sizeof(*o));
+  memcpy(o->par, m->par, sizeof(o->par));
+  if (m->id == BB_MODEL_FHN_DIAG || m->id == BB_MODEL_FHN_HYPO) o->der[0] = 1.0 / m->par[0];
+  double S[BB_MAXD * BB_MAXD];
+  model_sigma_host(m, S);
+  const int d = m->d, dp = m->dprime;
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++) {
+      double s = 0.0;
+      for (int l = 0; l < dp; l++) s += S[i * dp + l] * S[j * dp + l];
+      o->der[8 + i * d + j] = s;
+    }
+  if (d == dp) { /* inv(sigma) for innovations!  (src/euler.jl:372); stays zero if sigma is singular */
+    double Si[BB_MAXD * BB_MAXD];
+    if (bb_h_inv(d, S, Si) == 0) memcpy(o->der + 24, Si, sizeof(double) * d * d);
+  }
+}
+static bool model_sigma_invertible(const bb_model* m) {
+  if (m->d != m->dprime) return false;
+  double S[BB_MAXD * BB_MAXD], Si[BB_MAXD * BB_MAXD];
+  model_sigma_host(m, S);
+  return bb_h_inv(m->d, S, Si) == 0;
+}
+static bb_chain_launch_fn lookup_second(const bb_model* m, int gk, int gm, int auxc, int mode) {
+  switch (m->id) {
+    case BB_MODEL_WIENER: return gk == 0 ? bb_lookup2_wiener(m->d, mode) : nullptr;
+    case BB_MODEL_OU: return bb_lookup2_ou(gk, gm, auxc, mode);
+    case BB_MODEL_LINPRO:
+      return m->d == 1 ? bb_lookup2_linpro1(gk, gm, auxc, mode)
+                       : (m->d == 2 ? bb_lookup2_linpro2(gk, gm, auxc, mode) : bb_lookup2_linpro3(gk, gm, auxc, mode));
+    case BB_MODEL_FHN_DIAG: return bb_lookup2_fhn_diag(gk, gm, auxc, mode);
+    case BB_MODEL_FHN_HYPO: return bb_lookup2_fhn_hypo(gk, gm, auxc, mode);
+    case BB_MODEL_INTDIFF: return bb_lookup2_intdiff(gk, gm, auxc, mode);
+    case BB_MODEL_NCLAR3: return bb_lookup2_nclar3(gk, gm, auxc, mode);
+    case BB_MODEL_LORENZ: return bb_lookup2_lorenz(gk, gm, auxc, mode);
+    default: return nullptr;
+  }
+}
+static bb_chain_launch_fn lookup_kernel(const bb_model* m, int gk, int gm, int auxc, int rng) {
+  switch (m->id) {
+    case BB_MODEL_WIENER: return gk == 0 ? bb_lookup_wiener(m->d, rng) : nullptr;
+    case BB_MODEL_OU: return bb_lookup_ou(gk, gm, auxc, rng);
+    case BB_MODEL_LINPRO:
+      return m->d == 1 ? bb_lookup_linpro1(gk, gm, auxc, rng)
+                       : (m->d == 2 ? bb_lookup_linpro2(gk, gm, auxc, rng) : bb_lookup_linpro3(gk, gm, auxc, rng));
+    case BB_MODEL_FHN_DIAG: return bb_lookup_fhn_diag(gk, gm, auxc, rng);
+    case BB_MODEL_FHN_HYPO: return bb_lookup_fhn_hypo(gk, gm, auxc, rng);
+    case BB_MODEL_INTDIFF: return bb_lookup_intdiff(gk, gm, auxc, rng);
+    case BB_MODEL_NCLAR3: return bb_lookup_nclar3(gk, gm, auxc, rng);
+    case BB_MODEL_LORENZ: return bb_lookup_lorenz(gk, gm, auxc, rng);
+    default: return nullptr;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ ensemble */
+static inline int64_t ens_rows(const bb_ens* e) { return (int64_t)e->S * e->NC * e->P; }
+
+extern "C" int bb_ens_destroy(bb_ens* e) {
+  if (!e) return BB_ERR_ARG;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  for (int b = 0; b < 2; b++) {
+    if (e->W[b]) cudaFree(e->W[b]);
+    if (e->X[b]) cudaFree(e->X[b]);
+  }
+  void* ptrs[] = {e->par, e->accepted, e->ll, e->llprop, e->logu, e->xend, e->xendprop, e->acc, e->start};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (double* g : e->gridtab)
+    if (g) cudaFree(g);
+  delete e;
+  return BB_OK;
+}
+
+template <class T>
+static int dev_alloc(bb_ens* e, T** p, size_t count) {
+  BB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  BB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), e->ctx->stream));
+  e->bytes += (int64_t)(count * sizeof(T));
+  return BB_OK;
+}
+
+extern "C" int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32_t d, int32_t dprime,
+                             uint32_t flags, bb_ens** out) {
+  if (!out) return BB_ERR_ARG;
+  *out = nullptr;
+  if (!ctx) return BB_ERR_NODEVICE;
+  if (P <= 0 || S <= 0 || S > BB_MAXSEG || N < 2 || d < 1 || d > 3 || dprime < 1 || dprime > d) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  bb_ens* e = new (std::nothrow) bb_ens();
+  if (!e) return BB_ERR_NOMEM;
+  e->ctx = ctx; e->P = P; e->S = S; e->N = N; e->d = d; e->dp = dprime; e->flags = flags;
+  e->NC = (N + BB_TC - 1) / BB_TC;
+  const int nbuf = (flags & BB_ENS_DOUBLE_BUFFER) ? 2 : 1;
+  const size_t rows = (size_t)ens_rows(e);
+  int rc = BB_OK;
+  for (int b = 0; b < nbuf && rc == BB_OK; b++) {
+    rc = dev_alloc(e, &e->W[b], rows * BB_TC * dprime);
+    if (rc == BB_OK && !(flags & BB_ENS_NO_X)) rc = dev_alloc(e, &e->X[b], rows * BB_TC * d);
+  }
+  if (nbuf == 1) { e->W[1] = e->W[0]; e->X[1] = e->X[0]; }
+  if (rc == BB_OK) rc = dev_alloc(e, &e->par, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->accepted, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->ll, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->llprop, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->logu, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->xend, (size_t)P * d);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->xendprop, (size_t)P * d);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->acc, 1);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->start, (size_t)d);
+  e->gridtab.assign(S, nullptr);
+  e->tt.assign(S, std::vector<double>());
+  if (rc != BB_OK) {
+    if (nbuf == 1) { e->W[1] = nullptr; e->X[1] = nullptr; }
+    bb_ens_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return BB_OK;
+}
+
+extern "C" int bb_ens_set_chain_offset(bb_ens* e, int64_t off) {
+  if (!e || off < 0) return BB_ERR_ARG;
+  e->chain_offset = off;
+  return BB_OK;
+}
+
+/* table of a bare time grid: row j = (tt[j]-tt[j-1], sqrt of it), row 0 and padding rows are zero */
+static void grid_rows(const double* tt, int N, int NC, int rec, std::vector<double>& tab) {
+  tab.assign((size_t)NC * BB_TC * rec, 0.0);
+  for (int j = 1; j < N; j++) {
+    const double dt = tt[j] - tt[j - 1];
+    tab[(size_t)j * rec] = dt;
+    tab[(size_t)j * rec + 1] = sqrt(dt);
+  }
+}
+
+extern "C" int bb_ens_set_grid(bb_ens* e, int32_t seg, const double* tt, int32_t n) {
+  if (!e || !tt || seg < 0 || seg >= e->S) return BB_ERR_ARG;
+  if (n != e->N) return BB_ERR_LENGTH;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  std::vector<double> tab;
+  grid_rows(tt, e->N, e->NC, 2, tab);
+  if (!e->gridtab[seg]) {
+    BB_CUDA(cudaMalloc(&e->gridtab[seg], tab.size() * sizeof(double)));
+    e->bytes += (int64_t)(tab.size() * sizeof(double));
+  }
+  BB_CUDA(cudaMemcpyAsync(e->gridtab[seg], tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice,
+                          e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  e->tt[seg].assign(tt, tt + n);
+  return BB_OK;
+}
+extern "C" int bb_ens_get_grid(bb_ens* e, int32_t seg, double* tt, int32_t n) {
+  if (!e || !tt || seg < 0 || seg >= e->S) return BB_ERR_ARG;
+  if (n != e->N || (int)e->tt[seg].size() != n) return BB_ERR_LENGTH;
+  memcpy(tt, e->tt[seg].data(), sizeof(double) * n);
+  return BB_OK;
+}
+
+extern "C" int bb_ens_set_start(bb_ens* e, const double* u, int32_t n_u, int32_t broadcast) {
+  if (!e || !u) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int d = e->d;
+  if (broadcast) {
+    if (n_u != d) return BB_ERR_STARTPOINT;
+    if (!e->start_bcast) {
+      BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+      cudaFree(e->start);
+      e->start = nullptr;
+      BB_CUDA(cudaMalloc(&e->start, sizeof(double) * d));
+      e->start_bcast = 1;
+    }
+    BB_CUDA(cudaMemcpyAsync(e->start, u, sizeof(double) * d, cudaMemcpyHostToDevice, e->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return BB_OK;
+  }
+  if ((int64_t)n_u != e->P * d) return BB_ERR_STARTPOINT;
+  std::vector<double> t((size_t)e->P * d);
+  for (int64_t p = 0; p < e->P; p++)
+    for (int k = 0; k < d; k++) t[(size_t)k * e->P + p] = u[(size_t)p * d + k];
+  if (e->start_bcast) {
+    BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    cudaFree(e->start);
+    e->start = nullptr;
+    BB_CUDA(cudaMalloc(&e->start, sizeof(double) * e->P * d));
+    e->bytes += (int64_t)(sizeof(double) * e->P * d);
+    e->start_bcast = 0;
+  }
+  BB_CUDA(cudaMemcpyAsync(e->start, t.data(), sizeof(double) * e->P * d, cudaMemcpyHostToDevice, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return BB_OK;
+}
+
+/* ---- host [np][S][N][K] <-> device [S][NC][P][8][K]; which buffer a chain uses is decided per chain */
+template <bool TO_DEVICE>
+__global__ void __launch_bounds__(256) bb_transpose_kernel(double* __restrict__ buf0, double* __restrict__ buf1,
+                                                           double* __restrict__ stage,
+                                                           const uint8_t* __restrict__ par,
+                                                           const uint8_t* __restrict__ accepted, int which,
+                                                           long long P, long long p0, long long np, int S, int N,
+                                                           int NC, int K) {
+  const long long rowlen = (long long)BB_TC * K;
+  const long long total = (long long)S * NC * np * rowlen;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(t % rowlen);
+    long long q = t / rowlen;
+    const long long pl = q % np;
+    q /= np;
+    const int c = (int)(q % NC);
+    const int s = (int)(q / NC);
+    const int slot = e / K, k = e - slot * K;
+    const int j = c * BB_TC + slot;
+    if (j >= N) continue;
+    const long long p = p0 + pl;
+    int b = par[p];
+    if (which == BB_PROP && !accepted[p]) b = 1 - b;
+    double* dev = (b ? buf1 : buf0) + (((long long)s * NC + c) * P + p) * rowlen + e;
+    double* hst = stage + ((pl * S + s) * (long long)N + j) * K + k;
+    if (TO_DEVICE) *dev = *hst;
+    else *hst = *dev;
+  }
+}
+
+static int ens_transfer(bb_ens* e, int what, int which, int64_t p0, int64_t np, double* host, bool to_device) {
+  if (!e || !host || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  if (what != BB_W && what != BB_X) return BB_ERR_ARG;
+  if (which != BB_CUR && which != BB_PROP) return BB_ERR_ARG;
+  if (what == BB_X && !e->X[0]) return BB_ERR_ARG;
+  bb_ctx* c = e->ctx;
+  BB_CUDA(cudaSetDevice(c->device));
+  const int K = what == BB_W ? e->dp : e->d;
+  double* b0 = what == BB_W ? e->W[0] : e->X[0];
+  double* b1 = what == BB_W ? e->W[1] : e->X[1];
+  const size_t per_chain = (size_t)e->S * e->N * K;
+  int64_t slab = (int64_t)((size_t)(256u << 20) / (per_chain * sizeof(double)));
+  if (slab < 1) slab = 1;
+  if (slab > np) slab = np;
+  if (np == 0) return BB_OK;
+  int rc = ctx_stage(c, (size_t)slab * per_chain * sizeof(double));
+  if (rc != BB_OK) return rc;
+  for (int64_t q0 = 0; q0 < np; q0 += slab) {
+    const int64_t n = (np - q0 < slab) ? np - q0 : slab;
+    double* h = host + (size_t)q0 * per_chain;
+    const long long total = (long long)e->S * e->NC * n * BB_TC * K;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    if (to_device) {
+      BB_CUDA(cudaMemcpyAsync(c->stage, h, (size_t)n * per_chain * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      bb_transpose_kernel<true><<<grid, 256, 0, c->stream>>>(b0, b1, c->stage, e->par, e->accepted, which, e->P,
+                                                            p0 + q0, n, e->S, e->N, e->NC, K);
+    } else {
+      bb_transpose_kernel<false><<<grid, 256, 0, c->stream>>>(b0, b1, c->stage, e->par, e->accepted, which, e->P,
+                                                             p0 + q0, n, e->S, e->N, e->NC, K);
+      BB_CUDA(cudaMemcpyAsync(h, c->stage, (size_t)n * per_chain * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    BB_CUDA(cudaGetLastError());
+    c->launches++;
+    /* the staging buffer is reused by the next slab */
+    BB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return BB_OK;
+}
+extern "C" int bb_ens_upload(bb_ens* e, int what, int which, int64_t p0, int64_t np, const double* host) {
+  return ens_transfer(e, what, which, p0, np, const_cast<double*>(host), true);
+}
+extern "C" int bb_ens_download(bb_ens* e, int what, int which, int64_t p0, int64_t np, double* host) {
+  return ens_transfer(e, what, which, p0, np, host, false);
+}
+
+extern "C" int bb_ens_get_f64(bb_ens* e, int field, int64_t p0, int64_t np, double* host) {
+  if (!e || !host || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  cudaStream_t st = e->ctx->stream;
+  const double* src = nullptr;
+  switch (field) {
+    case BB_F_LL: src = e->ll; break;
+    case BB_F_LL_PROP: src = e->llprop; break;
+    case BB_F_LOGU: src = e->logu; break;
+    case BB_F_XEND: src = e->xend; break;
+    case BB_F_XEND_PROP: src = e->xendprop; break;
+    default: return BB_ERR_ARG;
+  }
+  if (field == BB_F_XEND || field == BB_F_XEND_PROP) {
+    const int d = e->d;
+    std::vector<double> t((size_t)np * d);
+    for (int k = 0; k < d; k++)
+      BB_CUDA(cudaMemcpyAsync(t.data() + (size_t)k * np, src + (size_t)k * e->P + p0, sizeof(double) * np,
+                              cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t p = 0; p < np; p++)
+      for (int k = 0; k < d; k++) host[(size_t)p * d + k] = t[(size_t)k * np + p];
+    return BB_OK;
+  }
+  BB_CUDA(cudaMemcpyAsync(host, src + p0, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+  BB_CUDA(cudaStreamSynchronize(st));
+  return BB_OK;
+}
+extern "C" int bb_ens_set_ll(bb_ens* e, int64_t p0, int64_t np, const double* host) {
+  if (!e || !host || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  BB_CUDA(cudaMemcpyAsync(e->ll + p0, host, sizeof(double) * np, cudaMemcpyHostToDevice, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return BB_OK;
+}
+extern "C" int bb_ens_get_accepted(bb_ens* e, int64_t p0, int64_t np, uint8_t* host) {
+  if (!e || !host || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  BB_CUDA(cudaMemcpyAsync(host, e->accepted + p0, (size_t)np, cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return BB_OK;
+}
+extern "C" int bb_ens_get_acc(bb_ens* e, int64_t* acc) {
+  if (!e || !acc) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  unsigned long long v = 0;
+  BB_CUDA(cudaMemcpyAsync(&v, e->acc, sizeof(v), cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  *acc = (int64_t)v;
+  return BB_OK;
+}
+extern "C" int bb_ens_reset_acc(bb_ens* e) {
+  if (!e) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  BB_CUDA(cudaMemsetAsync(e->acc, 0, sizeof(unsigned long long), e->ctx->stream));
+  return BB_OK;
+}
+extern "C" void* bb_ens_acc_device_ptr(bb_ens* e) { return e ? (void*)e->acc : nullptr; }
+extern "C" int64_t bb_ens_bytes(bb_ens* e) { return e ? e->bytes : -1; }
+
+/* ------------------------------------------------------------------------------------------------ guiding tables */
+extern "C" int bb_guide_destroy(bb_guide* g) {
+  if (!g) return BB_ERR_ARG;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  if (g->tab) cudaFree(g->tab);
+  if (g->segc) cudaFree(g->segc);
+  delete g;
+  return BB_OK;
+}
+
+extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                               const double* A, const double* b, const double* Mm, const double* v,
+                               const double* Bt, const double* betat, int32_t aux_const, bb_guide** out) {
+  if (!out) return BB_ERR_ARG;
+  *out = nullptr;
+  if (!ctx) return BB_ERR_NODEVICE;
+  if (!tt || !A || !b || !Bt || !betat || N < 2 || d < 1 || d > 3) return BB_ERR_ARG;
+  if (kind != BB_GUIDE_NUH && kind != BB_GUIDE_HV && kind != BB_GUIDE_LMMU) return BB_ERR_ARG;
+  if (kind == BB_GUIDE_LMMU) {
+    if (!Mm || !v || m < 1 || m > d) return BB_ERR_ARG;
+  } else {
+    m = 0;
+  }
+  BB_CUDA(cudaSetDevice(ctx->device));
+  const bool auxc = aux_const != 0;
+  const int rec = bb_rec_len(kind, d, m, auxc);
+  const int NC = (N + BB_TC - 1) / BB_TC;
+  const int nc = bb_rec_nc(kind, d, m), na1 = bb_rec_na1(kind, d, m), na2 = bb_rec_na2(kind, d, m);
+  const int off_c = 2, off_a1 = off_c + nc, off_a2 = off_a1 + na1, off_bt = off_a2 + na2, off_be = off_bt + d * d;
+  std::vector<double> tab;
+  grid_rows(tt, N, NC, rec, tab);
+  for (int j = 1; j < N; j++) {
+    const int i = j - 1;
+    double* R = tab.data() + (size_t)j * rec;
+    if (kind == BB_GUIDE_NUH) {
+      memcpy(R + off_c, b + (size_t)i * d, sizeof(double) * d);
+      memcpy(R + off_a2, A + (size_t)i * d * d, sizeof(double) * d * d);
+    } else if (kind == BB_GUIDE_HV) {
+      memcpy(R + off_c, b + (size_t)i * d, sizeof(double) * d);
+      /* r = H♢[i] \ (V[i] - x)  (src/guip.jl:193) evaluated as inv(H♢[i]) (V[i] - x) */
+      if (bb_h_inv(d, A + (size_t)i * d * d, R + off_a2)) return BB_ERR_SINGULAR;
+    } else {
+      const double* L = A + (size_t)i * m * d;
+      const double* mu = b + (size_t)i * m;
+      const double* Mi = Mm + (size_t)i * m * m;
+      for (int k = 0; k < m; k++) R[off_c + k] = v[k] - mu[k];
+      memcpy(R + off_a1, L, sizeof(double) * m * d);
+      /* L[i]' M[i]  (d x m), products accumulated as the oracle's mat_mul */
+      for (int r = 0; r < d; r++)
+        for (int c2 = 0; c2 < m; c2++) {
+          double s = L[0 * d + r] * Mi[0 * m + c2];
+          for (int l = 1; l < m; l++) s = fma(L[l * d + r], Mi[l * m + c2], s);
+          R[off_a2 + r * m + c2] = s;
+        }
+    }
+    if (!auxc) {
+      memcpy(R + off_bt, Bt + (size_t)i * d * d, sizeof(double) * d * d);
+      memcpy(R + off_be, betat + (size_t)i * d, sizeof(double) * d);
+    }
+  }
+  double segc[BB_SEGC];
+  memset(segc, 0, sizeof(segc));
+  if (auxc) {
+    memcpy(segc, Bt, sizeof(double) * d * d);
+    memcpy(segc + d * d, betat, sizeof(double) * d);
+  }
+  if (kind == BB_GUIDE_HV) {
+    /* endpoint(y, P) = norm(P.H♢[end], 1) < eps() ? P.V[end] : y   src/euler.jl:241-242 */
+    const double* K = A + (size_t)(N - 1) * d * d;
+    double n1 = 0;
+    for (int k = 0; k < d * d; k++) n1 += fabs(K[k]);
+    if (n1 < 2.220446049250313e-16) {
+      segc[d * d + d] = 1.0;
+      memcpy(segc + d * d + d + 1, b + (size_t)(N - 1) * d, sizeof(double) * d);
+    }
+  }
+  bb_guide* g = new (std::nothrow) bb_guide();
+  if (!g) return BB_ERR_NOMEM;
+  g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxc ? 1 : 0; g->NC = NC; g->rec = rec;
+  g->tt.assign(tt, tt + N);
+  cudaError_t e1 = cudaMalloc(&g->tab, tab.size() * sizeof(double));
+  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&g->segc, sizeof(segc)) : e1;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    bb_set_cuda_error(e1 != cudaSuccess ? e1 : e2, "cudaMalloc(guide)");
+    bb_guide_destroy(g);
+    return BB_ERR_NOMEM;
+  }
+  BB_CUDA(cudaMemcpyAsync(g->tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BB_CUDA(cudaMemcpyAsync(g->segc, segc, sizeof(segc), cudaMemcpyHostToDevice, ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = g;
+  return BB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ launches */
+struct run_spec {
+  int rng;            /* 0 read W, 1 pCN, 2 sample */
+  bool store_x, do_ll, write_end;
+  int skip;
+  double rho;
+  uint64_t seed;
+  uint32_t stream;
+};
+
+/* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations! */
+static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, const run_spec& rs) {
+  if (!e || !model) return BB_ERR_ARG;
+  bb_ctx* c = e->ctx;
+  if (!model_shape_ok(model)) return BB_ERR_MODEL;
+  if (model->d != e->d || model->dprime != e->dp) return BB_ERR_MODEL;
+  BB_CUDA(cudaSetDevice(c->device));
+  bb_chain_args a;
+  memset(&a, 0, sizeof(a));
+  int gk = 0, gm = 0, auxc = 1;
+  for (int s = 0; s < e->S; s++) {
+    if (guides) {
+      const bb_guide* g = guides[s];
+      if (!g) return BB_ERR_ARG;
+      if (g->N != e->N) return BB_ERR_LENGTH; /* "Y and W differ in length." src/euler.jl:251 */
+      if (g->d != e->d) return BB_ERR_MODEL;
+      if (s == 0) { gk = g->kind; gm = g->m; auxc = g->auxc; }
+      else if (g->kind != gk || g->m != gm || g->auxc != auxc) return BB_ERR_UNSUPPORTED;
+      a.tab[s] = g->tab;
+      a.segc[s] = g->segc;
+    } else {
+      if (!e->gridtab[s]) return BB_ERR_ARG; /* bb_ens_set_grid first */
+      a.tab[s] = e->gridtab[s];
+      a.segc[s] = nullptr;
+    }
+  }
+  bb_chain_launch_fn fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10)
+                                       : lookup_kernel(model, gk, gm, auxc, rs.rng);
+  if (!fn) return BB_ERR_UNSUPPORTED;
+  if (rs.rng >= 10 && !e->X[0]) return BB_ERR_ARG;
+  if (rs.rng == 11 && !model_sigma_invertible(model)) return BB_ERR_SINGULAR;
+  if (rs.rng == 1 && !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG;
+  if (rs.store_x && !e->X[0]) return BB_ERR_ARG;
+  if (rs.skip < 0) return BB_ERR_ARG;
+  a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X[0] = e->X[0]; a.X[1] = e->X[1];
+  a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
+  a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
+  a.accepted = e->accepted; a.acc = e->acc;
+  a.P = e->P; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC;
+  a.jll = e->N - 1 - rs.skip;
+  a.store_x = rs.store_x ? 1 : 0; a.do_ll = rs.do_ll ? 1 : 0; a.write_end = rs.write_end ? 1 : 0;
+  a.k0 = (uint32_t)rs.seed; a.k1 = (uint32_t)(rs.seed >> 32); a.stream = rs.stream;
+  a.rho = rs.rho;
+  a.rho2 = sqrt(1 - rs.rho * rs.rho); /* sqrt(1-ρ^2)  test/partialbridgenuH.jl:178 */
+  bb_prepare_model(model, &a.model);
+  bb_time_begin(c);
+  cudaError_t err = fn(a, c->stream);
+  bb_time_end(c);
+  if (err != cudaSuccess) {
+    bb_set_cuda_error(err, "bb_chain_kernel launch");
+    return BB_ERR_CUDA;
+  }
+  c->launches++;
+  return BB_OK;
+}
+
+extern "C" int bb_wiener_sample(bb_ens* e, uint64_t seed, uint32_t stream) {
+  if (!e) return BB_ERR_ARG;
+  /* the Wiener process of dimension d' as its own target: X is not touched */
+  bb_model w;
+  memset(&w, 0, sizeof(w));
+  w.id = BB_MODEL_WIENER; w.d = e->dp; w.dprime = e->dp;
+  bb_ens view = *e; /* same device buffers, state dimension d'; X is neither stored nor returned */
+  view.d = e->dp;
+  run_spec rs{2, false, false, false, 0, 0.0, seed, stream};
+  return run_chain(&view, &w, nullptr, rs);
+}
+extern "C" int bb_euler(bb_ens* e, const bb_model* model) {
+  run_spec rs{0, true, false, true, 0, 0.0, 0, 0};
+  return run_chain(e, model, nullptr, rs);
+}
+extern "C" int bb_sample_euler(bb_ens* e, const bb_model* model, uint64_t seed, uint32_t stream) {
+  run_spec rs{2, true, false, true, 0, 0.0, seed, stream};
+  return run_chain(e, model, nullptr, rs);
+}
+extern "C" int bb_guided_euler_ll(bb_ens* e, const bb_model* model, bb_guide* const* guides, int32_t skip,
+                                  uint32_t flags) {
+  if (!guides) return BB_ERR_ARG;
+  run_spec rs{0, (flags & BB_RUN_STORE_X) != 0, (flags & BB_RUN_NO_LL) == 0, true, skip, 0.0, 0, 0};
+  return run_chain(e, model, guides, rs);
+}
+extern "C" int bb_pcn_step(bb_ens* e, const bb_model* model, bb_guide* const* guides, double rho, uint64_t seed,
+                           uint32_t iter, int32_t skip, uint32_t flags) {
+  if (!guides) return BB_ERR_ARG;
+  if (!(rho >= -1.0 && rho <= 1.0)) return BB_ERR_ARG;
+  run_spec rs{1, (flags & BB_RUN_STORE_X) != 0, true, true, skip, rho, seed, iter};
+  return run_chain(e, model, guides, rs);
+}
+extern "C" int bb_llikelihood(bb_ens* e, const bb_model* model, bb_guide* const* guides, int32_t skip) {
+  if (!guides) return BB_ERR_ARG;
+  run_spec rs{10, false, true, false, skip, 0.0, 0, 0};
+  return run_chain(e, model, guides, rs);
+}
+extern "C" int bb_innovations(bb_ens* e, const bb_model* model, bb_guide* const* guides) {
+  run_spec rs{11, false, false, false, 0, 0.0, 0, 0};
+  return run_chain(e, model, guides, rs);
+}

@@ -1,0 +1,383 @@
+/*
+ * bb_chain.cuh -- the path kernel: one thread owns one chain and walks its S segments in time.
+ *
+ * Replaces, fused in ONE pass over the data (reference call stacks A, C, D, E of SURVEY.md section 3):
+ *   sample!(W2, Wiener())                      src/wiener.jl:50-58
+ *   Wo.yy .= rho*W.yy + sqrt(1-rho^2)*W2.yy    test/partialbridgenuH.jl:178
+ *   solve!(Euler(), Xo, x0, Wo, Po)            src/euler.jl:247-268 (guided) / :135-152 (plain)
+ *   llikelihood(LeftRule(), Xo, Po; skip)      src/partialbridgenuH.jl:171-189, guip.jl:429-446,
+ *                                              partialbridge.jl:67-87
+ *   if log(rand()) <= llo - ll ... end         test/partialbridgenuH.jl:183-190
+ *
+ * Data layout in HBM ("chunked AoSoA"): the N grid points of a segment are cut into chunks of
+ * BB_TC = 8; W is [S][NC][P][8][d'] and X is [S][NC][P][8][d] doubles.  One chain therefore owns
+ * 64*d' (64*d) contiguous, 64-byte aligned bytes per chunk: whole DRAM bursts whatever buffer the
+ * neighbouring chains use (each chain reads buffer par[p] and writes buffer 1-par[p]; accepting a
+ * proposal flips par[p] instead of copying the path), and a warp still covers 2 KB contiguous.
+ * All accesses are 256-bit (LDG.E.256 / STG.E.256).
+ *
+ * Per-step tables (dt, sqrt(dt), guiding term, auxiliary drift) are common to all chains: thread 0
+ * streams them with 1-D TMA bulk copies into a BB_STAGES-deep shared-memory ring (full/empty
+ * mbarriers), BB_LOOKAHEAD chunks ahead of the consumers; every thread reads them by broadcast LDS.
+ *
+ * State (y, W at the previous grid point, log-likelihood sum) lives in registers; noise comes from
+ * Philox4x32-10 keyed by (seed; quad, iteration, global row) so results do not depend on the launch
+ * geometry or on how chains are sharded over GPUs.
+ */
+#pragma once
+#include "bb_device.cuh"
+
+struct bb_chain_args {
+  double* W[2];
+  double* X[2];
+  uint8_t* par;                    /* [P] which buffer holds the chain's current state */
+  const double* tab[BB_MAXSEG];    /* per-segment step tables, [NC*8][REC] */
+  const double* segc[BB_MAXSEG];   /* per-segment constants, 32 doubles: Bt[d*d], betat[d], endflag, vend[d] */
+  const double* start;             /* [d] (broadcast) or [d][P] */
+  double* ll;                      /* [P] */
+  double* llprop;                  /* [P] */
+  double* logu;                    /* [P] */
+  double* xend;                    /* [d][P] */
+  double* xendprop;                /* [d][P] */
+  uint8_t* accepted;               /* [P] */
+  unsigned long long* acc;
+  long long P;
+  long long chain_offset;
+  int S, N, NC;
+  int jll;                         /* steps j <= jll (1-based end index) enter the log-likelihood */
+  int start_bcast, store_x, do_ll, write_end;
+  uint32_t k0, k1, stream;
+  double rho, rho2;
+  bb_model_dev model;
+};
+
+#define BB_SEGC 32
+
+/* collects the K doubles a chain produces per grid point and writes them as 256-bit stores */
+template <int K>
+struct bb_rowout {
+  double pend[3];
+  __device__ __forceinline__ void put(double* row, int slot, const double* v, bool act) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      int e = slot * K + k;
+      switch (e & 3) {
+        case 0: pend[0] = v[k]; break;
+        case 1: pend[1] = v[k]; break;
+        case 2: pend[2] = v[k]; break;
+        default:
+          if (act) bb_st4(row + (e - 3), pend[0], pend[1], pend[2], v[k]);
+      }
+    }
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void bb_load_row(const double* row, double* v) {
+#pragma unroll
+  for (int q = 0; q < 2 * K; q++) bb_ld4(row + 4 * q, v + 4 * q);
+}
+
+/* RNG: 0 = driving path W is read (solve!), 1 = pCN proposal (read W, write W°), 2 = fresh Wiener path
+ * (sample! fused with solve!).  GK: 0 = plain Euler-Maruyama, else bb_guide_kind; GM = rows of L (LMMU). */
+template <class M, int GK, int GM, bool AUXC, int RNG>
+struct bb_chain {
+  static constexpr int D = M::D, DP = M::DP;
+  static constexpr int REC = bb_rec_len(GK, D, GM, AUXC);
+  static constexpr int NCC = bb_rec_nc(GK, D, GM), NA1 = bb_rec_na1(GK, D, GM), NA2 = bb_rec_na2(GK, D, GM);
+  static constexpr int OFF_C = 2, OFF_A1 = OFF_C + NCC, OFF_A2 = OFF_A1 + NA1, OFF_BT = OFF_A2 + NA2,
+                       OFF_BE = OFF_BT + D * D;
+  static constexpr bool PREFETCH = (DP == 1) && (RNG != 2);
+
+  struct state {
+    double y[D];
+    double wprev[DP];
+    double w2[DP];
+    double som;
+  };
+
+  /* guided drift _b((i,t),x,P°) at x = y (plain b for GK = 0) and, if in_ll, the log-likelihood term */
+  static __device__ __forceinline__ void drift(const bb_chain_args& a, const double* __restrict__ R,
+                                               const double* __restrict__ sc, const double* y, double dt,
+                                               bool in_ll, double& som, double* bd) {
+    M::b(a.model, y, bd);
+    if constexpr (GK != 0) {
+      /* r((i,t),x,P°) = A2 (c - A1 x)  -- partialbridgenuH.jl:161, guip.jl:193, partialbridge.jl:57 */
+      double e[NCC], r[D];
+      if constexpr (GK == BB_GUIDE_LMMU) {
+        double Lx[GM];
+        bb_matvec<GM, D>(R + OFF_A1, y, Lx);
+#pragma unroll
+        for (int k = 0; k < GM; k++) e[k] = R[OFF_C + k] - Lx[k];
+        bb_matvec<D, GM>(R + OFF_A2, e, r);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) e[k] = R[OFF_C + k] - y[k];
+        bb_matvec<D, D>(R + OFF_A2, e, r);
+      }
+      /* llikelihood term  <b - b~, r> dt  with b~ = B~ x + beta~  (partialbridgenuH.jl:176-181) */
+      if (in_ll) {
+        const double* Bt = AUXC ? sc : R + OFF_BT;
+        const double* be = AUXC ? sc + D * D : R + OFF_BE;
+        double bt[D], ee[D];
+        bb_matvec<D, D>(Bt, y, bt);
+#pragma unroll
+        for (int k = 0; k < D; k++) ee[k] = bd[k] - (bt[k] + be[k]);
+        som = fma(bb_vdot<D>(ee, r), dt, som);
+      }
+      /* _b((i,t),x,P°) = b + a r   (partialbridgenuH.jl:157-159); a = sigma sigma' from der[8..] */
+      if constexpr (M::SPARSE) {
+#pragma unroll
+        for (int k = 0; k < D; k++)
+          if (M::col(k) >= 0) bd[k] = fma(a.model.der[8 + k * D + k], r[k], bd[k]);
+      } else {
+        double ar[D];
+        bb_matvec<D, D>(a.model.der + 8, r, ar);
+#pragma unroll
+        for (int k = 0; k < D; k++) bd[k] = bd[k] + ar[k];
+      }
+    }
+  }
+
+  /* one grid point j >= 1: the Euler step j-1 -> j */
+  static __device__ __forceinline__ void step(const bb_chain_args& a, const double* __restrict__ R,
+                                              const double* __restrict__ sc, state& st, const double* wj,
+                                              bool in_ll) {
+    const double dt = R[0];
+    double dw[DP];
+#pragma unroll
+    for (int k = 0; k < DP; k++) {
+      dw[k] = wj[k] - st.wprev[k];
+      st.wprev[k] = wj[k];
+    }
+    double bd[D];
+    drift(a, R, sc, st.y, dt, in_ll, st.som, bd);
+    bb_em_update<M>(a.model, bd, dt, dw, st.y);
+  }
+
+  template <bool EDGE>
+  static __device__ __forceinline__ void chunk(const bb_chain_args& a, const double* __restrict__ rec,
+                                               const double* __restrict__ sc, state& st, const double* wc,
+                                               double* wout_row, double* xout_row, int c, uint32_t row_lo,
+                                               uint32_t row_hi, bool act) {
+    bb_rowout<DP> wo;
+    bb_rowout<D> xo;
+    float z[4];
+    const int N = a.N;
+#pragma unroll
+    for (int slot = 0; slot < BB_TC; slot++) {
+      const int j = c * BB_TC + slot;
+      const double* R = rec + slot * REC;
+      double wj[DP];
+      /* ---- driving noise at grid point j */
+#pragma unroll
+      for (int k = 0; k < DP; k++) {
+        const int n = slot * DP + k;
+        if constexpr (RNG != 0) {
+          if ((n & 3) == 0)
+            bb_normal_quad(a.k0, a.k1, a.stream, row_lo, row_hi, (uint32_t)(2 * DP * c + (n >> 2)), z);
+          const double xi = (double)z[n & 3];
+          if constexpr (RNG == 1) {
+            /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
+            if (!EDGE || j > 0) st.w2[k] = fma(R[1], xi, st.w2[k]);
+            wj[k] = fma(a.rho2, st.w2[k], a.rho * wc[n]);
+          } else {
+            wj[k] = (EDGE && j == 0) ? wc[n] : fma(R[1], xi, st.wprev[k]);
+          }
+        } else {
+          wj[k] = wc[n];
+        }
+      }
+      if (EDGE && j == 0) {
+#pragma unroll
+        for (int k = 0; k < DP; k++) st.wprev[k] = wj[k];
+      } else if (!EDGE || j < N) {
+        step(a, R, sc, st, wj, a.do_ll && j <= a.jll);
+        if (EDGE && GK == BB_GUIDE_HV && j == N - 1 && sc[D * D + D] != 0.0) {
+          /* endpoint(y, P::GuidedBridge) = V[end] when H♢[end] = 0   src/euler.jl:241-242 */
+#pragma unroll
+          for (int k = 0; k < D; k++) st.y[k] = sc[D * D + D + 1 + k];
+        }
+      }
+      if constexpr (RNG != 0) wo.put(wout_row, slot, wj, act);
+      if (a.store_x) xo.put(xout_row, slot, st.y, act);
+    }
+  }
+
+  static __device__ __forceinline__ void run(const bb_chain_args& a) {
+    constexpr uint32_t STAGE_DOUBLES = BB_TC * REC;
+    constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    double* segc = ring + BB_STAGES * STAGE_DOUBLES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(segc + a.S * BB_SEGC);
+    uint64_t* empty = full + BB_STAGES;
+
+    const int S = a.S, NC = a.NC;
+    const int T = S * NC; /* table chunks this CTA walks through */
+    const int lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < BB_STAGES; i++) {
+        bb_mbar_init(&full[i], 1);
+        bb_mbar_init(&empty[i], nwarps);
+      }
+      bb_mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < S * BB_SEGC; i += blockDim.x)
+      segc[i] = a.segc[i / BB_SEGC] ? a.segc[i / BB_SEGC][i % BB_SEGC] : 0.0;
+    __syncthreads();
+
+    const long long P = a.P;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = p < P;
+    const long long pc = act ? p : P - 1;
+    const int par = a.par[pc];
+    const int rbuf = par;                        /* where the chain's current W (and X) live */
+    const int wbuf = (RNG == 1) ? 1 - par : par; /* where this launch writes */
+    const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
+
+    state st;
+#pragma unroll
+    for (int k = 0; k < D; k++) st.y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
+    st.som = 0.0;
+
+    const double* wr = a.W[rbuf] + pc * (BB_TC * DP);
+    double* ww = a.W[wbuf] + pc * (BB_TC * DP);
+    double* xw = a.store_x ? a.X[wbuf] + pc * (BB_TC * D) : nullptr;
+    const long long wstride = P * (BB_TC * DP), xstride = P * (BB_TC * D);
+
+    /* producer state (thread 0 only) */
+    int issued = 0, iseg = 0, ichunk = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    double wc[BB_TC * DP], wn[PREFETCH ? BB_TC * DP : 1];
+    const bool need_w = (RNG != 2);
+    if (PREFETCH) bb_load_row<DP>(wr, wn);
+
+    int g = 0;
+    for (int s = 0; s < S; s++) {
+      const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
+      const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
+      const double* sc = segc + s * BB_SEGC;
+#pragma unroll
+      for (int k = 0; k < DP; k++) st.w2[k] = 0.0;
+      for (int c = 0; c < NC; c++, g++) {
+        if (threadIdx.x == 0) {
+          while (issued < T && issued <= g + BB_LOOKAHEAD) {
+            const int ist = issued % BB_STAGES;
+            if (issued >= BB_STAGES) bb_mbar_wait(&empty[ist], ((issued / BB_STAGES) - 1) & 1);
+            bb_mbar_expect_tx(&full[ist], STAGE_BYTES);
+            bb_tma_load_1d(ring + ist * STAGE_DOUBLES, a.tab[iseg] + (size_t)ichunk * STAGE_DOUBLES,
+                           STAGE_BYTES, &full[ist]);
+            issued++;
+            if (++ichunk == NC) { ichunk = 0; iseg++; }
+          }
+        }
+        __syncwarp();
+        /* ---- this chunk's slice of the driving path */
+        if (PREFETCH) {
+#pragma unroll
+          for (int i = 0; i < BB_TC * DP; i++) wc[i] = wn[i];
+          if (g + 1 < T) bb_load_row<DP>(wr + wstride, wn);
+        } else if (need_w || c == 0) {
+          bb_load_row<DP>(wr, wc);
+        }
+        bb_mbar_wait(&full[stage], phase);
+        const double* rec = ring + stage * STAGE_DOUBLES;
+        if (c == 0 || c == NC - 1)
+          chunk<true>(a, rec, sc, st, wc, ww, xw, c, row_lo, row_hi, act);
+        else
+          chunk<false>(a, rec, sc, st, wc, ww, xw, c, row_lo, row_hi, act);
+        __syncwarp();
+        if (lane == 0) bb_mbar_arrive(&empty[stage]);
+        if (++stage == BB_STAGES) { stage = 0; phase ^= 1; }
+        wr += wstride;
+        ww += wstride;
+        if (a.store_x) xw += xstride;
+      }
+    }
+
+    /* ---- per-chain epilogue */
+    if constexpr (RNG == 1) {
+      /* accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
+      const double logu = bb_accept_logu(a.k0, a.k1, a.stream, chain);
+      const double llc = a.ll[pc];
+      const bool ok = act && (logu <= st.som - llc);
+      if (act) {
+        a.llprop[p] = st.som;
+        a.logu[p] = logu;
+        a.accepted[p] = ok ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = st.y[k];
+        if (ok) {
+          a.ll[p] = st.som;
+          a.par[p] = (uint8_t)(1 - par);
+#pragma unroll
+          for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+      if (lane == 0 && m) atomicAdd(a.acc, (unsigned long long)__popc(m));
+    } else {
+      if (act) {
+        if (a.do_ll) a.ll[p] = st.som;
+        if (a.write_end) {
+#pragma unroll
+          for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
+        }
+      }
+    }
+  }
+};
+
+template <class M, int GK, int GM, bool AUXC, int RNG>
+__global__ void __launch_bounds__(BB_THREADS) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
+  bb_chain<M, GK, GM, AUXC, RNG>::run(a);
+}
+
+template <class M, int GK, int GM, bool AUXC, int RNG>
+static inline size_t bb_chain_smem(int S) {
+  return (size_t)BB_STAGES * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + (size_t)S * BB_SEGC * 8 +
+         2 * BB_STAGES * 8;
+}
+
+/* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */
+typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
+
+template <class M, int GK, int GM, bool AUXC, int RNG>
+static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
+  const size_t smem = bb_chain_smem<M, GK, GM, AUXC, RNG>(a.S);
+  const unsigned grid = (unsigned)((a.P + BB_THREADS - 1) / BB_THREADS);
+  bb_chain_kernel<M, GK, GM, AUXC, RNG><<<grid, BB_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class M, int GK, int GM>
+static bb_chain_launch_fn bb_lookup_guide(int auxc, int rng) {
+  if (rng == 0) return auxc ? &bb_chain_launch<M, GK, GM, true, 0> : &bb_chain_launch<M, GK, GM, false, 0>;
+  if (rng == 1) return auxc ? &bb_chain_launch<M, GK, GM, true, 1> : &bb_chain_launch<M, GK, GM, false, 1>;
+  return nullptr;
+}
+template <class M>
+static bb_chain_launch_fn bb_lookup_unguided(int rng) {
+  if (rng == 0) return &bb_chain_launch<M, 0, 0, true, 0>;
+  if (rng == 2) return &bb_chain_launch<M, 0, 0, true, 2>;
+  return nullptr;
+}
+template <class M>
+static bb_chain_launch_fn bb_lookup_model(int gk, int gm, int auxc, int rng) {
+  if (gk == 0) return bb_lookup_unguided<M>(rng);
+  if (gk == BB_GUIDE_NUH) return bb_lookup_guide<M, BB_GUIDE_NUH, 0>(auxc, rng);
+  if (gk == BB_GUIDE_HV) return bb_lookup_guide<M, BB_GUIDE_HV, 0>(auxc, rng);
+  if (gk == BB_GUIDE_LMMU) {
+    if (gm == 1) return bb_lookup_guide<M, BB_GUIDE_LMMU, 1>(auxc, rng);
+    if constexpr (M::D >= 2)
+      if (gm == 2) return bb_lookup_guide<M, BB_GUIDE_LMMU, 2>(auxc, rng);
+    if constexpr (M::D >= 3)
+      if (gm == 3) return bb_lookup_guide<M, BB_GUIDE_LMMU, 3>(auxc, rng);
+  }
+  return nullptr;
+}

@@ -1,0 +1,96 @@
+/*
+ * bb_host.h -- host-side structures of libbridge_b200.so (not part of the public ABI).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bridge_b200.h"
+#include "bb_chain.cuh"
+
+struct bb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int backend = BB_BACKEND_AUTO;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int sm_count = 0;
+  /* staging for host <-> device transposes */
+  double* stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+struct bb_guide {
+  bb_ctx* ctx = nullptr;
+  int kind = 0, N = 0, d = 0, m = 0, auxc = 1, NC = 0, rec = 0;
+  double* tab = nullptr;  /* device [NC*8][rec] */
+  double* segc = nullptr; /* device [32] */
+  std::vector<double> tt;
+};
+
+struct bb_ens {
+  bb_ctx* ctx = nullptr;
+  int64_t P = 0;
+  int S = 0, N = 0, d = 0, dp = 0, NC = 0;
+  uint32_t flags = 0;
+  int64_t chain_offset = 0;
+  double* W[2] = {nullptr, nullptr};
+  double* X[2] = {nullptr, nullptr};
+  uint8_t* par = nullptr;
+  uint8_t* accepted = nullptr;
+  double *ll = nullptr, *llprop = nullptr, *logu = nullptr, *xend = nullptr, *xendprop = nullptr;
+  unsigned long long* acc = nullptr;
+  double* start = nullptr; /* [d] or [d][P] */
+  int start_bcast = 1;
+  std::vector<double*> gridtab; /* per segment: device [NC*8][2] (dt, sqrt dt) */
+  std::vector<std::vector<double>> tt;
+  int64_t bytes = 0;
+};
+
+/* thread-local error text for bb_last_cuda_error */
+void bb_set_cuda_error(cudaError_t e, const char* where);
+
+#define BB_CUDA(call)                          \
+  do {                                         \
+    cudaError_t e__ = (call);                  \
+    if (e__ != cudaSuccess) {                  \
+      bb_set_cuda_error(e__, #call);           \
+      return e__ == cudaErrorMemoryAllocation ? BB_ERR_NOMEM : BB_ERR_CUDA; \
+    }                                          \
+  } while (0)
+
+/* per-model kernel lookup (bb_inst_*.cu) */
+bb_chain_launch_fn bb_lookup_wiener(int d, int rng);
+bb_chain_launch_fn bb_lookup_ou(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_linpro1(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_linpro2(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_linpro3(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_fhn_diag(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_fhn_hypo(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_intdiff(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_nclar3(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_lorenz(int gk, int gm, int auxc, int rng);
+
+bb_chain_launch_fn bb_lookup2_wiener(int d, int mode);
+bb_chain_launch_fn bb_lookup2_ou(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_linpro1(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_linpro2(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_linpro3(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_fhn_diag(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_fhn_hypo(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_intdiff(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_nclar3(int gk, int gm, int auxc, int mode);
+bb_chain_launch_fn bb_lookup2_lorenz(int gk, int gm, int auxc, int mode);
+
+/* timing brackets around compute calls */
+void bb_time_begin(bb_ctx* ctx);
+void bb_time_end(bb_ctx* ctx);
+
+/* small host algebra in the oracle's operation order (bb_linalg.cpp-style helpers in bb_api.cu) */
+int bb_h_inv(int d, const double* A, double* Ai);

@@ -1,0 +1,100 @@
+/*
+ * bb_second.cuh -- the two passes over a STORED path that the reference also has:
+ *   MODE 0: llikelihood(LeftRule(), X, P°; skip)   src/partialbridgenuH.jl:171-189, guip.jl:429-446,
+ *                                                  partialbridge.jl:67-87, guip!.jl:5-31
+ *   MODE 1: innovations!(EulerMaruyama(), W, X, P) src/euler.jl:357-376   (W <- the increments that drive X)
+ * (the fused kernel of bb_chain.cuh computes the log-likelihood while it builds the path; these exist
+ * because callers may hold a path and ask for either quantity).  One thread per chain, X read once with
+ * 256-bit loads, tables read by warp-uniform loads (L1 broadcast).
+ */
+#pragma once
+#include "bb_chain.cuh"
+
+template <class M, int GK, int GM, bool AUXC, int MODE>
+__global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_constant__ bb_chain_args a) {
+  using CH = bb_chain<M, GK, GM, AUXC, 0>;
+  constexpr int D = M::D, DP = M::DP, REC = CH::REC;
+  const long long P = a.P;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int par = a.par[p];
+  const double* xr = a.X[par] + p * (BB_TC * D);
+  double* ww = a.W[par] + p * (BB_TC * DP);
+  const long long wstride = P * (BB_TC * DP), xstride = P * (BB_TC * D);
+  double som = 0.0;
+  double zero[BB_SEGC];
+#pragma unroll
+  for (int i = 0; i < BB_SEGC; i++) zero[i] = 0.0;
+  for (int s = 0; s < a.S; s++) {
+    const double* tab = a.tab[s];
+    const double* sc = a.segc[s] ? a.segc[s] : zero;
+    double xprev[D], w[DP];
+#pragma unroll
+    for (int k = 0; k < DP; k++) w[k] = 0.0;
+    for (int c = 0; c < a.NC; c++) {
+      double x[BB_TC * D];
+      bb_load_row<D>(xr, x);
+      bb_rowout<DP> wo;
+#pragma unroll
+      for (int slot = 0; slot < BB_TC; slot++) {
+        const int j = c * BB_TC + slot;
+        if (j > 0 && j < a.N) {
+          const double* R = tab + (size_t)j * REC;
+          const double dt = R[0];
+          double bd[D];
+          CH::drift(a, R, sc, xprev, dt, MODE == 0 && j <= a.jll, som, bd);
+          if constexpr (MODE == 1) {
+            double e[D], de[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) e[k] = (x[slot * D + k] - xprev[k]) - bd[k] * dt;
+            bb_matvec<D, D>(a.model.der + 24, e, de);
+#pragma unroll
+            for (int k = 0; k < DP; k++) w[k] = w[k] + de[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) xprev[k] = x[slot * D + k];
+        if constexpr (MODE == 1) wo.put(ww, slot, w, true);
+      }
+      xr += xstride;
+      ww += wstride;
+    }
+  }
+  if (MODE == 0) a.ll[p] = som;
+}
+
+template <class M, int GK, int GM, bool AUXC, int MODE>
+static cudaError_t bb_second_launch(const bb_chain_args& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.P + BB_THREADS - 1) / BB_THREADS);
+  bb_second_kernel<M, GK, GM, AUXC, MODE><<<grid, BB_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class M, int GK, int GM>
+static bb_chain_launch_fn bb_lookup_second_guide(int auxc, int mode) {
+  if (mode == 0) return auxc ? &bb_second_launch<M, GK, GM, true, 0> : &bb_second_launch<M, GK, GM, false, 0>;
+  if constexpr (M::D == M::DP) {
+    if (mode == 1) return auxc ? &bb_second_launch<M, GK, GM, true, 1> : &bb_second_launch<M, GK, GM, false, 1>;
+  }
+  return nullptr;
+}
+/* mode 0 = llikelihood (needs a guide), 1 = innovations (guide optional, needs d' = d) */
+template <class M>
+static bb_chain_launch_fn bb_lookup_second(int gk, int gm, int auxc, int mode) {
+  if (gk == 0) {
+    if constexpr (M::D == M::DP) {
+      if (mode == 1) return &bb_second_launch<M, 0, 0, true, 1>;
+    }
+    return nullptr;
+  }
+  if (gk == BB_GUIDE_NUH) return bb_lookup_second_guide<M, BB_GUIDE_NUH, 0>(auxc, mode);
+  if (gk == BB_GUIDE_HV) return bb_lookup_second_guide<M, BB_GUIDE_HV, 0>(auxc, mode);
+  if (gk == BB_GUIDE_LMMU) {
+    if (gm == 1) return bb_lookup_second_guide<M, BB_GUIDE_LMMU, 1>(auxc, mode);
+    if constexpr (M::D >= 2)
+      if (gm == 2) return bb_lookup_second_guide<M, BB_GUIDE_LMMU, 2>(auxc, mode);
+    if constexpr (M::D >= 3)
+      if (gm == 3) return bb_lookup_second_guide<M, BB_GUIDE_LMMU, 3>(auxc, mode);
+  }
+  return nullptr;
+}

@@ -210,55 +210,92 @@ void bbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* sin(pi v), cos(pi v) for v in [0,2]; quadrant reduction then libm on [-pi/4, pi/4] */
-static void sincospi_(double v, double* s, double* c) {
-  double n = nearbyint(2.0 * v); /* 0..4 */
-  double r = v - 0.5 * n;        /* exact: |r| <= 1/4 */
-  double sr = sin(M_PI * r), cr = cos(M_PI * r);
-  switch (((int)n) & 3) {
-    case 0: *s = sr;  *c = cr;  break;
-    case 1: *s = cr;  *c = -sr; break;
-    case 2: *s = -sr; *c = -cr; break;
-    default: *s = -cr; *c = sr; break;
+/* ---- float32 Box-Muller built from +, *, fma and IEEE sqrt only, so that this CPU evaluation and
+ * the kernels' (bridge.jl_b200/csrc/rng.cuh) are BIT-IDENTICAL.  Coefficients: tools/gen_rng_poly.py
+ * (log: max rel. error 9e-8; sinpi/cospi: max abs. error 9e-8).  A normal therefore carries a 24-bit
+ * mantissa and |z| <= 6.77; it is widened to double before use. */
+static inline float bb_logf(float u) { /* u in [2^-33, 1] */
+  uint32_t ix;
+  memcpy(&ix, &u, 4);
+  ix += 0x3F800000u - 0x3F3504F3u;
+  int e = (int)(ix >> 23) - 127;
+  ix = (ix & 0x007FFFFFu) + 0x3F3504F3u;
+  float m;
+  memcpy(&m, &ix, 4); /* m in [sqrt(1/2), sqrt(2)) */
+  float f = m - 1.0f;
+  float p = -0x1.4bde76p-4f;
+  p = fmaf(p, f, 0x1.045b0cp-3f);
+  p = fmaf(p, f, -0x1.09ab66p-3f);
+  p = fmaf(p, f, 0x1.22dbfcp-3f);
+  p = fmaf(p, f, -0x1.54d552p-3f);
+  p = fmaf(p, f, 0x1.99a15p-3f);
+  p = fmaf(p, f, -0x1.0000c6p-2f);
+  p = fmaf(p, f, 0x1.555552p-2f);
+  float f2 = f * f;
+  float t = p * f;
+  t = fmaf(t, f2, -0.5f * f2); /* f^3 P(f) - f^2/2 */
+  float r = t + f;
+  return fmaf((float)e, 0x1.62e43p-1f, r);
+}
+static inline float bb_unif(uint32_t w) { /* (w + 1/2) / 2^32 rounded to float, in (0, 1] */
+  return fmaf((float)w, 0x1p-32f, 0x1p-33f);
+}
+/* one Box-Muller pair from two 32-bit words: radius from wu, angle pi*t with t = (int32)wa / 2^31 */
+static inline void bb_box_muller(uint32_t wu, uint32_t wa, float* z0, float* z1) {
+  float rad = sqrtf(-2.0f * bb_logf(bb_unif(wu)));
+  float t = (float)(int32_t)wa * 0x1p-31f; /* [-1, 1] */
+  float q = rintf(t * 2.0f);               /* -2..2 */
+  float r = fmaf(q, -0.5f, t);             /* exact, |r| <= 1/4 */
+  float s2 = r * r;
+  float ps = -0x1.2d9b7cp-1f;
+  ps = fmaf(ps, s2, 0x1.465ec4p+1f);
+  ps = fmaf(ps, s2, -0x1.4abbbap+2f);
+  ps = fmaf(ps, s2, 0x1.921fb6p+1f);
+  float sr = ps * r; /* sin(pi r) */
+  float pc = 0x1.d9c326p-3f;
+  pc = fmaf(pc, s2, -0x1.55c57ap+0f);
+  pc = fmaf(pc, s2, 0x1.03c1dcp+2f);
+  pc = fmaf(pc, s2, -0x1.3bd3ccp+2f);
+  float cr = fmaf(pc, s2, 1.0f); /* cos(pi r) */
+  float sn, cs;
+  switch (((int)q) & 3) {
+    case 0: sn = sr;  cs = cr;  break;
+    case 1: sn = cr;  cs = -sr; break;
+    case 2: sn = -sr; cs = -cr; break;
+    default: sn = -cr; cs = sr; break;
   }
+  *z0 = rad * sn;
+  *z1 = rad * cs;
 }
 
 /* Counter layout shared with the kernels:
  *   key = (seed lo, seed hi);  counter = (q, stream, id lo, id hi)
- *   normals: id = global row  = chain*S + seg ; q = pair index; normal n = j*d' + k of the row
- *            (time index j, noise component k, the reference's draw order src/wiener.jl:28-33)
- *            is element (n & 1) of pair q = n >> 1.  Index j = 0 is drawn but unused.
- *   accept : id = global chain, q = 0xFFFFFFFF, U from the first two words.
- * Box-Muller in double on 53-bit uniforms: u in (0,1), v in (0,2):
- *   z0 = sqrt(-2 ln u) sin(pi v), z1 = sqrt(-2 ln u) cos(pi v). */
-static inline double u53(uint32_t lo, uint32_t hi) {
-  return (double)((uint64_t)lo ^ ((uint64_t)hi << 21));
-}
-void bbo_normal_pair(uint64_t seed, uint32_t stream, uint64_t row, uint32_t q, double z[2]) {
+ *   normals: id = global row = chain*S + seg ; one Philox call gives FOUR normals: words (0,1) -> elements
+ *            0,1 and words (2,3) -> elements 2,3 of quad q.  Normal n = j*d' + k of the row (time index j,
+ *            noise component k, the reference's draw order src/wiener.jl:28-33) is element n & 3 of quad
+ *            q = n >> 2.  Index j = 0 is drawn but unused.
+ *   accept : id = global chain, q = 0xFFFFFFFF, log U = (double) bb_logf(bb_unif(word 0)). */
+void bbo_normal_quad(uint64_t seed, uint32_t stream, uint64_t row, uint32_t q, double z[4]) {
   uint32_t ctr[4] = {q, stream, (uint32_t)row, (uint32_t)(row >> 32)};
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t o[4];
   bbo_philox4x32_10(ctr, key, o);
-  double u = u53(o[0], o[1]) * 0x1p-53 + 0x1p-54;
-  double v = u53(o[2], o[3]) * 0x1p-52 + 0x1p-53;
-  double s = sqrt(-2.0 * log(u));
-  double sn, cs;
-  sincospi_(v, &sn, &cs);
-  z[0] = s * sn;
-  z[1] = s * cs;
+  float a, b, c, d;
+  bb_box_muller(o[0], o[1], &a, &b);
+  bb_box_muller(o[2], o[3], &c, &d);
+  z[0] = (double)a; z[1] = (double)b; z[2] = (double)c; z[3] = (double)d;
 }
 double bbo_normal(uint64_t seed, uint32_t stream, uint64_t row, uint64_t n) {
-  double z[2];
-  bbo_normal_pair(seed, stream, row, (uint32_t)(n >> 1), z);
-  return z[n & 1];
+  double z[4];
+  bbo_normal_quad(seed, stream, row, (uint32_t)(n >> 2), z);
+  return z[n & 3];
 }
 double bbo_accept_logu(uint64_t seed, uint32_t stream, uint64_t chain) {
   uint32_t ctr[4] = {0xFFFFFFFFu, stream, (uint32_t)chain, (uint32_t)(chain >> 32)};
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t o[4];
   bbo_philox4x32_10(ctr, key, o);
-  double u = u53(o[0], o[1]) * 0x1p-53 + 0x1p-54;
-  return log(u);
+  return (double)bb_logf(bb_unif(o[0]));
 }
 
 /* ======================================================================= A1: sample!(W, Wiener{T}())

@@ -6,6 +6,7 @@ cpu_baseline / --impl reference legs.  The product package never imports this mo
 Two builds are exposed:
     load("ref")  reference arithmetic (no FMA contraction; what Julia computes)
     load("fma")  identical algorithm in the CUDA kernels' rounding order
+    load("fast") -O3 -march=native speed build of the reference arithmetic (CPU baseline timing only)
 """
 from __future__ import annotations
 

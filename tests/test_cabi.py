@@ -1,0 +1,54 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/bridge_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as G
+    path = os.path.join(ROOT, "bridge.jl_b200", "lib", "libbridge_b200.so")
+    if not os.path.exists(path):
+        G.build()
+    return ctypes.CDLL(path)
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "bridge_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(bb_[a-zA-Z0-9_]+)\(", hdr)))
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    import bridge_jl_b200 as B
+    assert sorted(B.SYMBOLS) == names  # the Python binding covers the whole ABI
+
+
+def test_status_strings_are_the_reference_messages(lib):
+    lib.bb_strerror.restype = ctypes.c_char_p
+    assert lib.bb_strerror(-1) == b"Y and W differ in length."                              # src/euler.jl:137
+    assert lib.bb_strerror(-2) == b"Time axis mismatch between bridge P and driving W."     # src/euler.jl:248
+    assert lib.bb_strerror(-3) == b"Starting point has wrong length."                       # src/sde!.jl:30
+    assert lib.bb_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product refuses to compute (BB_ERR_NODEVICE); it never routes to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = ctypes.c_void_p()
+    assert lib.bb_ctx_create(0, ctypes.byref(ctx)) == -10
+    import bridge_jl_b200 as B
+    with pytest.raises(B.BridgeError) as ei:
+        B.Context(0)
+    assert ei.value.status == -10
+    src = ""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "bridge.jl_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src += open(os.path.join(dp, f), errors="ignore").read()
+    assert "liboracle" not in src.replace("liboracle_fma.so)", "") and "from oracle" not in src and "import oracle" not in src

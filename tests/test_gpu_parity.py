@@ -1,0 +1,584 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.  GPU only.
+
+Two comparisons per case:
+  * against liboracle_fma.so (the oracle evaluated in the kernels' rounding order): BIT-EXACT
+    (np.array_equal), except where libm's sin enters (INTDIFF / NCLAR3 drifts) or a device log;
+  * against liboracle_ref.so (reference arithmetic: no fused multiply-add, true divisions):
+    |dX| <= 1e-10 (1 + |X|),  |dll| <= 1e-6 |ll| + 1e-9   (north_star: ll within 1e-6 rel).
+Accept/reject bookkeeping is compared exactly.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+XTOL = 1e-10
+LLREL, LLABS = 1e-6, 1e-9
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bridge_jl_b200 as B
+    B.default_context()
+    return B
+
+
+def close_x(a, b):
+    return np.max(np.abs(a - b)) <= XTOL * (1 + np.max(np.abs(b)))
+
+
+def close_ll(a, b):
+    return np.all(np.abs(a - b) <= LLREL * np.abs(b) + LLABS)
+
+
+def warped(t0, t1, n):
+    s = np.linspace(0, t1 - t0, n)
+    return t0 + s * (2 - s / (t1 - t0))
+
+
+# ----------------------------------------------------------------------------------------------- a4: sample!
+@pytest.mark.parametrize("dp,N,S", [(1, 37, 2), (2, 64, 1), (3, 9, 3), (1, 5, 1)])
+def test_wiener_sample_bit_exact(B, oracle_fma, dp, N, S):
+    P = 70
+    ens = B.PathEnsemble(P, S, N, dp, dp, double_buffer=False, chain_offset=1000)
+    grids = [warped(0.3 * s, 0.3 * s + 1.0, N) for s in range(S)]
+    for s, tt in enumerate(grids):
+        ens.set_grid(s, tt)
+    W0 = np.zeros((P, S, N, dp))
+    W0[:, :, 0, :] = np.arange(P)[:, None, None] * 0.25  # y1 = W.yy[1] is kept (src/wiener.jl:50-51)
+    ens.upload(B.W, W0)
+    ens.sample_(seed=0x1234567890ABCDEF, stream=7)
+    W = ens.download(B.W)
+    for p in (0, 1, 31, 32, 69):
+        for s in range(S):
+            want = oracle_fma.wiener_sample(grids[s], dp, 0x1234567890ABCDEF, 7, (1000 + p) * S + s,
+                                            y1=W0[p, s, 0])
+            assert np.array_equal(W[p, s], want), (p, s)
+    ens.close()
+
+
+def test_upload_download_roundtrip(B):
+    rng = np.random.default_rng(0)
+    ens = B.PathEnsemble(33, 2, 21, 3, 2, double_buffer=True)
+    Wh = rng.standard_normal((33, 2, 21, 2)); Xh = rng.standard_normal((33, 2, 21, 3))
+    ens.upload(B.W, Wh); ens.upload(B.X, Xh)
+    assert np.array_equal(ens.download(B.W), Wh) and np.array_equal(ens.download(B.X), Xh)
+    assert np.array_equal(ens.download(B.W, p0=5, np_=7), Wh[5:12])
+    ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- a5: Euler-Maruyama
+GOLD_TT = np.arange(11) * 0.1
+GOLD_W = np.array([0.0, 0.0940107, 0.214935, 0.0259463, 0.0226432, -0.24268, -0.144298, 0.581472, -0.135443,
+                   0.0321464, 0.168574])
+GOLD_X = np.array([0.1, -0.00598928, 0.126914, -0.315902, 0.312599, -0.577923, 0.676305, 0.0494658, -0.766381,
+                   0.933971, -0.797544])
+
+
+def test_docs_golden_vector_through_solve(B):
+    """docs/src/manual.md:59-77: X = solve(Euler(), 0.1, W, OrnsteinUhlenbeck(20.0, 1.0))."""
+    W = B.SamplePath(GOLD_TT, GOLD_W)
+    X = B.solve(B.Euler(), 0.1, W, B.OrnsteinUhlenbeck(20.0, 1.0))
+    assert X.yy.shape == (11,)
+    assert np.max(np.abs(X.yy - GOLD_X)) < 1e-5
+    assert np.array_equal(X.tt, GOLD_TT)
+
+
+def test_config1_ou_single_path(B, oracle_ref, oracle_fma):
+    """BASELINE config 1: 1-D OU, one path, n = 1001, tt = 0:0.01:10, u = 0.1 (plumbing of solve / solve!)."""
+    tt = np.arange(1001) * 0.01
+    for beta in (2.0, 20.0):
+        Wy = oracle_ref.wiener_sample(tt, 1, 1, 0, 0)[:, 0]
+        X = B.solve(B.EulerMaruyama(), 0.1, B.SamplePath(tt, Wy), B.OrnsteinUhlenbeck(beta, 1.0))
+        m = O.make_model(O.OU, 1, 1, [beta, 1.0])
+        assert np.array_equal(X.yy, oracle_fma.euler(m, tt, [0.1], Wy)[:, 0])
+        assert close_x(X.yy, oracle_ref.euler(m, tt, [0.1], Wy)[:, 0])
+
+
+MODELS = [
+    ("wiener1", lambda B: B.Wiener(1), O.make_model(O.WIENER, 1, 1), True),
+    ("wiener3", lambda B: B.Wiener(3), O.make_model(O.WIENER, 3, 3), True),
+    ("ou", lambda B: B.OrnsteinUhlenbeck(2.0, 0.7), O.make_model(O.OU, 1, 1, [2.0, 0.7]), True),
+    ("lorenz", lambda B: B.Lorenz([10.0, 28.0, 8 / 3], 3.0),
+     O.make_model(O.LORENZ, 3, 3, [10.0, 28.0, 8 / 3, 3.0, 3.0, 3.0]), True),
+    ("fhn_diag", lambda B: B.FitzHughNagumo(0.1, 0.0, 1.5, 0.8, 0.3, 0.2),
+     O.make_model(O.FHN_DIAG, 2, 2, [0.1, 0.0, 1.5, 0.8, 0.3, 0.2]), True),
+    ("fhn_hypo", lambda B: B.FitzhughDiffusion(0.1, 0.0, 1.5, 0.8, 0.3),
+     O.make_model(O.FHN_HYPO, 2, 1, [0.1, 0.0, 1.5, 0.8, 0.3]), True),
+    ("intdiff", lambda B: B.IntegratedDiffusion(0.7), O.make_model(O.INTDIFF, 2, 1, [0.7]), False),
+    ("nclar3", lambda B: B.NclarDiffusion(1.5, 2.0, 0.4), O.make_model(O.NCLAR3, 3, 1, [1.5, 2.0, 0.4]), False),
+    ("linpro2", lambda B: B.LinPro([[-1.0, 0.1], [-0.2, -1.0]], [0.1, -0.2], [[0.4, 0.1], [0.2, 0.8]]),
+     O.linpro_model([[-1.0, 0.1], [-0.2, -1.0]], [0.1, -0.2], [[0.4, 0.1], [0.2, 0.8]]), True),
+    ("linpro3", lambda B: B.LinPro(-np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]]), np.zeros(3),
+                                   0.5 * np.eye(3)),
+     O.linpro_model(-np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]]), np.zeros(3), 0.5 * np.eye(3)),
+     True),
+]
+
+
+@pytest.mark.parametrize("name,mk,om,exact", MODELS, ids=[m[0] for m in MODELS])
+def test_euler_ensemble_vs_oracle(B, oracle_ref, oracle_fma, name, mk, om, exact):
+    """solve!(EulerMaruyama(), X, u, W, P) for an ensemble with per-chain starting points, two chained
+    segments (the second starts at the first's end point) and a ragged N."""
+    Pm = mk(B)
+    d, dp = om.d, om.dprime
+    P, S, N = 45, 2, 203
+    grids = [warped(0.0, 0.5, N), warped(0.5, 1.2, N)]
+    rng = np.random.default_rng(1)
+    u = rng.standard_normal((P, d)) * 0.3
+    ens = B.PathEnsemble(P, S, N, d, dp, double_buffer=False)
+    for s in range(S):
+        ens.set_grid(s, grids[s])
+    ens.set_start(u)
+    ens.sample_(seed=11, stream=0)
+    W = ens.download(B.W)
+    ens.euler_(Pm)
+    X = ens.download(B.X)
+    xend = ens.xend
+    for p in (0, 7, 44):
+        start = u[p]
+        for s in range(S):
+            Xf = oracle_fma.euler(om, grids[s], start, W[p, s])
+            Xr = oracle_ref.euler(om, grids[s], start, W[p, s])
+            if exact:
+                assert np.array_equal(X[p, s], Xf), (name, p, s)
+            assert close_x(X[p, s], Xr), (name, p, s, np.max(np.abs(X[p, s] - Xr)))
+            start = X[p, s, -1]
+        assert np.array_equal(xend[p], X[p, -1, -1])
+    # fused sample! + solve! gives the same W and X
+    ens2 = B.PathEnsemble(P, S, N, d, dp, double_buffer=False)
+    for s in range(S):
+        ens2.set_grid(s, grids[s])
+    ens2.set_start(u)
+    ens2.sample_euler_(Pm, seed=11, stream=0)
+    assert np.array_equal(ens2.download(B.W), W)
+    assert np.array_equal(ens2.download(B.X), X)
+    ens.close(); ens2.close()
+
+
+def test_config2_wiener_process_property(B):
+    """BASELINE config 2 at reduced P: the Wiener process as target gives X = u + W for every chain (size-independent)."""
+    P, N = 20000, 1001
+    ens = B.PathEnsemble(P, 1, N, 1, 1, double_buffer=False)
+    ens.set_grid(0, np.linspace(0, 1, N))
+    ens.set_start([0.0])
+    ens.sample_euler_(B.Wiener(1), seed=2, stream=0)
+    W = ens.download(B.W); X = ens.download(B.X)
+    assert np.allclose(X, W, rtol=0, atol=1e-13)
+    inc = np.diff(W[:, 0, :, 0], axis=1) / np.sqrt(1 / 1000)
+    assert abs(inc.mean()) < 5 / np.sqrt(inc.size) and abs(inc.var() - 1) < 5 * np.sqrt(2 / inc.size)
+    ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- guided proposals
+FHN_PAR = [0.1, 0.0, 1.5, 0.8, 0.3]
+
+
+def fhn_aux(v):
+    Bt = np.array([[10.0, -10.0], [1.5, -1.0]])
+    bt = np.array([0.0 / 0.1 - v ** 3 / 0.1, 0.8])
+    at = np.array([[0.0, 0.0], [0.0, 0.09]])
+    return Bt, bt, at
+
+
+def oracle_fhn_chain(orc, grids, obs_v, eps=1e-3, Sig=1e-10):
+    """Backward chain of partialbridge_bolus3.jl:162-180 with the oracle (Lyapunov step + observation updates)."""
+    S = len(grids)
+    L = np.array([[1.0, 0.0]]); Sg = np.array([[Sig]])
+    nu = np.zeros(2); Hp = np.eye(2) / eps
+    nu, Hp = orc.gpupdate_nuH(nu, Hp, L, Sg, [obs_v[-1]])
+    out = [None] * S
+    for i in range(S - 1, -1, -1):
+        Bt, bt, at = fhn_aux(obs_v[i])
+        nut, Ht, nu, Hp, C = orc.backward_nuH(O.ODE_LYAP, grids[i], O.const_aux(Bt, bt, at), nu, Hp, 0.0)
+        out[i] = (nut, Ht, Bt, bt)
+        if i > 0:
+            nu, Hp = orc.gpupdate_nuH(nu, Hp, L, Sg, [obs_v[i - 1]])
+    return out
+
+
+def test_guided_nuH_fhn_multisegment(B, oracle_ref, oracle_fma):
+    """solve!(Euler(), X, u, W, P°) + llikelihood for PartialBridgeνH, 3 chained segments, FHN hypoelliptic."""
+    N, P = 301, 40
+    obs_t, obs_v = (0.5, 1.0, 1.5), (-1.0, -0.5, 0.5)
+    grids = [warped(a, b, N) for a, b in zip((0.0,) + obs_t[:-1], obs_t)]
+    S = len(grids)
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    x0 = np.array([-0.5, -0.6])
+    for orc, exact in ((oracle_fma, True), (oracle_ref, False)):
+        om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+        tabs = oracle_fhn_chain(orc, grids, obs_v)
+        guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+                  for s in range(S)]
+        og = [O.GuideHolder(O.GUIDE_NUH, grids[s], tabs[s][1], tabs[s][0], Bt=tabs[s][2], betat=tabs[s][3])
+              for s in range(S)]
+        ens = B.PathEnsemble(P, S, N, 2, 1, double_buffer=False)
+        for s in range(S):
+            ens.set_grid(s, grids[s])
+        ens.set_start(x0)
+        ens.sample_(seed=5, stream=1)
+        W = ens.download(B.W)
+        for skip in (0, 3):
+            ens.guided_euler_ll_(Pm, guides, skip=skip, store_x=True)
+            X = ens.download(B.X); ll = ens.ll; xend = ens.xend
+            for p in (0, 13, 39):
+                start, llo = x0, 0.0
+                for s in range(S):
+                    Xo, xe = orc.guided_euler(om, og[s], start, W[p, s])
+                    llo += orc.llikelihood(om, og[s], Xo, skip)
+                    if exact:
+                        assert np.array_equal(X[p, s], Xo), (p, s)
+                    else:
+                        assert close_x(X[p, s], Xo), (p, s)
+                    start = xe
+                if exact:
+                    assert ll[p] == llo and np.array_equal(xend[p], start)
+                else:
+                    assert close_ll(ll[p], llo), (ll[p], llo)
+            # second-pass llikelihood on the stored X equals the fused value
+            ens.set_ll(np.zeros(P))
+            ens.llikelihood_(Pm, guides, skip=skip)
+            assert np.array_equal(ens.ll, ll)
+            # the guided paths end near the observations
+            assert np.max(np.abs(X[:, :, -1, 0] - np.array(obs_v))) < 2e-2
+        # without storing X the log-likelihood is unchanged
+        ens.guided_euler_ll_(Pm, guides, skip=0, store_x=False)
+        ens.guided_euler_ll_(Pm, guides, skip=3, store_x=False)
+        assert np.array_equal(ens.ll, ll)
+        ens.close()
+
+
+def test_guided_nuH_intdiff_partialparam(B, oracle_ref):
+    """test/partialparam.jl setup (IntegratedDiffusion, N = 1501): tolerance parity (the drift contains sin)."""
+    tt = np.arange(1501) / 1000
+    Pm = B.IntegratedDiffusion(0.7)
+    om = O.make_model(O.INTDIFF, 2, 1, [0.7])
+    aux = dict(B=np.array([[0.0, 1.0], [0.0, -1.0]]), beta=np.array([0.0, 0.5]), a=np.array([[0.0, 0.0], [0.0, 0.49]]))
+    nuT, HpT, C_ = oracle_ref.update_nuHC([[1.0, 0.0]], [[0.1]], [2.5], 1e-5)
+    nu, H, _, _, _ = oracle_ref.backward_nuH(O.ODE_R3, tt, O.const_aux(**aux), nuT, HpT, C_)
+    og = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=aux["B"], betat=aux["beta"])
+    g = B.GuideTables(B.api.K.GUIDE_NUH, tt, Pm, H, nu, aux["B"], aux["beta"])
+    P = 16
+    ens = B.PathEnsemble(P, 1, 1501, 2, 1, double_buffer=False)
+    ens.set_grid(0, tt); ens.set_start([2.0, 1.0]); ens.sample_(3, 0)
+    W = ens.download(B.W)
+    ens.guided_euler_ll_(Pm, [g])
+    X = ens.download(B.X); ll = ens.ll
+    for p in range(P):
+        Xo, _ = oracle_ref.guided_euler(om, og, [2.0, 1.0], W[p, 0])
+        assert close_x(X[p, 0], Xo)
+        assert close_ll(ll[p], oracle_ref.llikelihood(om, og, Xo))
+    ens.close()
+
+
+def test_guidedbridge_linpro3_config3(B, oracle_ref, oracle_fma):
+    """BASELINE config 3 at reduced P: GuidedBridge (H♢, V), LinPro d = 3 with dense sigma, end point = v."""
+    N, P = 1001, 24
+    tt = np.linspace(0, 1, N)
+    B1 = -np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]])
+    sig = 0.5 * np.eye(3) + 0.05 * np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]])
+    v = np.array([0.5, 0.0, -0.5])
+    Pm = B.LinPro(B1, np.zeros(3), sig)
+    om = O.linpro_model(B1, np.zeros(3), sig)
+    aux = O.const_aux(-np.eye(3), np.zeros(3), sig @ sig.T)
+    for orc, exact in ((oracle_fma, True), (oracle_ref, False)):
+        Hd, V = orc.backward_HV(tt, aux, v)
+        og = O.GuideHolder(O.GUIDE_HV, tt, Hd, V, Bt=-np.eye(3), betat=np.zeros(3))
+        g = B.GuideTables(B.api.K.GUIDE_HV, tt, Pm, Hd, V, -np.eye(3), np.zeros(3))
+        ens = B.PathEnsemble(P, 1, N, 3, 3, double_buffer=False)
+        ens.set_grid(0, tt); ens.set_start(np.zeros(3)); ens.sample_(3, 0)
+        W = ens.download(B.W)
+        ens.guided_euler_ll_(Pm, [g])
+        X = ens.download(B.X); ll = ens.ll
+        assert np.array_equal(X[:, 0, -1], np.tile(v, (P, 1)))  # endpoint override  src/euler.jl:241-242
+        for p in (0, 5, 23):
+            Xo, xe = orc.guided_euler(om, og, np.zeros(3), W[p, 0])
+            llo = orc.llikelihood(om, og, Xo)
+            if exact:
+                assert np.array_equal(X[p, 0], Xo) and ll[p] == llo
+            else:
+                # the last steps divide by H♢ -> 0: compare away from the singular end, and ll relatively
+                assert close_x(X[p, 0, :-1], Xo[:-1]) and close_ll(ll[p], llo)
+        ens.close()
+
+
+def test_partialbridge_LMmu_and_time_dependent_aux(B, oracle_ref, oracle_fma):
+    """PartialBridge (L, M, μ) drift and a time-dependent auxiliary process (B̃(t), β̃(t) tabulated per grid point;
+    the `linearised_startend` choice of partialbridge_fitzhugh.jl:101-104)."""
+    N, P = 401, 12
+    tt = warped(0.0, 0.5, N)
+    v, u0 = -1.0, -0.5
+    uv = lambda t: v * (t / 0.5) + u0 * (1 - t / 0.5)
+    Bf = lambda t: np.array([[10.0 - 30.0 * uv(t) ** 2, -10.0], [1.5, -1.0]])
+    bf = lambda t: np.array([20.0 * uv(t) ** 3, 0.8])
+    af = lambda t: np.array([[0.0, 0.0], [0.0, 0.09]])
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    Btg = np.stack([Bf(t) for t in tt]); btg = np.stack([bf(t) for t in tt])
+    L = np.array([[1.0, 0.0]]); Sg = np.array([[1e-4]])
+    for orc, exact in ((oracle_fma, True), (oracle_ref, False)):
+        aux = O.staged_aux(tt, Bf, bf, af)
+        Lt, Mt, mut = orc.backward_LMmu(tt, aux, L, Sg)
+        og = O.GuideHolder(O.GUIDE_LMMU, tt, Lt, mut, Mm=Mt, v=[v], Bt=Btg, betat=btg, aux_const=False, m=1)
+        g = B.GuideTables(B.api.K.GUIDE_LMMU, tt, Pm, Lt, mut, Btg, btg, Mm=Mt, v=[v], aux_const=False, m=1)
+        ens = B.PathEnsemble(P, 1, N, 2, 1, double_buffer=False)
+        ens.set_grid(0, tt); ens.set_start([-0.5, -0.6]); ens.sample_(8, 0)
+        W = ens.download(B.W)
+        ens.guided_euler_ll_(Pm, [g])
+        X = ens.download(B.X); ll = ens.ll
+        for p in range(P):
+            Xo, _ = orc.guided_euler(om, og, [-0.5, -0.6], W[p, 0])
+            llo = orc.llikelihood(om, og, Xo)
+            if exact:
+                assert np.array_equal(X[p, 0], Xo) and ll[p] == llo
+            else:
+                assert close_x(X[p, 0], Xo) and close_ll(ll[p], llo)
+        ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- a15: pCN
+def test_pcn_replay_bit_exact(B, oracle_fma):
+    """Several pCN iterations of a 4-segment FHN chain ensemble, replayed chain by chain with the oracle:
+    W°, X°, ll°, log U, the accept decision, the surviving state and the acceptance counter agree exactly."""
+    N, P, iters, rho, seed = 121, 96, 6, 0.9, 4
+    obs_t, obs_v = (0.5, 1.0, 1.5, 2.0), (-1.0, -0.5, 0.5, 1.1)
+    grids = [warped(a, b, N) for a, b in zip((0.0,) + obs_t[:-1], obs_t)]
+    S = 4
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, grids, obs_v)
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    og = [O.GuideHolder(O.GUIDE_NUH, grids[s], tabs[s][1], tabs[s][0], Bt=tabs[s][2], betat=tabs[s][3])
+          for s in range(S)]
+    x0 = np.array([-0.5, -0.6])
+    ens = B.PathEnsemble(P, S, N, 2, 1, double_buffer=True, chain_offset=500)
+    for s in range(S):
+        ens.set_grid(s, grids[s])
+    ens.set_start(x0)
+    ens.sample_(seed, 0xFFFFFFFE)
+    ens.guided_euler_ll_(Pm, guides)
+    Wc = ens.download(B.W); Xc = ens.download(B.X); ll = ens.ll.copy()
+    acc = 0
+    for it in range(iters):
+        ens.pcn_step_(Pm, guides, rho, seed, it)
+        Wp = ens.download(B.W, which=B.PROP); Xp = ens.download(B.X, which=B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
+        for p in range(P):
+            llo, lu, Wo, Xo, xe = oracle_fma.pcn_propose(om, og, x0, Wc[p], rho, seed, it, 500 + p)
+            assert np.array_equal(Wp[p], Wo) and np.array_equal(Xp[p], Xo), (it, p)
+            assert llp[p] == llo and logu[p] == lu
+            ok = lu <= llo - ll[p]
+            assert bool(flags[p]) == ok
+            if ok:
+                Wc[p], Xc[p], ll[p] = Wo, Xo, llo
+                acc += 1
+        assert np.array_equal(ens.download(B.W), Wc) and np.array_equal(ens.download(B.X), Xc)
+        assert np.array_equal(ens.ll, ll)
+        assert ens.acc == acc
+    assert 0 < acc < iters * P
+    ens.close()
+
+
+def test_pcn_against_reference_arithmetic(B, oracle_ref):
+    """The same iteration against the reference arithmetic (no fma): ll° within 1e-6 relative, decisions
+    replayed from the kernel's own ll values are exact, flips against the oracle's ll are counted."""
+    N, P, rho, seed = 201, 64, 0.95, 9
+    tt = warped(0.0, 0.5, N)
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    Bt, bt, at = fhn_aux(-1.0)
+    nuT, HpT, C_ = oracle_ref.update_nuHC([[1.0, 0.0]], [[1e-10]], [-1.0], 1e-3)
+    nu, H, _, _, _ = oracle_ref.backward_nuH(O.ODE_R3, tt, O.const_aux(Bt, bt, at), nuT, HpT, C_)
+    g = B.GuideTables(B.api.K.GUIDE_NUH, tt, Pm, H, nu, Bt, bt)
+    og = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=Bt, betat=bt)
+    x0 = np.array([-0.5, -0.6])
+    ens = B.PathEnsemble(P, 1, N, 2, 1)
+    ens.set_grid(0, tt); ens.set_start(x0); ens.sample_(seed, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, [g])
+    flips = 0
+    for it in range(4):
+        Wc = ens.download(B.W); ll = ens.ll
+        ens.pcn_step_(Pm, [g], rho, seed, it)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
+        assert np.array_equal(flags.astype(bool), logu <= llp - ll)  # replay on the kernel's own values
+        for p in range(P):
+            llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(om, [og], x0, Wc[p], rho, seed, it, p)
+            assert lu == logu[p]
+            assert close_ll(llp[p], llo), (llp[p], llo)
+            flips += int(bool(flags[p]) != (lu <= llo - ll[p]))
+    assert flips == 0
+    ens.close()
+
+
+def test_pcn_properties_large(B):
+    """Size-independent properties at a production-like ensemble size (4 segments x N = 1001, 20 000 chains):
+    rho = 1 reproduces the current state (ll° = ll, every proposal accepted); acc = sum of flags; parity swap
+    keeps the accepted proposal as the new current path."""
+    import bridge_jl_b200.configs as cfg
+    P, n = 20000, 1001
+    Pm, guides, x0, rho = cfg.fhn_config4(n)
+    S = len(guides)
+    ens = B.PathEnsemble(P, S, n, 2, 1)
+    for s, g in enumerate(guides):
+        ens.set_grid(s, g.tt)
+    ens.set_start(x0); ens.sample_(4, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+    ll0 = ens.ll
+    assert np.all(np.isfinite(ll0))
+    X = ens.download(B.X, p0=0, np_=50)
+    assert np.max(np.abs(X[:, :, -1, 0] - np.array(cfg.FHN_OBS_V))) < 2e-2  # bridges hit the observations
+    ens.pcn_step_(Pm, guides, 1.0, 4, 0)
+    assert np.array_equal(ens.ll_prop, ll0) and ens.acc == P and np.all(ens.accepted == 1)
+    assert np.array_equal(ens.download(B.X, p0=0, np_=50), X)
+    ens.reset_acc()
+    total = 0
+    for it in range(1, 4):
+        ll = ens.ll
+        ens.pcn_step_(Pm, guides, rho, 4, it)
+        flags = ens.accepted.astype(bool)
+        assert np.array_equal(flags, ens.logu <= ens.ll_prop - ll)
+        assert np.array_equal(ens.ll, np.where(flags, ens.ll_prop, ll))
+        total += int(flags.sum())
+        assert ens.acc == total
+    assert 0.05 * 3 * P < total < 0.999 * 3 * P
+    # accepted proposals became the current state: recomputing ll from the stored current X agrees
+    ll = ens.ll
+    ens.llikelihood_(Pm, guides)
+    assert np.array_equal(ens.ll, ll)
+    ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- constructors
+def test_backward_constructors_vs_oracle(B, oracle_fma, oracle_ref):
+    """updateνH⁺C, partialbridgeodeνH! (R3 and Lyap), gpHinv!/gpV!, partialbridgeode!, gpupdate on the device."""
+    tt = warped(0.0, 1.5, 301)
+    auxd = dict(B=np.array([[0.0, 1.0], [0.0, -1.0]]), beta=np.array([0.0, 0.5]), a=np.array([[0.0, 0.0], [0.0, 0.49]]))
+    Pt = B.LinearAux(auxd["B"], auxd["beta"], auxd["a"])
+    Pm = B.IntegratedDiffusion(0.7)
+    L, Sg, v = [[1.0, 0.0]], [[0.1]], [2.5]
+    Po = B.PartialBridgeνH(tt, Pm, Pt, L, v, 1e-5, Sg)
+    for orc, tol in ((oracle_fma, 0.0), (oracle_ref, 1e-9)):
+        nuT, HpT, C_ = orc.update_nuHC(L, Sg, v, 1e-5)
+        nu, H, _, _, Cc = orc.backward_nuH(O.ODE_R3, tt, O.const_aux(**auxd), nuT, HpT, C_)
+        if tol == 0.0:
+            assert np.array_equal(Po.ν, nu) and np.array_equal(Po.H, H)
+            assert abs(Po.C - Cc) <= 1e-14 * abs(Cc)
+        else:
+            assert np.allclose(Po.ν, nu, rtol=tol, atol=tol) and np.allclose(Po.H, H, rtol=1e-6)
+    # Lyapunov variant + time-dependent auxiliary + chaining outputs
+    Bf = lambda t: np.array([[-1.0 - t, 0.3], [0.1 * t, -0.5]])
+    bf = lambda t: np.array([0.2, np.sin(t)])
+    af = lambda t: np.array([[0.3 + 0.1 * t, 0.05], [0.05, 0.2]])
+    Pt2 = B.LinearAux(Bf, bf, af)
+    Po2, nul, Hl, C2 = B.partialbridgeνH(tt, Pm, Pt2, [0.1, -0.2], [[2.0, 0.1], [0.1, 1.0]])
+    nu, H, nul_o, Hl_o, C_o = oracle_fma.backward_nuH(O.ODE_LYAP, tt, O.staged_aux(tt, Bf, bf, af), [0.1, -0.2],
+                                                      [[2.0, 0.1], [0.1, 1.0]], 0.0)
+    assert np.array_equal(Po2.ν, nu) and np.array_equal(Po2.H, H)
+    assert np.array_equal(nul, nul_o) and np.array_equal(Hl, Hl_o) and C2 == C_o
+    # GuidedBridge tables, d = 3
+    B3 = -np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]])
+    P3 = B.LinPro(B3, [0.1, 0.0, -0.1], 0.5 * np.eye(3))
+    tt1 = np.linspace(0, 1, 201)
+    G = B.GuidedBridge(tt1, P3, P3, [0.5, 0.0, -0.5])
+    Hd, V = oracle_fma.backward_HV(tt1, O.const_aux(B3, -B3 @ np.array([0.1, 0.0, -0.1]), 0.25 * np.eye(3)),
+                                   [0.5, 0.0, -0.5])
+    assert np.array_equal(G.Hdia, Hd) and np.array_equal(G.V, V)
+    # PartialBridge tables
+    PB = B.PartialBridge(tt, Pm, Pt, L, v, Sg)
+    Lt, Mt, mut = oracle_fma.backward_LMmu(tt, O.const_aux(**auxd), L, Sg)
+    assert np.array_equal(PB.L, Lt) and np.array_equal(PB.M, Mt) and np.array_equal(PB.μ, mut)
+    # gpupdate
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((3, 3)); Hp = A @ A.T + np.eye(3); nu0 = rng.standard_normal(3)
+    L2 = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.5]]); S2 = np.diag([0.1, 0.2]); v2 = np.array([0.3, -0.2])
+    n1, H1 = B.gpupdate_νH(nu0, Hp, L2, S2, v2)
+    n2, H2 = oracle_fma.gpupdate_nuH(nu0, Hp, L2, S2, v2)
+    assert np.array_equal(n1, n2) and np.array_equal(H1, H2)
+    Hd2, V2 = B.gpupdate(Hp, nu0, L2, S2, v2)
+    assert np.array_equal(Hd2, H2) and np.array_equal(V2, n2)
+    n3, H3 = B.gpupdate_νH(np.zeros(2), np.diag([np.inf, np.inf]), np.eye(2), 0.5 * np.eye(2), [1.0, 2.0])
+    assert np.allclose(H3, 0.5 * np.eye(2)) and np.allclose(n3, [1.0, 2.0])
+
+
+def test_reference_style_sampler_single_chain(B, oracle_ref):
+    """The loop of test/partialbridgenuH.jl:155-198 written with the mirrored API on one chain:
+    sample!, solve!(Euler(), Xo, x0, Wo, Po) (returns the end point), llikelihood; 1 < acc < iterations."""
+    tt = np.arange(301) / 200
+    Pm = B.IntegratedDiffusion(0.7)
+    Pt = B.LinearAux([[0.0, 1.0], [0.0, -1.0]], [0.0, 0.5], [[0.0, 0.0], [0.0, 0.49]])
+    Po = B.PartialBridgeνH(tt, Pm, Pt, [[1.0, 0.0]], [2.5], 1e-5, [[0.1]])
+    x0 = np.array([2.0, 1.0])
+    B.seed_(1)
+    W = B.sample(tt, B.Wiener(1))
+    assert W.yy.shape == (301,) and W.yy[0] == 0.0
+    X = B.SamplePath(tt, np.zeros((301, 2)))
+    xe = B.solve_(B.Euler(), X, x0, W, Po)
+    assert np.array_equal(xe, X.yy[-1]) and np.array_equal(X.yy[0], x0)
+    ll = B.llikelihood(B.LeftRule(), X, Po)
+    W2 = W.copy(); Wo = W.copy(); Xo = X.copy()
+    rng = np.random.default_rng(0)
+    acc, iters, rho = 0, 60, 0.9
+    for it in range(iters):
+        B.sample_(W2, B.Wiener(1))
+        Wo.yy[...] = rho * W.yy + np.sqrt(1 - rho ** 2) * W2.yy
+        B.bridge_(Xo, x0, Wo, Po)
+        llo = B.llikelihood(B.LeftRule(), Xo, Po)
+        if np.log(rng.random()) <= llo - ll:
+            X, Xo = Xo, X
+            W, Wo = Wo, W
+            ll = llo
+            acc += 1
+    assert 1 < acc < iters
+    # the device llikelihood of the final path equals the oracle's on the same path and tables
+    og = O.GuideHolder(O.GUIDE_NUH, tt, Po.H, Po.ν, Bt=[[0.0, 1.0], [0.0, -1.0]], betat=[0.0, 0.5])
+    assert close_ll(ll, oracle_ref.llikelihood(O.make_model(O.INTDIFF, 2, 1, [0.7]), og, X.yy))
+
+
+def test_innovations_roundtrip(B, oracle_fma):
+    """innovations!(EulerMaruyama(), W, X, P) inverts solve! (src/euler.jl:357-376)."""
+    tt = warped(0, 1, 257)
+    Pm = B.FitzHughNagumo(0.1, 0.0, 1.5, 0.8, 0.3, 0.2)
+    om = O.make_model(O.FHN_DIAG, 2, 2, [0.1, 0.0, 1.5, 0.8, 0.3, 0.2])
+    B.seed_(5)
+    W = B.sample(tt, B.Wiener(2))
+    X = B.solve(B.Euler(), [-0.5, -0.6], W, Pm)
+    W2 = B.innovations_(B.EulerMaruyama(), B.SamplePath(tt, np.zeros((257, 2))), X, Pm)
+    assert np.array_equal(W2.yy, oracle_fma.innovations(om, None, tt, X.yy))
+    assert np.max(np.abs(W2.yy - W.yy)) < 1e-10
+    with pytest.raises(B.BridgeError) as ei:  # hypoelliptic model: sigma is not invertible
+        Ph = B.FitzhughDiffusion(*FHN_PAR)
+        Wh = B.sample(tt, B.Wiener(1))
+        Xh = B.solve(B.Euler(), [-0.5, -0.6], Wh, Ph)
+        B.innovations_(B.EulerMaruyama(), Wh.copy(), Xh, Ph)
+    assert ei.value.status in (-11, -12)
+
+
+# ----------------------------------------------------------------------------------------------- error behaviour
+def test_reference_error_messages(B):
+    tt = np.linspace(0, 1, 11)
+    W = B.SamplePath(tt, np.zeros(11))
+    Y = B.SamplePath(np.linspace(0, 1, 12), np.zeros(12))
+    with pytest.raises(B.BridgeError, match="Y and W differ in length."):
+        B.solve_(B.Euler(), Y, 0.1, W, B.OrnsteinUhlenbeck(1.0, 1.0))
+    Pm = B.LinPro([[-1.0]], [0.0], [[1.0]])
+    G = B.GuidedBridge(tt, Pm, Pm, [0.3])
+    with pytest.raises(B.BridgeError, match="Time axis mismatch between bridge P and driving W."):
+        Wsame = B.SamplePath.__new__(B.SamplePath); Wsame.tt, Wsame.yy = G.tt, np.zeros(11)
+        B.solve(B.Euler(), 0.1, Wsame, G)
+    with pytest.raises(B.BridgeError, match="Starting point has wrong length."):
+        B.solve(B.Euler(), [0.1, 0.2], W, B.OrnsteinUhlenbeck(1.0, 1.0))
+    with pytest.raises(B.BridgeError):
+        B.VSamplePath(tt, np.zeros((2, 12)))
+    with pytest.raises(B.BridgeError, match="m == length"):
+        B.PartialBridgeνH(tt, B.IntegratedDiffusion(0.7), B.LinearAux(np.eye(2), np.zeros(2), np.eye(2)),
+                          [[1.0, 0.0]], [1.0, 2.0], 1e-3, [[0.1]])
+    ens = B.PathEnsemble(4, 1, 11, 1, 1, double_buffer=False)
+    with pytest.raises(B.BridgeError) as ei:  # a model whose dimensions do not match the ensemble
+        ens.set_grid(0, tt)
+        ens.euler_(B.Lorenz([10.0, 28.0, 8 / 3], 3.0))
+    assert ei.value.status == -6
+    with pytest.raises(B.BridgeError) as ei:  # pCN needs the proposal buffers
+        ens.pcn_step_(Pm, [G], 0.5, 1, 0)
+    assert ei.value.status == -7
+    ens.close()
