@@ -13,13 +13,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbridge_b200.so")
+LIB_PATH = os.environ.get("BB_LIB") or os.path.join(_HERE, "lib", "libbridge_b200.so")  # BB_LIB: tuning builds
 
 BB_NPAR = 32
 # status codes
 OK, ERR_LENGTH, ERR_TIMEAXIS, ERR_STARTPOINT, ERR_DIM, ERR_ASSERT_M, ERR_MODEL, ERR_ARG, ERR_CUDA, \
-    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR = (0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10,
-                                                              -11, -12)
+    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE = (0, -1, -2, -3, -4, -5, -6, -7, -8, -9,
+                                                                         -10, -11, -12, -13)
 # model ids
 WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ = range(8)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
@@ -104,6 +104,7 @@ def _load():
         "bb_llikelihood": (C.c_int, [vp, C.POINTER(Model), pp, i32]),
         "bb_innovations": (C.c_int, [vp, C.POINTER(Model), pp]),
         "bb_pcn_step": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32]),
+        "bb_ens_refresh_x": (C.c_int, [vp, C.POINTER(Model), pp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

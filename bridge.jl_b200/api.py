@@ -402,6 +402,7 @@ class PathEnsemble:
         check(lib.bb_ens_create(self.ctx.h, P, S, N, d, dprime, flags, C.byref(h)))
         self.h = h
         self.has_x = store_x
+        self._last = None  # (P, guides) of the last pCN step: what refresh_x needs
         if chain_offset:
             check(lib.bb_ens_set_chain_offset(self.h, chain_offset))
 
@@ -431,6 +432,8 @@ class PathEnsemble:
     def download(self, what, which=K.CUR, p0=0, np_=None, out=None):
         k = self.dprime if what == K.W else self.d
         n = self.P - p0 if np_ is None else np_
+        if what == K.X and which == K.CUR:
+            self.refresh_x_()
         if out is None:
             out = np.empty((n, self.S, self.N, k))
         check(lib.bb_ens_download(self.h, what, which, p0, n, ptr(out)))
@@ -511,7 +514,16 @@ class PathEnsemble:
         flags = (K.RUN_STORE_X if store_x else 0) | (0 if ll else K.RUN_NO_LL)
         check(lib.bb_guided_euler_ll(self.h, C.byref(m), self._garr(guides), skip, flags))
 
+    def refresh_x_(self):
+        """Make X the CURRENT path of every chain again (X holds the last proposal; chains that rejected it
+        get their path recomputed from W by the same guided Euler kernel).  No-op if nothing is stale."""
+        if self._last is not None:
+            P, guides = self._last
+            m = P.cmodel()
+            check(lib.bb_ens_refresh_x(self.h, C.byref(m), self._garr(guides)))
+
     def llikelihood_(self, P, guides, skip: int = 0):
+        self.refresh_x_()
         m = P.cmodel()
         check(lib.bb_llikelihood(self.h, C.byref(m), self._garr(guides), skip))
 
@@ -522,6 +534,7 @@ class PathEnsemble:
     def pcn_step_(self, P, guides, ρ: float, seed: int, it: int, skip: int = 0, store_x: bool = True):
         """One pCN / Metropolis-Hastings update of every chain (test/partialbridgenuH.jl:176-191)."""
         m = P.cmodel()
+        self._last = (P, list(guides))
         check(lib.bb_pcn_step(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip,
                               K.RUN_STORE_X if store_x else 0))
 
@@ -564,7 +577,7 @@ class GuideTables(_Proposal):
     def __init__(self, kind, tt, P, A, b, Bt, betat, Mm=None, v=None, aux_const=True, m=0, ctx=None):
         self.ctx = ctx or default_context()
         self.kind, self.m = kind, m
-        self.tt, self.Target, self.Pt = f64(tt), P, None
+        self.tt, self.Target, self.Pt = np.array(tt, dtype=np.float64), P, None
         h = C.c_void_p()
         A, b, Bt, betat = f64(A), f64(b), f64(Bt), f64(betat)
         Mm = None if Mm is None else f64(Mm)
@@ -599,7 +612,7 @@ class PartialBridgeνH(_Proposal):
 
     def __init__(self, tt, P, Pt, L=None, v=None, ϵ=None, Σ=None, *, _tables=None, ctx=None):
         self.ctx = ctx or default_context()
-        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        self.tt, self.Target, self.Pt = np.array(tt, dtype=np.float64), P, Pt  # tt = collect(tt_)
         if _tables is not None:
             self.ν, self.H, self.C = _tables
         else:
@@ -631,7 +644,7 @@ class GuidedBridge(_Proposal):
 
     def __init__(self, tt, P, Pt, v, hdia=None, *, ctx=None):
         self.ctx = ctx or default_context()
-        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        self.tt, self.Target, self.Pt = np.array(tt, dtype=np.float64), P, Pt  # tt = collect(tt_)
         aux = _AuxC(Pt, self.tt); N, d = len(self.tt), aux.d
         v = np.atleast_1d(f64(v))
         he = None if hdia is None else np.atleast_2d(f64(hdia))
@@ -647,7 +660,7 @@ class PartialBridge(_Proposal):
 
     def __init__(self, tt, P, Pt, L, v, Σ=None, *, ctx=None):
         self.ctx = ctx or default_context()
-        self.tt, self.Target, self.Pt = f64(tt), P, Pt
+        self.tt, self.Target, self.Pt = np.array(tt, dtype=np.float64), P, Pt  # tt = collect(tt_)
         L = np.atleast_2d(f64(L)); m, d = L.shape
         self.m = m
         self.v = np.atleast_1d(f64(v))
@@ -717,6 +730,7 @@ def sample_(W: SamplePath, P: Wiener, y1=None, ctx=None) -> SamplePath:
 def sample(tt, P: Wiener, y1=None, ctx=None) -> SamplePath:
     """sample(tt, Wiener{T}()[, y1])  src/wiener.jl:11-21."""
     d = P.d
+    tt = np.array(tt, dtype=np.float64)  # tt = collect(tt): a fresh vector  (src/wiener.jl:12)
     yy = np.zeros(len(tt)) if d == 1 else np.zeros((len(tt), d))
     return sample_(SamplePath(tt, yy), P, y1, ctx)
 

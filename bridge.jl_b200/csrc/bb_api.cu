@@ -33,6 +33,7 @@ extern "C" const char* bb_strerror(int status) {
     case BB_ERR_NODEVICE: return "no CUDA device: libbridge_b200 has no CPU path";
     case BB_ERR_UNSUPPORTED: return "combination of model, guide and dimensions is not instantiated";
     case BB_ERR_SINGULAR: return "singular matrix";
+    case BB_ERR_STALE: return "X holds rejected proposals for some chains: call bb_ens_refresh_x first";
     default: return "unknown status";
   }
 }
@@ -294,11 +295,9 @@ extern "C" int bb_ens_destroy(bb_ens* e) {
   if (!e) return BB_ERR_ARG;
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
-  for (int b = 0; b < 2; b++) {
-    if (e->W[b]) cudaFree(e->W[b]);
-    if (e->X[b]) cudaFree(e->X[b]);
-  }
-  void* ptrs[] = {e->par, e->accepted, e->ll, e->llprop, e->logu, e->xend, e->xendprop, e->acc, e->start};
+  if (e->W[0]) cudaFree(e->W[0]);
+  if (e->X) cudaFree(e->X);
+  void* ptrs[] = {e->par, e->accepted, e->xstale, e->ll, e->llprop, e->logu, e->xend, e->xendprop, e->acc, e->start};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* g : e->gridtab)
@@ -329,13 +328,14 @@ extern "C" int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32
   const int nbuf = (flags & BB_ENS_DOUBLE_BUFFER) ? 2 : 1;
   const size_t rows = (size_t)ens_rows(e);
   int rc = BB_OK;
-  for (int b = 0; b < nbuf && rc == BB_OK; b++) {
-    rc = dev_alloc(e, &e->W[b], rows * BB_TC * dprime);
-    if (rc == BB_OK && !(flags & BB_ENS_NO_X)) rc = dev_alloc(e, &e->X[b], rows * BB_TC * d);
-  }
-  if (nbuf == 1) { e->W[1] = e->W[0]; e->X[1] = e->X[0]; }
+  /* the two buffers of a chain are adjacent rows of one allocation (see bb_chain.cuh) */
+  e->nbuf = nbuf;
+  rc = dev_alloc(e, &e->W[0], rows * nbuf * BB_TC * dprime);
+  if (rc == BB_OK && !(flags & BB_ENS_NO_X)) rc = dev_alloc(e, &e->X, rows * BB_TC * d);
+  e->W[1] = (nbuf == 2 && e->W[0]) ? e->W[0] + BB_TC * dprime : e->W[0];
   if (rc == BB_OK) rc = dev_alloc(e, &e->par, (size_t)P);
   if (rc == BB_OK) rc = dev_alloc(e, &e->accepted, (size_t)P);
+  if (rc == BB_OK) rc = dev_alloc(e, &e->xstale, (size_t)P);
   if (rc == BB_OK) rc = dev_alloc(e, &e->ll, (size_t)P);
   if (rc == BB_OK) rc = dev_alloc(e, &e->llprop, (size_t)P);
   if (rc == BB_OK) rc = dev_alloc(e, &e->logu, (size_t)P);
@@ -346,7 +346,6 @@ extern "C" int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32
   e->gridtab.assign(S, nullptr);
   e->tt.assign(S, std::vector<double>());
   if (rc != BB_OK) {
-    if (nbuf == 1) { e->W[1] = nullptr; e->X[1] = nullptr; }
     bb_ens_destroy(e);
     return rc;
   }
@@ -434,7 +433,7 @@ __global__ void __launch_bounds__(256) bb_transpose_kernel(double* __restrict__ 
                                                            const uint8_t* __restrict__ par,
                                                            const uint8_t* __restrict__ accepted, int which,
                                                            long long P, long long p0, long long np, int S, int N,
-                                                           int NC, int K) {
+                                                           int NC, int K, int nbuf) {
   const long long rowlen = (long long)BB_TC * K;
   const long long total = (long long)S * NC * np * rowlen;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -451,7 +450,7 @@ __global__ void __launch_bounds__(256) bb_transpose_kernel(double* __restrict__ 
     const long long p = p0 + pl;
     int b = par[p];
     if (which == BB_PROP && !accepted[p]) b = 1 - b;
-    double* dev = (b ? buf1 : buf0) + (((long long)s * NC + c) * P + p) * rowlen + e;
+    double* dev = (b ? buf1 : buf0) + (((long long)s * NC + c) * P + p) * (rowlen * nbuf) + e;
     double* hst = stage + ((pl * S + s) * (long long)N + j) * K + k;
     if (TO_DEVICE) *dev = *hst;
     else *hst = *dev;
@@ -462,12 +461,16 @@ static int ens_transfer(bb_ens* e, int what, int which, int64_t p0, int64_t np, 
   if (!e || !host || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
   if (what != BB_W && what != BB_X) return BB_ERR_ARG;
   if (which != BB_CUR && which != BB_PROP) return BB_ERR_ARG;
-  if (what == BB_X && !e->X[0]) return BB_ERR_ARG;
+  if (what == BB_X && !e->X) return BB_ERR_ARG;
+  /* X is single buffered and holds the last proposal of every chain; the CURRENT path of a chain whose
+   * proposal was rejected has to be recomputed first (bb_ens_refresh_x) */
+  if (what == BB_X && which == BB_CUR && !to_device && e->x_maybe_stale) return BB_ERR_STALE;
   bb_ctx* c = e->ctx;
   BB_CUDA(cudaSetDevice(c->device));
   const int K = what == BB_W ? e->dp : e->d;
-  double* b0 = what == BB_W ? e->W[0] : e->X[0];
-  double* b1 = what == BB_W ? e->W[1] : e->X[1];
+  double* b0 = what == BB_W ? e->W[0] : e->X;
+  double* b1 = what == BB_W ? e->W[1] : e->X;
+  const int nb = what == BB_W ? e->nbuf : 1;
   const size_t per_chain = (size_t)e->S * e->N * K;
   int64_t slab = (int64_t)((size_t)(256u << 20) / (per_chain * sizeof(double)));
   if (slab < 1) slab = 1;
@@ -483,10 +486,10 @@ static int ens_transfer(bb_ens* e, int what, int which, int64_t p0, int64_t np, 
     if (to_device) {
       BB_CUDA(cudaMemcpyAsync(c->stage, h, (size_t)n * per_chain * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       bb_transpose_kernel<true><<<grid, 256, 0, c->stream>>>(b0, b1, c->stage, e->par, e->accepted, which, e->P,
-                                                            p0 + q0, n, e->S, e->N, e->NC, K);
+                                                            p0 + q0, n, e->S, e->N, e->NC, K, nb);
     } else {
       bb_transpose_kernel<false><<<grid, 256, 0, c->stream>>>(b0, b1, c->stage, e->par, e->accepted, which, e->P,
-                                                             p0 + q0, n, e->S, e->N, e->NC, K);
+                                                             p0 + q0, n, e->S, e->N, e->NC, K, nb);
       BB_CUDA(cudaMemcpyAsync(h, c->stage, (size_t)n * per_chain * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     BB_CUDA(cudaGetLastError());
@@ -569,7 +572,6 @@ extern "C" int bb_guide_destroy(bb_guide* g) {
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   if (g->tab) cudaFree(g->tab);
-  if (g->segc) cudaFree(g->segc);
   delete g;
   return BB_OK;
 }
@@ -644,15 +646,14 @@ extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, 
   if (!g) return BB_ERR_NOMEM;
   g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxc ? 1 : 0; g->NC = NC; g->rec = rec;
   g->tt.assign(tt, tt + N);
+  memcpy(g->segc, segc, sizeof(segc));
   cudaError_t e1 = cudaMalloc(&g->tab, tab.size() * sizeof(double));
-  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&g->segc, sizeof(segc)) : e1;
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    bb_set_cuda_error(e1 != cudaSuccess ? e1 : e2, "cudaMalloc(guide)");
+  if (e1 != cudaSuccess) {
+    bb_set_cuda_error(e1, "cudaMalloc(guide)");
     bb_guide_destroy(g);
     return BB_ERR_NOMEM;
   }
   BB_CUDA(cudaMemcpyAsync(g->tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  BB_CUDA(cudaMemcpyAsync(g->segc, segc, sizeof(segc), cudaMemcpyHostToDevice, ctx->stream));
   BB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = g;
   return BB_OK;
@@ -666,6 +667,7 @@ struct run_spec {
   double rho;
   uint64_t seed;
   uint32_t stream;
+  bool only_stale = false;
 };
 
 /* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations! */
@@ -687,22 +689,23 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
       if (s == 0) { gk = g->kind; gm = g->m; auxc = g->auxc; }
       else if (g->kind != gk || g->m != gm || g->auxc != auxc) return BB_ERR_UNSUPPORTED;
       a.tab[s] = g->tab;
-      a.segc[s] = g->segc;
+      memcpy(a.segc[s], g->segc, sizeof(a.segc[s]));
     } else {
       if (!e->gridtab[s]) return BB_ERR_ARG; /* bb_ens_set_grid first */
       a.tab[s] = e->gridtab[s];
-      a.segc[s] = nullptr;
     }
   }
   bb_chain_launch_fn fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10)
                                        : lookup_kernel(model, gk, gm, auxc, rs.rng);
   if (!fn) return BB_ERR_UNSUPPORTED;
-  if (rs.rng >= 10 && !e->X[0]) return BB_ERR_ARG;
+  if (rs.rng >= 10 && !e->X) return BB_ERR_ARG;
   if (rs.rng == 11 && !model_sigma_invertible(model)) return BB_ERR_SINGULAR;
   if (rs.rng == 1 && !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG;
-  if (rs.store_x && !e->X[0]) return BB_ERR_ARG;
+  if (rs.store_x && !e->X) return BB_ERR_ARG;
   if (rs.skip < 0) return BB_ERR_ARG;
-  a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X[0] = e->X[0]; a.X[1] = e->X[1];
+  a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X = e->X;
+  a.xstale = e->xstale; a.only = rs.only_stale ? e->xstale : nullptr;
+  a.nbuf = e->nbuf;
   a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
   a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
   a.accepted = e->accepted; a.acc = e->acc;
@@ -721,6 +724,8 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
     return BB_ERR_CUDA;
   }
   c->launches++;
+  if (rs.rng == 1) e->x_maybe_stale = true;
+  else if (rs.rng < 10 && rs.store_x) e->x_maybe_stale = false;
   return BB_OK;
 }
 
@@ -733,7 +738,9 @@ extern "C" int bb_wiener_sample(bb_ens* e, uint64_t seed, uint32_t stream) {
   bb_ens view = *e; /* same device buffers, state dimension d'; X is neither stored nor returned */
   view.d = e->dp;
   run_spec rs{2, false, false, false, 0, 0.0, seed, stream};
-  return run_chain(&view, &w, nullptr, rs);
+  const int rc = run_chain(&view, &w, nullptr, rs);
+  if (rc == BB_OK && e->X) e->x_maybe_stale = true; /* X no longer belongs to the new W */
+  return rc;
 }
 extern "C" int bb_euler(bb_ens* e, const bb_model* model) {
   run_spec rs{0, true, false, true, 0, 0.0, 0, 0};
@@ -763,5 +770,12 @@ extern "C" int bb_llikelihood(bb_ens* e, const bb_model* model, bb_guide* const*
 }
 extern "C" int bb_innovations(bb_ens* e, const bb_model* model, bb_guide* const* guides) {
   run_spec rs{11, false, false, false, 0, 0.0, 0, 0};
+  return run_chain(e, model, guides, rs);
+}
+extern "C" int bb_ens_refresh_x(bb_ens* e, const bb_model* model, bb_guide* const* guides) {
+  if (!e) return BB_ERR_ARG;
+  if (!e->x_maybe_stale) return BB_OK;
+  run_spec rs{0, true, false, false, 0, 0.0, 0, 0};
+  rs.only_stale = true;
   return run_chain(e, model, guides, rs);
 }

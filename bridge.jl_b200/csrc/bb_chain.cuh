@@ -10,11 +10,17 @@
  *   if log(rand()) <= llo - ll ... end         test/partialbridgenuH.jl:183-190
  *
  * Data layout in HBM ("chunked AoSoA"): the N grid points of a segment are cut into chunks of
- * BB_TC = 8; W is [S][NC][P][8][d'] and X is [S][NC][P][8][d] doubles.  One chain therefore owns
- * 64*d' (64*d) contiguous, 64-byte aligned bytes per chunk: whole DRAM bursts whatever buffer the
- * neighbouring chains use (each chain reads buffer par[p] and writes buffer 1-par[p]; accepting a
- * proposal flips par[p] instead of copying the path), and a warp still covers 2 KB contiguous.
- * All accesses are 256-bit (LDG.E.256 / STG.E.256).
+ * BB_TC = 8; W is [S][NC][P][nbuf][8][d'] and X is [S][NC][P][8][d] doubles.  One chain therefore
+ * owns 64*d' (64*d) contiguous, 64-byte aligned bytes per chunk: whole DRAM bursts.
+ * W is double buffered per chain: a chain reads buffer par[p] and writes its proposal to buffer
+ * 1-par[p]; accepting flips par[p] instead of copying the path.  The two buffers of a chain are
+ * ADJACENT, so a warp reads half and writes the other half of the same contiguous 4 KB (d'=1)
+ * whatever the accept/reject history of its 32 chains was.
+ * X is single buffered: it always holds the path of the chain's last proposal (dense 128 B rows, no
+ * per-chain scatter); xstale[p] marks chains whose proposal was rejected, and bb_ens_refresh_x
+ * recomputes their current path from W on demand.  (Measured on B200: half-dense access -- two
+ * separate double-buffer arrays, or an interleaved double-buffered X -- costs 25-35 % of the DRAM
+ * bandwidth.)  All accesses are 256-bit (LDG.E.256 / STG.E.256).
  *
  * Per-step tables (dt, sqrt(dt), guiding term, auxiliary drift) are common to all chains: thread 0
  * streams them with 1-D TMA bulk copies into a BB_STAGES-deep shared-memory ring (full/empty
@@ -29,10 +35,9 @@
 
 struct bb_chain_args {
   double* W[2];
-  double* X[2];
+  double* X;                       /* [S][NC][P][8][d]: the path of the LAST solve / proposal of every chain */
   uint8_t* par;                    /* [P] which buffer holds the chain's current state */
   const double* tab[BB_MAXSEG];    /* per-segment step tables, [NC*8][REC] */
-  const double* segc[BB_MAXSEG];   /* per-segment constants, 32 doubles: Bt[d*d], betat[d], endflag, vend[d] */
   const double* start;             /* [d] (broadcast) or [d][P] */
   double* ll;                      /* [P] */
   double* llprop;                  /* [P] */
@@ -40,18 +45,23 @@ struct bb_chain_args {
   double* xend;                    /* [d][P] */
   double* xendprop;                /* [d][P] */
   uint8_t* accepted;               /* [P] */
+  uint8_t* xstale;                 /* [P] 1: X is not the path of the chain's current W (rejected proposal) */
+  const uint8_t* only;             /* if set, only chains with only[p] != 0 are processed (X refresh) */
   unsigned long long* acc;
   long long P;
   long long chain_offset;
   int S, N, NC;
   int jll;                         /* steps j <= jll (1-based end index) enter the log-likelihood */
   int start_bcast, store_x, do_ll, write_end;
+  int nbuf;                        /* 1, or 2 when the ensemble is double buffered */
   uint32_t k0, k1, stream;
   double rho, rho2;
   bb_model_dev model;
+  /* per-segment constants: Bt[d*d], betat[d] (constant auxiliary drift), endflag, vend[d] (GuidedBridge end
+   * point).  They sit in the kernel parameter bank, indexed by the warp-uniform segment number, so the
+   * compiler keeps them in uniform registers / constant operands instead of per-thread registers. */
+  double segc[BB_MAXSEG][BB_SEGC];
 };
-
-#define BB_SEGC 32
 
 /* collects the K doubles a chain produces per grid point and writes them as 256-bit stores */
 template <int K>
@@ -87,7 +97,6 @@ struct bb_chain {
   static constexpr int NCC = bb_rec_nc(GK, D, GM), NA1 = bb_rec_na1(GK, D, GM), NA2 = bb_rec_na2(GK, D, GM);
   static constexpr int OFF_C = 2, OFF_A1 = OFF_C + NCC, OFF_A2 = OFF_A1 + NA1, OFF_BT = OFF_A2 + NA2,
                        OFF_BE = OFF_BT + D * D;
-  static constexpr bool PREFETCH = (DP == 1) && (RNG != 2);
 
   struct state {
     double y[D];
@@ -155,66 +164,99 @@ struct bb_chain {
     bb_em_update<M>(a.model, bd, dt, dw, st.y);
   }
 
-  template <bool EDGE>
+  /* One chunk of BB_TC grid points.  GENERIC = false is the steady state: every slot is a full step that
+   * enters the log-likelihood; GENERIC = true also handles j = 0 (no step), j >= N (padding), steps that
+   * `skip` excludes from the log-likelihood and the GuidedBridge end-point rule.
+   * The driving path is consumed in pieces of 4 doubles (one LDG.E.256); piece q+1 is requested when piece q
+   * starts being used, so a chain keeps one 32-byte request in flight while it computes ~4/d' steps. */
+  template <bool GENERIC>
   static __device__ __forceinline__ void chunk(const bb_chain_args& a, const double* __restrict__ rec,
-                                               const double* __restrict__ sc, state& st, const double* wc,
+                                               const double* __restrict__ sc, state& st, double* wq, double* wnx,
+                                               const double* wr, const double* wr_next, bool more_rows,
                                                double* wout_row, double* xout_row, int c, uint32_t row_lo,
-                                               uint32_t row_hi, bool act) {
-    bb_rowout<DP> wo;
+                                               uint32_t row_hi, bool wact, bool xact, bool ract) {
+    constexpr int NPIECE = 2 * DP; /* pieces of 4 doubles per chunk row */
     bb_rowout<D> xo;
-    float z[4];
     const int N = a.N;
+    /* two half-chunks of 4 grid points: the body is unrolled over one half only, which bounds code size and
+     * the registers the scheduler spends on hoisted shared-memory loads */
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
 #pragma unroll
-    for (int slot = 0; slot < BB_TC; slot++) {
-      const int j = c * BB_TC + slot;
-      const double* R = rec + slot * REC;
-      double wj[DP];
-      /* ---- driving noise at grid point j */
+      for (int s4 = 0; s4 < 4; s4++) {
+        const int slot = 4 * h + s4;
+        const int j = c * BB_TC + slot;
+        const double* R = rec + slot * REC;
+        double wj[DP];
 #pragma unroll
-      for (int k = 0; k < DP; k++) {
-        const int n = slot * DP + k;
-        if constexpr (RNG != 0) {
-          if ((n & 3) == 0)
-            bb_normal_quad(a.k0, a.k1, a.stream, row_lo, row_hi, (uint32_t)(2 * DP * c + (n >> 2)), z);
-          const double xi = (double)z[n & 3];
-          if constexpr (RNG == 1) {
-            /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
-            if (!EDGE || j > 0) st.w2[k] = fma(R[1], xi, st.w2[k]);
-            wj[k] = fma(a.rho2, st.w2[k], a.rho * wc[n]);
-          } else {
-            wj[k] = (EDGE && j == 0) ? wc[n] : fma(R[1], xi, st.wprev[k]);
+        for (int k = 0; k < DP; k++) {
+          const int m = s4 * DP + k; /* element within the half-chunk (compile time) */
+          if ((m & 3) == 0) {
+            /* ---- piece q = 4 consecutive values of the driving path: fetch W (unless it is sampled afresh),
+             * turn it into the values that drive the Euler steps, and write those back in one 256-bit store.
+             * None of this depends on the state y, so it overlaps the dependent fp64 chain of the steps. */
+            const int q = h * DP + (m >> 2);
+            if constexpr (RNG != 2) {
+              if (BB_PF) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) wq[i] = wnx[i];
+                if (q + 1 < NPIECE) { if (ract) bb_ld4(wr + 4 * (q + 1), wnx); }
+                else if (more_rows && ract) bb_ld4(wr_next, wnx);
+              } else {
+                if (ract) bb_ld4(wr + 4 * q, wq);
+              }
+            }
+            if constexpr (RNG != 0) {
+              float z[4];
+              bb_normal_quad(a.k0, a.k1, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP; /* slot / component of element i */
+                const bool first = GENERIC && (c * BB_TC + sl == 0);
+                const double rootdt = rec[sl * REC + 1];
+                if constexpr (RNG == 1) {
+                  /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
+                  if (!first) st.w2[kk] = fma(rootdt, (double)z[i], st.w2[kk]);
+                  wq[i] = fma(a.rho2, st.w2[kk], a.rho * wq[i]);
+                } else {
+                  /* W[j] = W[j-1] + sqrt(dt) xi, W[0] kept   (src/wiener.jl:50-58); w2 carries W[j-1] */
+                  st.w2[kk] = first ? wq[i] : fma(rootdt, (double)z[i], st.w2[kk]);
+                  wq[i] = st.w2[kk];
+                }
+              }
+              if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+            }
           }
-        } else {
-          wj[k] = wc[n];
+          wj[k] = wq[m & 3];
         }
-      }
-      if (EDGE && j == 0) {
+        if (GENERIC && j == 0) {
 #pragma unroll
-        for (int k = 0; k < DP; k++) st.wprev[k] = wj[k];
-      } else if (!EDGE || j < N) {
-        step(a, R, sc, st, wj, a.do_ll && j <= a.jll);
-        if (EDGE && GK == BB_GUIDE_HV && j == N - 1 && sc[D * D + D] != 0.0) {
-          /* endpoint(y, P::GuidedBridge) = V[end] when H♢[end] = 0   src/euler.jl:241-242 */
+          for (int k = 0; k < DP; k++) st.wprev[k] = wj[k];
+        } else if (!GENERIC || j < N) {
+          step(a, R, sc, st, wj, !GENERIC || j <= a.jll);
+          if (GENERIC && GK == BB_GUIDE_HV && j == N - 1 && sc[D * D + D] != 0.0) {
+            /* endpoint(y, P::GuidedBridge) = V[end] when H♢[end] = 0   src/euler.jl:241-242 */
 #pragma unroll
-          for (int k = 0; k < D; k++) st.y[k] = sc[D * D + D + 1 + k];
+            for (int k = 0; k < D; k++) st.y[k] = sc[D * D + D + 1 + k];
+          }
         }
+        xo.put(xout_row + 4 * h * D, s4, st.y, xact);
       }
-      if constexpr (RNG != 0) wo.put(wout_row, slot, wj, act);
-      if (a.store_x) xo.put(xout_row, slot, st.y, act);
     }
   }
 
   static __device__ __forceinline__ void run(const bb_chain_args& a) {
-    constexpr uint32_t STAGE_DOUBLES = BB_TC * REC;
-    constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+    /* the table ring: BB_STAGES stages of BB_TSTAGE chunks (the last stage of a segment may be shorter) */
+    constexpr uint32_t CHUNK_DOUBLES = BB_TC * REC;
+    constexpr uint32_t STAGE_DOUBLES = BB_TSTAGE * CHUNK_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    double* segc = ring + BB_STAGES * STAGE_DOUBLES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(segc + a.S * BB_SEGC);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BB_STAGES * STAGE_DOUBLES);
     uint64_t* empty = full + BB_STAGES;
 
     const int S = a.S, NC = a.NC;
-    const int T = S * NC; /* table chunks this CTA walks through */
+    const int NST = (NC + BB_TSTAGE - 1) / BB_TSTAGE; /* stages per segment */
+    const int T = S * NST;                            /* stages this CTA walks through */
     const int lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
 
@@ -225,79 +267,91 @@ struct bb_chain {
       }
       bb_mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < S * BB_SEGC; i += blockDim.x)
-      segc[i] = a.segc[i / BB_SEGC] ? a.segc[i / BB_SEGC][i % BB_SEGC] : 0.0;
     __syncthreads();
 
     const long long P = a.P;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = p < P;
-    const long long pc = act ? p : P - 1;
+    const long long pc = p < P ? p : P - 1;
+    const bool act = p < P && (!a.only || a.only[pc] != 0);
     const int par = a.par[pc];
     const int rbuf = par;                        /* where the chain's current W (and X) live */
     const int wbuf = (RNG == 1) ? 1 - par : par; /* where this launch writes */
     const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
+    const bool xact = act && a.store_x;
 
     state st;
 #pragma unroll
     for (int k = 0; k < D; k++) st.y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
     st.som = 0.0;
+    double lltot = 0.0; /* sum over segments of the per-segment log-likelihoods (bolus3.jl:331-333) */
 
-    const double* wr = a.W[rbuf] + pc * (BB_TC * DP);
-    double* ww = a.W[wbuf] + pc * (BB_TC * DP);
-    double* xw = a.store_x ? a.X[wbuf] + pc * (BB_TC * D) : nullptr;
-    const long long wstride = P * (BB_TC * DP), xstride = P * (BB_TC * D);
+    /* a chain's two buffers are adjacent: W[1] = W[0] + 8 d', slot of chain p = p * nbuf * 8 d' */
+    const double* wr = a.W[rbuf] + pc * (a.nbuf * BB_TC * DP);
+    double* ww = a.W[wbuf] + pc * (a.nbuf * BB_TC * DP);
+    double* xw = a.store_x ? a.X + pc * (BB_TC * D) : nullptr;
+    const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
 
-    /* producer state (thread 0 only) */
-    int issued = 0, iseg = 0, ichunk = 0;
-    int stage = 0;
+    /* producer state (thread 0 only): next stage to request */
+    int issued = 0, iseg = 0, ist_in_seg = 0;
+    int stage = 0, gs = 0; /* consumer: ring slot and global stage index */
     uint32_t phase = 0;
 
-    double wc[BB_TC * DP], wn[PREFETCH ? BB_TC * DP : 1];
-    const bool need_w = (RNG != 2);
-    if (PREFETCH) bb_load_row<DP>(wr, wn);
+    double wq[4] = {0.0, 0.0, 0.0, 0.0}, wnx[4] = {0.0, 0.0, 0.0, 0.0};
+    if (RNG != 2 && BB_PF && act) bb_ld4(wr, wnx); /* piece 0 of the first row */
 
-    int g = 0;
     for (int s = 0; s < S; s++) {
       const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
       const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
-      const double* sc = segc + s * BB_SEGC;
+      const double* sc = a.segc[s];
 #pragma unroll
       for (int k = 0; k < DP; k++) st.w2[k] = 0.0;
-      for (int c = 0; c < NC; c++, g++) {
-        if (threadIdx.x == 0) {
-          while (issued < T && issued <= g + BB_LOOKAHEAD) {
-            const int ist = issued % BB_STAGES;
-            if (issued >= BB_STAGES) bb_mbar_wait(&empty[ist], ((issued / BB_STAGES) - 1) & 1);
-            bb_mbar_expect_tx(&full[ist], STAGE_BYTES);
-            bb_tma_load_1d(ring + ist * STAGE_DOUBLES, a.tab[iseg] + (size_t)ichunk * STAGE_DOUBLES,
-                           STAGE_BYTES, &full[ist]);
-            issued++;
-            if (++ichunk == NC) { ichunk = 0; iseg++; }
+      st.som = 0.0;
+      if constexpr (RNG == 2) { if (act) bb_ld4(wr, wq); } /* only W[0] of the segment is read (it is kept) */
+      const double* rec = ring;
+      for (int c = 0; c < NC; c++) {
+        if ((c % BB_TSTAGE) == 0) {
+          if (threadIdx.x == 0) {
+            while (issued < T && issued <= gs + BB_LOOKAHEAD) {
+              const int ist = issued % BB_STAGES;
+              if (issued >= BB_STAGES) bb_mbar_wait(&empty[ist], ((issued / BB_STAGES) - 1) & 1);
+              const int c0 = ist_in_seg * BB_TSTAGE;
+              const int nch = (NC - c0 < BB_TSTAGE) ? NC - c0 : BB_TSTAGE;
+              const uint32_t bytes = (uint32_t)nch * CHUNK_DOUBLES * 8;
+              bb_mbar_expect_tx(&full[ist], bytes);
+              bb_tma_load_1d(ring + ist * STAGE_DOUBLES, a.tab[iseg] + (size_t)c0 * CHUNK_DOUBLES, bytes,
+                             &full[ist]);
+              issued++;
+              if (++ist_in_seg == NST) { ist_in_seg = 0; iseg++; }
+            }
+          }
+          __syncwarp();
+          bb_mbar_wait(&full[stage], phase);
+          rec = ring + stage * STAGE_DOUBLES;
+        }
+        if constexpr (RNG != 2 && BB_L2PF > 0) {
+          if (c + BB_L2PF < NC || s + 1 < S) {
+#pragma unroll
+            for (int i = 0; i < DP; i++) bb_prefetch_l2(wr + BB_L2PF * wstride + 8 * i);
           }
         }
-        __syncwarp();
-        /* ---- this chunk's slice of the driving path */
-        if (PREFETCH) {
-#pragma unroll
-          for (int i = 0; i < BB_TC * DP; i++) wc[i] = wn[i];
-          if (g + 1 < T) bb_load_row<DP>(wr + wstride, wn);
-        } else if (need_w || c == 0) {
-          bb_load_row<DP>(wr, wc);
-        }
-        bb_mbar_wait(&full[stage], phase);
-        const double* rec = ring + stage * STAGE_DOUBLES;
-        if (c == 0 || c == NC - 1)
-          chunk<true>(a, rec, sc, st, wc, ww, xw, c, row_lo, row_hi, act);
+        const bool generic = (c == 0) || (c == NC - 1) || (c * BB_TC + BB_TC - 1 > a.jll);
+        const bool more = (c + 1 < NC) || (s + 1 < S);
+        if (generic)
+          chunk<true>(a, rec, sc, st, wq, wnx, wr, wr + wstride, more, ww, xw, c, row_lo, row_hi, act, xact, act);
         else
-          chunk<false>(a, rec, sc, st, wc, ww, xw, c, row_lo, row_hi, act);
-        __syncwarp();
-        if (lane == 0) bb_mbar_arrive(&empty[stage]);
-        if (++stage == BB_STAGES) { stage = 0; phase ^= 1; }
+          chunk<false>(a, rec, sc, st, wq, wnx, wr, wr + wstride, true, ww, xw, c, row_lo, row_hi, act, xact, act);
+        rec += CHUNK_DOUBLES;
+        if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
+          __syncwarp();
+          if (lane == 0) bb_mbar_arrive(&empty[stage]);
+          if (++stage == BB_STAGES) { stage = 0; phase ^= 1; }
+          gs++;
+        }
         wr += wstride;
         ww += wstride;
-        if (a.store_x) xw += xstride;
+        xw += xstride;
       }
+      lltot += st.som;
     }
 
     /* ---- per-chain epilogue */
@@ -305,15 +359,17 @@ struct bb_chain {
       /* accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
       const double logu = bb_accept_logu(a.k0, a.k1, a.stream, chain);
       const double llc = a.ll[pc];
-      const bool ok = act && (logu <= st.som - llc);
+      const bool ok = act && (logu <= lltot - llc);
       if (act) {
-        a.llprop[p] = st.som;
+        a.llprop[p] = lltot;
         a.logu[p] = logu;
         a.accepted[p] = ok ? 1 : 0;
+        /* X now holds this proposal's path (if stored): it is the chain's current path iff accepted */
+        a.xstale[p] = a.store_x ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
 #pragma unroll
         for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = st.y[k];
         if (ok) {
-          a.ll[p] = st.som;
+          a.ll[p] = lltot;
           a.par[p] = (uint8_t)(1 - par);
 #pragma unroll
           for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
@@ -323,7 +379,8 @@ struct bb_chain {
       if (lane == 0 && m) atomicAdd(a.acc, (unsigned long long)__popc(m));
     } else {
       if (act) {
-        if (a.do_ll) a.ll[p] = st.som;
+        if (a.do_ll) a.ll[p] = lltot;
+        if (a.store_x) a.xstale[p] = 0;
         if (a.write_end) {
 #pragma unroll
           for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
@@ -334,14 +391,14 @@ struct bb_chain {
 };
 
 template <class M, int GK, int GM, bool AUXC, int RNG>
-__global__ void __launch_bounds__(BB_THREADS) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
+__global__ void __launch_bounds__(BB_THREADS, BB_MINB) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
   bb_chain<M, GK, GM, AUXC, RNG>::run(a);
 }
 
 template <class M, int GK, int GM, bool AUXC, int RNG>
 static inline size_t bb_chain_smem(int S) {
-  return (size_t)BB_STAGES * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + (size_t)S * BB_SEGC * 8 +
-         2 * BB_STAGES * 8;
+  (void)S;
+  return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + 2 * BB_STAGES * 8;
 }
 
 /* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */

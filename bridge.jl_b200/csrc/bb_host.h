@@ -30,18 +30,20 @@ struct bb_guide {
   bb_ctx* ctx = nullptr;
   int kind = 0, N = 0, d = 0, m = 0, auxc = 1, NC = 0, rec = 0;
   double* tab = nullptr;  /* device [NC*8][rec] */
-  double* segc = nullptr; /* device [32] */
+  double segc[BB_SEGC] = {0}; /* per-segment constants handed to the kernels by value */
   std::vector<double> tt;
 };
 
 struct bb_ens {
   bb_ctx* ctx = nullptr;
   int64_t P = 0;
-  int S = 0, N = 0, d = 0, dp = 0, NC = 0;
+  int S = 0, N = 0, d = 0, dp = 0, NC = 0, nbuf = 1;
   uint32_t flags = 0;
   int64_t chain_offset = 0;
   double* W[2] = {nullptr, nullptr};
-  double* X[2] = {nullptr, nullptr};
+  double* X = nullptr;
+  uint8_t* xstale = nullptr;
+  bool x_maybe_stale = false;
   uint8_t* par = nullptr;
   uint8_t* accepted = nullptr;
   double *ll = nullptr, *llprop = nullptr, *logu = nullptr, *xend = nullptr, *xendprop = nullptr;

@@ -18,17 +18,15 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const int par = a.par[p];
-  const double* xr = a.X[par] + p * (BB_TC * D);
-  double* ww = a.W[par] + p * (BB_TC * DP);
-  const long long wstride = P * (BB_TC * DP), xstride = P * (BB_TC * D);
-  double som = 0.0;
-  double zero[BB_SEGC];
-#pragma unroll
-  for (int i = 0; i < BB_SEGC; i++) zero[i] = 0.0;
+  const double* xr = a.X + p * (BB_TC * D);
+  double* ww = a.W[par] + p * (a.nbuf * BB_TC * DP);
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+  double lltot = 0.0;
   for (int s = 0; s < a.S; s++) {
     const double* tab = a.tab[s];
-    const double* sc = a.segc[s] ? a.segc[s] : zero;
+    const double* sc = a.segc[s];
     double xprev[D], w[DP];
+    double som = 0.0;
 #pragma unroll
     for (int k = 0; k < DP; k++) w[k] = 0.0;
     for (int c = 0; c < a.NC; c++) {
@@ -59,8 +57,9 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
       xr += xstride;
       ww += wstride;
     }
+    lltot += som;
   }
-  if (MODE == 0) a.ll[p] = som;
+  if (MODE == 0) a.ll[p] = lltot;
 }
 
 template <class M, int GK, int GM, bool AUXC, int MODE>

@@ -61,7 +61,8 @@ typedef enum {
   BB_ERR_NOMEM = -9,       /* device allocation failed */
   BB_ERR_NODEVICE = -10,   /* no CUDA device: the library has no CPU path */
   BB_ERR_UNSUPPORTED = -11,/* combination not instantiated (model x guide x dims) */
-  BB_ERR_SINGULAR = -12    /* singular matrix in a backward solve / update */
+  BB_ERR_SINGULAR = -12,   /* singular matrix in a backward solve / update */
+  BB_ERR_STALE = -13       /* X holds rejected proposals; bb_ens_refresh_x recomputes the current paths */
 } bb_status;
 
 const char* bb_strerror(int status);
@@ -154,7 +155,7 @@ double bb_ctx_last_kernel_ms(bb_ctx* ctx);
  * (test/partialbridgenuH.jl:168-170).
  */
 enum {
-  BB_ENS_DOUBLE_BUFFER = 1u, /* allocate proposal buffers (needed by bb_pcn_step) */
+  BB_ENS_DOUBLE_BUFFER = 1u, /* allocate the proposal buffer of W (needed by bb_pcn_step) */
   BB_ENS_NO_X = 2u           /* do not allocate X (paths are never stored) */
 };
 int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32_t d, int32_t dprime,
@@ -287,6 +288,12 @@ int bb_innovations(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
  */
 int bb_pcn_step(bb_ens* ens, const bb_model* model, bb_guide* const* guides, double rho,
                 uint64_t seed, uint32_t iter, int32_t skip, uint32_t flags);
+/* X is kept ONCE per chain and always holds the path of the chain's last proposal X° (the reference's Xo);
+ * for a chain whose proposal was rejected the reference's X (current path) is a pure function of the
+ * chain's current W, and this call recomputes it in place for exactly those chains (solve!(Euler(), X, x0,
+ * W, P°) again).  bb_ens_download(BB_X, BB_CUR) returns BB_ERR_STALE until it has been called; BB_X/BB_PROP
+ * downloads need no refresh.  No-op if nothing is stale. */
+int bb_ens_refresh_x(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
 
 #ifdef __cplusplus
 }
