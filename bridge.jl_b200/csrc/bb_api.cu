@@ -5,6 +5,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -50,6 +51,12 @@ extern "C" int bb_ctx_create(int device, bb_ctx** out) {
   }
   if (device < 0 || device >= n) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(device));
+  if (const char* g = getenv("BB_L2_FETCH")) { /* tuning aid: L2 -> DRAM fetch granularity hint (32/64/128) */
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "[bb] cudaLimitMaxL2FetchGranularity = %zu\n", got);
+  }
   bb_ctx* c = new (std::nothrow) bb_ctx();
   if (!c) return BB_ERR_NOMEM;
   c->device = device;

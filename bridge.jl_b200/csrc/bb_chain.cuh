@@ -167,21 +167,20 @@ struct bb_chain {
   /* One chunk of BB_TC grid points.  GENERIC = false is the steady state: every slot is a full step that
    * enters the log-likelihood; GENERIC = true also handles j = 0 (no step), j >= N (padding), steps that
    * `skip` excludes from the log-likelihood and the GuidedBridge end-point rule.
-   * The driving path is consumed in pieces of 4 doubles (one LDG.E.256); piece q+1 is requested when piece q
-   * starts being used, so a chain keeps one 32-byte request in flight while it computes ~4/d' steps. */
+   * The chain's row of the driving path (8 d' doubles) is already in shared memory (`wrow`, brought there by
+   * a per-chain TMA bulk copy issued BB_WSTAGES-1 chunks earlier) and is consumed in pieces of 4 doubles. */
   template <bool GENERIC>
   static __device__ __forceinline__ void chunk(const bb_chain_args& a, const double* __restrict__ rec,
-                                               const double* __restrict__ sc, state& st, double* wq, double* wnx,
-                                               const double* wr, const double* wr_next, bool more_rows,
-                                               double* wout_row, double* xout_row, int c, uint32_t row_lo,
-                                               uint32_t row_hi, bool wact, bool xact, bool ract) {
-    constexpr int NPIECE = 2 * DP; /* pieces of 4 doubles per chunk row */
+                                               const double* __restrict__ sc, state& st, double* wq,
+                                               const double* wrow, double* wout_row, double* xout_row, int c,
+                                               uint32_t row_lo, uint32_t row_hi, bool wact, bool xact) {
+    constexpr int NPIECE = BB_TC * DP / 4; /* pieces of 4 doubles per chunk row */
     bb_rowout<D> xo;
     const int N = a.N;
-    /* two half-chunks of 4 grid points: the body is unrolled over one half only, which bounds code size and
-     * the registers the scheduler spends on hoisted shared-memory loads */
+    /* groups of 4 grid points: the body is unrolled over one group only, which bounds code size and the
+     * registers the scheduler spends on hoisted shared-memory loads */
 #pragma unroll 1
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < BB_TC / 4; h++) {
 #pragma unroll
       for (int s4 = 0; s4 < 4; s4++) {
         const int slot = 4 * h + s4;
@@ -196,16 +195,7 @@ struct bb_chain {
              * turn it into the values that drive the Euler steps, and write those back in one 256-bit store.
              * None of this depends on the state y, so it overlaps the dependent fp64 chain of the steps. */
             const int q = h * DP + (m >> 2);
-            if constexpr (RNG != 2) {
-              if (BB_PF) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) wq[i] = wnx[i];
-                if (q + 1 < NPIECE) { if (ract) bb_ld4(wr + 4 * (q + 1), wnx); }
-                else if (more_rows && ract) bb_ld4(wr_next, wnx);
-              } else {
-                if (ract) bb_ld4(wr + 4 * q, wq);
-              }
-            }
+            if constexpr (RNG != 2) bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
             if constexpr (RNG != 0) {
               float z[4];
               bb_normal_quad(a.k0, a.k1, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
@@ -253,6 +243,11 @@ struct bb_chain {
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + BB_STAGES * STAGE_DOUBLES);
     uint64_t* empty = full + BB_STAGES;
+    /* staging of the driving path: BB_WSTAGES x (one row per chain of the CTA).  The 16-byte pieces of every
+     * 128-byte block of a row are XOR-swizzled with the chain's index (piece k of chain t sits at k ^ (t & 7)),
+     * which keeps the 128-bit reads of a quarter-warp conflict free without padding. */
+    constexpr int WROWP = BB_TC * DP;
+    double* wstage = reinterpret_cast<double*>(empty + BB_STAGES);
 
     const int S = a.S, NC = a.NC;
     const int NST = (NC + BB_TSTAGE - 1) / BB_TSTAGE; /* stages per segment */
@@ -294,10 +289,45 @@ struct bb_chain {
     /* producer state (thread 0 only): next stage to request */
     int issued = 0, iseg = 0, ist_in_seg = 0;
     int stage = 0, gs = 0; /* consumer: ring slot and global stage index */
+    bool tab_ready = false;
     uint32_t phase = 0;
 
-    double wq[4] = {0.0, 0.0, 0.0, 0.0}, wnx[4] = {0.0, 0.0, 0.0, 0.0};
-    if (RNG != 2 && BB_PF && act) bb_ld4(wr, wnx); /* piece 0 of the first row */
+    double wq[4] = {0.0, 0.0, 0.0, 0.0};
+    /* ---- driving path: the warp copies the rows of its 32 chains for one chunk with 4 d' cp.async
+     * instructions (LDGSTS.128, L1 bypassed): lane l moves 16-byte piece t % (4 d') of chain t / (4 d'),
+     * t = 32 r + l, so every chain's 64 d'-byte row is requested by ONE instruction -- whole DRAM bursts even
+     * though neighbouring chains read different buffers -- and lands in the chain's padded row of the stage.
+     * Rows are requested BB_WSTAGES-1 chunks before they are used; no registers are tied up meanwhile. */
+    constexpr int NCP = BB_TC * DP / 2; /* 16-byte pieces per row = cp.async instructions per chunk and warp */
+    const int warp = threadIdx.x >> 5;
+    const unsigned amask = __ballot_sync(0xFFFFFFFFu, act);
+    const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
+    const long long warp_p0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+    const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP); /* doubles between the slots of consecutive chains */
+    /* instruction r, lane l: chain cw = t / NCP, piece = t % NCP, t = 32 r + l */
+    const uint32_t l_cw = (uint32_t)lane / NCP, l_pc = (uint32_t)lane % NCP; /* used when NCP <= 32 divides 32 */
+    const double* wsrc = a.W[0] + warp_p0 * wrow_d; /* + chunk * wstride */
+    const int TW = S * NC;                          /* rows this chain walks through */
+    int gcur = 0;                                   /* global chunk index of the row consumed next */
+    auto w_issue = [&](int gc) { /* request chunk gc for the whole warp; always commits a (possibly empty) group */
+      if (RNG != 2 && gc < TW) {
+        const double* src = wsrc + (long long)gc * wstride;
+        double* dst = wstage + ((size_t)(gc % BB_WSTAGES) * BB_THREADS + warp * 32) * WROWP;
+#pragma unroll
+        for (int r = 0; r < NCP; r++) {
+          uint32_t cw, piece;
+          if constexpr (32 % NCP == 0) { cw = (32 / NCP) * r + l_cw; piece = l_pc; }
+          else { const uint32_t t = 32u * r + lane; cw = t / NCP; piece = t % NCP; }
+          if ((amask >> cw) & 1u)
+            bb_cp_async16(dst + cw * WROWP + 2 * ((piece & ~7u) | ((piece ^ cw) & 7u)),
+                          src + (cw * wrow_d + ((pmask >> cw) & 1u) * (BB_TC * DP) + 2 * piece));
+        }
+      }
+      bb_cp_async_commit();
+    };
+    const double* wslot = wstage + (size_t)threadIdx.x * WROWP; /* + stage * BB_THREADS * WROWP */
+#pragma unroll 1
+    for (int i = 0; i < BB_WSTAGES - 1; i++) w_issue(i);
 
     for (int s = 0; s < S; s++) {
       const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
@@ -325,22 +355,32 @@ struct bb_chain {
             }
           }
           __syncwarp();
-          bb_mbar_wait(&full[stage], phase);
+          /* the stage was requested BB_LOOKAHEAD stages ago; `tab_ready` is the answer of a non-blocking probe
+           * made one chunk earlier, so the barrier's round trip is normally off the critical path */
+          if (!tab_ready) bb_mbar_wait(&full[stage], phase);
           rec = ring + stage * STAGE_DOUBLES;
         }
-        if constexpr (RNG != 2 && BB_L2PF > 0) {
-          if (c + BB_L2PF < NC || s + 1 < S) {
-#pragma unroll
-            for (int i = 0; i < DP; i++) bb_prefetch_l2(wr + BB_L2PF * wstride + 8 * i);
-          }
+        const double* wrow = wslot + (size_t)(gcur % BB_WSTAGES) * BB_THREADS * WROWP;
+        if constexpr (RNG != 2) {
+          /* rows of chunk gcur were requested a whole chunk ago: wait for them first (normally no wait at all),
+           * then refill the other stage -- which every lane has finished reading -- with chunk gcur+1 */
+          bb_cp_async_wait<BB_WSTAGES - 2>();
+          __syncwarp();
+          w_issue(gcur + BB_WSTAGES - 1);
+        }
+        if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
+          /* probe the next table stage now; its result is needed only after this chunk */
+          const int nst = (stage + 1 == BB_STAGES) ? 0 : stage + 1;
+          const uint32_t nph = (stage + 1 == BB_STAGES) ? phase ^ 1 : phase;
+          tab_ready = (gs + 1 < T) ? bb_mbar_test(&full[nst], nph) : true;
         }
         const bool generic = (c == 0) || (c == NC - 1) || (c * BB_TC + BB_TC - 1 > a.jll);
-        const bool more = (c + 1 < NC) || (s + 1 < S);
         if (generic)
-          chunk<true>(a, rec, sc, st, wq, wnx, wr, wr + wstride, more, ww, xw, c, row_lo, row_hi, act, xact, act);
+          chunk<true>(a, rec, sc, st, wq, wrow, ww, xw, c, row_lo, row_hi, act, xact);
         else
-          chunk<false>(a, rec, sc, st, wq, wnx, wr, wr + wstride, true, ww, xw, c, row_lo, row_hi, act, xact, act);
+          chunk<false>(a, rec, sc, st, wq, wrow, ww, xw, c, row_lo, row_hi, act, xact);
         rec += CHUNK_DOUBLES;
+        gcur++;
         if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
           __syncwarp();
           if (lane == 0) bb_mbar_arrive(&empty[stage]);
@@ -398,7 +438,8 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bb_chain_kernel(const __g
 template <class M, int GK, int GM, bool AUXC, int RNG>
 static inline size_t bb_chain_smem(int S) {
   (void)S;
-  return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + 2 * BB_STAGES * 8;
+  return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + 2 * BB_STAGES * 8 +
+         (size_t)BB_WSTAGES * BB_THREADS * (BB_TC * M::DP) * 8;
 }
 
 /* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */
@@ -407,6 +448,13 @@ typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 template <class M, int GK, int GM, bool AUXC, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   const size_t smem = bb_chain_smem<M, GK, GM, AUXC, RNG>(a.S);
+  static bool attr_done = false; /* per instantiation; the attribute is idempotent */
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(bb_chain_kernel<M, GK, GM, AUXC, RNG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
   const unsigned grid = (unsigned)((a.P + BB_THREADS - 1) / BB_THREADS);
   bb_chain_kernel<M, GK, GM, AUXC, RNG><<<grid, BB_THREADS, smem, st>>>(a);
   return cudaGetLastError();

@@ -30,29 +30,33 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < DP; k++) w[k] = 0.0;
     for (int c = 0; c < a.NC; c++) {
-      double x[BB_TC * D];
-      bb_load_row<D>(xr, x);
       bb_rowout<DP> wo;
+#pragma unroll 1
+      for (int h = 0; h < BB_TC / 4; h++) {
+        double x[4 * D];
 #pragma unroll
-      for (int slot = 0; slot < BB_TC; slot++) {
-        const int j = c * BB_TC + slot;
-        if (j > 0 && j < a.N) {
-          const double* R = tab + (size_t)j * REC;
-          const double dt = R[0];
-          double bd[D];
-          CH::drift(a, R, sc, xprev, dt, MODE == 0 && j <= a.jll, som, bd);
-          if constexpr (MODE == 1) {
-            double e[D], de[D];
+        for (int q = 0; q < D; q++) bb_ld4(xr + 4 * h * D + 4 * q, x + 4 * q);
 #pragma unroll
-            for (int k = 0; k < D; k++) e[k] = (x[slot * D + k] - xprev[k]) - bd[k] * dt;
-            bb_matvec<D, D>(a.model.der + 24, e, de);
+        for (int s4 = 0; s4 < 4; s4++) {
+          const int j = c * BB_TC + 4 * h + s4;
+          if (j > 0 && j < a.N) {
+            const double* R = tab + (size_t)j * REC;
+            const double dt = R[0];
+            double bd[D];
+            CH::drift(a, R, sc, xprev, dt, MODE == 0 && j <= a.jll, som, bd);
+            if constexpr (MODE == 1) {
+              double e[D], de[D];
 #pragma unroll
-            for (int k = 0; k < DP; k++) w[k] = w[k] + de[k];
+              for (int k = 0; k < D; k++) e[k] = (x[s4 * D + k] - xprev[k]) - bd[k] * dt;
+              bb_matvec<D, D>(a.model.der + 24, e, de);
+#pragma unroll
+              for (int k = 0; k < DP; k++) w[k] = w[k] + de[k];
+            }
           }
-        }
 #pragma unroll
-        for (int k = 0; k < D; k++) xprev[k] = x[slot * D + k];
-        if constexpr (MODE == 1) wo.put(ww, slot, w, true);
+          for (int k = 0; k < D; k++) xprev[k] = x[s4 * D + k];
+          if constexpr (MODE == 1) wo.put(ww + 4 * h * DP, s4, w, true);
+        }
       }
       xr += xstride;
       ww += wstride;
