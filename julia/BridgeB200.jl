@@ -1,0 +1,145 @@
+# BridgeB200.jl -- thin ccall shim that puts libbridge_b200.so (hand-written CUDA, sm_100a) behind Bridge.jl's
+# own generic functions for the data-parallel hot path.  Host code stays Julia; see include/bridge_b200.h for the ABI
+# and INTEGRATION.md for how a maintainer wires it in.
+#
+# STATUS: written against the header; NOT executed (no Julia runtime exists in the build environment).  The Python
+# binding bridge.jl_b200/_cabi.py makes exactly the same calls and IS tested on the GPU (tests/test_gpu_parity.py).
+#
+# What it adds (methods only; no Bridge.jl source is modified):
+#   PathEnsemble            device-resident container of P chains x S segments (replaces P*S (W, X) SamplePath pairs)
+#   Bridge.sample!(E, Wiener())                         -> bb_wiener_sample          (src/wiener.jl:50-58)
+#   Bridge.solve!(EulerMaruyama(), E, u, P)             -> bb_euler                  (src/euler.jl:135-152)
+#   Bridge.solve!(Euler(), E, u, Po::Vector{<:Guide})   -> bb_guided_euler_ll        (src/euler.jl:247-268)
+#   Bridge.llikelihood(LeftRule(), E, Po; skip)         -> bb_llikelihood / fused    (src/partialbridgenuH.jl:171-189)
+#   pcn!(E, P, Po, rho, seed, iter)                     -> bb_pcn_step               (test/partialbridgenuH.jl:176-191)
+#   solve!/llikelihood on plain SamplePath (P = 1 plumbing) go through a one-chain ensemble.
+module BridgeB200
+
+using Bridge, StaticArrays, LinearAlgebra
+import Bridge: sample!, solve!, llikelihood, EulerMaruyama, Euler, LeftRule, SamplePath, Wiener, ContinuousTimeProcess
+
+const lib = get(ENV, "BRIDGE_B200_LIB", joinpath(@__DIR__, "..", "bridge.jl_b200", "lib", "libbridge_b200.so"))
+
+# ---- status codes -> the reference's own errors (include/bridge_b200.h)
+function check(st::Cint)
+    st == 0 && return nothing
+    msg = unsafe_string(ccall((:bb_strerror, lib), Cstring, (Cint,), st))
+    st == -4 && throw(DimensionMismatch("length(tt) != size(yy, 2)"))        # src/types.jl:127
+    st == -5 && throw(AssertionError("m == length(v)"))                      # src/partialbridgenuH.jl:3
+    if st == -8 || st == -9
+        msg *= ": " * unsafe_string(ccall((:bb_last_cuda_error, lib), Cstring, ()))
+    end
+    error(msg)   # "Y and W differ in length." / "Time axis mismatch ..." / "Starting point has wrong length."
+end
+
+# ---- registry models (bb_model): the device cannot call Julia closures
+struct BBModel
+    id::Int32; d::Int32; dprime::Int32; reserved::Int32
+    par::NTuple{32,Float64}
+end
+pad32(v) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 32)
+bbmodel(::Wiener{Float64}) = BBModel(0, 1, 1, 0, pad32(()))
+bbmodel(::Wiener{SVector{d,Float64}}) where {d} = BBModel(0, d, d, 0, pad32(()))
+bbmodel(P::Bridge.LinPro) = (d = size(P.B, 1); BBModel(2, d, d, 0, pad32(vcat(vec(P.B'), P.μ, vec(P.σ')))))   # row-major
+bbmodel(P::Bridge.Models.FitzHughNagumo) = BBModel(3, 2, 2, 0, pad32((P.ϵ, P.s, P.γ, P.β, P.σ1, P.σ2)))        # src/Models.jl:9-20
+# user structs opt in by defining bbmodel(P), e.g. for project_partialbridge/partialbridge_fitzhugh.jl:36-46
+#   BridgeB200.bbmodel(P::FitzhughDiffusion) = BridgeB200.BBModel(4, 2, 1, 0, BridgeB200.pad32((P.ϵ, P.s, P.γ, P.β, P.σ)))
+
+# ---- context / ensemble handles
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bb_ctx_create, lib), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r))
+        c = new(r[]); finalizer(c -> ccall((:bb_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), c); c
+    end
+end
+
+mutable struct PathEnsemble
+    h::Ptr{Cvoid}; ctx::Context
+    P::Int; S::Int; N::Int; d::Int; dprime::Int
+    function PathEnsemble(ctx::Context, P, S, N, d, dprime; double_buffer = true, store_x = true, chain_offset = 0)
+        flags = UInt32((double_buffer ? 1 : 0) | (store_x ? 0 : 2))
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bb_ens_create, lib), Cint, (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Int32, UInt32, Ref{Ptr{Cvoid}}),
+                    ctx.h, P, S, N, d, dprime, flags, r))
+        E = new(r[], ctx, P, S, N, d, dprime)
+        chain_offset != 0 && check(ccall((:bb_ens_set_chain_offset, lib), Cint, (Ptr{Cvoid}, Int64), E.h, chain_offset))
+        finalizer(E -> ccall((:bb_ens_destroy, lib), Cint, (Ptr{Cvoid},), E.h), E); E
+    end
+end
+setgrid!(E::PathEnsemble, seg, tt::Vector{Float64}) =
+    check(ccall((:bb_ens_set_grid, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32), E.h, seg - 1, tt, length(tt)))
+setstart!(E::PathEnsemble, u::SVector) = (v = collect(u);
+    check(ccall((:bb_ens_set_start, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), E.h, v, length(v), 1)))
+
+# ---- guiding tables: the constructors of Bridge.jl have already run the backward ODE on the host, or use
+#      bb_backward_nuH / bb_backward_HV / bb_backward_LMmu to run it on the device (same R3 / Lyapunov schemes)
+mutable struct Guide
+    h::Ptr{Cvoid}
+end
+rowmajor(A::AbstractMatrix) = collect(vec(permutedims(A)))
+function Guide(ctx::Context, Po::Bridge.PartialBridgeνH)           # fields Target, Pt, tt, ν, H, C  (src/partialbridgenuH.jl:122-130)
+    d = length(Po.ν[1]); N = length(Po.tt)
+    H = reduce(vcat, rowmajor.(Po.H)); ν = reduce(vcat, collect.(Po.ν))
+    Bt = reduce(vcat, [rowmajor(Bridge.B(t, Po.Pt)) for t in Po.tt]); βt = reduce(vcat, [collect(Bridge.β(t, Po.Pt)) for t in Po.tt])
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve H ν Bt βt check(ccall((:bb_guide_create, lib), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, 1, N, d, 0, Po.tt, H, ν, C_NULL, C_NULL, Bt, βt, 0, r))
+    g = Guide(r[]); finalizer(g -> ccall((:bb_guide_destroy, lib), Cint, (Ptr{Cvoid},), g.h), g); g
+end
+# GuidedBridge (kind 2: A = H♢, b = V) and PartialBridge (kind 3: A = L, b = μ, Mm = M, v) are built the same way.
+
+# ---- the methods added to Bridge's generic functions
+function sample!(E::PathEnsemble, ::Wiener; seed::UInt64 = UInt64(0), stream::UInt32 = UInt32(0))
+    check(ccall((:bb_wiener_sample, lib), Cint, (Ptr{Cvoid}, UInt64, UInt32), E.h, seed, stream)); E
+end
+function solve!(::EulerMaruyama, E::PathEnsemble, u, P::ContinuousTimeProcess)
+    setstart!(E, u); m = Ref(bbmodel(P))
+    check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, m)); E
+end
+function solve!(::EulerMaruyama, E::PathEnsemble, u, P::ContinuousTimeProcess, guides::Vector{Guide}; skip = 0, store_x = true)
+    setstart!(E, u); m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_guided_euler_ll, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32, UInt32),
+                                    E.h, m, hs, skip, store_x ? 1 : 0))
+    E   # end points: bb_ens_get_f64(E, BB_F_XEND, ...)
+end
+function llikelihood(::LeftRule, E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}; skip = 0)
+    m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_llikelihood, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32), E.h, m, hs, skip))
+    ll = Vector{Float64}(undef, E.P)
+    check(ccall((:bb_ens_get_f64, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, E.P, ll)); ll
+end
+"""One pCN / MH update of every chain: the body of `for iter in 1:iterations` in test/partialbridgenuH.jl:176-191."""
+function pcn!(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}, ρ, seed::UInt64, iter::Integer; skip = 0, store_x = true)
+    m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_pcn_step, lib), Cint,
+        (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Float64, UInt64, UInt32, Int32, UInt32), E.h, m, hs, ρ, seed, iter, skip, store_x ? 1 : 0))
+    acc = Ref{Int64}(0); check(ccall((:bb_ens_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, acc)); acc[]
+end
+
+"""Current paths of all chains as an array [d, N, S, P] (refreshes the chains whose last proposal was rejected)."""
+function download_x(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide})
+    m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_ens_refresh_x, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}), E.h, m, hs))
+    X = Array{Float64}(undef, E.d, E.N, E.S, E.P)   # column-major == the ABI's [P][S][N][d]
+    check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, E.P, X)); X
+end
+
+# ---- P = 1 plumbing: the reference's own signatures on SamplePath (a one-chain ensemble per call)
+function solve!(::EulerMaruyama, Y::SamplePath{T}, u::T, W::SamplePath, P::ContinuousTimeProcess{T}, ctx::Context) where {T}
+    N = length(W); N != length(Y) && error("Y and W differ in length.")
+    d = length(u); dp = length(W.yy[1])
+    E = PathEnsemble(ctx, 1, 1, N, d, dp; double_buffer = false)
+    setgrid!(E, 1, W.tt); setstart!(E, SVector{d}(u...))
+    w = reinterpret(Float64, W.yy)
+    check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+    m = Ref(bbmodel(P)); check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, m))
+    x = reinterpret(Float64, Y.yy)
+    check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+    Y.tt .= W.tt; Y
+end
+
+end # module
