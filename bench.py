@@ -134,7 +134,7 @@ def oracle_workload(n):
 def cpu_run(n, seconds, iters=None, chains=None):
     """Times the oracle's OpenMP pCN driver on a bounded sample; returns (steps/s, cores, sample text)."""
     orc, model, guides, x0 = oracle_workload(n)
-    cores = orc.max_threads()
+    cores = len(os.sched_getaffinity(0))  # all host threads (torchrun presets OMP_NUM_THREADS=1; it is overridden)
     steps_per_chain_iter = SEGMENTS * (n - 1)
     if chains is None:
         pc = max(64, 8 * cores)
