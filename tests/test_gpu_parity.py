@@ -582,3 +582,151 @@ def test_reference_error_messages(B):
         ens.pcn_step_(Pm, [G], 0.5, 1, 0)
     assert ei.value.status == -7
     ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("N,P,S", [(2, 1, 1), (3, 31, 2), (16, 33, 1), (17, 257, 3), (33, 5, 16), (48, 300, 1)])
+def test_ragged_sizes_bit_exact(B, oracle_fma, N, P, S):
+    """Shortest path (one step), grids that end exactly on / one past a 16-point chunk, chain counts around the
+    warp and CTA sizes, the maximum number of chained segments: pCN proposal and bookkeeping stay exact."""
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    T = 0.05 * S
+    edges = np.linspace(0.0, T, S + 1)
+    grids = [warped(edges[s], edges[s + 1], N) for s in range(S)]
+    obs_v = [-0.5 + 0.02 * s for s in range(S)]
+    tabs = oracle_fhn_chain(oracle_fma, grids, obs_v, eps=1e-2, Sig=1e-4)
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    og = [O.GuideHolder(O.GUIDE_NUH, grids[s], tabs[s][1], tabs[s][0], Bt=tabs[s][2], betat=tabs[s][3])
+          for s in range(S)]
+    x0 = np.array([-0.5, -0.6])
+    ens = B.PathEnsemble(P, S, N, 2, 1)
+    for s in range(S):
+        ens.set_grid(s, grids[s])
+    ens.set_start(x0); ens.sample_(21, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+    Wc = ens.download(B.W); ll = ens.ll.copy()
+    acc = 0
+    for it in range(3):
+        ens.pcn_step_(Pm, guides, 0.7, 21, it)
+        Wp = ens.download(B.W, which=B.PROP); Xp = ens.download(B.X, which=B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
+        for p in sorted(set([0, P // 2, P - 1])):
+            llo, lu, Wo, Xo, xe = oracle_fma.pcn_propose(om, og, x0, Wc[p], 0.7, 21, it, p)
+            assert np.array_equal(Wp[p], Wo) and np.array_equal(Xp[p], Xo) and llp[p] == llo and logu[p] == lu
+        ok = logu <= llp - ll
+        assert np.array_equal(flags.astype(bool), ok)
+        Wc[ok] = Wp[ok]; ll[ok] = llp[ok]; acc += int(ok.sum())
+        assert ens.acc == acc and np.array_equal(ens.download(B.W), Wc)
+    ens.close()
+
+
+def test_skip_and_rho_limits(B, oracle_fma):
+    """skip >= N-1 removes every term of the log-likelihood (ll = 0, everything accepted: log U <= 0);
+    rho = 0 gives proposals that do not depend on the current W; rho = -1 mirrors it."""
+    N, P = 40, 64
+    tt = warped(0.0, 0.3, N)
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, [tt], [-0.6], eps=1e-2, Sig=1e-4)
+    g = B.GuideTables(B.api.K.GUIDE_NUH, tt, Pm, tabs[0][1], tabs[0][0], tabs[0][2], tabs[0][3])
+    ens = B.PathEnsemble(P, 1, N, 2, 1)
+    ens.set_grid(0, tt); ens.set_start([-0.5, -0.6]); ens.sample_(5, 0)
+    ens.guided_euler_ll_(Pm, [g], skip=N - 1)
+    assert np.all(ens.ll == 0.0)
+    ens.pcn_step_(Pm, [g], 0.5, 5, 1, skip=N + 7)
+    assert np.all(ens.ll_prop == 0.0) and ens.acc == P
+    W1 = ens.download(B.W)
+    ens.pcn_step_(Pm, [g], 0.0, 5, 2)
+    Wp = ens.download(B.W, which=B.PROP)
+    fresh = B.PathEnsemble(P, 1, N, 1, 1, double_buffer=False)
+    fresh.set_grid(0, tt); fresh.sample_(5, 2)
+    assert np.array_equal(Wp, fresh.download(B.W))          # rho = 0: W° = W2 exactly
+    ens2 = B.PathEnsemble(P, 1, N, 2, 1)
+    ens2.set_grid(0, tt); ens2.set_start([-0.5, -0.6]); ens2.upload(B.W, W1)
+    ens2.pcn_step_(Pm, [g], -1.0, 5, 3)
+    assert np.array_equal(ens2.download(B.W, which=B.PROP), -W1)
+    with pytest.raises(B.BridgeError):
+        ens.pcn_step_(Pm, [g], 1.5, 5, 4)
+    ens.close(); ens2.close(); fresh.close()
+
+
+def test_x_is_last_proposal_and_refresh(B, oracle_fma):
+    """X is kept once per chain and holds the last proposal; the current path of a chain that rejected is
+    recomputed by bb_ens_refresh_x and equals solve!(Euler(), X, x0, W, P°) on its current W."""
+    N, P = 65, 96
+    tt = warped(0.0, 0.5, N)
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, [tt], [-1.0])
+    g = B.GuideTables(B.api.K.GUIDE_NUH, tt, Pm, tabs[0][1], tabs[0][0], tabs[0][2], tabs[0][3])
+    og = O.GuideHolder(O.GUIDE_NUH, tt, tabs[0][1], tabs[0][0], Bt=tabs[0][2], betat=tabs[0][3])
+    ens = B.PathEnsemble(P, 1, N, 2, 1)
+    ens.set_grid(0, tt); ens.set_start([-0.5, -0.6]); ens.sample_(8, 0); ens.guided_euler_ll_(Pm, [g])
+    for it in range(4):
+        ens.pcn_step_(Pm, [g], 0.3, 8, it)   # low rho: many rejections
+    flags = ens.accepted.astype(bool)
+    assert 0 < flags.sum() < P
+    import ctypes
+    raw = np.empty((P, 1, N, 2))
+    st = B.api.lib.bb_ens_download(ens.h, B.X, B.CUR, 0, P, raw.ctypes.data_as(ctypes.c_void_p))
+    assert st == -13                                        # BB_ERR_STALE until refreshed
+    Xprop = ens.download(B.X, which=B.PROP)
+    Wc = ens.download(B.W)
+    Xc = ens.download(B.X)                                  # refreshes
+    for p in range(P):
+        Xo, _ = oracle_fma.guided_euler(om, og, [-0.5, -0.6], Wc[p, 0])
+        assert np.array_equal(Xc[p, 0], Xo)
+        if flags[p]:
+            assert np.array_equal(Xprop[p], Xc[p])          # accepted proposals ARE the current path
+    assert np.array_equal(ens.xend, Xc[:, 0, -1])
+    ens.close()
+
+
+def test_sqrt_of_box_muller_radius_is_ieee(B):
+    """bb_sqrtf (rsqrt + two fma, no slow path) against IEEE sqrt: the radius sqrt(-2 log u) of every possible
+    uniform is reproduced bit for bit by the oracle, which uses sqrtf; checked over a dense sweep of the generator's
+    output through sample! with a unit grid (W[1] = normal 1 of quad 0 ...)."""
+    N, P = 9, 200000
+    ens = B.PathEnsemble(P, 1, N, 1, 1, double_buffer=False)
+    ens.set_grid(0, np.arange(N, dtype=float))   # dt = 1: increments are the normals themselves
+    ens.sample_(123, 0)
+    W = ens.download(B.W)[:, 0, :, 0]
+    from oracle import oracle as OO
+    orc = OO.load("fma")
+    z = np.diff(W, axis=1)
+    for p in range(0, P, 997):
+        want = np.array([orc.normal(123, 0, p, n) for n in range(1, N)])
+        assert np.array_equal(np.cumsum(want), W[p, 1:])
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 0.01
+    assert np.abs(z).max() < 6.8
+    ens.close()
+
+
+def test_config3_full_size_properties(B):
+    """BASELINE config 3 at full size (1e5 paths, d = 3, N = 1001): end point = v for every path, finite ll,
+    importance weights E[exp(ll) p~/p] within Monte-Carlo error of 1 (test/guip.jl:245-274 at scale)."""
+    import bridge_jl_b200.configs as cfg
+    from scipy.linalg import expm, solve_continuous_lyapunov
+    n, P = 1001, 100000
+    Pm, G, u = cfg.linpro_config3(n)
+    ens = B.PathEnsemble(P, 1, n, 3, 3, double_buffer=False)
+    ens.set_grid(0, G.tt); ens.set_start(u)
+    ens.sample_(3, 0)
+    ens.guided_euler_ll_(Pm, [G])
+    ll = ens.ll
+    assert np.all(np.isfinite(ll))
+    assert np.array_equal(ens.xend, np.tile(cfg.LIN3_V, (P, 1)))
+    a = cfg.LIN3_SIG @ cfg.LIN3_SIG.T
+
+    def logp(Bm):  # Gaussian transition density of dX = B X dt + sigma dW from 0 to v over T = 1
+        mean = np.zeros(3)
+        lam = solve_continuous_lyapunov(Bm, -a)
+        E = expm(Bm)
+        cov = lam - E @ lam @ E.T
+        dv = cfg.LIN3_V - mean
+        return -0.5 * dv @ np.linalg.solve(cov, dv) - 0.5 * np.log(np.linalg.det(2 * np.pi * cov))
+
+    w = np.exp(ll + logp(cfg.LIN3_B2) - logp(cfg.LIN3_B1))
+    z = abs(w.mean() - 1) * np.sqrt(P) / w.std()
+    assert abs(w.mean() - 1) < 0.02, (w.mean(), z)   # discretisation bias of the left rule at N = 1001 (SURVEY 8c caveat)
+    ens.close()
