@@ -719,7 +719,8 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   a.P = e->P; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC;
   a.jll = e->N - 1 - rs.skip;
   a.store_x = rs.store_x ? 1 : 0; a.do_ll = rs.do_ll ? 1 : 0; a.write_end = rs.write_end ? 1 : 0;
-  a.k0 = (uint32_t)rs.seed; a.k1 = (uint32_t)(rs.seed >> 32); a.stream = rs.stream;
+  bb_philox_key_schedule(rs.seed, a.keys);
+  a.stream = rs.stream;
   a.rho = rs.rho;
   a.rho2 = sqrt(1 - rs.rho * rs.rho); /* sqrt(1-ρ^2)  test/partialbridgenuH.jl:178 */
   bb_prepare_model(model, &a.model);

@@ -54,7 +54,8 @@ struct bb_chain_args {
   int jll;                         /* steps j <= jll (1-based end index) enter the log-likelihood */
   int start_bcast, store_x, do_ll, write_end;
   int nbuf;                        /* 1, or 2 when the ensemble is double buffered */
-  uint32_t k0, k1, stream;
+  bb_philox_keys keys;             /* Philox round keys of the seed */
+  uint32_t stream;
   double rho, rho2;
   bb_model_dev model;
   /* per-segment constants: Bt[d*d], betat[d] (constant auxiliary drift), endflag, vend[d] (GuidedBridge end
@@ -198,7 +199,7 @@ struct bb_chain {
             if constexpr (RNG != 2) bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
             if constexpr (RNG != 0) {
               float z[4];
-              bb_normal_quad(a.k0, a.k1, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+              bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
 #pragma unroll
               for (int i = 0; i < 4; i++) {
                 const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP; /* slot / component of element i */
@@ -304,23 +305,50 @@ struct bb_chain {
     const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
     const long long warp_p0 = (long long)blockIdx.x * blockDim.x + warp * 32;
     const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP); /* doubles between the slots of consecutive chains */
-    /* instruction r, lane l: chain cw = t / NCP, piece = t % NCP, t = 32 r + l */
-    const uint32_t l_cw = (uint32_t)lane / NCP, l_pc = (uint32_t)lane % NCP; /* used when NCP <= 32 divides 32 */
+    constexpr bool COOP_FAST = (32 % NCP == 0); /* an instruction covers CPI = 32 / NCP whole chains */
+    constexpr int CPI = COOP_FAST ? 32 / NCP : 1;
+    /* instruction r, lane l: chain cw = CPI r + l / NCP, piece = l % NCP (fast mapping) */
+    const uint32_t l_cw = (uint32_t)lane / NCP, l_pc = (uint32_t)lane % NCP;
+    uint32_t parbits = 0, actbits = 0; /* bit r: buffer parity / activity of the chain instruction r serves */
+#pragma unroll
+    for (int r = 0; r < NCP; r++) {
+      const uint32_t cw = COOP_FAST ? CPI * r + l_cw : (32u * r + lane) / NCP;
+      parbits |= ((pmask >> cw) & 1u) << r;
+      actbits |= ((amask >> cw) & 1u) << r;
+    }
+    /* per-lane constants: source offset within a chunk (doubles) and swizzled smem offsets (doubles) for the
+     * 8 / CPI distinct values of (chain index & 7) that the instructions of this lane meet */
+    const uint32_t src_l = l_cw * wrow_d + 2 * l_pc;
+    constexpr int NSW = COOP_FAST ? (8 / CPI > 0 ? 8 / CPI : 1) : 1;
+    uint32_t dsw[NSW];
+#pragma unroll
+    for (int i = 0; i < NSW; i++) {
+      const uint32_t cw = CPI * i + l_cw;
+      dsw[i] = (warp * 32 + l_cw) * WROWP + 2 * ((l_pc & ~7u) | ((l_pc ^ cw) & 7u));
+    }
     const double* wsrc = a.W[0] + warp_p0 * wrow_d; /* + chunk * wstride */
     const int TW = S * NC;                          /* rows this chain walks through */
     int gcur = 0;                                   /* global chunk index of the row consumed next */
     auto w_issue = [&](int gc) { /* request chunk gc for the whole warp; always commits a (possibly empty) group */
       if (RNG != 2 && gc < TW) {
-        const double* src = wsrc + (long long)gc * wstride;
-        double* dst = wstage + ((size_t)(gc % BB_WSTAGES) * BB_THREADS + warp * 32) * WROWP;
+        double* dst = wstage + (size_t)(gc % BB_WSTAGES) * BB_THREADS * WROWP;
+        if constexpr (COOP_FAST) {
+          const double* src = wsrc + (long long)gc * wstride + src_l;
 #pragma unroll
-        for (int r = 0; r < NCP; r++) {
-          uint32_t cw, piece;
-          if constexpr (32 % NCP == 0) { cw = (32 / NCP) * r + l_cw; piece = l_pc; }
-          else { const uint32_t t = 32u * r + lane; cw = t / NCP; piece = t % NCP; }
-          if ((amask >> cw) & 1u)
-            bb_cp_async16(dst + cw * WROWP + 2 * ((piece & ~7u) | ((piece ^ cw) & 7u)),
-                          src + (cw * wrow_d + ((pmask >> cw) & 1u) * (BB_TC * DP) + 2 * piece));
+          for (int r = 0; r < NCP; r++) {
+            const uint32_t poff = ((parbits >> r) & 1u) * (uint32_t)(BB_TC * DP);
+            if ((actbits >> r) & 1u)
+              bb_cp_async16(dst + dsw[r % NSW] + r * (CPI * WROWP), src + (r * CPI * wrow_d + poff));
+          }
+        } else {
+          const double* src = wsrc + (long long)gc * wstride;
+#pragma unroll
+          for (int r = 0; r < NCP; r++) {
+            const uint32_t t = 32u * r + lane, cw = t / NCP, piece = t % NCP;
+            if ((amask >> cw) & 1u)
+              bb_cp_async16(dst + (warp * 32 + cw) * WROWP + 2 * ((piece & ~7u) | ((piece ^ cw) & 7u)),
+                            src + (cw * wrow_d + ((pmask >> cw) & 1u) * (BB_TC * DP) + 2 * piece));
+          }
         }
       }
       bb_cp_async_commit();
@@ -397,7 +425,7 @@ struct bb_chain {
     /* ---- per-chain epilogue */
     if constexpr (RNG == 1) {
       /* accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
-      const double logu = bb_accept_logu(a.k0, a.k1, a.stream, chain);
+      const double logu = bb_accept_logu(a.keys, a.stream, chain);
       const double llc = a.ll[pc];
       const bool ok = act && (logu <= lltot - llc);
       if (act) {
