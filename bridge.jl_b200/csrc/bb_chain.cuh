@@ -294,10 +294,10 @@ struct bb_chain {
     uint32_t phase = 0;
 
     double wq[4] = {0.0, 0.0, 0.0, 0.0};
-    /* ---- driving path: the warp copies the rows of its 32 chains for one chunk with 4 d' cp.async
-     * instructions (LDGSTS.128, L1 bypassed): lane l moves 16-byte piece t % (4 d') of chain t / (4 d'),
-     * t = 32 r + l, so every chain's 64 d'-byte row is requested by ONE instruction -- whole DRAM bursts even
-     * though neighbouring chains read different buffers -- and lands in the chain's padded row of the stage.
+    /* ---- driving path: the warp copies the rows of its 32 chains for one chunk with 8 d' cp.async
+     * instructions (LDGSTS.128, L1 bypassed): lane l moves 16-byte piece t % (8 d') of chain t / (8 d'),
+     * t = 32 r + l, so every chain's 128 d'-byte row is requested by ONE instruction -- whole L2 lines even
+     * though neighbouring chains read different buffers -- and lands in the chain's swizzled row of the stage.
      * Rows are requested BB_WSTAGES-1 chunks before they are used; no registers are tied up meanwhile. */
     constexpr int NCP = BB_TC * DP / 2; /* 16-byte pieces per row = cp.async instructions per chunk and warp */
     const int warp = threadIdx.x >> 5;
