@@ -299,12 +299,13 @@ def main():
         hostXo = torch.empty((P, S, n, 2), dtype=torch.float64, pin_memory=True).numpy()
         ens.download(B.W, out=hostW)
 
+        hostLL = torch.empty(P, dtype=torch.float64, pin_memory=True).numpy()
+        hostAcc = torch.empty(P, dtype=torch.uint8, pin_memory=True).numpy()
+
         def e2e_step(itn):
-            ens.upload(B.W, hostW)                       # H2D: the chain state the host owns
-            ens.pcn_step_(Pm, guides, rho, seed, itn)
-            ens.download(B.W, which=B.PROP, out=hostWo)  # D2H: proposal W°, X°
-            ens.download(B.X, which=B.PROP, out=hostXo)
-            return ens.ll_prop, ens.accepted, ens.acc    # D2H: ll°, accept flags, counter
+            # one call on host buffers: W up; W°, X°, ll°, accept flags down (pipelined over chain slabs)
+            ens.pcn_step_host_(Pm, guides, rho, seed, itn, hostW, hostWo, hostXo, hostLL, hostAcc)
+            return ens.acc
 
         e2e_step(it); it += 1
         barrier()
@@ -321,7 +322,8 @@ def main():
                "unit": "path-steps/s", "h2d_bytes_per_step": int(hostW.nbytes),
                "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
                "steps": args.e2e_steps,
-               "what": "per step: upload W (pinned host) -> bb_pcn_step -> download W°, X°, ll°, accept flags"}
+               "what": "bb_pcn_step_host on pinned host buffers: per step W up; W°, X°, ll°, accept flags down; "
+                       "H2D | kernel | D2H pipelined over chain slabs"}
         # device-resident ensemble API: per step only the guide tables go up and ll°/flags/acc come back
         barrier()
         e0.record(stream)

@@ -105,6 +105,7 @@ def _load():
         "bb_innovations": (C.c_int, [vp, C.POINTER(Model), pp]),
         "bb_pcn_step": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32]),
         "bb_ens_refresh_x": (C.c_int, [vp, C.POINTER(Model), pp]),
+        "bb_pcn_step_host": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -514,6 +514,16 @@ class PathEnsemble:
         flags = (K.RUN_STORE_X if store_x else 0) | (0 if ll else K.RUN_NO_LL)
         check(lib.bb_guided_euler_ll(self.h, C.byref(m), self._garr(guides), skip, flags))
 
+    def pcn_step_host_(self, P, guides, ρ: float, seed: int, it: int, W, Wo, Xo=None, llo=None, accepted=None,
+                       skip: int = 0):
+        """One pCN iteration on HOST arrays (the reference loop's dataflow): W [P,S,N,d'] in; Wo, Xo, llo, accepted
+        out.  Pipelined H2D | kernel | D2H over chain slabs; use pinned arrays for full overlap."""
+        m = P.cmodel()
+        self._last = (P, list(guides))
+        check(lib.bb_pcn_step_host(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip,
+                                   K.RUN_STORE_X if Xo is not None else 0, ptr(W), ptr(Wo), ptr(Xo), ptr(llo),
+                                   ptr(accepted)))
+
     def refresh_x_(self):
         """Make X the CURRENT path of every chain again (X holds the last proposal; chains that rejected it
         get their path recomputed from W by the same guided Euler kernel).  No-op if nothing is stale."""

@@ -675,6 +675,7 @@ struct run_spec {
   uint64_t seed;
   uint32_t stream;
   bool only_stale = false;
+  int64_t p_begin = 0, p_end = -1; /* chain sub-range (default: all) */
 };
 
 /* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations! */
@@ -716,7 +717,9 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
   a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
   a.accepted = e->accepted; a.acc = e->acc;
-  a.P = e->P; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC;
+  a.P = e->P; a.p_begin = rs.p_begin; a.p_end = rs.p_end < 0 ? e->P : rs.p_end;
+  if (a.p_begin < 0 || a.p_end > e->P || a.p_begin >= a.p_end) return BB_ERR_ARG;
+  a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC;
   a.jll = e->N - 1 - rs.skip;
   a.store_x = rs.store_x ? 1 : 0; a.do_ll = rs.do_ll ? 1 : 0; a.write_end = rs.write_end ? 1 : 0;
   bb_philox_key_schedule(rs.seed, a.keys);
@@ -786,4 +789,129 @@ extern "C" int bb_ens_refresh_x(bb_ens* e, const bb_model* model, bb_guide* cons
   run_spec rs{0, true, false, false, 0, 0.0, 0, 0};
   rs.only_stale = true;
   return run_chain(e, model, guides, rs);
+}
+
+/* ------------------------------------------------------------------------------------------------ host-buffer pCN
+ * The reference loop keeps W, X in host memory.  This entry point runs one pCN iteration on HOST buffers:
+ * W (current) goes up, W°, X°, ll°, accept flags come back, in slabs of chains that are pipelined over three
+ * streams (H2D of slab k+1 | transpose + path kernel of slab k | D2H of slab k-1), so the PCIe link is busy in
+ * both directions while the GPU computes.  The chains' device state is updated as by bb_pcn_step. */
+__global__ void __launch_bounds__(256) bb_slab_in_kernel(double* __restrict__ W0, const double* __restrict__ stage,
+                                                         const uint8_t* __restrict__ par, long long P, long long p0,
+                                                         long long np, int S, int N, int NC, int K, int nbuf) {
+  const long long rowlen = (long long)BB_TC * K, total = (long long)S * NC * np * rowlen;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(t % rowlen);
+    long long q = t / rowlen;
+    const long long pl = q % np;
+    q /= np;
+    const int c = (int)(q % NC), s = (int)(q / NC);
+    const int slot = e / K, k = e - slot * K, j = c * BB_TC + slot;
+    if (j >= N) continue;
+    const long long p = p0 + pl;
+    W0[((((long long)s * NC + c) * P + p) * nbuf + par[p]) * rowlen + e] = stage[((pl * S + s) * (long long)N + j) * K + k];
+  }
+}
+/* proposal W° (buffer the chain did NOT read from in this step = par_before ^ 1; par may have flipped on accept) and X° */
+__global__ void __launch_bounds__(256) bb_slab_out_kernel(const double* __restrict__ W0, const double* __restrict__ X,
+                                                          double* __restrict__ stageW, double* __restrict__ stageX,
+                                                          const uint8_t* __restrict__ par,
+                                                          const uint8_t* __restrict__ accepted, long long P,
+                                                          long long p0, long long np, int S, int N, int NC, int dp,
+                                                          int d, int nbuf) {
+  const long long rw = (long long)BB_TC * dp, rx = (long long)BB_TC * d;
+  const long long totw = (long long)S * NC * np * rw, totx = stageX ? (long long)S * NC * np * rx : 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < totw + totx;
+       t += (long long)gridDim.x * blockDim.x) {
+    const bool isx = t >= totw;
+    const long long u = isx ? t - totw : t, rowlen = isx ? rx : rw;
+    const int K = isx ? d : dp;
+    const int e = (int)(u % rowlen);
+    long long q = u / rowlen;
+    const long long pl = q % np;
+    q /= np;
+    const int c = (int)(q % NC), s = (int)(q / NC);
+    const int slot = e / K, k = e - slot * K, j = c * BB_TC + slot;
+    if (j >= N) continue;
+    const long long p = p0 + pl;
+    const long long h = ((pl * S + s) * (long long)N + j) * K + k;
+    if (isx) {
+      stageX[h] = X[(((long long)s * NC + c) * P + p) * rowlen + e];
+    } else {
+      const int b = accepted[p] ? par[p] : 1 - par[p];
+      stageW[h] = W0[((((long long)s * NC + c) * P + p) * nbuf + b) * rowlen + e];
+    }
+  }
+}
+
+extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* const* guides, double rho, uint64_t seed,
+                                uint32_t iter, int32_t skip, uint32_t flags, const double* W_host, double* Wo_host,
+                                double* Xo_host, double* llo_host, uint8_t* accepted_host) {
+  if (!e || !guides || !W_host || !Wo_host) return BB_ERR_ARG;
+  if (!(rho >= -1.0 && rho <= 1.0)) return BB_ERR_ARG;
+  const bool want_x = Xo_host != nullptr;
+  if (want_x && !e->X) return BB_ERR_ARG;
+  bb_ctx* c = e->ctx;
+  BB_CUDA(cudaSetDevice(c->device));
+  if (!c->s_h2d) {
+    BB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    BB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      BB_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+      BB_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+      BB_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t wpc = (size_t)e->S * e->N * e->dp, xpc = (size_t)e->S * e->N * e->d; /* doubles per chain */
+  int64_t slab = (int64_t)((size_t)(192u << 20) / (wpc * sizeof(double)));
+  slab = slab < 256 ? 256 : (slab / 256) * 256; /* whole CTAs */
+  if (slab > e->P) slab = e->P;
+  const size_t per_slab = (size_t)slab * (2 * wpc + (want_x ? xpc : 0));
+  int rc = ctx_stage(c, 2 * per_slab * sizeof(double));
+  if (rc != BB_OK) return rc;
+  double* st[2] = {c->stage, c->stage + per_slab};
+  BB_CUDA(cudaStreamSynchronize(c->stream)); /* earlier work on the context's stream is complete */
+  run_spec rs{1, want_x && (flags & BB_RUN_STORE_X) != 0, true, true, skip, rho, seed, iter};
+  if (want_x) rs.store_x = true;
+  int k = 0;
+  for (int64_t p0 = 0; p0 < e->P; p0 += slab, k++) {
+    const int64_t n = (e->P - p0 < slab) ? e->P - p0 : slab;
+    const int b = k & 1;
+    double *sWin = st[b], *sWo = st[b] + (size_t)slab * wpc, *sXo = want_x ? st[b] + 2 * (size_t)slab * wpc : nullptr;
+    /* staging buffers of parity b are free once the D2H of slab k-2 has finished */
+    if (k >= 2) BB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_out[b], 0));
+    BB_CUDA(cudaMemcpyAsync(sWin, W_host + (size_t)p0 * wpc, (size_t)n * wpc * sizeof(double), cudaMemcpyHostToDevice,
+                            c->s_h2d));
+    BB_CUDA(cudaEventRecord(c->ev_in[b], c->s_h2d));
+    BB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+    const long long tin = (long long)e->S * e->NC * n * BB_TC * e->dp;
+    bb_slab_in_kernel<<<(unsigned)((tin + 255) / 256 > 148 * 16 ? 148 * 16 : (tin + 255) / 256), 256, 0, c->stream>>>(
+        e->W[0], sWin, e->par, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->nbuf);
+    rs.p_begin = p0; rs.p_end = p0 + n;
+    rc = run_chain(e, model, guides, rs);
+    if (rc != BB_OK) return rc;
+    const long long tout = (long long)e->S * e->NC * n * BB_TC * (e->dp + (want_x ? e->d : 0));
+    bb_slab_out_kernel<<<(unsigned)((tout + 255) / 256 > 148 * 16 ? 148 * 16 : (tout + 255) / 256), 256, 0, c->stream>>>(
+        e->W[0], e->X, sWo, sXo, e->par, e->accepted, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->d, e->nbuf);
+    BB_CUDA(cudaGetLastError());
+    c->launches += 2;
+    BB_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
+    BB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+    BB_CUDA(cudaMemcpyAsync(Wo_host + (size_t)p0 * wpc, sWo, (size_t)n * wpc * sizeof(double), cudaMemcpyDeviceToHost,
+                            c->s_d2h));
+    if (want_x)
+      BB_CUDA(cudaMemcpyAsync(Xo_host + (size_t)p0 * xpc, sXo, (size_t)n * xpc * sizeof(double), cudaMemcpyDeviceToHost,
+                              c->s_d2h));
+    if (llo_host)
+      BB_CUDA(cudaMemcpyAsync(llo_host + p0, e->llprop + p0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
+    if (accepted_host)
+      BB_CUDA(cudaMemcpyAsync(accepted_host + p0, e->accepted + p0, (size_t)n, cudaMemcpyDeviceToHost, c->s_d2h));
+    BB_CUDA(cudaEventRecord(c->ev_out[b], c->s_d2h));
+    /* the next slab's input transpose must not overwrite sWin of parity b^1 ... it uses the other buffer; the
+     * compute stream itself orders slab k+1's kernels after slab k's */
+  }
+  BB_CUDA(cudaStreamSynchronize(c->s_d2h));
+  BB_CUDA(cudaStreamSynchronize(c->stream));
+  return BB_OK;
 }

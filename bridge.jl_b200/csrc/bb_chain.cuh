@@ -49,6 +49,7 @@ struct bb_chain_args {
   const uint8_t* only;             /* if set, only chains with only[p] != 0 are processed (X refresh) */
   unsigned long long* acc;
   long long P;
+  long long p_begin, p_end;        /* chains [p_begin, p_end) are processed by this launch */
   long long chain_offset;
   int S, N, NC;
   int jll;                         /* steps j <= jll (1-based end index) enter the log-likelihood */
@@ -266,9 +267,9 @@ struct bb_chain {
     __syncthreads();
 
     const long long P = a.P;
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pc = p < P ? p : P - 1;
-    const bool act = p < P && (!a.only || a.only[pc] != 0);
+    const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pc = p < a.p_end ? p : a.p_end - 1;
+    const bool act = p < a.p_end && (!a.only || a.only[pc] != 0);
     const int par = a.par[pc];
     const int rbuf = par;                        /* where the chain's current W (and X) live */
     const int wbuf = (RNG == 1) ? 1 - par : par; /* where this launch writes */
@@ -303,7 +304,7 @@ struct bb_chain {
     const int warp = threadIdx.x >> 5;
     const unsigned amask = __ballot_sync(0xFFFFFFFFu, act);
     const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
-    const long long warp_p0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+    const long long warp_p0 = a.p_begin + (long long)blockIdx.x * blockDim.x + warp * 32;
     const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP); /* doubles between the slots of consecutive chains */
     constexpr bool COOP_FAST = (32 % NCP == 0); /* an instruction covers CPI = 32 / NCP whole chains */
     constexpr int CPI = COOP_FAST ? 32 / NCP : 1;
@@ -483,7 +484,7 @@ static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  const unsigned grid = (unsigned)((a.P + BB_THREADS - 1) / BB_THREADS);
+  const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_chain_kernel<M, GK, GM, AUXC, RNG><<<grid, BB_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }

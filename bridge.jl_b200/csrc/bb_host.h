@@ -24,6 +24,9 @@ struct bb_ctx {
   /* staging for host <-> device transposes */
   double* stage = nullptr;
   size_t stage_bytes = 0;
+  /* host-buffer pipeline (bb_pcn_step_host) */
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 struct bb_guide {

@@ -15,8 +15,8 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
   using CH = bb_chain<M, GK, GM, AUXC, 0>;
   constexpr int D = M::D, DP = M::DP, REC = CH::REC;
   const long long P = a.P;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+  const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.p_end) return;
   const int par = a.par[p];
   const double* xr = a.X + p * (BB_TC * D);
   double* ww = a.W[par] + p * (a.nbuf * BB_TC * DP);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
 
 template <class M, int GK, int GM, bool AUXC, int MODE>
 static cudaError_t bb_second_launch(const bb_chain_args& a, cudaStream_t st) {
-  const unsigned grid = (unsigned)((a.P + BB_THREADS - 1) / BB_THREADS);
+  const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_second_kernel<M, GK, GM, AUXC, MODE><<<grid, BB_THREADS, 0, st>>>(a);
   return cudaGetLastError();
 }

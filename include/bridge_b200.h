@@ -288,6 +288,15 @@ int bb_innovations(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
  */
 int bb_pcn_step(bb_ens* ens, const bb_model* model, bb_guide* const* guides, double rho,
                 uint64_t seed, uint32_t iter, int32_t skip, uint32_t flags);
+/* The same iteration on HOST buffers, for callers that keep W, X in host memory as the reference loop does
+ * (test/partialbridgenuH.jl:168-191): W_host [P][S][N][d'] (current W of every chain) goes up; the proposal
+ * Wo_host [P][S][N][d'], Xo_host [P][S][N][d] (may be NULL), llo_host [P] (may be NULL) and accepted_host [P]
+ * (may be NULL) come back.  Slabs of chains are pipelined over three streams so that both PCIe directions and
+ * the GPU are busy at once; pinned host memory is needed for that overlap (pageable memory works, serially).
+ * The ensemble's device state is updated exactly as by bb_pcn_step. */
+int bb_pcn_step_host(bb_ens* ens, const bb_model* model, bb_guide* const* guides, double rho, uint64_t seed,
+                     uint32_t iter, int32_t skip, uint32_t flags, const double* W_host, double* Wo_host,
+                     double* Xo_host, double* llo_host, uint8_t* accepted_host);
 /* X is kept ONCE per chain and always holds the path of the chain's last proposal X° (the reference's Xo);
  * for a chain whose proposal was rejected the reference's X (current path) is a pure function of the
  * chain's current W, and this call recomputes it in place for exactly those chains (solve!(Euler(), X, x0,

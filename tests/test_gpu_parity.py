@@ -730,3 +730,31 @@ def test_config3_full_size_properties(B):
     z = abs(w.mean() - 1) * np.sqrt(P) / w.std()
     assert abs(w.mean() - 1) < 0.02, (w.mean(), z)   # discretisation bias of the left rule at N = 1001 (SURVEY 8c caveat)
     ens.close()
+
+
+def test_pcn_step_host_buffers_matches_resident(B, oracle_fma):
+    """bb_pcn_step_host (W up, W°/X°/ll°/flags down, pipelined over chain slabs) gives exactly what bb_pcn_step +
+    downloads give, and leaves the same device state."""
+    N, P, S = 49, 700, 2
+    grids = [warped(0.0, 0.5, N), warped(0.5, 1.0, N)]
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, grids, [-1.0, -0.5])
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    enss = []
+    for _ in range(2):
+        ens = B.PathEnsemble(P, S, N, 2, 1)
+        for s in range(S):
+            ens.set_grid(s, grids[s])
+        ens.set_start([-0.5, -0.6]); ens.sample_(6, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+        enss.append(ens)
+    a, b = enss
+    for it in range(3):
+        Wh = a.download(B.W)
+        a.pcn_step_(Pm, guides, 0.8, 6, it)
+        Wo = np.empty((P, S, N, 1)); Xo = np.empty((P, S, N, 2)); llo = np.empty(P); acc = np.empty(P, dtype=np.uint8)
+        b.pcn_step_host_(Pm, guides, 0.8, 6, it, Wh, Wo, Xo, llo, acc)
+        assert np.array_equal(Wo, a.download(B.W, which=B.PROP)) and np.array_equal(Xo, a.download(B.X, which=B.PROP))
+        assert np.array_equal(llo, a.ll_prop) and np.array_equal(acc, a.accepted)
+        assert np.array_equal(b.download(B.W), a.download(B.W)) and np.array_equal(b.ll, a.ll) and a.acc == b.acc
+    a.close(); b.close()
