@@ -100,6 +100,13 @@ struct bb_chain {
   static constexpr int OFF_C = 2, OFF_A1 = OFF_C + NCC, OFF_A2 = OFF_A1 + NA1, OFF_BT = OFF_A2 + NA2,
                        OFF_BE = OFF_BT + D * D;
 
+  /* Stores that trickle out 32 bytes at a time while the chain computes leave partially written lines in L2 for
+   * microseconds and cost 15-20 % of DRAM bandwidth (tools/membench.cu: 5.8 TB/s in bursts vs 4.8 TB/s dripped),
+   * so rows are completed in shared memory and written back to back.  The X° window needs 128 B per chain:
+   * enabled where two CTAs per SM still fit (scalar noise, d <= 2). */
+  static constexpr bool XBUF = BB_XFLUSH && (D <= 2) && (DP == 1);
+  static constexpr int XWIN = 16 / D; /* steps per 128-byte window */
+
   struct state {
     double y[D];
     double wprev[DP];
@@ -174,8 +181,8 @@ struct bb_chain {
   template <bool GENERIC>
   static __device__ __forceinline__ void chunk(const bb_chain_args& a, const double* __restrict__ rec,
                                                const double* __restrict__ sc, state& st, double* wq,
-                                               const double* wrow, double* wout_row, double* xout_row, int c,
-                                               uint32_t row_lo, uint32_t row_hi, bool wact, bool xact) {
+                                               double* wrow, double* wout_row, double* xout_row, double* xbuf,
+                                               int c, uint32_t row_lo, uint32_t row_hi, bool wact, bool xact) {
     constexpr int NPIECE = BB_TC * DP / 4; /* pieces of 4 doubles per chunk row */
     bb_rowout<D> xo;
     const int N = a.N;
@@ -216,7 +223,10 @@ struct bb_chain {
                   wq[i] = st.w2[kk];
                 }
               }
-              if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+              /* memory-bound launches (X° stored too) complete the W° row in the staged row and write it as a whole
+               * line at the end of the chunk; compute-bound ones store the piece directly */
+              if (BB_WFLUSH && a.store_x) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+              else if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
             }
           }
           wj[k] = wq[m & 3];
@@ -232,7 +242,40 @@ struct bb_chain {
             for (int k = 0; k < D; k++) st.y[k] = sc[D * D + D + 1 + k];
           }
         }
-        xo.put(xout_row + 4 * h * D, s4, st.y, xact);
+        if constexpr (XBUF) {
+          if (a.store_x) {
+            const int ls = (4 * h + s4) % XWIN;
+            if constexpr (D == 2)
+              *reinterpret_cast<double2*>(xbuf + 2 * ((ls ^ threadIdx.x) & 7)) = make_double2(st.y[0], st.y[1]);
+            else
+              xbuf[2 * (((ls >> 1) ^ threadIdx.x) & 7) + (ls & 1)] = st.y[0];
+          }
+        } else {
+          xo.put(xout_row + 4 * h * D, s4, st.y, xact);
+        }
+      }
+      if constexpr (XBUF) {
+        /* a 128-byte window of X° is complete: write it back to back (whole line) */
+        if (((4 * h + 3) % XWIN) == XWIN - 1 && xact) {
+          double* xdst = xout_row + (4 * h + 4 - XWIN) * D;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            double v[4];
+            bb_lds4_swz(xbuf, 2 * q, threadIdx.x & 7, v);
+            bb_st4(xdst + 4 * q, v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    }
+    if constexpr (RNG != 0 && BB_WFLUSH) {
+      /* the chain's row of W° is complete in shared memory: write its 128 d' bytes back to back */
+      if (wact && a.store_x) {
+#pragma unroll
+        for (int q = 0; q < NPIECE; q++) {
+          double v[4];
+          bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, v);
+          bb_st4(wout_row + 4 * q, v[0], v[1], v[2], v[3]);
+        }
       }
     }
   }
@@ -250,6 +293,7 @@ struct bb_chain {
      * which keeps the 128-bit reads of a quarter-warp conflict free without padding. */
     constexpr int WROWP = BB_TC * DP;
     double* wstage = reinterpret_cast<double*>(empty + BB_STAGES);
+    double* xbuf = wstage + (size_t)BB_WSTAGES * BB_THREADS * (BB_TC * DP) + (size_t)threadIdx.x * 16;
 
     const int S = a.S, NC = a.NC;
     const int NST = (NC + BB_TSTAGE - 1) / BB_TSTAGE; /* stages per segment */
@@ -354,7 +398,7 @@ struct bb_chain {
       }
       bb_cp_async_commit();
     };
-    const double* wslot = wstage + (size_t)threadIdx.x * WROWP; /* + stage * BB_THREADS * WROWP */
+    double* wslot = wstage + (size_t)threadIdx.x * WROWP; /* + stage * BB_THREADS * WROWP */
 #pragma unroll 1
     for (int i = 0; i < BB_WSTAGES - 1; i++) w_issue(i);
 
@@ -389,7 +433,7 @@ struct bb_chain {
           if (!tab_ready) bb_mbar_wait(&full[stage], phase);
           rec = ring + stage * STAGE_DOUBLES;
         }
-        const double* wrow = wslot + (size_t)(gcur % BB_WSTAGES) * BB_THREADS * WROWP;
+        double* wrow = wslot + (size_t)(gcur % BB_WSTAGES) * BB_THREADS * WROWP;
         if constexpr (RNG != 2) {
           /* rows of chunk gcur were requested a whole chunk ago: wait for them first (normally no wait at all),
            * then refill the other stage -- which every lane has finished reading -- with chunk gcur+1 */
@@ -405,9 +449,9 @@ struct bb_chain {
         }
         const bool generic = (c == 0) || (c == NC - 1) || (c * BB_TC + BB_TC - 1 > a.jll);
         if (generic)
-          chunk<true>(a, rec, sc, st, wq, wrow, ww, xw, c, row_lo, row_hi, act, xact);
+          chunk<true>(a, rec, sc, st, wq, wrow, ww, xw, xbuf, c, row_lo, row_hi, act, xact);
         else
-          chunk<false>(a, rec, sc, st, wq, wrow, ww, xw, c, row_lo, row_hi, act, xact);
+          chunk<false>(a, rec, sc, st, wq, wrow, ww, xw, xbuf, c, row_lo, row_hi, act, xact);
         rec += CHUNK_DOUBLES;
         gcur++;
         if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
@@ -468,7 +512,8 @@ template <class M, int GK, int GM, bool AUXC, int RNG>
 static inline size_t bb_chain_smem(int S) {
   (void)S;
   return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + 2 * BB_STAGES * 8 +
-         (size_t)BB_WSTAGES * BB_THREADS * (BB_TC * M::DP) * 8;
+         (size_t)BB_WSTAGES * BB_THREADS * (BB_TC * M::DP) * 8 +
+         (bb_chain<M, GK, GM, AUXC, RNG>::XBUF ? (size_t)BB_THREADS * 128 : 0);
 }
 
 /* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */
