@@ -91,6 +91,7 @@ def _load():
         "bb_euler": (C.c_int, [vp, C.POINTER(Model)]),
         "bb_sample_euler": (C.c_int, [vp, C.POINTER(Model), u64, u32]),
         "bb_guide_create": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, pp]),
+        "bb_guide_create_ncd": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, pp]),
         "bb_guide_destroy": (C.c_int, [vp]),
         "bb_update_nuHC": (C.c_int, [vp, i32, i32, vp, vp, vp, dbl, vp, vp, C.POINTER(dbl)]),
         "bb_gpupdate_nuH": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp]),

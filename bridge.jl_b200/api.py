@@ -569,8 +569,25 @@ class _Proposal:
         A, b = f64(A), f64(b)
         Mm = None if Mm is None else f64(Mm)
         v = None if v is None else f64(v)
-        check(lib.bb_guide_create(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt), ptr(A),
-                                  ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, C.byref(h)))
+        # constdiff(P°) = constdiff(Target) && constdiff(Pt) and a == a~ (src/partialbridge.jl:63): if the auxiliary
+        # diffusion differs from the target's, the extra log-likelihood terms of src/partialbridge.jl:79-84 apply
+        a_t = np.atleast_2d(f64(self.Target.a(self.tt[0], None)))
+        if const:
+            Ad = a_t - np.atleast_2d(f64(self.Pt.a(self.tt[0])))
+            ad_const = 1
+        else:
+            Ad = np.stack([a_t - np.atleast_2d(f64(self.Pt.a(t))) for t in self.tt])
+            ad_const = 0
+        if np.any(Ad != 0.0):
+            Ad = f64(Ad)
+            check(lib.bb_guide_create_ncd(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt),
+                                          ptr(A), ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, ptr(Ad), ad_const,
+                                          C.byref(h)))
+            self.constdiff = False
+        else:
+            check(lib.bb_guide_create(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt), ptr(A),
+                                      ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, C.byref(h)))
+            self.constdiff = True
         self._guide = h
 
     def __del__(self):
@@ -584,7 +601,8 @@ class GuideTables(_Proposal):
     """A guided proposal from tables the caller already holds (values on the grid `tt`, layouts of
     bb_guide_create): kind NUH (A=H, b=ν), HV (A=H♢, b=V) or LMMU (A=L, b=μ, Mm=M, v)."""
 
-    def __init__(self, kind, tt, P, A, b, Bt, betat, Mm=None, v=None, aux_const=True, m=0, ctx=None):
+    def __init__(self, kind, tt, P, A, b, Bt, betat, Mm=None, v=None, aux_const=True, m=0, Adiff=None,
+                 adiff_const=True, ctx=None):
         self.ctx = ctx or default_context()
         self.kind, self.m = kind, m
         self.tt, self.Target, self.Pt = np.array(tt, dtype=np.float64), P, None
@@ -592,8 +610,14 @@ class GuideTables(_Proposal):
         A, b, Bt, betat = f64(A), f64(b), f64(Bt), f64(betat)
         Mm = None if Mm is None else f64(Mm)
         v = None if v is None else f64(v)
-        check(lib.bb_guide_create(self.ctx.h, kind, len(self.tt), P.d, m, ptr(self.tt), ptr(A), ptr(b), ptr(Mm),
-                                  ptr(v), ptr(Bt), ptr(betat), 1 if aux_const else 0, C.byref(h)))
+        if Adiff is None:
+            check(lib.bb_guide_create(self.ctx.h, kind, len(self.tt), P.d, m, ptr(self.tt), ptr(A), ptr(b), ptr(Mm),
+                                      ptr(v), ptr(Bt), ptr(betat), 1 if aux_const else 0, C.byref(h)))
+        else:
+            Adiff = f64(Adiff)
+            check(lib.bb_guide_create_ncd(self.ctx.h, kind, len(self.tt), P.d, m, ptr(self.tt), ptr(A), ptr(b),
+                                          ptr(Mm), ptr(v), ptr(Bt), ptr(betat), 1 if aux_const else 0, ptr(Adiff),
+                                          1 if adiff_const else 0, C.byref(h)))
         self._guide = h
 
 

@@ -583,9 +583,26 @@ extern "C" int bb_guide_destroy(bb_guide* g) {
   return BB_OK;
 }
 
+static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                             const double* A, const double* b, const double* Mm, const double* v, const double* Bt,
+                             const double* betat, int32_t aux_const, const double* Adiff, int32_t adiff_const,
+                             bb_guide** out);
 extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
                                const double* A, const double* b, const double* Mm, const double* v,
                                const double* Bt, const double* betat, int32_t aux_const, bb_guide** out) {
+  return guide_create_impl(ctx, kind, N, d, m, tt, A, b, Mm, v, Bt, betat, aux_const, nullptr, 1, out);
+}
+extern "C" int bb_guide_create_ncd(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                                   const double* A, const double* b, const double* Mm, const double* v,
+                                   const double* Bt, const double* betat, int32_t aux_const, const double* Adiff,
+                                   int32_t adiff_const, bb_guide** out) {
+  if (!Adiff) return BB_ERR_ARG;
+  return guide_create_impl(ctx, kind, N, d, m, tt, A, b, Mm, v, Bt, betat, aux_const, Adiff, adiff_const, out);
+}
+static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                             const double* A, const double* b, const double* Mm, const double* v, const double* Bt,
+                             const double* betat, int32_t aux_const, const double* Adiff, int32_t adiff_const,
+                             bb_guide** out) {
   if (!out) return BB_ERR_ARG;
   *out = nullptr;
   if (!ctx) return BB_ERR_NODEVICE;
@@ -597,11 +614,13 @@ extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, 
     m = 0;
   }
   BB_CUDA(cudaSetDevice(ctx->device));
-  const bool auxc = aux_const != 0;
-  const int rec = bb_rec_len(kind, d, m, auxc);
+  const int auxm = Adiff ? 2 : (aux_const != 0 ? 1 : 0);
+  const bool auxc = auxm == 1;
+  const int rec = bb_rec_len(kind, d, m, auxm);
   const int NC = (N + BB_TC - 1) / BB_TC;
   const int nc = bb_rec_nc(kind, d, m), na1 = bb_rec_na1(kind, d, m), na2 = bb_rec_na2(kind, d, m);
-  const int off_c = 2, off_a1 = off_c + nc, off_a2 = off_a1 + na1, off_bt = off_a2 + na2, off_be = off_bt + d * d;
+  const int off_c = 2, off_a1 = off_c + nc, off_a2 = off_a1 + na1, off_bt = off_a2 + na2, off_be = off_bt + d * d,
+            off_tr = off_be + d, off_ad = off_tr + 1;
   std::vector<double> tab;
   grid_rows(tt, N, NC, rec, tab);
   for (int j = 1; j < N; j++) {
@@ -628,9 +647,34 @@ extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, 
           R[off_a2 + r * m + c2] = s;
         }
     }
-    if (!auxc) {
-      memcpy(R + off_bt, Bt + (size_t)i * d * d, sizeof(double) * d * d);
-      memcpy(R + off_be, betat + (size_t)i * d, sizeof(double) * d);
+    if (!auxc) { /* tabulated auxiliary drift (a constant one is replicated when the record carries it) */
+      memcpy(R + off_bt, aux_const ? Bt : Bt + (size_t)i * d * d, sizeof(double) * d * d);
+      memcpy(R + off_be, aux_const ? betat : betat + (size_t)i * d, sizeof(double) * d);
+    }
+    if (auxm == 2) {
+      /* H((i,s),x,P°): H[i] (νH), inv(H♢[i]) (GuidedBridge), L[i]'M[i]L[i] (PartialBridge  src/partialbridge.jl:58) */
+      const double* Ad = adiff_const ? Adiff : Adiff + (size_t)i * d * d;
+      double Hm[BB_MAXD * BB_MAXD];
+      if (kind == BB_GUIDE_LMMU) {
+        const double* L = A + (size_t)i * m * d;
+        for (int r = 0; r < d; r++)
+          for (int c2 = 0; c2 < d; c2++) {
+            double s2 = R[off_a2 + r * m] * L[c2];
+            for (int l = 1; l < m; l++) s2 = fma(R[off_a2 + r * m + l], L[l * d + c2], s2);
+            Hm[r * d + c2] = s2;
+          }
+      } else {
+        memcpy(Hm, R + off_a2, sizeof(double) * d * d);
+      }
+      /* tr(A H), products accumulated as the oracle's mat_trace_prod */
+      double tr = 0.0;
+      for (int r = 0; r < d; r++) {
+        double s2 = Ad[r * d] * Hm[r];
+        for (int l = 1; l < d; l++) s2 = fma(Ad[r * d + l], Hm[l * d + r], s2);
+        tr = (r == 0) ? s2 : tr + s2;
+      }
+      R[off_tr] = tr;
+      memcpy(R + off_ad, Ad, sizeof(double) * d * d);
     }
   }
   double segc[BB_SEGC];
@@ -651,7 +695,7 @@ extern "C" int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, 
   }
   bb_guide* g = new (std::nothrow) bb_guide();
   if (!g) return BB_ERR_NOMEM;
-  g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxc ? 1 : 0; g->NC = NC; g->rec = rec;
+  g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxm; g->NC = NC; g->rec = rec;
   g->tt.assign(tt, tt + N);
   memcpy(g->segc, segc, sizeof(segc));
   cudaError_t e1 = cudaMalloc(&g->tab, tab.size() * sizeof(double));
@@ -687,7 +731,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   BB_CUDA(cudaSetDevice(c->device));
   bb_chain_args a;
   memset(&a, 0, sizeof(a));
-  int gk = 0, gm = 0, auxc = 1;
+  int gk = 0, gm = 0, auxc = 1; /* auxc carries the guide's auxiliary mode (1 const, 0 tabulated, 2 non-constdiff) */
   for (int s = 0; s < e->S; s++) {
     if (guides) {
       const bb_guide* g = guides[s];

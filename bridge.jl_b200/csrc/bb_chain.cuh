@@ -92,13 +92,16 @@ __device__ __forceinline__ void bb_load_row(const double* row, double* v) {
 
 /* RNG: 0 = driving path W is read (solve!), 1 = pCN proposal (read W, write W°), 2 = fresh Wiener path
  * (sample! fused with solve!).  GK: 0 = plain Euler-Maruyama, else bb_guide_kind; GM = rows of L (LMMU). */
-template <class M, int GK, int GM, bool AUXC, int RNG>
+template <class M, int GK, int GM, int AUXM, int RNG>
 struct bb_chain {
   static constexpr int D = M::D, DP = M::DP;
-  static constexpr int REC = bb_rec_len(GK, D, GM, AUXC);
+  /* AUXM: 1 = constant auxiliary drift (per-segment constants), 0 = B~, beta~ tabulated per grid point,
+   * 2 = tabulated + the terms of a non-constant-diffusion pair (a != a~): tr((a-a~)H) and a-a~ per grid point */
+  static constexpr bool AUXC = (AUXM == 1), NCD = (AUXM == 2);
+  static constexpr int REC = bb_rec_len(GK, D, GM, AUXM);
   static constexpr int NCC = bb_rec_nc(GK, D, GM), NA1 = bb_rec_na1(GK, D, GM), NA2 = bb_rec_na2(GK, D, GM);
   static constexpr int OFF_C = 2, OFF_A1 = OFF_C + NCC, OFF_A2 = OFF_A1 + NA1, OFF_BT = OFF_A2 + NA2,
-                       OFF_BE = OFF_BT + D * D;
+                       OFF_BE = OFF_BT + D * D, OFF_TR = OFF_BE + D, OFF_AD = OFF_TR + 1;
 
   /* Stores that trickle out 32 bytes at a time while the chain computes leave partially written lines in L2 for
    * microseconds and cost 15-20 % of DRAM bandwidth (tools/membench.cu: 5.8 TB/s in bursts vs 4.8 TB/s dripped),
@@ -142,6 +145,19 @@ struct bb_chain {
 #pragma unroll
         for (int k = 0; k < D; k++) ee[k] = bd[k] - (bt[k] + be[k]);
         som = fma(bb_vdot<D>(ee, r), dt, som);
+        if constexpr (NCD) {
+          /* if !constdiff(P°):  som -= 0.5 tr((a - a~) H) dt;  som += 0.5 r'(a - a~) r dt   src/partialbridge.jl:79-84 */
+          som = fma(-(0.5 * R[OFF_TR]), dt, som);
+          double rA[D];
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            double q = r[0] * R[OFF_AD + j];
+#pragma unroll
+            for (int i = 1; i < D; i++) q = fma(r[i], R[OFF_AD + i * D + j], q);
+            rA[j] = q;
+          }
+          som = fma(0.5 * bb_vdot<D>(rA, r), dt, som);
+        }
       }
       /* _b((i,t),x,P°) = b + a r   (partialbridgenuH.jl:157-159); a = sigma sigma' from der[8..] */
       if constexpr (M::SPARSE) {
@@ -503,41 +519,43 @@ struct bb_chain {
   }
 };
 
-template <class M, int GK, int GM, bool AUXC, int RNG>
+template <class M, int GK, int GM, int AUXM, int RNG>
 __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
-  bb_chain<M, GK, GM, AUXC, RNG>::run(a);
+  bb_chain<M, GK, GM, AUXM, RNG>::run(a);
 }
 
-template <class M, int GK, int GM, bool AUXC, int RNG>
+template <class M, int GK, int GM, int AUXM, int RNG>
 static inline size_t bb_chain_smem(int S) {
   (void)S;
-  return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXC) * 8 + 2 * BB_STAGES * 8 +
+  return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * bb_rec_len(GK, M::D, GM, AUXM) * 8 + 2 * BB_STAGES * 8 +
          (size_t)BB_WSTAGES * BB_THREADS * (BB_TC * M::DP) * 8 +
-         (bb_chain<M, GK, GM, AUXC, RNG>::XBUF ? (size_t)BB_THREADS * 128 : 0);
+         (bb_chain<M, GK, GM, AUXM, RNG>::XBUF ? (size_t)BB_THREADS * 128 : 0);
 }
 
 /* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */
 typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 
-template <class M, int GK, int GM, bool AUXC, int RNG>
+template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
-  const size_t smem = bb_chain_smem<M, GK, GM, AUXC, RNG>(a.S);
+  const size_t smem = bb_chain_smem<M, GK, GM, AUXM, RNG>(a.S);
   static bool attr_done = false; /* per instantiation; the attribute is idempotent */
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(bb_chain_kernel<M, GK, GM, AUXC, RNG>,
+    cudaError_t e = cudaFuncSetAttribute(bb_chain_kernel<M, GK, GM, AUXM, RNG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
-  bb_chain_kernel<M, GK, GM, AUXC, RNG><<<grid, BB_THREADS, smem, st>>>(a);
+  bb_chain_kernel<M, GK, GM, AUXM, RNG><<<grid, BB_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 template <class M, int GK, int GM>
-static bb_chain_launch_fn bb_lookup_guide(int auxc, int rng) {
-  if (rng == 0) return auxc ? &bb_chain_launch<M, GK, GM, true, 0> : &bb_chain_launch<M, GK, GM, false, 0>;
-  if (rng == 1) return auxc ? &bb_chain_launch<M, GK, GM, true, 1> : &bb_chain_launch<M, GK, GM, false, 1>;
+static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
+  if (rng == 0) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 0>
+                                 : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 0> : &bb_chain_launch<M, GK, GM, 2, 0>);
+  if (rng == 1) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 1>
+                                 : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 1> : &bb_chain_launch<M, GK, GM, 2, 1>);
   return nullptr;
 }
 template <class M>

@@ -10,9 +10,9 @@
 #pragma once
 #include "bb_chain.cuh"
 
-template <class M, int GK, int GM, bool AUXC, int MODE>
+template <class M, int GK, int GM, int AUXM, int MODE>
 __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_constant__ bb_chain_args a) {
-  using CH = bb_chain<M, GK, GM, AUXC, 0>;
+  using CH = bb_chain<M, GK, GM, AUXM, 0>;
   constexpr int D = M::D, DP = M::DP, REC = CH::REC;
   const long long P = a.P;
   const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,18 +66,20 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
   if (MODE == 0) a.ll[p] = lltot;
 }
 
-template <class M, int GK, int GM, bool AUXC, int MODE>
+template <class M, int GK, int GM, int AUXM, int MODE>
 static cudaError_t bb_second_launch(const bb_chain_args& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
-  bb_second_kernel<M, GK, GM, AUXC, MODE><<<grid, BB_THREADS, 0, st>>>(a);
+  bb_second_kernel<M, GK, GM, AUXM, MODE><<<grid, BB_THREADS, 0, st>>>(a);
   return cudaGetLastError();
 }
 
 template <class M, int GK, int GM>
-static bb_chain_launch_fn bb_lookup_second_guide(int auxc, int mode) {
-  if (mode == 0) return auxc ? &bb_second_launch<M, GK, GM, true, 0> : &bb_second_launch<M, GK, GM, false, 0>;
+static bb_chain_launch_fn bb_lookup_second_guide(int auxm, int mode) {
+  if (mode == 0) return auxm == 1 ? &bb_second_launch<M, GK, GM, 1, 0>
+                                  : (auxm == 0 ? &bb_second_launch<M, GK, GM, 0, 0> : &bb_second_launch<M, GK, GM, 2, 0>);
   if constexpr (M::D == M::DP) {
-    if (mode == 1) return auxc ? &bb_second_launch<M, GK, GM, true, 1> : &bb_second_launch<M, GK, GM, false, 1>;
+    if (mode == 1) return auxm == 1 ? &bb_second_launch<M, GK, GM, 1, 1>
+                                    : (auxm == 0 ? &bb_second_launch<M, GK, GM, 0, 1> : &bb_second_launch<M, GK, GM, 2, 1>);
   }
   return nullptr;
 }

@@ -228,6 +228,13 @@ typedef enum {
 int bb_guide_create(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
                     const double* A, const double* b, const double* Mm, const double* v,
                     const double* Bt, const double* betat, int32_t aux_const, bb_guide** out);
+/* The same for a pair with a(t,x,Target) != a~(t) (constdiff(P°) == false): Adiff = a - a~ on the grid ([d*d] if
+ * adiff_const != 0, else [N][d*d]) adds the terms  -1/2 tr((a-a~)H) dt + 1/2 r'(a-a~)r dt  of
+ * src/partialbridge.jl:79-84 to the log-likelihood (H = H[i], inv(H♢[i]) or L[i]'M[i]L[i]). */
+int bb_guide_create_ncd(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, int32_t m, const double* tt,
+                        const double* A, const double* b, const double* Mm, const double* v, const double* Bt,
+                        const double* betat, int32_t aux_const, const double* Adiff, int32_t adiff_const,
+                        bb_guide** out);
 int bb_guide_destroy(bb_guide* g);
 
 /* ------------------------------------------------------------------ a7-a10: backward ODEs (constructors)

@@ -849,6 +849,8 @@ typedef struct {
   const double* v;                 /* LMMU: v */
   const double* Bt; const double* betat; /* auxiliary drift on the grid */
   int32_t aux_const;
+  const double* Adiff;             /* a(Target) - a~ ([d*d] or [N][d*d]); NULL: constdiff(P°)  */
+  int32_t adiff_const;
 } bbo_guide;
 
 /* r((i,t),x,P°):  νH src/partialbridgenuH.jl:161; GuidedBridge src/guip.jl:193; PartialBridge src/partialbridge.jl:57 */
@@ -957,6 +959,45 @@ double bbo_llikelihood(const bb_model* P, const bbo_guide* G, const double* X, i
     double e[DM];
     for (int k = 0; k < d; k++) e[k] = b[k] - (bt[k] + be[k]);
     som = MA(vdot(d, e, r), tt[i + 1] - tt[i], som);
+    if (G->Adiff) {
+      /* if !constdiff(Po): H = H((i,s),x,Po); A = a(target) - a(aux);
+       *   som -= 0.5*tr(A*H)*dt;  som += 0.5*(r'*A*r)*dt          src/partialbridge.jl:79-84 */
+      const double* A = G->adiff_const ? G->Adiff : G->Adiff + (size_t)i * d * d;
+      double dt = tt[i + 1] - tt[i];
+      double H[DM2], rA[DM];
+      int m = G->m;
+      if (G->kind == BB_GUIDE_NUH) memcpy(H, G->A + (size_t)i * d * d, sizeof(double) * d * d);
+      else if (G->kind == BB_GUIDE_HV) mat_inv(d, G->A + (size_t)i * d * d, H);
+      else {
+        const double *L = G->A + (size_t)i * m * d, *M = G->Mm + (size_t)i * m * m;
+        double Lt[DM2], LtM[DM2];
+        mat_tr(m, d, L, Lt);
+        mat_mul(d, m, m, Lt, M, LtM);
+        mat_mul(d, m, d, LtM, L, H); /* L'*M*L   src/partialbridge.jl:58 */
+      }
+      double trAH;
+      {
+        double s2 = 0;
+        for (int rr = 0; rr < d; rr++) {
+          double s3 = A[rr * d] * H[rr];
+          for (int l = 1; l < d; l++) s3 = MA(A[rr * d + l], H[l * d + rr], s3);
+          s2 = (rr == 0) ? s3 : s2 + s3;
+        }
+        trAH = s2;
+      }
+      for (int j = 0; j < d; j++) { /* r'*A */
+        double q = r[0] * A[j];
+        for (int l = 1; l < d; l++) q = MA(r[l], A[l * d + j], q);
+        rA[j] = q;
+      }
+#ifdef ORACLE_GPU_ORDER
+      som = fma(-(0.5 * trAH), dt, som);
+      som = fma(0.5 * vdot(d, rA, r), dt, som);
+#else
+      som -= 0.5 * trAH * dt;
+      som += 0.5 * vdot(d, rA, r) * dt;
+#endif
+    }
   }
   return som;
 }

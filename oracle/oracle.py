@@ -39,7 +39,7 @@ class Guide(C.Structure):
     _fields_ = [("kind", C.c_int32), ("N", C.c_int32), ("d", C.c_int32), ("m", C.c_int32),
                 ("tt", C.c_void_p), ("A", C.c_void_p), ("b", C.c_void_p), ("Mm", C.c_void_p),
                 ("v", C.c_void_p), ("Bt", C.c_void_p), ("betat", C.c_void_p),
-                ("aux_const", C.c_int32)]
+                ("aux_const", C.c_int32), ("Adiff", C.c_void_p), ("adiff_const", C.c_int32)]
 
 
 def build(force: bool = False) -> None:
@@ -108,7 +108,8 @@ def staged_aux(tt, Bf, betaf, af) -> AuxHolder:
 
 
 class GuideHolder:
-    def __init__(self, kind, tt, A, b, Mm=None, v=None, Bt=None, betat=None, aux_const=True, m=0):
+    def __init__(self, kind, tt, A, b, Mm=None, v=None, Bt=None, betat=None, aux_const=True, m=0, Adiff=None,
+                 adiff_const=True):
         self.tt = _f64(tt)
         self.A, self.b = _f64(A), _f64(b)
         self.Mm = None if Mm is None else _f64(Mm)
@@ -118,7 +119,11 @@ class GuideHolder:
         d = self.Bt.shape[-1]
         self.kind, self.N, self.d, self.m = kind, N, d, m
         self.c = Guide(kind, N, d, m, _p(self.tt), _p(self.A), _p(self.b), _p(self.Mm),
-                       _p(self.v), _p(self.Bt), _p(self.betat), 1 if aux_const else 0)
+                       _p(self.v), _p(self.Bt), _p(self.betat), 1 if aux_const else 0, None, 1)
+        self.Adiff = None if Adiff is None else _f64(Adiff)
+        if self.Adiff is not None:
+            self.c.Adiff = _p(self.Adiff)
+            self.c.adiff_const = 1 if adiff_const else 0
 
 
 class Oracle:

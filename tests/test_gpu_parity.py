@@ -758,3 +758,53 @@ def test_pcn_step_host_buffers_matches_resident(B, oracle_fma):
         assert np.array_equal(llo, a.ll_prop) and np.array_equal(acc, a.accepted)
         assert np.array_equal(b.download(B.W), a.download(B.W)) and np.array_equal(b.ll, a.ll) and a.acc == b.acc
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("kind", ["nuH", "LMmu"])
+def test_nonconstdiff_pair(B, oracle_ref, oracle_fma, kind):
+    """a != a~: the extra terms -1/2 tr((a-a~)H)dt + 1/2 r'(a-a~)r dt (src/partialbridge.jl:79-84) in the fused
+    log-likelihood, in the second-pass llikelihood and in the pCN accept rule; time-dependent a~(t)."""
+    N, P = 161, 40
+    tt = np.arange(N) / 1000
+    Pm = B.IntegratedDiffusion(0.7)
+    om = O.make_model(O.INTDIFF, 2, 1, [0.7])
+    Bm, be, a_t = np.array([[0.0, 1.0], [0.0, -1.0]]), np.array([0.0, 0.5]), np.array([[0.0, 0.0], [0.0, 0.49]])
+    af = lambda t: np.array([[0.02 + 0.1 * t, 0.0], [0.0, 0.3 + t]])
+    Pt = B.LinearAux(lambda t: Bm, lambda t: be, af)
+    for orc, exact in ((oracle_fma, True), (oracle_ref, False)):
+        aux = O.staged_aux(tt, lambda t: Bm, lambda t: be, af)
+        Ad = np.stack([a_t - af(t) for t in tt])
+        Btg, btg = np.tile(Bm, (N, 1, 1)), np.tile(be, (N, 1))
+        if kind == "nuH":
+            nuT, HpT, C_ = orc.update_nuHC([[1.0, 0.0]], [[0.1]], [2.5], 1e-3)
+            nu, H, _, _, _ = orc.backward_nuH(O.ODE_R3, tt, aux, nuT, HpT, C_)
+            og = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=Btg, betat=btg, aux_const=False, Adiff=Ad, adiff_const=False)
+            g = B.GuideTables(B.api.K.GUIDE_NUH, tt, Pm, H, nu, Btg, btg, aux_const=False, Adiff=Ad, adiff_const=False)
+        else:
+            Lt, Mt, mut = orc.backward_LMmu(tt, aux, [[1.0, 0.0]], [[0.1]])
+            og = O.GuideHolder(O.GUIDE_LMMU, tt, Lt, mut, Mm=Mt, v=[2.5], Bt=Btg, betat=btg, aux_const=False, m=1,
+                               Adiff=Ad, adiff_const=False)
+            g = B.GuideTables(B.api.K.GUIDE_LMMU, tt, Pm, Lt, mut, Btg, btg, Mm=Mt, v=[2.5], aux_const=False, m=1,
+                              Adiff=Ad, adiff_const=False)
+        ens = B.PathEnsemble(P, 1, N, 2, 1)
+        ens.set_grid(0, tt); ens.set_start([2.0, 1.0]); ens.sample_(13, 0); ens.guided_euler_ll_(Pm, [g])
+        W = ens.download(B.W); X = ens.download(B.X); ll = ens.ll.copy()
+        og0 = O.GuideHolder(og.kind, tt, og.A, og.b, Mm=og.Mm, v=og.v, Bt=Btg, betat=btg, aux_const=False, m=og.m)
+        for p in (0, 17, 39):
+            Xo, _ = orc.guided_euler(om, og, [2.0, 1.0], W[p, 0])
+            llo = orc.llikelihood(om, og, Xo)
+            assert abs(llo - orc.llikelihood(om, og0, Xo)) > 1e-4          # the extra terms are not negligible here
+            assert close_x(X[p, 0], Xo) and close_ll(ll[p], llo)           # sin in the drift: tolerance
+        ens.llikelihood_(Pm, [g])
+        assert np.array_equal(ens.ll, ll)
+        ens.pcn_step_(Pm, [g], 0.9, 13, 1)
+        assert np.array_equal(ens.accepted.astype(bool), ens.logu <= ens.ll_prop - ll)
+        for p in (0, 39):
+            llo, lu, Wo, Xo, _ = orc.pcn_propose(om, [og], [2.0, 1.0], W[p], 0.9, 13, 1, p)
+            assert close_ll(ens.ll_prop[p], llo) and lu == ens.logu[p]
+        ens.close()
+    # the mirrored constructors detect the pair automatically
+    Po = B.PartialBridgeνH(tt, Pm, Pt, [[1.0, 0.0]], [2.5], 1e-3, [[0.1]])
+    assert Po.constdiff is False
+    Pc = B.PartialBridgeνH(tt, Pm, B.LinearAux(Bm, be, [[0.0, 0.0], [0.0, 0.7 * 0.7]]), [[1.0, 0.0]], [2.5], 1e-3, [[0.1]])
+    assert Pc.constdiff is True

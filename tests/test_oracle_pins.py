@@ -431,3 +431,27 @@ def test_ref_and_fma_builds_agree_to_rounding(oracle_ref, oracle_fma):
     assert np.max(np.abs(X1 - X2)) < 1e-9 * (1 + np.max(np.abs(X1)))
     assert abs(l1 - l2) < 1e-6 * abs(l1) + 1e-9
     assert abs(X1[-1, 0] - v) < 1e-3
+
+
+def test_nonconstdiff_llikelihood_terms(oracle_ref):
+    """src/partialbridge.jl:79-84: for a pair with a != a~ the log-likelihood gains
+    -0.5 tr((a-a~)H) dt + 0.5 r'(a-a~)r dt with H = L'ML; restated here in numpy on the PartialBridge tables."""
+    tt = TT_PB[:151]
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    at = np.array([[0.05, 0.0], [0.0, 0.6 * GAMMA ** 2]])      # auxiliary diffusion differs from the target's
+    aux = O.const_aux(AUX_PB["B"], AUX_PB["beta"], at)
+    Lt, Mt, mut = oracle_ref.backward_LMmu(tt, aux, L_PB, SIG_PB)
+    Ad = AUX_PB["a"] - at
+    G0 = O.GuideHolder(O.GUIDE_LMMU, tt, Lt, mut, Mm=Mt, v=V_PB, Bt=AUX_PB["B"], betat=AUX_PB["beta"], m=1)
+    G1 = O.GuideHolder(O.GUIDE_LMMU, tt, Lt, mut, Mm=Mt, v=V_PB, Bt=AUX_PB["B"], betat=AUX_PB["beta"], m=1, Adiff=Ad)
+    W = oracle_ref.wiener_sample(tt, 1, 2, 0, 0)
+    X, _ = oracle_ref.guided_euler(P, G1, X0_PB, W)
+    ll0, ll1 = oracle_ref.llikelihood(P, G0, X), oracle_ref.llikelihood(P, G1, X)
+    extra = 0.0
+    for i in range(len(tt) - 1):
+        dt = tt[i + 1] - tt[i]
+        H = Lt[i].T @ Mt[i] @ Lt[i]
+        r = Lt[i].T @ Mt[i] @ (V_PB - mut[i] - Lt[i] @ X[i])
+        extra += -0.5 * np.trace(Ad @ H) * dt + 0.5 * (r @ Ad @ r) * dt
+    assert abs(extra) > 1e-3
+    assert abs((ll1 - ll0) - extra) < 1e-10 * max(1.0, abs(extra))
