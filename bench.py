@@ -294,36 +294,56 @@ def main():
     # ---- end to end through host buffers: the reference loop keeps W, X in host memory
     e2e = None
     if not args.no_e2e:
-        hostW = torch.empty((P, S, n, 1), dtype=torch.float64, pin_memory=True).numpy()
-        hostWo = torch.empty((P, S, n, 1), dtype=torch.float64, pin_memory=True).numpy()
-        hostXo = torch.empty((P, S, n, 2), dtype=torch.float64, pin_memory=True).numpy()
-        ens.download(B.W, out=hostW)
-
-        hostLL = torch.empty(P, dtype=torch.float64, pin_memory=True).numpy()
-        hostAcc = torch.empty(P, dtype=torch.uint8, pin_memory=True).numpy()
-
-        def e2e_step(itn):
-            # one call on host buffers: W up; W°, X°, ll°, accept flags down (pipelined over chain slabs)
-            ens.pcn_step_host_(Pm, guides, rho, seed, itn, hostW, hostWo, hostXo, hostLL, hostAcc)
-            return ens.acc
-
-        e2e_step(it); it += 1
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.e2e_steps):
-            e2e_step(it); it += 1
-        e1.record(stream)
-        barrier()
-        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=acc_t.device)
+        # host-buffer leg: every rank pins 4 x (W-sized) arrays; all ranks agree first whether that succeeded, so that a
+        # rank that cannot allocate never leaves the others waiting in a collective
+        bufs, ok, why = None, 1, ""
+        try:
+            import psutil
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            need = P * S * n * 8 * 4
+            if psutil.virtual_memory().available / local_world < 1.2 * need:
+                raise MemoryError(f"host RAM: need {need / 2**30:.0f} GiB per rank")
+            bufs = [torch.empty((P, S, n, k), dtype=torch.float64, pin_memory=True).numpy() for k in (1, 1, 2)]
+            bufs.append(torch.empty(P, dtype=torch.float64, pin_memory=True).numpy())
+            bufs.append(torch.empty(P, dtype=torch.uint8, pin_memory=True).numpy())
+        except Exception as ex:  # noqa: BLE001
+            ok, why, bufs = 0, f"{type(ex).__name__}: {ex}", None
+        okt = torch.tensor([ok], dtype=torch.int64, device=acc_t.device)
         if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * steps_per_iter_rank * args.e2e_steps / (float(ems.item()) * 1e-3),
-               "unit": "path-steps/s", "h2d_bytes_per_step": int(hostW.nbytes),
-               "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
-               "steps": args.e2e_steps,
-               "what": "bb_pcn_step_host on pinned host buffers: per step W up; W°, X°, ll°, accept flags down; "
-                       "H2D | kernel | D2H pipelined over chain slabs"}
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        e2e = {}
+        if int(okt.item()) == 1:
+            hostW, hostWo, hostXo, hostLL, hostAcc = bufs
+            ens.download(B.W, out=hostW)
+
+            def e2e_step(itn):
+                # one call on host buffers: W up; W°, X°, ll°, accept flags down (pipelined over chain slabs)
+                ens.pcn_step_host_(Pm, guides, rho, seed, itn, hostW, hostWo, hostXo, hostLL, hostAcc)
+                return ens.acc
+
+            e2e_step(it); it += 1
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.e2e_steps):
+                e2e_step(it); it += 1
+            e1.record(stream)
+            barrier()
+            ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=acc_t.device)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * steps_per_iter_rank * args.e2e_steps / (float(ems.item()) * 1e-3),
+                   "unit": "path-steps/s", "h2d_bytes_per_step": int(hostW.nbytes),
+                   "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
+                   "steps": args.e2e_steps,
+                   "what": "bb_pcn_step_host on pinned host buffers: per step W up; W°, X°, ll°, accept flags down; "
+                           "H2D | kernel | D2H pipelined over chain slabs"}
+        else:
+            e2e = {"value": None, "unit": "path-steps/s", "h2d_bytes_per_step": P * S * n * 8,
+                   "d2h_bytes_per_step": P * S * n * 24 + P * 9 + 8,
+                   "unavailable": "host-buffer leg skipped on all ranks: " + (why or "another rank could not pin memory")}
+        bufs = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # device-resident ensemble API: per step only the guide tables go up and ll°/flags/acc come back
         barrier()
         e0.record(stream)

@@ -67,8 +67,6 @@ def _load():
         "bb_ctx_synchronize": (C.c_int, [vp]),
         "bb_ctx_set_stream": (C.c_int, [vp, vp]),
         "bb_ctx_get_stream": (vp, [vp]),
-        "bb_ctx_set_backend": (C.c_int, [vp, C.c_int]),
-        "bb_ctx_get_backend": (C.c_int, [vp]),
         "bb_ctx_launch_count": (i64, [vp]),
         "bb_ctx_set_timing": (C.c_int, [vp, C.c_int]),
         "bb_ctx_last_kernel_ms": (dbl, [vp]),

@@ -99,12 +99,6 @@ extern "C" int bb_ctx_set_stream(bb_ctx* c, void* s) {
   return BB_OK;
 }
 extern "C" void* bb_ctx_get_stream(bb_ctx* c) { return c ? (void*)c->stream : nullptr; }
-extern "C" int bb_ctx_set_backend(bb_ctx* c, int b) {
-  if (!c || b < BB_BACKEND_AUTO || b > BB_BACKEND_TMA) return BB_ERR_ARG;
-  c->backend = b;
-  return BB_OK;
-}
-extern "C" int bb_ctx_get_backend(bb_ctx* c) { return c ? c->backend : BB_ERR_ARG; }
 extern "C" int64_t bb_ctx_launch_count(bb_ctx* c) { return c ? c->launches : -1; }
 extern "C" int bb_ctx_set_timing(bb_ctx* c, int on) {
   if (!c) return BB_ERR_ARG;

@@ -84,12 +84,6 @@ struct bb_rowout {
   }
 };
 
-template <int K>
-__device__ __forceinline__ void bb_load_row(const double* row, double* v) {
-#pragma unroll
-  for (int q = 0; q < 2 * K; q++) bb_ld4(row + 4 * q, v + 4 * q);
-}
-
 /* RNG: 0 = driving path W is read (solve!), 1 = pCN proposal (read W, write W°), 2 = fresh Wiener path
  * (sample! fused with solve!).  GK: 0 = plain Euler-Maruyama, else bb_guide_kind; GM = rows of L (LMMU). */
 template <class M, int GK, int GM, int AUXM, int RNG>

@@ -15,7 +15,6 @@ struct bb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  int backend = BB_BACKEND_AUTO;
   int64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -136,10 +136,6 @@ int bb_ctx_synchronize(bb_ctx* ctx);
 /* adopt an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
 int bb_ctx_set_stream(bb_ctx* ctx, void* cuda_stream);
 void* bb_ctx_get_stream(bb_ctx* ctx);
-/* data-movement backend of the chain kernel */
-enum { BB_BACKEND_AUTO = 0, BB_BACKEND_LSU = 1, BB_BACKEND_TMA = 2 };
-int bb_ctx_set_backend(bb_ctx* ctx, int backend);
-int bb_ctx_get_backend(bb_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t bb_ctx_launch_count(bb_ctx* ctx);
 /* elapsed device time (ms) of the most recent compute call, measured with CUDA
