@@ -729,7 +729,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   for (int s = 0; s < e->S; s++) {
     if (guides) {
       const bb_guide* g = guides[s];
-      if (!g) return BB_ERR_ARG;
+      if (!g || g->ctx->device != c->device) return BB_ERR_ARG; /* tables live on the guide's device */
       if (g->N != e->N) return BB_ERR_LENGTH; /* "Y and W differ in length." src/euler.jl:251 */
       if (g->d != e->d) return BB_ERR_MODEL;
       if (s == 0) { gk = g->kind; gm = g->m; auxc = g->auxc; }

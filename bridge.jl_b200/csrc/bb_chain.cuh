@@ -532,12 +532,14 @@ typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   const size_t smem = bb_chain_smem<M, GK, GM, AUXM, RNG>(a.S);
-  static bool attr_done = false; /* per instantiation; the attribute is idempotent */
-  if (!attr_done) {
+  static unsigned long long attr_done = 0; /* per instantiation: bit i = set on device i (the attribute is per device) */
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(bb_chain_kernel<M, GK, GM, AUXM, RNG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_chain_kernel<M, GK, GM, AUXM, RNG><<<grid, BB_THREADS, smem, st>>>(a);

@@ -808,3 +808,25 @@ def test_nonconstdiff_pair(B, oracle_ref, oracle_fma, kind):
     assert Po.constdiff is False
     Pc = B.PartialBridgeνH(tt, Pm, B.LinearAux(Bm, be, [[0.0, 0.0], [0.0, 0.7 * 0.7]]), [[1.0, 0.0]], [2.5], 1e-3, [[0.1]])
     assert Pc.constdiff is True
+
+
+def test_config2_full_size(B):
+    """BASELINE config 2 at FULL size: 1e6 independent Float64 paths, n = 1001, Wiener + EulerMaruyama on one GPU
+    (8 GB W + 8 GB X): fused sample! + solve! with the Wiener process as target gives X = u + W (checked on a strided
+    subset of chains and through the end points of all chains), and a second plain solve! of the stored W reproduces X."""
+    P, N = 1000000, 1001
+    ens = B.PathEnsemble(P, 1, N, 1, 1, double_buffer=False)
+    ens.set_grid(0, np.linspace(0, 1, N))
+    ens.set_start([0.25])
+    ens.sample_euler_(B.Wiener(1), seed=2, stream=0)
+    xend = ens.xend[:, 0]
+    for p0 in (0, 333333, P - 64):
+        W = ens.download(B.W, p0=p0, np_=64)[:, 0, :, 0]
+        X = ens.download(B.X, p0=p0, np_=64)[:, 0, :, 0]
+        assert np.allclose(X, 0.25 + W, rtol=0, atol=1e-13)
+        assert np.array_equal(X[:, -1], xend[p0:p0 + 64])
+    assert abs(np.mean(xend) - 0.25) < 5e-3 and abs(np.var(xend) - 1.0) < 5e-3   # W_1 ~ N(0, 1) over 1e6 paths
+    Xa = ens.download(B.X, p0=500000, np_=32)
+    ens.euler_(B.Wiener(1))
+    assert np.array_equal(ens.download(B.X, p0=500000, np_=32), Xa)
+    ens.close()
