@@ -104,6 +104,9 @@ def _load():
         "bb_innovations": (C.c_int, [vp, C.POINTER(Model), pp]),
         "bb_pcn_step": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32]),
         "bb_ens_refresh_x": (C.c_int, [vp, C.POINTER(Model), pp]),
+        "bb_ens_mc_reset": (C.c_int, [vp]),
+        "bb_ens_mc_update": (C.c_int, [vp]),
+        "bb_ens_mc_stats": (C.c_int, [vp, vp, vp, C.POINTER(i64)]),
         "bb_pcn_step_host": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -524,6 +524,28 @@ class PathEnsemble:
                                    K.RUN_STORE_X if Xo is not None else 0, ptr(W), ptr(Wo), ptr(Xo), ptr(llo),
                                    ptr(accepted)))
 
+    # ---- pooled online statistics: mcstart / mcnext! / mcstats of src/mclog.jl for the whole ensemble
+    def mc_reset_(self):
+        check(lib.bb_ens_mc_reset(self.h))
+
+    def mc_update_(self):
+        """mcnext!: add the CURRENT path of every chain to the running first and second moments."""
+        self.refresh_x_()
+        check(lib.bb_ens_mc_update(self.h))
+
+    def mc_stats(self):
+        """mcstats: (mean [S,N,d], cov [S,N,d,d], n) over all chains and all mc_update_ calls."""
+        mean = np.empty((self.S, self.N, self.d)); cov = np.empty((self.S, self.N, self.d, self.d)); n = C.c_int64(0)
+        check(lib.bb_ens_mc_stats(self.h, ptr(mean), ptr(cov), C.byref(n)))
+        return mean, cov, n.value
+
+    def mc_band(self):
+        """mcband: marginal 95 % band mean -/+ Q std with Q = sqrt(2) erfinv(0.95)  (src/mclog.jl:75-85)."""
+        mean, cov, _ = self.mc_stats()
+        std = np.sqrt(np.einsum("snii->sni", cov))
+        Q = 1.959963984540054
+        return mean - Q * std, mean + Q * std
+
     def refresh_x_(self):
         """Make X the CURRENT path of every chain again (X holds the last proposal; chains that rejected it
         get their path recomputed from W by the same guided Euler kernel).  No-op if nothing is stale."""

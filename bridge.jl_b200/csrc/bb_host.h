@@ -55,6 +55,9 @@ struct bb_ens {
   std::vector<double*> gridtab; /* per segment: device [NC*8][2] (dt, sqrt dt) */
   std::vector<std::vector<double>> tt;
   int64_t bytes = 0;
+  /* pooled online statistics (bb_stats.cu) */
+  double *mc_sum = nullptr, *mc_sq = nullptr;
+  int64_t mc_n = 0;
 };
 
 /* thread-local error text for bb_last_cuda_error */

@@ -1,0 +1,125 @@
+/*
+ * bb_stats.cu -- online statistics of the chains' current paths, pooled over chains and over calls: the ensemble
+ * analogue of mcstart / mcnext! / mcstats (src/mclog.jl:22-56, 88-93).  The reference keeps, for ONE chain,
+ * m = running mean path and m2 = sum of outer products of deviations over the iterations; a sampler that runs P
+ * chains at once wants the same two moments over all chains and all recorded iterations without downloading
+ * P paths per iteration (project_partialbridge/partialbridge_fitzhugh.jl:169-189 stores every 1000th path).
+ *
+ * Accumulators: sum[S][N][d], sq[S][N][d][d] (double), n.  One CTA reduces the 16 grid points of one chunk over 256
+ * chains in shared memory and issues d + d*d atomic adds per grid point; X is read once (8 d bytes per path-step).
+ */
+#include <string.h>
+
+#include <vector>
+
+#include "bb_host.h"
+
+template <int D>
+__global__ void __launch_bounds__(256) bb_mc_update_kernel(const double* __restrict__ X, double* __restrict__ sum,
+                                                           double* __restrict__ sq, long long P, int N, int NC) {
+  constexpr int ROW = BB_TC * D, SUB = 64; /* chains per shared-memory tile; a CTA covers 256 chains in 4 tiles */
+  constexpr int NM = BB_TC * (D + D * D);  /* moments per chunk: thread t < NM owns one of them */
+  __shared__ double tile[SUB][ROW + 1];
+  const int chunk = blockIdx.y; /* s * NC + c */
+  const int s = chunk / NC, c = chunk - s * NC;
+  int slot = 0, a = 0, b = -1;
+  if ((int)threadIdx.x < BB_TC * D) { slot = threadIdx.x / D; a = threadIdx.x % D; }
+  else if ((int)threadIdx.x < NM) {
+    const int u = threadIdx.x - BB_TC * D;
+    slot = u / (D * D); a = (u % (D * D)) / D; b = u % D;
+  }
+  double acc = 0.0;
+  for (int sub = 0; sub < 256 / SUB; sub++) {
+    /* 4 threads per chain load a quarter row each */
+    const int lc = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const long long p = (long long)blockIdx.x * 256 + sub * SUB + lc;
+    constexpr int Q4 = ROW / 4; /* 256-bit pieces per row */
+    for (int q = part; q < Q4; q += 4) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      if (p < P) bb_ld4(X + ((long long)chunk * P + p) * ROW + 4 * q, v);
+#pragma unroll
+      for (int i = 0; i < 4; i++) tile[lc][4 * q + i] = v[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NM) {
+      if (b < 0) {
+        for (int q = 0; q < SUB; q++) acc += tile[q][slot * D + a];
+      } else {
+        for (int q = 0; q < SUB; q++) acc = fma(tile[q][slot * D + a], tile[q][slot * D + b], acc);
+      }
+    }
+    __syncthreads();
+  }
+  const int j = c * BB_TC + slot;
+  if ((int)threadIdx.x < NM && j < N) {
+    if (b < 0) atomicAdd(&sum[((long long)s * N + j) * D + a], acc);
+    else atomicAdd(&sq[(((long long)s * N + j) * D + a) * D + b], acc);
+  }
+}
+
+extern "C" int bb_ens_mc_reset(bb_ens* e) {
+  if (!e) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const size_t n1 = (size_t)e->S * e->N * e->d, n2 = n1 * e->d;
+  if (!e->mc_sum) {
+    BB_CUDA(cudaMalloc(&e->mc_sum, (n1 + n2) * sizeof(double)));
+    e->mc_sq = e->mc_sum + n1;
+    e->bytes += (int64_t)((n1 + n2) * sizeof(double));
+  }
+  BB_CUDA(cudaMemsetAsync(e->mc_sum, 0, (n1 + n2) * sizeof(double), e->ctx->stream));
+  e->mc_n = 0;
+  return BB_OK;
+}
+
+extern "C" int bb_ens_mc_update(bb_ens* e) {
+  if (!e || !e->X) return BB_ERR_ARG;
+  if (e->x_maybe_stale) return BB_ERR_STALE; /* statistics are over CURRENT paths: bb_ens_refresh_x first */
+  if (!e->mc_sum) {
+    int rc = bb_ens_mc_reset(e);
+    if (rc != BB_OK) return rc;
+  }
+  bb_ctx* c = e->ctx;
+  BB_CUDA(cudaSetDevice(c->device));
+  const dim3 grid((unsigned)((e->P + 255) / 256), (unsigned)(e->S * e->NC));
+  bb_time_begin(c);
+  switch (e->d) {
+    case 1: bb_mc_update_kernel<1><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
+    case 2: bb_mc_update_kernel<2><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
+    case 3: bb_mc_update_kernel<3><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
+    default: return BB_ERR_UNSUPPORTED;
+  }
+  bb_time_end(c);
+  BB_CUDA(cudaGetLastError());
+  c->launches++;
+  e->mc_n += e->P;
+  return BB_OK;
+}
+
+/* mcstats(mc) = (m, m2/(k - 1))  src/mclog.jl:88-93;  mean [S][N][d], cov [S][N][d][d] (either may be NULL) */
+extern "C" int bb_ens_mc_stats(bb_ens* e, double* mean, double* cov, int64_t* n) {
+  if (!e) return BB_ERR_ARG;
+  if (n) *n = e->mc_n;
+  if (!e->mc_sum || e->mc_n == 0) return (mean || cov) ? BB_ERR_ARG : BB_OK;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int d = e->d;
+  const size_t n1 = (size_t)e->S * e->N * d, n2 = n1 * d;
+  std::vector<double> h(n1 + n2);
+  BB_CUDA(cudaMemcpyAsync(h.data(), e->mc_sum, (n1 + n2) * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  const double k = (double)e->mc_n;
+  for (size_t g = 0; g < (size_t)e->S * e->N; g++) {
+    double m[BB_MAXD];
+    for (int a = 0; a < d; a++) {
+      m[a] = h[g * d + a] / k;
+      if (mean) mean[g * d + a] = m[a];
+    }
+    if (cov)
+      for (int a = 0; a < d; a++)
+        for (int b = 0; b < d; b++) {
+          double v = (h[n1 + (g * d + a) * d + b] - k * m[a] * m[b]) / (k - 1.0);
+          if (a == b && v < 0.0) v = 0.0; /* rounding of sum(x^2) - n mean^2 at (numerically) constant grid points */
+          cov[(g * d + a) * d + b] = v;
+        }
+  }
+  return BB_OK;
+}

@@ -307,6 +307,15 @@ int bb_pcn_step_host(bb_ens* ens, const bb_model* model, bb_guide* const* guides
  * downloads need no refresh.  No-op if nothing is stale. */
 int bb_ens_refresh_x(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
 
+/* ------------------------------------------------------------------ online statistics
+ * mcstart / mcnext! / mcstats (src/mclog.jl:22-56, 88-93) for an ensemble: first and second moments of the chains'
+ * CURRENT paths per grid point, pooled over the P chains and over calls (n = calls x P samples).  bb_ens_mc_update
+ * returns BB_ERR_STALE while X holds rejected proposals (bb_ens_refresh_x first).
+ * bb_ens_mc_stats: mean [S][N][d], cov = m2/(n-1) [S][N][d][d]; either pointer may be NULL. */
+int bb_ens_mc_reset(bb_ens* ens);
+int bb_ens_mc_update(bb_ens* ens);
+int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -830,3 +830,34 @@ def test_config2_full_size(B):
     ens.euler_(B.Wiener(1))
     assert np.array_equal(ens.download(B.X, p0=500000, np_=32), Xa)
     ens.close()
+
+
+def test_pooled_online_statistics(B, oracle_fma):
+    """mcstart / mcnext! / mcstats (src/mclog.jl:22-56, 88-93) pooled over chains and iterations: device moments of the
+    CURRENT paths equal numpy's over the downloaded paths."""
+    N, P, S = 37, 300, 2
+    grids = [warped(0.0, 0.5, N), warped(0.5, 1.0, N)]
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, grids, [-1.0, -0.5])
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    ens = B.PathEnsemble(P, S, N, 2, 1)
+    for s in range(S):
+        ens.set_grid(s, grids[s])
+    ens.set_start([-0.5, -0.6]); ens.sample_(31, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+    ens.mc_reset_()
+    samples = []
+    for it in range(3):
+        ens.pcn_step_(Pm, guides, 0.5, 31, it)
+        ens.mc_update_()                       # refreshes the chains that rejected, then accumulates
+        samples.append(ens.download(B.X))
+    Xs = np.concatenate(samples, axis=0)       # [3P, S, N, d]
+    mean, cov, n = ens.mc_stats()
+    assert n == 3 * P
+    assert np.allclose(mean, Xs.mean(axis=0), rtol=1e-12, atol=1e-13)
+    want = np.einsum("ksni,ksnj->snij", Xs - Xs.mean(axis=0), Xs - Xs.mean(axis=0)) / (n - 1)
+    assert np.allclose(cov, want, rtol=1e-9, atol=1e-12)
+    lo, hi = ens.mc_band()
+    assert np.all(lo <= mean) and np.all(mean <= hi)
+    assert np.allclose(mean[0, 0], [-0.5, -0.6]) and np.allclose(cov[0, 0], 0.0, atol=1e-12)   # fixed start point
+    ens.close()

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small pCN / guided / Euler run for compute-sanitizer (memcheck, racecheck, synccheck) under gpurun."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bridge_jl_b200 as B
+import bridge_jl_b200.configs as cfg
+
+n, P = 49, 700   # ragged: N not a multiple of 16, P not a multiple of 256
+Pm, guides, x0, rho = cfg.fhn_config4(n, obs_t=(0.5, 1.0, 1.5), obs_v=(-1.0, -0.5, 0.5))
+ens = B.PathEnsemble(P, len(guides), n, 2, 1)
+for s, g in enumerate(guides):
+    ens.set_grid(s, g.tt)
+ens.set_start(x0)
+ens.sample_(1, 0)
+ens.guided_euler_ll_(Pm, guides)
+for it in range(3):
+    ens.pcn_step_(Pm, guides, rho, 1, it)
+ens.pcn_step_(Pm, guides, rho, 1, 3, store_x=False)
+X = ens.download(B.X)
+ens.llikelihood_(Pm, guides)
+ens.euler_(Pm)
+L3 = B.Lorenz([10.0, 28.0, 8 / 3], 3.0)
+e3 = B.PathEnsemble(300, 2, 33, 3, 3, double_buffer=False)
+for s in range(2):
+    e3.set_grid(s, np.linspace(s, s + 1, 33))
+e3.set_start([1.0, 0.0, 0.0]); e3.sample_euler_(L3, 3, 0); e3.innovations_(L3)
+print("ok", float(np.sum(X)) != 0.0, ens.acc)
