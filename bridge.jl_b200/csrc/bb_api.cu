@@ -742,8 +742,9 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
       a.tab[s] = e->gridtab[s];
     }
   }
+  const int krng = (rs.rng == 1 && !rs.store_x) ? 3 : rs.rng; /* pCN without X° is its own instantiation */
   bb_chain_launch_fn fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10)
-                                       : lookup_kernel(model, gk, gm, auxc, rs.rng);
+                                       : lookup_kernel(model, gk, gm, auxc, krng);
   if (!fn) return BB_ERR_UNSUPPORTED;
   if (rs.rng >= 10 && !e->X) return BB_ERR_ARG;
   if (rs.rng == 11 && !model_sigma_invertible(model)) return BB_ERR_SINGULAR;

@@ -85,13 +85,20 @@ struct bb_rowout {
 };
 
 /* RNG: 0 = driving path W is read (solve!), 1 = pCN proposal (read W, write W°), 2 = fresh Wiener path
- * (sample! fused with solve!).  GK: 0 = plain Euler-Maruyama, else bb_guide_kind; GM = rows of L (LMMU). */
+ * (sample! fused with solve!), 3 = pCN proposal without storing X°.  GK: 0 = plain Euler-Maruyama, else
+ * bb_guide_kind; GM = rows of L (LMMU). */
 template <class M, int GK, int GM, int AUXM, int RNG>
 struct bb_chain {
   static constexpr int D = M::D, DP = M::DP;
   /* AUXM: 1 = constant auxiliary drift (per-segment constants), 0 = B~, beta~ tabulated per grid point,
    * 2 = tabulated + the terms of a non-constant-diffusion pair (a != a~): tr((a-a~)H) and a-a~ per grid point */
   static constexpr bool AUXC = (AUXM == 1), NCD = (AUXM == 2);
+  /* RNG: 0 read W, 2 fresh Wiener path, 1 / 3 pCN proposal with X° stored / not stored (compile-time, so that the
+   * compute-bound no-X launch carries none of the write-back staging code) */
+  static constexpr bool PCN = (RNG == 1 || RNG == 3);
+  static __device__ __forceinline__ bool sx(const bb_chain_args& a) {
+    return RNG == 1 ? true : (RNG == 3 ? false : a.store_x != 0);
+  }
   static constexpr int REC = bb_rec_len(GK, D, GM, AUXM);
   static constexpr int NCC = bb_rec_nc(GK, D, GM), NA1 = bb_rec_na1(GK, D, GM), NA2 = bb_rec_na2(GK, D, GM);
   static constexpr int OFF_C = 2, OFF_A1 = OFF_C + NCC, OFF_A2 = OFF_A1 + NA1, OFF_BT = OFF_A2 + NA2,
@@ -223,7 +230,7 @@ struct bb_chain {
                 const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP; /* slot / component of element i */
                 const bool first = GENERIC && (c * BB_TC + sl == 0);
                 const double rootdt = rec[sl * REC + 1];
-                if constexpr (RNG == 1) {
+                if constexpr (PCN) {
                   /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
                   if (!first) st.w2[kk] = fma(rootdt, (double)z[i], st.w2[kk]);
                   wq[i] = fma(a.rho2, st.w2[kk], a.rho * wq[i]);
@@ -235,7 +242,7 @@ struct bb_chain {
               }
               /* memory-bound launches (X° stored too) complete the W° row in the staged row and write it as a whole
                * line at the end of the chunk; compute-bound ones store the piece directly */
-              if (BB_WFLUSH && a.store_x) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+              if (BB_WFLUSH && sx(a)) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
               else if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
             }
           }
@@ -253,7 +260,7 @@ struct bb_chain {
           }
         }
         if constexpr (XBUF) {
-          if (a.store_x) {
+          if (sx(a)) {
             const int ls = (4 * h + s4) % XWIN;
             if constexpr (D == 2)
               *reinterpret_cast<double2*>(xbuf + 2 * ((ls ^ threadIdx.x) & 7)) = make_double2(st.y[0], st.y[1]);
@@ -279,7 +286,7 @@ struct bb_chain {
     }
     if constexpr (RNG != 0 && BB_WFLUSH) {
       /* the chain's row of W° is complete in shared memory: write its 128 d' bytes back to back */
-      if (wact && a.store_x) {
+      if (wact && sx(a)) {
 #pragma unroll
         for (int q = 0; q < NPIECE; q++) {
           double v[4];
@@ -326,9 +333,9 @@ struct bb_chain {
     const bool act = p < a.p_end && (!a.only || a.only[pc] != 0);
     const int par = a.par[pc];
     const int rbuf = par;                        /* where the chain's current W (and X) live */
-    const int wbuf = (RNG == 1) ? 1 - par : par; /* where this launch writes */
+    const int wbuf = PCN ? 1 - par : par; /* where this launch writes */
     const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
-    const bool xact = act && a.store_x;
+    const bool xact = act && sx(a);
 
     state st;
 #pragma unroll
@@ -339,7 +346,7 @@ struct bb_chain {
     /* a chain's two buffers are adjacent: W[1] = W[0] + 8 d', slot of chain p = p * nbuf * 8 d' */
     const double* wr = a.W[rbuf] + pc * (a.nbuf * BB_TC * DP);
     double* ww = a.W[wbuf] + pc * (a.nbuf * BB_TC * DP);
-    double* xw = a.store_x ? a.X + pc * (BB_TC * D) : nullptr;
+    double* xw = sx(a) ? a.X + pc * (BB_TC * D) : nullptr;
     const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
 
     /* producer state (thread 0 only): next stage to request */
@@ -478,7 +485,7 @@ struct bb_chain {
     }
 
     /* ---- per-chain epilogue */
-    if constexpr (RNG == 1) {
+    if constexpr (PCN) {
       /* accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
       const double logu = bb_accept_logu(a.keys, a.stream, chain);
       const double llc = a.ll[pc];
@@ -488,7 +495,7 @@ struct bb_chain {
         a.logu[p] = logu;
         a.accepted[p] = ok ? 1 : 0;
         /* X now holds this proposal's path (if stored): it is the chain's current path iff accepted */
-        a.xstale[p] = a.store_x ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
+        a.xstale[p] = sx(a) ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
 #pragma unroll
         for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = st.y[k];
         if (ok) {
@@ -503,7 +510,7 @@ struct bb_chain {
     } else {
       if (act) {
         if (a.do_ll) a.ll[p] = lltot;
-        if (a.store_x) a.xstale[p] = 0;
+        if (sx(a)) a.xstale[p] = 0;
         if (a.write_end) {
 #pragma unroll
           for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
@@ -552,6 +559,8 @@ static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
                                  : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 0> : &bb_chain_launch<M, GK, GM, 2, 0>);
   if (rng == 1) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 1>
                                  : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 1> : &bb_chain_launch<M, GK, GM, 2, 1>);
+  if (rng == 3) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 3>
+                                 : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 3> : &bb_chain_launch<M, GK, GM, 2, 3>);
   return nullptr;
 }
 template <class M>
