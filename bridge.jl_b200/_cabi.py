@@ -45,6 +45,18 @@ class Model(C.Structure):
                 ("par", C.c_double * BB_NPAR)]
 
 
+BB_NTHETA, BB_MAXD, BB_MAXSEG = 8, 4, 16
+AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END = 1, 2
+PRIOR_FLAT, PRIOR_GAMMA = 0, 1
+
+
+class ThetaSpec(C.Structure):  # bb_theta_spec
+    _fields_ = [("m", C.c_int32), ("aux_kind", C.c_int32), ("L", C.c_double * (BB_MAXD * BB_MAXD)),
+                ("Sigma", C.c_double * (BB_MAXD * BB_MAXD)), ("eps", C.c_double),
+                ("v", (C.c_double * BB_MAXD) * BB_MAXSEG), ("prior_kind", C.c_int32 * BB_NTHETA),
+                ("prior_a", C.c_double * BB_NTHETA), ("prior_b", C.c_double * BB_NTHETA)]
+
+
 class Aux(C.Structure):
     _fields_ = [("d", C.c_int32), ("is_const", C.c_int32), ("B", C.c_void_p), ("beta", C.c_void_p),
                 ("a", C.c_void_p), ("a_left", C.c_void_p)]
@@ -108,6 +120,18 @@ def _load():
         "bb_ens_mc_update": (C.c_int, [vp]),
         "bb_ens_mc_stats": (C.c_int, [vp, vp, vp, C.POINTER(i64)]),
         "bb_pcn_step_host": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32, vp, vp, vp, vp, vp]),
+        "bb_theta_attach": (C.c_int, [vp, C.POINTER(Model), C.POINTER(ThetaSpec)]),
+        "bb_theta_set": (C.c_int, [vp, i64, i64, vp]),
+        "bb_theta_get": (C.c_int, [vp, C.c_int, i64, i64, vp]),
+        "bb_theta_guides": (C.c_int, [vp]),
+        "bb_theta_get_left": (C.c_int, [vp, C.c_int, i64, i64, vp]),
+        "bb_theta_get_tables": (C.c_int, [vp, i64, vp, vp]),
+        "bb_theta_guided_euler_ll": (C.c_int, [vp, i32, u32]),
+        "bb_theta_pcn_step": (C.c_int, [vp, dbl, u64, u32, i32, u32]),
+        "bb_theta_param_step": (C.c_int, [vp, vp, u64, u32, i32, u32]),
+        "bb_theta_refresh_x": (C.c_int, [vp]),
+        "bb_theta_get_acc": (C.c_int, [vp, C.POINTER(i64)]),
+        "bb_theta_acc_device_ptr": (vp, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

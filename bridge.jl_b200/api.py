@@ -403,6 +403,7 @@ class PathEnsemble:
         self.h = h
         self.has_x = store_x
         self._last = None  # (P, guides) of the last pCN step: what refresh_x needs
+        self._theta = False  # per-chain parameters attached (theta_attach_)
         if chain_offset:
             check(lib.bb_ens_set_chain_offset(self.h, chain_offset))
 
@@ -549,7 +550,9 @@ class PathEnsemble:
     def refresh_x_(self):
         """Make X the CURRENT path of every chain again (X holds the last proposal; chains that rejected it
         get their path recomputed from W by the same guided Euler kernel).  No-op if nothing is stale."""
-        if self._last is not None:
+        if self._theta:
+            check(lib.bb_theta_refresh_x(self.h))
+        elif self._last is not None:
             P, guides = self._last
             m = P.cmodel()
             check(lib.bb_ens_refresh_x(self.h, C.byref(m), self._garr(guides)))
@@ -569,6 +572,78 @@ class PathEnsemble:
         self._last = (P, list(guides))
         check(lib.bb_pcn_step(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip,
                               K.RUN_STORE_X if store_x else 0))
+
+
+    # ---- per-chain parameters: the `updateparams` branch of partialbridge_bolus3.jl:248-365 for P chains
+    def theta_attach_(self, P: ContinuousTimeProcess, L, Σ, ϵ: float, obs_v, aux_kind: int = K.AUX_FHN_MATCHING,
+                      priors=None):
+        """Give every chain its own copy θ_p of P's parameters (all chains start at P's) and its own guiding tables.
+        L (m x d), Σ (m x m), ϵ: observation scheme and H⁺ = I/ϵ right of the last observation (bolus3.jl:162-165);
+        obs_v[s]: observation at the right end of segment s; priors: {index: ("gamma", shape, scale)} (logπ, :237)."""
+        L = np.atleast_2d(f64(L)); m, d = L.shape
+        Σ = np.atleast_2d(f64(Σ))
+        sp = K.ThetaSpec()
+        sp.m, sp.aux_kind, sp.eps = m, aux_kind, float(ϵ)
+        for i in range(m):
+            for j in range(d):
+                sp.L[i * d + j] = L[i, j]
+            for j in range(m):
+                sp.Sigma[i * m + j] = Σ[i, j]
+        obs_v = np.asarray(obs_v, dtype=np.float64).reshape(self.S, m)
+        for s in range(self.S):
+            for i in range(m):
+                sp.v[s][i] = obs_v[s, i]
+        for k, pr in (priors or {}).items():
+            if pr[0] != "gamma":
+                raise ValueError("priors: ('gamma', shape, scale)")
+            sp.prior_kind[k], sp.prior_a[k], sp.prior_b[k] = K.PRIOR_GAMMA, float(pr[1]), float(pr[2])
+        mdl = P.cmodel()
+        check(lib.bb_theta_attach(self.h, C.byref(mdl), C.byref(sp)))
+        self._theta = True
+
+    def set_theta(self, θ, p0: int = 0):
+        θ = f64(θ).reshape(-1, K.BB_NTHETA)
+        check(lib.bb_theta_set(self.h, p0, θ.shape[0], ptr(θ)))
+
+    def theta(self, which=K.CUR):
+        out = np.empty((self.P, K.BB_NTHETA))
+        check(lib.bb_theta_get(self.h, which, 0, self.P, ptr(out)))
+        return out
+
+    def theta_guides_(self):
+        """Backward pass (Lyapunov step + observation updates) for the current θ of every chain."""
+        check(lib.bb_theta_guides(self.h))
+
+    def theta_left(self, which=K.CUR):
+        """[P, d+d*d+4]: ν(0), H⁺(0), C, logpdfnormal(x0-ν(0), H⁺(0)), trace term, logπ(θ) of the last backward pass."""
+        out = np.empty((self.P, self.d + self.d * self.d + 4))
+        check(lib.bb_theta_get_left(self.h, which, 0, self.P, ptr(out)))
+        return out
+
+    def theta_tables(self, p: int):
+        ν = np.empty((self.S, self.N, self.d)); H = np.empty((self.S, self.N, self.d, self.d))
+        check(lib.bb_theta_get_tables(self.h, p, ptr(ν), ptr(H)))
+        return ν, H
+
+    def theta_guided_euler_ll_(self, skip: int = 0, store_x: bool = True):
+        check(lib.bb_theta_guided_euler_ll(self.h, skip, K.RUN_STORE_X if store_x else 0))
+
+    def theta_pcn_step_(self, ρ: float, seed: int, it: int, skip: int = 0, store_x: bool = True):
+        check(lib.bb_theta_pcn_step(self.h, ρ, seed, it, skip, K.RUN_STORE_X if store_x else 0))
+
+    def theta_param_step_(self, rw_sd, seed: int, it: int, skip: int = 0, store_x: bool = True):
+        """One parameter-update MH iteration with W held fixed; rw_sd[k] = random-walk sd of parameter k (0: fixed)."""
+        sd = np.zeros(K.BB_NTHETA); rw = f64(rw_sd).ravel(); sd[:rw.size] = rw
+        check(lib.bb_theta_param_step(self.h, ptr(sd), seed, it, skip, K.RUN_STORE_X if store_x else 0))
+
+    @property
+    def acc_theta(self) -> int:
+        v = C.c_int64(0)
+        check(lib.bb_theta_get_acc(self.h, C.byref(v)))
+        return v.value
+
+    def theta_acc_device_ptr(self) -> int:
+        return lib.bb_theta_acc_device_ptr(self.h) or 0
 
 
 def _small_ens(ctx: Context, S, N, d, dp, double_buffer=False) -> PathEnsemble:

@@ -33,7 +33,7 @@ def fhn_matching_aux(v: float, par=FHN_PAR):
     """The "matching" auxiliary process of partialbridge_fitzhugh.jl:106-108 (constant in t)."""
     ϵ, s, γ, β, σ = par
     Bt = np.array([[1 / ϵ, -1 / ϵ], [γ, -1.0]])
-    bt = np.array([s / ϵ - v ** 3 / ϵ, β])
+    bt = np.array([s / ϵ - (v * v * v) / ϵ, β])  # P.v^3 is a product in Julia (literal_pow)
     at = np.array([[0.0, 0.0], [0.0, σ * σ]])
     return Bt, bt, at
 

@@ -299,6 +299,7 @@ extern "C" int bb_ens_destroy(bb_ens* e) {
   if (e->W[0]) cudaFree(e->W[0]);
   if (e->X) cudaFree(e->X);
   if (e->mc_sum) cudaFree(e->mc_sum);
+  bb_theta_free(e);
   void* ptrs[] = {e->par, e->accepted, e->xstale, e->ll, e->llprop, e->logu, e->xend, e->xendprop, e->acc, e->start};
   for (void* p : ptrs)
     if (p) cudaFree(p);

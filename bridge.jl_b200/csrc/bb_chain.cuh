@@ -119,10 +119,10 @@ struct bb_chain {
   };
 
   /* guided drift _b((i,t),x,P°) at x = y (plain b for GK = 0) and, if in_ll, the log-likelihood term */
-  static __device__ __forceinline__ void drift(const bb_chain_args& a, const double* __restrict__ R,
+  static __device__ __forceinline__ void drift(const bb_model_dev& model, const double* __restrict__ R,
                                                const double* __restrict__ sc, const double* y, double dt,
                                                bool in_ll, double& som, double* bd) {
-    M::b(a.model, y, bd);
+    M::b(model, y, bd);
     if constexpr (GK != 0) {
       /* r((i,t),x,P°) = A2 (c - A1 x)  -- partialbridgenuH.jl:161, guip.jl:193, partialbridge.jl:57 */
       double e[NCC], r[D];
@@ -164,10 +164,10 @@ struct bb_chain {
       if constexpr (M::SPARSE) {
 #pragma unroll
         for (int k = 0; k < D; k++)
-          if (M::col(k) >= 0) bd[k] = fma(a.model.der[8 + k * D + k], r[k], bd[k]);
+          if (M::col(k) >= 0) bd[k] = fma(model.der[8 + k * D + k], r[k], bd[k]);
       } else {
         double ar[D];
-        bb_matvec<D, D>(a.model.der + 8, r, ar);
+        bb_matvec<D, D>(model.der + 8, r, ar);
 #pragma unroll
         for (int k = 0; k < D; k++) bd[k] = bd[k] + ar[k];
       }
@@ -186,7 +186,7 @@ struct bb_chain {
       st.wprev[k] = wj[k];
     }
     double bd[D];
-    drift(a, R, sc, st.y, dt, in_ll, st.som, bd);
+    drift(a.model, R, sc, st.y, dt, in_ll, st.som, bd);
     bb_em_update<M>(a.model, bd, dt, dw, st.y);
   }
 

@@ -55,10 +55,14 @@ struct bb_ens {
   std::vector<double*> gridtab; /* per segment: device [NC*8][2] (dt, sqrt dt) */
   std::vector<std::vector<double>> tt;
   int64_t bytes = 0;
+  /* per-chain parameters and guiding tables (bb_theta.cu) */
+  struct bb_theta* th = nullptr;
   /* pooled online statistics (bb_stats.cu) */
   double *mc_sum = nullptr, *mc_sq = nullptr;
   int64_t mc_n = 0;
 };
+
+void bb_theta_free(bb_ens* e); /* bb_theta.cu */
 
 /* thread-local error text for bb_last_cuda_error */
 void bb_set_cuda_error(cudaError_t e, const char* where);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
             const double* R = tab + (size_t)j * REC;
             const double dt = R[0];
             double bd[D];
-            CH::drift(a, R, sc, xprev, dt, MODE == 0 && j <= a.jll, som, bd);
+            CH::drift(a.model, R, sc, xprev, dt, MODE == 0 && j <= a.jll, som, bd);
             if constexpr (MODE == 1) {
               double e[D], de[D];
 #pragma unroll

@@ -1,0 +1,750 @@
+/*
+ * bb_theta.cu -- per-chain parameters: parameter-update Metropolis-Hastings with the guiding tables of every
+ * chain built on the device.
+ *
+ * Follows the `updateparams` branch of the script loop project_partialbridge/partialbridge_bolus3.jl:248-365 for
+ * P independent chains, each with its own θ (see include/bridge_b200.h for the step-by-step correspondence):
+ *   bb_theta_backward_kernel   propose(σ, P) (:239-242), then per chain: ν = 0, H⁺ = I/ϵ, gpupdate with the last
+ *                              observation (:162-165), and for s = S-1 .. 0 the Lyapunov backward step of
+ *                              partialbridgeνH (src/partialbridgenuH.jl:86-103,148-155, src/lyap.jl:2-6) followed by
+ *                              gpupdate with v[s-1] (:284-291, :128-137); logpdfnormal(x0 - ν(0), H⁺(0))
+ *                              (src/gaussian.jl:66-75), the trace term and logπ of :319,:336.
+ *   bb_theta_forward_kernel    solve!(Euler(), X°, x0, W, Q°) + llikelihood (:324-333) with the chain's own θ and
+ *                              tables, and the accept test (:340); the same kernel runs the pCN iteration
+ *                              (test/partialbridgenuH.jl:176-191) for chains with their own tables.
+ *
+ * Layout: the tables are T [S][N][K][P] doubles, K = d + d*d (ν[i], H[i]), chain-minor, so that the 32 chains of a
+ * warp read/write 256 contiguous bytes per value (no staging needed); they are written once by the backward
+ * kernel and read once by the forward kernel: 8K bytes per path-step each way.  Lanes 0..2K-1 of a warp prefetch
+ * the 2K lines of the row BB_TPF steps ahead into L2; the record of the next step is loaded into registers while
+ * the current step computes.  W / X keep the chunked layout of bb_chain.cuh (shared with the other kernels).
+ * The per-step arithmetic is bb_chain<...>::drift / bb_em_update / nuH_step, i.e. the same instruction sequence
+ * as the shared-table kernels and the one-system constructors.
+ */
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "bb_backward.cuh"
+#include "bb_host.h"
+
+#define BB_TPF 8 /* table rows prefetched ahead into L2 */
+
+struct bb_theta {
+  bb_model model;
+  bb_theta_spec spec;
+  int K = 0, NL = 0;
+  double* theta[2] = {nullptr, nullptr}; /* [BB_NTHETA][P]: current, last proposal */
+  double* T = nullptr;                   /* [S][N][K][P] */
+  double* left[2] = {nullptr, nullptr};  /* [NL][P]: ν(0), H⁺(0), C, logpdfnormal, trace term, log prior */
+  double* tt = nullptr;                  /* [S][N] */
+  unsigned long long* acc = nullptr;
+  int tstate = 0; /* 0: T invalid; 1: T belongs to the current θ; 2: T belongs to the last proposal */
+};
+
+struct bb_theta_args {
+  double* W[2];
+  double* X;
+  uint8_t* par;
+  const double* start;
+  double *ll, *llprop, *logu, *xend, *xendprop;
+  uint8_t *accepted, *xstale;
+  unsigned long long *acc, *acc_theta;
+  long long P, chain_offset;
+  int S, N, NC, nbuf, jll, start_bcast, store_x;
+  const double* gridtab[BB_MAXSEG]; /* rows (dt, sqrt dt) */
+  const double* tt;
+  double* theta[2];
+  double* T;
+  double* left[2];
+  int which;   /* θ / left block the kernel works with: 0 current, 1 proposal */
+  int propose; /* backward: draw θ° = θ + rw_sd ξ first */
+  int mode;    /* forward without pCN: 0 = ll <- ll° (initialisation), 2 = parameter accept test,
+                * 3 = recompute X of the chains whose X is stale (rejected proposals), nothing else */
+  double rw_sd[BB_NTHETA];
+  bb_philox_keys keys;
+  uint32_t stream;
+  double rho, rho2;
+  bb_theta_spec spec;
+  double log2pi;
+  double prior_c0[BB_NTHETA];
+  double seg_len[BB_MAXSEG];
+};
+
+namespace {
+using namespace bbk;
+
+template <class M>
+__device__ __forceinline__ void theta_model(const double* th, bb_model_dev& m) {
+  constexpr int D = M::D;
+  static_assert(M::SPARSE, "per-chain parameters: sparse-sigma models only");
+#pragma unroll
+  for (int k = 0; k < M::NTH; k++) m.par[k] = th[k];
+  if (M::ID == BB_MODEL_FHN_DIAG || M::ID == BB_MODEL_FHN_HYPO) m.der[0] = 1.0 / m.par[0];
+  /* a = sigma sigma' (bb_prepare_model) */
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = 0; j < D; j++)
+      m.der[8 + i * D + j] = (M::col(i) >= 0 && M::col(i) == M::col(j)) ? M::sig(m, i) * M::sig(m, j) : 0.0;
+}
+
+/* B~, beta~ of a segment from (θ, v): partialbridge_fitzhugh.jl:98-108 (x^2, x^3 are products, as Julia's literal_pow) */
+template <class M, int AUXK>
+__device__ __forceinline__ void theta_aux(const bb_model_dev& m, double v, double* Bt, double* be) {
+  static_assert(M::ID == BB_MODEL_FHN_DIAG || M::ID == BB_MODEL_FHN_HYPO, "auxiliary registry: FitzHugh-Nagumo");
+  const double eps = m.par[0], s = m.par[1], gam = m.par[2], beta = m.par[3];
+  const double ie = 1.0 / eps;
+  if (AUXK == BB_AUX_FHN_MATCHING) {
+    Bt[0] = ie; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
+    be[0] = s / eps - (v * v * v) / eps;
+    be[1] = beta;
+  } else {
+    Bt[0] = ie - (3.0 * (v * v)) / eps; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
+    be[0] = s / eps + (2.0 * (v * v * v)) / eps;
+    be[1] = beta;
+  }
+}
+
+/* logpdfnormal(x, Σ)  src/gaussian.jl:66-75 (oracle bbo_logpdfnormal) */
+template <int d>
+__device__ __forceinline__ double logpdfnormal_dev(const double* x, const double* Sigma, double log2pi) {
+  if constexpr (d == 1) {
+    return -(x[0] * x[0] / Sigma[0] + log(Sigma[0]) + log2pi) / 2;
+  } else {
+    double Ssym[d * d], S[d * d], y[d];
+#pragma unroll
+    for (int i = 0; i < d; i++)
+#pragma unroll
+      for (int j = 0; j < d; j++) Ssym[i * d + j] = 0.5 * (Sigma[i * d + j] + Sigma[j * d + i]);
+    if (chol_lower<d>(Ssym, S)) return nan("");
+    double n2 = 0, sld = 0;
+#pragma unroll
+    for (int i = 0; i < d; i++) {
+      double t = x[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) t -= S[i * d + k] * y[k];
+      y[i] = t / S[i * d + i];
+      n2 += y[i] * y[i];
+      sld += log(S[i * d + i]);
+    }
+    return -(n2 + 2 * sld + d * log2pi) / 2;
+  }
+}
+
+__device__ __forceinline__ double theta_logu(const bb_philox_keys& k, uint32_t stream, uint64_t chain) {
+  uint32_t o[4];
+  bb_philox4x32_10(0xFFFFFFFDu, stream, (uint32_t)chain, (uint32_t)(chain >> 32), k, o);
+  return (double)bb_logf(bb_unif(o[0]));
+}
+
+/* ------------------------------------------------------------------------------------------------ backward */
+template <class M, int AUXK, int MOBS>
+__global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_constant__ bb_theta_args a) {
+  constexpr int D = M::D, K = D + D * D, NTH = M::NTH;
+  const long long P = a.P;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const unsigned long long chain = (unsigned long long)(a.chain_offset + p);
+  double th[NTH];
+#pragma unroll
+  for (int k = 0; k < NTH; k++) th[k] = a.theta[a.propose ? 0 : a.which][(long long)k * P + p];
+  if (a.propose) {
+    /* propose(σ, P): θ° = θ + σ .* randn  (bolus3.jl:239-242); the n-th updated parameter takes the n-th normal */
+    float z[4];
+    bb_normal_quad(a.keys, a.stream, (uint32_t)chain, (uint32_t)(chain >> 32), 0xFFFFFFFEu, z);
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < NTH; k++) {
+      if (a.rw_sd[k] != 0.0) {
+        const float zz = n == 0 ? z[0] : (n == 1 ? z[1] : (n == 2 ? z[2] : z[3]));
+        th[k] = th[k] + a.rw_sd[k] * (double)zz;
+        n++;
+      }
+      a.theta[1][(long long)k * P + p] = th[k];
+    }
+  }
+  bb_model_dev m;
+  theta_model<M>(th, m);
+  const double* at = m.der + 8;
+  bool bad = false;
+  double nu[D], Hp[D * D], Hc[D * D];
+  /* νend = 0, Hend⁺ = I/ϵ, then the update with the last observation  (bolus3.jl:162-165) */
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    nu[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) Hp[i * D + j] = (i == j) ? 1.0 / a.spec.eps : 0.0;
+  }
+  const int S = a.S, N = a.N;
+  if (gpupdate_dev<D, MOBS>(nu, Hp, a.spec.L, a.spec.Sigma, a.spec.v[S - 1])) bad = true;
+  double Cc = 0.0, trsum = 0.0;
+  for (int s = S - 1; s >= 0; s--) {
+    double Bt[D * D], be[D];
+    theta_aux<M, AUXK>(m, a.spec.v[s][0], Bt, be);
+    const aux_dev A{Bt, be, at, at, 1};
+    if (minv<D>(Hp, Hc)) bad = true;
+    double* Trow = a.T + ((long long)s * N + (N - 1)) * K * P + p;
+#pragma unroll
+    for (int k = 0; k < D; k++) Trow[(long long)k * P] = nu[k];
+#pragma unroll
+    for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * P] = Hc[k];
+    const double* tt = a.tt + (long long)s * N;
+    for (int i = N - 2; i >= 0; i--) {
+      const double dt = tt[i] - tt[i + 1];
+      if (nuH_step<D>(BB_ODE_LYAP, A, i, dt, Hp, Hc, nu, Cc)) bad = true;
+      Trow -= (long long)K * P;
+#pragma unroll
+      for (int k = 0; k < D; k++) Trow[(long long)k * P] = nu[k];
+#pragma unroll
+      for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * P] = Hc[k];
+    }
+    double tr = Bt[0];
+#pragma unroll
+    for (int i = 1; i < D; i++) tr += Bt[i * D + i];
+    trsum += a.seg_len[s] * tr;
+    if (s > 0)
+      if (gpupdate_dev<D, MOBS>(nu, Hp, a.spec.L, a.spec.Sigma, a.spec.v[s - 1])) bad = true;
+  }
+  /* left end: ν(0), H⁺(0), C, logpdfnormal(x0 - ν(0), symmetrize(H⁺(0)))  (bolus3.jl:319), trace term, logπ(θ) */
+  double x[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) x[k] = (a.start_bcast ? a.start[k] : a.start[(long long)k * P + p]) - nu[k];
+  double lpn = logpdfnormal_dev<D>(x, Hp, a.log2pi);
+  if (bad) lpn = nan("");
+  double lpri = 0.0;
+#pragma unroll
+  for (int k = 0; k < NTH; k++) {
+    if (a.spec.prior_kind[k] == BB_PRIOR_GAMMA) {
+      const double xk = th[k], sh = a.spec.prior_a[k] - 1.0;
+      double t = a.prior_c0[k];
+      if (sh != 0.0) t += sh * log(xk);
+      t -= xk / a.spec.prior_b[k];
+      lpri += (xk > 0.0) ? t : -INFINITY;
+    }
+  }
+  double* Lw = a.left[a.which] + p;
+#pragma unroll
+  for (int k = 0; k < D; k++) Lw[(long long)k * P] = nu[k];
+#pragma unroll
+  for (int k = 0; k < D * D; k++) Lw[(long long)(D + k) * P] = Hp[k];
+  Lw[(long long)(K + 0) * P] = Cc;
+  Lw[(long long)(K + 1) * P] = lpn;
+  Lw[(long long)(K + 2) * P] = trsum;
+  Lw[(long long)(K + 3) * P] = lpri;
+}
+
+/* ------------------------------------------------------------------------------------------------ forward */
+template <class M, int AUXK, bool PCN>
+__global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const __grid_constant__ bb_theta_args a) {
+  using CH = bb_chain<M, BB_GUIDE_NUH, 0, 1, 0>;
+  constexpr int D = M::D, DP = M::DP, K = D + D * D, NTH = M::NTH, REC = CH::REC;
+  constexpr int NPIECE = BB_TC * DP / 4;
+  const long long P = a.P;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pc = p < P ? p : P - 1;
+  const bool act = p < P && (PCN || a.mode != 3 || a.xstale[pc] != 0);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
+  const int S = a.S, N = a.N, NC = a.NC;
+
+  double th[NTH];
+#pragma unroll
+  for (int k = 0; k < NTH; k++) th[k] = a.theta[a.which][(long long)k * P + pc];
+  bb_model_dev m;
+  theta_model<M>(th, m);
+
+  const int par = a.par[pc];
+  const int wbuf = PCN ? 1 - par : par;
+  const bool sx = a.store_x != 0;
+  const double* wr = a.W[par] + pc * (a.nbuf * BB_TC * DP);
+  double* ww = a.W[wbuf] + pc * (a.nbuf * BB_TC * DP);
+  double* xw = sx ? a.X + pc * (BB_TC * D) : nullptr;
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+
+  double y[D], wprev[DP], w2[DP];
+#pragma unroll
+  for (int k = 0; k < D; k++) y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
+  double lltot = 0.0;
+
+  /* the chain's table rows in the order they are used: g = s N + i, i = 0 .. N-2 */
+  const double* Tp = a.T + pc;
+  const long long rowstride = (long long)K * P;
+  const long long warp_p0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const long long grows = (long long)S * N;
+  auto prefetch_row = [&](long long g) {
+    /* lane l < 2K: line (l & 1) of value l >> 1 of row g (256 bytes per value and warp) */
+    if (lane < 2 * K && g < grows) {
+      const double* q = a.T + g * rowstride + (long long)(lane >> 1) * P + warp_p0 + (lane & 1) * 16;
+      if (warp_p0 + (lane & 1) * 16 < P) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+  };
+  double Tn[K];
+  auto load_row = [&](long long g) {
+#pragma unroll
+    for (int k = 0; k < K; k++) Tn[k] = Tp[g * rowstride + (long long)k * P];
+  };
+#pragma unroll 1
+  for (int g = 0; g < BB_TPF; g++) prefetch_row(g);
+  load_row(0);
+
+  double wq[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int s = 0; s < S; s++) {
+    const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
+    const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
+    double sc[D * D + D];
+    theta_aux<M, AUXK>(m, a.spec.v[s][0], sc, sc + D * D);
+    const double* gt = a.gridtab[s];
+    double som = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; k++) w2[k] = 0.0;
+    for (int c = 0; c < NC; c++) {
+      bb_rowout<D> xo;
+      if (act && c + 1 < NC) { /* the chain's next row of W (whole lines) */
+#pragma unroll
+        for (int l = 0; l < (BB_TC * DP * 8 + 127) / 128; l++)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + wstride + l * 16));
+      }
+#pragma unroll 1
+      for (int h = 0; h < BB_TC / 4; h++) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+          const int slot = 4 * h + s4;
+          const int j = c * BB_TC + slot;
+          double wj[DP];
+#pragma unroll
+          for (int k = 0; k < DP; k++) {
+            const int mm = s4 * DP + k;
+            if ((mm & 3) == 0) {
+              const int q = h * DP + (mm >> 2);
+              if (act) bb_ld4(wr + 4 * q, wq);
+              if constexpr (PCN) {
+                float z[4];
+                bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  const int sl = 4 * h + (mm + i) / DP, kk = (mm + i) % DP;
+                  const int jj = c * BB_TC + sl;
+                  const double rootdt = gt[2 * jj + 1];
+                  /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
+                  if (jj != 0) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);
+                  wq[i] = fma(a.rho2, w2[kk], a.rho * wq[i]);
+                }
+                if (act) bb_st4(ww + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+              }
+            }
+            wj[k] = wq[mm & 3];
+          }
+          if (j == 0) {
+#pragma unroll
+            for (int k = 0; k < DP; k++) wprev[k] = wj[k];
+          } else if (j < N) {
+            double R[REC];
+            R[0] = gt[2 * j];
+            R[1] = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) R[2 + k] = Tn[k];
+            const long long g = (long long)s * N + (j - 1);
+            const long long gn = (j == N - 1) ? g + 2 : g + 1; /* row N-1 of a segment drives no step */
+            if (gn < grows - 1) load_row(gn);
+            prefetch_row(gn + BB_TPF - 1);
+            double dw[DP], bd[D];
+#pragma unroll
+            for (int k = 0; k < DP; k++) {
+              dw[k] = wj[k] - wprev[k];
+              wprev[k] = wj[k];
+            }
+            CH::drift(m, R, sc, y, R[0], j <= a.jll, som, bd);
+            bb_em_update<M>(m, bd, R[0], dw, y);
+          }
+          if (sx) xo.put(xw + 4 * h * D, s4, y, act);
+        }
+      }
+      wr += wstride;
+      ww += wstride;
+      if (sx) xw += xstride;
+    }
+    lltot += som;
+  }
+
+  if constexpr (PCN) {
+    /* accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
+    const double logu = bb_accept_logu(a.keys, a.stream, chain);
+    const bool ok = act && (logu <= lltot - a.ll[pc]);
+    if (act) {
+      a.llprop[p] = lltot;
+      a.logu[p] = logu;
+      a.accepted[p] = ok ? 1 : 0;
+      a.xstale[p] = sx ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
+#pragma unroll
+      for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = y[k];
+      if (ok) {
+        a.ll[p] = lltot;
+        a.par[p] = (uint8_t)(1 - par);
+#pragma unroll
+        for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
+      }
+    }
+    const unsigned mk = __ballot_sync(0xFFFFFFFFu, ok);
+    if (lane == 0 && mk) atomicAdd(a.acc, (unsigned long long)__popc(mk));
+  } else if (a.mode == 2) {
+    /* diffll (bolus3.jl:319,331-336) and the MH step (:340): θ, the left-end values, ll follow on accept */
+    const double logu = theta_logu(a.keys, a.stream, chain);
+    const double* Lc = a.left[0] + pc;
+    const double* Lo = a.left[1] + pc;
+    double diff = Lo[(long long)(K + 1) * P] - Lc[(long long)(K + 1) * P];
+    diff += lltot - a.ll[pc];
+    diff += ((Lo[(long long)(K + 2) * P] - Lc[(long long)(K + 2) * P]) + Lo[(long long)(K + 3) * P]) -
+            Lc[(long long)(K + 3) * P];
+    const bool ok = act && (logu <= diff);
+    if (act) {
+      a.llprop[p] = lltot;
+      a.logu[p] = logu;
+      a.accepted[p] = ok ? 1 : 0;
+      a.xstale[p] = sx ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
+#pragma unroll
+      for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = y[k];
+      if (ok) {
+        a.ll[p] = lltot;
+#pragma unroll
+        for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
+#pragma unroll
+        for (int k = 0; k < NTH; k++) a.theta[0][(long long)k * P + p] = th[k];
+#pragma unroll
+        for (int k = 0; k < K + 4; k++) a.left[0][(long long)k * P + p] = Lo[(long long)k * P];
+      }
+    }
+    const unsigned mk = __ballot_sync(0xFFFFFFFFu, ok);
+    if (lane == 0 && mk) atomicAdd(a.acc_theta, (unsigned long long)__popc(mk));
+  } else if (a.mode == 3) {
+    if (act) a.xstale[p] = 0;
+  } else if (act) {
+    a.ll[p] = lltot;
+    if (sx) a.xstale[p] = 0;
+#pragma unroll
+    for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
+  }
+}
+
+typedef void (*theta_kernel_fn)(const bb_theta_args);
+
+template <class M>
+static theta_kernel_fn lookup_backward(int auxk, int mobs) {
+  if (auxk == BB_AUX_FHN_MATCHING) {
+    if (mobs == 1) return &bb_theta_backward_kernel<M, BB_AUX_FHN_MATCHING, 1>;
+    if (mobs == 2) return &bb_theta_backward_kernel<M, BB_AUX_FHN_MATCHING, 2>;
+  }
+  if (auxk == BB_AUX_FHN_LINEARISED_END) {
+    if (mobs == 1) return &bb_theta_backward_kernel<M, BB_AUX_FHN_LINEARISED_END, 1>;
+    if (mobs == 2) return &bb_theta_backward_kernel<M, BB_AUX_FHN_LINEARISED_END, 2>;
+  }
+  return nullptr;
+}
+template <class M>
+static theta_kernel_fn lookup_forward(int auxk, bool pcn) {
+  if (auxk == BB_AUX_FHN_MATCHING)
+    return pcn ? &bb_theta_forward_kernel<M, BB_AUX_FHN_MATCHING, true>
+               : &bb_theta_forward_kernel<M, BB_AUX_FHN_MATCHING, false>;
+  if (auxk == BB_AUX_FHN_LINEARISED_END)
+    return pcn ? &bb_theta_forward_kernel<M, BB_AUX_FHN_LINEARISED_END, true>
+               : &bb_theta_forward_kernel<M, BB_AUX_FHN_LINEARISED_END, false>;
+  return nullptr;
+}
+
+static int fill_args(bb_ens* e, bb_theta_args& a) {
+  bb_theta* t = e->th;
+  memset(&a, 0, sizeof(a));
+  a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X = e->X;
+  a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
+  a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
+  a.accepted = e->accepted; a.xstale = e->xstale; a.acc = e->acc; a.acc_theta = t->acc;
+  a.P = e->P; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC; a.nbuf = e->nbuf;
+  for (int s = 0; s < e->S; s++) {
+    if (!e->gridtab[s] || (int)e->tt[s].size() != e->N) return BB_ERR_ARG; /* bb_ens_set_grid first */
+    a.gridtab[s] = e->gridtab[s];
+    a.seg_len[s] = e->tt[s][e->N - 1] - e->tt[s][0];
+  }
+  a.tt = t->tt;
+  a.theta[0] = t->theta[0]; a.theta[1] = t->theta[1];
+  a.T = t->T;
+  a.left[0] = t->left[0]; a.left[1] = t->left[1];
+  a.spec = t->spec;
+  a.log2pi = log(2 * M_PI);
+  for (int k = 0; k < BB_NTHETA; k++)
+    if (t->spec.prior_kind[k] == BB_PRIOR_GAMMA) /* -lgamma(a) - a log(b) */
+      a.prior_c0[k] = -lgamma(t->spec.prior_a[k]) - t->spec.prior_a[k] * log(t->spec.prior_b[k]);
+  return BB_OK;
+}
+
+static int upload_grids(bb_ens* e) {
+  bb_theta* t = e->th;
+  std::vector<double> h((size_t)e->S * e->N);
+  for (int s = 0; s < e->S; s++) {
+    if ((int)e->tt[s].size() != e->N) return BB_ERR_ARG;
+    memcpy(h.data() + (size_t)s * e->N, e->tt[s].data(), sizeof(double) * e->N);
+  }
+  BB_CUDA(cudaMemcpyAsync(t->tt, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return BB_OK;
+}
+
+static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd, uint64_t seed, uint32_t stream) {
+  bb_theta* t = e->th;
+  bb_ctx* c = e->ctx;
+  bb_theta_args a;
+  int rc = fill_args(e, a);
+  if (rc != BB_OK) return rc;
+  rc = upload_grids(e); /* the grids may have changed since attach */
+  if (rc != BB_OK) return rc;
+  a.which = which;
+  a.propose = propose ? 1 : 0;
+  if (rw_sd) memcpy(a.rw_sd, rw_sd, sizeof(a.rw_sd));
+  bb_philox_key_schedule(seed, a.keys);
+  a.stream = stream;
+  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO ? lookup_backward<MFhnHypo>(t->spec.aux_kind, t->spec.m)
+                                                        : lookup_backward<MFhnDiag>(t->spec.aux_kind, t->spec.m);
+  if (!fn) return BB_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)((e->P + 127) / 128);
+  fn<<<grid, 128, 0, c->stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    bb_set_cuda_error(err, "bb_theta_backward_kernel launch");
+    return BB_ERR_CUDA;
+  }
+  c->launches++;
+  t->tstate = which == 0 ? 1 : 2;
+  return BB_OK;
+}
+
+static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool store_x, double rho, uint64_t seed,
+                       uint32_t stream) {
+  bb_theta* t = e->th;
+  bb_ctx* c = e->ctx;
+  if (skip < 0) return BB_ERR_ARG;
+  if (store_x && !e->X) return BB_ERR_ARG;
+  if (pcn && !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG;
+  bb_theta_args a;
+  int rc = fill_args(e, a);
+  if (rc != BB_OK) return rc;
+  a.which = which;
+  a.mode = mode;
+  a.jll = e->N - 1 - skip;
+  a.store_x = store_x ? 1 : 0;
+  a.rho = rho;
+  a.rho2 = sqrt(1 - rho * rho);
+  bb_philox_key_schedule(seed, a.keys);
+  a.stream = stream;
+  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO ? lookup_forward<MFhnHypo>(t->spec.aux_kind, pcn)
+                                                        : lookup_forward<MFhnDiag>(t->spec.aux_kind, pcn);
+  if (!fn) return BB_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)((e->P + BB_THREADS - 1) / BB_THREADS);
+  fn<<<grid, BB_THREADS, 0, c->stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    bb_set_cuda_error(err, "bb_theta_forward_kernel launch");
+    return BB_ERR_CUDA;
+  }
+  c->launches++;
+  if (pcn || mode == 2) e->x_maybe_stale = true;
+  else if (store_x) e->x_maybe_stale = false; /* modes 0 and 3 leave X current for every chain */
+  return BB_OK;
+}
+
+}  // namespace
+
+void bb_theta_free(bb_ens* e) {
+  bb_theta* t = e->th;
+  if (!t) return;
+  void* ptrs[] = {t->theta[0], t->theta[1], t->T, t->left[0], t->left[1], t->tt, t->acc};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete t;
+  e->th = nullptr;
+}
+
+template <class T>
+static int th_alloc(bb_ens* e, T** p, size_t count) {
+  BB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  BB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), e->ctx->stream));
+  e->bytes += (int64_t)(count * sizeof(T));
+  return BB_OK;
+}
+
+extern "C" int bb_theta_attach(bb_ens* e, const bb_model* model, const bb_theta_spec* spec) {
+  if (!e || !model || !spec) return BB_ERR_ARG;
+  if (e->th) return BB_ERR_ARG;
+  if (model->id != BB_MODEL_FHN_HYPO && model->id != BB_MODEL_FHN_DIAG) return BB_ERR_UNSUPPORTED;
+  if (model->d != e->d || model->dprime != e->dp) return BB_ERR_MODEL;
+  if (model->d != 2 || model->dprime != (model->id == BB_MODEL_FHN_HYPO ? 1 : 2)) return BB_ERR_MODEL;
+  if (spec->m < 1 || spec->m > e->d) return BB_ERR_ASSERT_M;
+  if (spec->aux_kind != BB_AUX_FHN_MATCHING && spec->aux_kind != BB_AUX_FHN_LINEARISED_END) return BB_ERR_UNSUPPORTED;
+  for (int k = 0; k < BB_NTHETA; k++) {
+    if (spec->prior_kind[k] != BB_PRIOR_FLAT && spec->prior_kind[k] != BB_PRIOR_GAMMA) return BB_ERR_ARG;
+    if (spec->prior_kind[k] == BB_PRIOR_GAMMA && !(spec->prior_a[k] > 0 && spec->prior_b[k] > 0)) return BB_ERR_ARG;
+  }
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  bb_theta* t = new (std::nothrow) bb_theta();
+  if (!t) return BB_ERR_NOMEM;
+  e->th = t;
+  t->model = *model;
+  t->spec = *spec;
+  const int d = e->d;
+  t->K = d + d * d;
+  t->NL = t->K + 4;
+  const size_t P = (size_t)e->P;
+  int rc = th_alloc(e, &t->theta[0], (size_t)BB_NTHETA * P);
+  if (rc == BB_OK) rc = th_alloc(e, &t->theta[1], (size_t)BB_NTHETA * P);
+  if (rc == BB_OK) rc = th_alloc(e, &t->T, (size_t)e->S * e->N * t->K * P);
+  if (rc == BB_OK) rc = th_alloc(e, &t->left[0], (size_t)t->NL * P);
+  if (rc == BB_OK) rc = th_alloc(e, &t->left[1], (size_t)t->NL * P);
+  if (rc == BB_OK) rc = th_alloc(e, &t->tt, (size_t)e->S * e->N);
+  if (rc == BB_OK) rc = th_alloc(e, &t->acc, 1);
+  if (rc != BB_OK) {
+    bb_theta_free(e);
+    return rc;
+  }
+  std::vector<double> h((size_t)BB_NTHETA * P);
+  for (int k = 0; k < BB_NTHETA; k++)
+    for (size_t p = 0; p < P; p++) h[(size_t)k * P + p] = model->par[k];
+  BB_CUDA(cudaMemcpyAsync(t->theta[0], h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  return BB_OK;
+}
+
+extern "C" int bb_theta_set(bb_ens* e, int64_t p0, int64_t np, const double* theta) {
+  if (!e || !e->th || !theta || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  std::vector<double> h((size_t)np);
+  for (int k = 0; k < BB_NTHETA; k++) {
+    for (int64_t p = 0; p < np; p++) h[(size_t)p] = theta[(size_t)p * BB_NTHETA + k];
+    BB_CUDA(cudaMemcpyAsync(e->th->theta[0] + (size_t)k * e->P + p0, h.data(), sizeof(double) * np,
+                            cudaMemcpyHostToDevice, e->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  }
+  e->th->tstate = 0;
+  return BB_OK;
+}
+
+extern "C" int bb_theta_get(bb_ens* e, int which, int64_t p0, int64_t np, double* theta) {
+  if (!e || !e->th || !theta || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  if (which != BB_CUR && which != BB_PROP) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  std::vector<double> h((size_t)np * BB_NTHETA);
+  for (int k = 0; k < BB_NTHETA; k++)
+    BB_CUDA(cudaMemcpyAsync(h.data() + (size_t)k * np, e->th->theta[which] + (size_t)k * e->P + p0,
+                            sizeof(double) * np, cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  for (int64_t p = 0; p < np; p++)
+    for (int k = 0; k < BB_NTHETA; k++) theta[(size_t)p * BB_NTHETA + k] = h[(size_t)k * np + p];
+  return BB_OK;
+}
+
+extern "C" int bb_theta_guides(bb_ens* e) {
+  if (!e || !e->th) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  bb_time_begin(e->ctx);
+  const int rc = run_backward(e, 0, false, nullptr, 0, 0);
+  bb_time_end(e->ctx);
+  return rc;
+}
+
+extern "C" int bb_theta_get_left(bb_ens* e, int which, int64_t p0, int64_t np, double* out) {
+  if (!e || !e->th || !out || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  if (which != BB_CUR && which != BB_PROP) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int NL = e->th->NL;
+  std::vector<double> h((size_t)np * NL);
+  for (int k = 0; k < NL; k++)
+    BB_CUDA(cudaMemcpyAsync(h.data() + (size_t)k * np, e->th->left[which] + (size_t)k * e->P + p0, sizeof(double) * np,
+                            cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  for (int64_t p = 0; p < np; p++)
+    for (int k = 0; k < NL; k++) out[(size_t)p * NL + k] = h[(size_t)k * np + p];
+  return BB_OK;
+}
+
+extern "C" int bb_theta_get_tables(bb_ens* e, int64_t p, double* nu, double* H) {
+  if (!e || !e->th || !nu || !H || p < 0 || p >= e->P) return BB_ERR_ARG;
+  if (e->th->tstate == 0) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int K = e->th->K, d = e->d;
+  const size_t rows = (size_t)e->S * e->N;
+  std::vector<double> h(rows * K);
+  BB_CUDA(cudaMemcpy2DAsync(h.data(), sizeof(double), e->th->T + p, sizeof(double) * e->P, sizeof(double), rows * K,
+                            cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  for (size_t g = 0; g < rows; g++) {
+    memcpy(nu + g * d, h.data() + g * K, sizeof(double) * d);
+    memcpy(H + g * d * d, h.data() + g * K + d, sizeof(double) * d * d);
+  }
+  return BB_OK;
+}
+
+/* the tables must belong to the chains' CURRENT θ */
+static int ensure_current_tables(bb_ens* e) {
+  if (e->th->tstate == 1) return BB_OK;
+  return run_backward(e, 0, false, nullptr, 0, 0);
+}
+
+extern "C" int bb_theta_guided_euler_ll(bb_ens* e, int32_t skip, uint32_t flags) {
+  if (!e || !e->th) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  bb_time_begin(e->ctx);
+  int rc = ensure_current_tables(e);
+  if (rc == BB_OK) rc = run_forward(e, false, 0, 0, skip, (flags & BB_RUN_STORE_X) != 0, 0.0, 0, 0);
+  bb_time_end(e->ctx);
+  return rc;
+}
+
+extern "C" int bb_theta_pcn_step(bb_ens* e, double rho, uint64_t seed, uint32_t iter, int32_t skip, uint32_t flags) {
+  if (!e || !e->th) return BB_ERR_ARG;
+  if (!(rho >= -1.0 && rho <= 1.0)) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  bb_time_begin(e->ctx);
+  int rc = ensure_current_tables(e);
+  if (rc == BB_OK) rc = run_forward(e, true, 0, 0, skip, (flags & BB_RUN_STORE_X) != 0, rho, seed, iter);
+  bb_time_end(e->ctx);
+  return rc;
+}
+
+extern "C" int bb_theta_param_step(bb_ens* e, const double* rw_sd, uint64_t seed, uint32_t iter, int32_t skip,
+                                   uint32_t flags) {
+  if (!e || !e->th || !rw_sd) return BB_ERR_ARG;
+  int nz = 0;
+  for (int k = 0; k < BB_NTHETA; k++) {
+    if (!(rw_sd[k] >= 0.0)) return BB_ERR_ARG;
+    if (rw_sd[k] != 0.0) nz++;
+  }
+  if (nz > 4) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  bb_time_begin(e->ctx);
+  int rc = BB_OK;
+  /* the left-end values of the current θ (logpdfnormal, trace term, prior) enter the accept test */
+  if (e->th->tstate == 0) rc = run_backward(e, 0, false, nullptr, 0, 0);
+  if (rc == BB_OK) rc = run_backward(e, 1, true, rw_sd, seed, iter);
+  if (rc == BB_OK) rc = run_forward(e, false, 1, 2, skip, (flags & BB_RUN_STORE_X) != 0, 0.0, seed, iter);
+  bb_time_end(e->ctx);
+  return rc;
+}
+
+extern "C" int bb_theta_refresh_x(bb_ens* e) {
+  if (!e || !e->th) return BB_ERR_ARG;
+  if (!e->x_maybe_stale) return BB_OK;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  int rc = ensure_current_tables(e);
+  if (rc == BB_OK) rc = run_forward(e, false, 0, 3, 0, true, 0.0, 0, 0);
+  return rc;
+}
+
+extern "C" int bb_theta_get_acc(bb_ens* e, int64_t* acc) {
+  if (!e || !e->th || !acc) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  unsigned long long v = 0;
+  BB_CUDA(cudaMemcpyAsync(&v, e->th->acc, sizeof(v), cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  *acc = (int64_t)v;
+  return BB_OK;
+}
+extern "C" void* bb_theta_acc_device_ptr(bb_ens* e) { return (e && e->th) ? (void*)e->th->acc : nullptr; }

@@ -316,6 +316,72 @@ int bb_ens_mc_reset(bb_ens* ens);
 int bb_ens_mc_update(bb_ens* ens);
 int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
 
+/* ------------------------------------------------------------------ per-chain parameters
+ * Every chain p carries its own parameter vector θ_p of the target model (the leading BB_NTHETA entries of the
+ * model's par[] block) and therefore its own guiding tables.  This is the parameter-update branch of the script
+ * loop  project_partialbridge/partialbridge_bolus3.jl:248-365  (`updateparams == true`) for P independent chains:
+ *
+ *   θ° = θ + rw_sd .* ξ                                    propose(σ, P)                         bolus3.jl:239-242
+ *   (ν, H⁺) right of the last observation: ν = 0, H⁺ = I/ϵ, then gpupdate with v[S-1]             :162-165
+ *   for s = S-1 .. 0:  partialbridgeνH(tt_s, P°, Pt°, ν, H⁺)  (Lyapunov backward step,           :276-283,
+ *                      src/partialbridgenuH.jl:86-103,148-155, src/lyap.jl:2-6);
+ *                      if s > 0: gpupdate(ν, H⁺, Σ, L, v[s-1])                                    :284-291, :128-137
+ *   W° = W (innovations held fixed)                                                               :306
+ *   X° = solve!(Euler(), x0, W, Q°) over all segments;  ll° = Σ_s llikelihood(LeftRule(), X°_s, Q°_s)   :324-333
+ *   diffll = logpdfnormal(x0 - ν°(0), symmetrize(H⁺°(0))) - logpdfnormal(x0 - ν(0), symmetrize(H⁺(0)))   :319
+ *          + ll° - ll  + Σ_s (t_s,end - t_s,0) (tr B~°_s - tr B~_s) + logπ(θ°) - logπ(θ)          :331-336
+ *   accept iff log(U) <= diffll:  θ <- θ°, tables, X, ll follow                                   :340-355
+ *
+ * The guiding tables of ALL chains are built on the device (one thread per chain) into a table array
+ * T [S][N][d+d*d][P] (ν[i], H[i] per grid point, chain-minor: warp accesses are contiguous), so that no
+ * θ-proposal round-trips to the host.  The auxiliary process follows from (θ, v_s) by a closed registry
+ * (bb_aux_kind), for the same reason the target models do.  The starting point is not updated (the script's
+ * random-walk on x0 is specific to its L = [.5 .5]).
+ */
+#define BB_NTHETA 8
+typedef enum {
+  BB_AUX_FHN_MATCHING = 1,      /* B~ = [1/ϵ -1/ϵ; γ -1], β~ = (s/ϵ - v³/ϵ, β)           partialbridge_fitzhugh.jl:106-108 */
+  BB_AUX_FHN_LINEARISED_END = 2 /* B~ = [1/ϵ - 3v²/ϵ  -1/ϵ; γ -1], β~ = (s/ϵ + 2v³/ϵ, β)  partialbridge_fitzhugh.jl:98-100 */
+} bb_aux_kind;
+enum { BB_PRIOR_FLAT = 0, BB_PRIOR_GAMMA = 1 /* Gamma(shape a, scale b): logπ of bolus3.jl:237 */ };
+typedef struct {
+  int32_t m;                         /* rows of L */
+  int32_t aux_kind;                  /* bb_aux_kind; a~ = a(θ) of the target (constdiff pairs) */
+  double L[BB_MAXD * BB_MAXD];       /* m x d, row-major */
+  double Sigma[BB_MAXD * BB_MAXD];   /* m x m */
+  double eps;                        /* H⁺ = I/eps right of the last observation */
+  double v[16][BB_MAXD];             /* v[s][0..m-1]: observation at the right end of segment s */
+  int32_t prior_kind[BB_NTHETA];
+  double prior_a[BB_NTHETA], prior_b[BB_NTHETA];
+} bb_theta_spec;
+
+/* allocate θ (all chains start at model->par), the table array T and the per-chain left-end values */
+int bb_theta_attach(bb_ens* ens, const bb_model* model, const bb_theta_spec* spec);
+/* theta: [np][BB_NTHETA] */
+int bb_theta_set(bb_ens* ens, int64_t p0, int64_t np, const double* theta);
+int bb_theta_get(bb_ens* ens, int which /* BB_CUR | BB_PROP */, int64_t p0, int64_t np, double* theta);
+/* backward pass for the CURRENT θ of every chain -> T, left-end values */
+int bb_theta_guides(bb_ens* ens);
+/* left-end values of the last backward pass: out [np][d + d*d + 4] = ν(0), H⁺(0), C,
+ * logpdfnormal(x0 - ν(0), H⁺(0)), Σ_s (t_s,end - t_s,0) tr B~_s, logπ(θ) */
+int bb_theta_get_left(bb_ens* ens, int which, int64_t p0, int64_t np, double* out);
+/* tables of one chain as the reference holds them: nu [S][N][d], H [S][N][d][d] */
+int bb_theta_get_tables(bb_ens* ens, int64_t p, double* nu, double* H);
+/* solve!(Euler(), X, x0, W, Q_p) + llikelihood with each chain's own θ and tables (initialisation, bolus3.jl:186-192) */
+int bb_theta_guided_euler_ll(bb_ens* ens, int32_t skip, uint32_t flags);
+/* one pCN iteration (as bb_pcn_step) with each chain's own θ and tables */
+int bb_theta_pcn_step(bb_ens* ens, double rho, uint64_t seed, uint32_t iter, int32_t skip, uint32_t flags);
+/* one parameter-update MH iteration; rw_sd [BB_NTHETA] (0 = parameter not updated, at most 4 non-zero).
+ * Random numbers: Philox counter (0xFFFFFFFE, iter, chain) for ξ, (0xFFFFFFFD, iter, chain) for U. */
+int bb_theta_param_step(bb_ens* ens, const double* rw_sd, uint64_t seed, uint32_t iter, int32_t skip,
+                        uint32_t flags);
+/* bb_ens_refresh_x for chains with their own tables: X <- current path of the chains whose last proposal (pCN or
+ * parameter) was rejected */
+int bb_theta_refresh_x(bb_ens* ens);
+/* accepted parameter proposals since attach, summed over this ensemble's chains */
+int bb_theta_get_acc(bb_ens* ens, int64_t* acc);
+void* bb_theta_acc_device_ptr(bb_ens* ens);
+
 #ifdef __cplusplus
 }
 #endif

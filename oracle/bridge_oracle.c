@@ -298,6 +298,16 @@ double bbo_accept_logu(uint64_t seed, uint32_t stream, uint64_t chain) {
   return (double)bb_logf(bb_unif(o[0]));
 }
 
+/* log U of the parameter-update accept test: the same generator with q = 0xFFFFFFFD (the pCN accept test of the
+ * same iteration keeps 0xFFFFFFFF; the parameter proposal's normals are quad 0xFFFFFFFE of row = chain) */
+double bbo_logu_q(uint64_t seed, uint32_t stream, uint64_t chain, uint32_t q) {
+  uint32_t ctr[4] = {q, stream, (uint32_t)chain, (uint32_t)(chain >> 32)};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t o[4];
+  bbo_philox4x32_10(ctr, key, o);
+  return (double)bb_logf(bb_unif(o[0]));
+}
+
 /* ======================================================================= A1: sample!(W, Wiener{T}())
  * src/wiener.jl:50-58 (scalar), :24-35 (SVector), :37-48 (VSamplePath):
  *   yy[1] = y1 (kept);  yy[i] = yy[i-1] + sqrt(tt[i]-tt[i-1]) * randn()   component-minor draw order.

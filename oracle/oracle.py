@@ -136,6 +136,7 @@ class Oracle:
         L.bbo_logpdfnormal.restype = C.c_double
         L.bbo_normal.restype = C.c_double
         L.bbo_accept_logu.restype = C.c_double
+        L.bbo_logu_q.restype = C.c_double
         L.bbo_llikelihood.restype = C.c_double
         L.bbo_pcn_propose.restype = C.c_double
         L.bbo_pcn_bench.restype = C.c_longlong
@@ -154,6 +155,9 @@ class Oracle:
 
     def accept_logu(self, seed, stream, chain):
         return self.lib.bbo_accept_logu(C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(chain))
+
+    def logu_q(self, seed, stream, chain, q):
+        return self.lib.bbo_logu_q(C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(chain), C.c_uint32(q))
 
     def logpdfnormal(self, x, Sigma):
         x = np.atleast_1d(_f64(x)); S = np.atleast_2d(_f64(Sigma))
@@ -294,3 +298,98 @@ def load(variant: str = "ref") -> Oracle:
     if variant not in _cache:
         _cache[variant] = Oracle(variant)
     return _cache[variant]
+
+
+# ======================================================================= per-chain parameters
+# The `updateparams` branch of project_partialbridge/partialbridge_bolus3.jl:248-365 for ONE chain, composed from
+# the oracle's restatements of the reference functions it calls (partialbridgeνH / Lyap, gpupdate, solve!,
+# llikelihood, logpdfnormal).  Mirrors bb_theta.cu; the summation orders of the script-level quantities
+# (trace term, diffll) are the ones written here.
+AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END = 1, 2
+Q_THETA_NORMALS, Q_THETA_LOGU = 0xFFFFFFFE, 0xFFFFFFFD
+
+
+def fhn_aux(kind, par, v):
+    """B~, beta~, a~ from (θ, v): partialbridge_fitzhugh.jl:98-108 (x^2, x^3 as products: Julia literal_pow)."""
+    eps, s, gam, beta = (float(x) for x in par[:4])
+    ie = 1.0 / eps
+    if kind == AUX_FHN_MATCHING:
+        Bt = np.array([[ie, -ie], [gam, -1.0]])
+        bt = np.array([s / eps - (v * v * v) / eps, beta])
+    else:
+        Bt = np.array([[ie - (3.0 * (v * v)) / eps, -ie], [gam, -1.0]])
+        bt = np.array([s / eps + (2.0 * (v * v * v)) / eps, beta])
+    return Bt, bt
+
+
+def fhn_a(model_id, par):
+    if model_id == FHN_HYPO:
+        return np.array([[0.0, 0.0], [0.0, float(par[4]) * float(par[4])]])
+    return np.array([[float(par[4]) * float(par[4]), 0.0], [0.0, float(par[5]) * float(par[5])]])
+
+
+def theta_backward(o: Oracle, model_id, par, grids, x0, L, Sigma, eps, obs_v, aux_kind, priors=None):
+    """-> (guides [S], left dict): bolus3.jl:162-165, 276-291 for one θ."""
+    S = len(grids)
+    L = np.atleast_2d(_f64(L)); d = L.shape[1]
+    at = fhn_a(model_id, par)
+    nu = np.zeros(d); Hp = np.eye(d) * (1.0 / eps)
+    nu, Hp = o.gpupdate_nuH(nu, Hp, L, Sigma, np.atleast_1d(obs_v[S - 1]))
+    guides = [None] * S
+    Cc = 0.0; trsum = 0.0
+    for s in range(S - 1, -1, -1):
+        Bt, bt = fhn_aux(aux_kind, par, float(np.atleast_1d(obs_v[s])[0]))
+        aux = const_aux(Bt, bt, at)
+        nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], aux, nu, Hp, Cc)
+        guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=Bt, betat=bt)
+        tr = Bt[0, 0]
+        for i in range(1, d):
+            tr += Bt[i, i]
+        trsum += (grids[s][-1] - grids[s][0]) * tr
+        if s > 0:
+            nu, Hp = o.gpupdate_nuH(nu, Hp, L, Sigma, np.atleast_1d(obs_v[s - 1]))
+    lpn = o.logpdfnormal(np.asarray(x0, dtype=np.float64) - nu, Hp)
+    lpri = 0.0
+    for k in sorted((priors or {})):
+        _, a, b = priors[k]
+        x = float(par[k])
+        import math
+        t = -math.lgamma(a) - a * math.log(b)
+        if a - 1.0 != 0.0:
+            t += (a - 1.0) * math.log(x) if x > 0 else 0.0
+        t -= x / b
+        lpri += t if x > 0.0 else -math.inf
+    return guides, dict(nu=nu, Hp=Hp, C=Cc, lpn=lpn, trsum=trsum, lpri=lpri)
+
+
+def theta_forward(o: Oracle, model_id, dprime, par, guides, x0, W, skip=0):
+    """solve!(Euler(), X, x0, W, Q) over all segments + Σ llikelihood: -> (X [S,N,d], ll, xend)"""
+    S = len(guides)
+    mdl = make_model(model_id, 2, dprime, par)
+    X = []; ll = 0.0; u = np.asarray(x0, dtype=np.float64)
+    for s in range(S):
+        Xs, u = o.guided_euler(mdl, guides[s], u, W[s])
+        ll += o.llikelihood(mdl, guides[s], Xs, skip)
+        X.append(Xs)
+    return np.stack(X), ll, u
+
+
+def theta_propose(o: Oracle, par, rw_sd, seed, it, chain):
+    """propose(σ, P): θ° = θ + σ .* randn (bolus3.jl:239-242); the n-th updated parameter takes normal n of quad
+    0xFFFFFFFE of row = chain."""
+    par = np.array(par, dtype=np.float64)
+    n = 0
+    for k in range(len(rw_sd)):
+        if rw_sd[k] != 0.0:
+            z = o.normal(seed, it, chain, 4 * Q_THETA_NORMALS + n)
+            par[k] = par[k] + rw_sd[k] * z
+            n += 1
+    return par
+
+
+def theta_diffll(left_c, left_o, ll_c, ll_o):
+    """diffll of bolus3.jl:319,331-336 in the kernel's summation order."""
+    diff = left_o["lpn"] - left_c["lpn"]
+    diff += ll_o - ll_c
+    diff += ((left_o["trsum"] - left_c["trsum"]) + left_o["lpri"]) - left_c["lpri"]
+    return diff

@@ -1,0 +1,251 @@
+"""Per-chain parameters: device-built guiding tables, forward pass, pCN and the parameter-update
+MH step of partialbridge_bolus3.jl:248-365, against the oracle composition in oracle/oracle.py.  GPU only.
+
+  * guiding tables, ν(0), H⁺(0), C vs liboracle_fma: BIT-EXACT; logpdfnormal / Gamma prior (device log): 1e-13 rel;
+  * paths and log-likelihoods vs liboracle_fma: BIT-EXACT; vs liboracle_ref: the tolerances of test_gpu_parity.py;
+  * accept decisions: replayed exactly from the kernel's own numbers, and against the oracle's diffll;
+  * with identical θ in every chain the per-chain kernels reproduce the shared-table kernels bit for bit.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+XTOL = 1e-10
+LLREL, LLABS = 1e-6, 1e-9
+RW = np.array([0.0, 0.0, 0.02, 0.03, 0.01, 0, 0, 0])  # γ, β, σ are updated
+PRIORS = {2: ("gamma", 1.0, 100.0), 3: ("gamma", 1.0, 100.0), 4: ("gamma", 2.0, 50.0)}
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bridge_jl_b200 as B
+    B.default_context()
+    return B
+
+
+def setup(B, P, n, S, aux_kind=O.AUX_FHN_MATCHING, priors=None, diag=False, seed=11, spread=True, offset=0):
+    import bridge_jl_b200.configs as cfg
+    obs_t, obs_v = cfg.FHN_OBS_T[:S], cfg.FHN_OBS_V[:S]
+    grids = cfg.fhn_segment_grids(n, obs_t)
+    if diag:
+        Pm = B.FitzHughNagumo(*cfg.FHN_PAR[:4], 0.3, 0.25)
+        dp = 2
+    else:
+        Pm = B.FitzhughDiffusion(*cfg.FHN_PAR)
+        dp = 1
+    ens = B.PathEnsemble(P, S, n, 2, dp, chain_offset=offset)
+    for s, g in enumerate(grids):
+        ens.set_grid(s, g)
+    ens.set_start(cfg.FHN_X0)
+    ens.theta_attach_(Pm, cfg.FHN_L, cfg.FHN_SIGMA, cfg.FHN_EPS, obs_v, aux_kind=aux_kind, priors=priors)
+    th = ens.theta()
+    if spread:
+        rng = np.random.default_rng(5)
+        th[:, 2] += 0.2 * rng.standard_normal(P)   # γ
+        th[:, 3] += 0.1 * rng.standard_normal(P)   # β
+        th[:, 4] *= np.exp(0.2 * rng.standard_normal(P))  # σ
+        ens.set_theta(th)
+    ens.sample_(seed, 0xFFFFFFF0)
+    return ens, Pm, grids, obs_v, th, dp
+
+
+def oracle_left(o, Pm, th, grids, obs_v, aux_kind, priors):
+    import bridge_jl_b200.configs as cfg
+    npar = len(Pm.par())
+    return O.theta_backward(o, Pm.model_id, th[:npar], grids, cfg.FHN_X0, cfg.FHN_L, cfg.FHN_SIGMA, cfg.FHN_EPS,
+                            obs_v, aux_kind, priors)
+
+
+@pytest.mark.parametrize("aux_kind,diag,n,S", [(O.AUX_FHN_MATCHING, False, 101, 3), (O.AUX_FHN_LINEARISED_END, False, 50, 2),
+                                               (O.AUX_FHN_MATCHING, True, 33, 4)])
+def test_theta_tables_bit_exact(B, oracle_fma, aux_kind, diag, n, S):
+    P = 70
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, n, S, aux_kind, PRIORS, diag)
+    ens.theta_guides_()
+    left = ens.theta_left()
+    for p in (0, 1, 31, 32, 69):
+        guides, lo = oracle_left(oracle_fma, Pm, th[p], grids, obs_v, aux_kind, PRIORS)
+        ν, H = ens.theta_tables(p)
+        for s in range(S):
+            assert np.array_equal(ν[s], guides[s].b), (p, s)
+            assert np.array_equal(H[s], guides[s].A), (p, s)
+        assert np.array_equal(left[p, 0:2], lo["nu"]) and np.array_equal(left[p, 2:6].reshape(2, 2), lo["Hp"])
+        assert left[p, 6] == lo["C"]
+        assert abs(left[p, 7] - lo["lpn"]) <= 1e-13 * abs(lo["lpn"])
+        assert left[p, 8] == lo["trsum"]
+        assert abs(left[p, 9] - lo["lpri"]) <= 1e-13 * abs(lo["lpri"]) + 1e-15
+    ens.close()
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_theta_forward_and_pcn_vs_oracle(B, oracle_fma, oracle_ref, diag):
+    import bridge_jl_b200.configs as cfg
+    P, n, S, seed = 96, 65, 3, 21
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, n, S, diag=diag, offset=500)
+    ens.theta_guided_euler_ll_()
+    Wc = ens.download(B.W); Xc = ens.download(B.X); ll = ens.ll
+    npar = len(Pm.par())
+    mid = Pm.model_id
+    for p in (0, 5, 33, 95):
+        # the tables are ill-conditioned in rounding (Σ = 1e-10: H of the fma and the reference arithmetic agree to
+        # ~1e-6 only, as in test_gpu_parity.py::test_backward_constructors_vs_oracle), so the forward pass in
+        # reference arithmetic is run on the SAME tables
+        guides, _ = oracle_left(oracle_fma, Pm, th[p], grids, obs_v, O.AUX_FHN_MATCHING, None)
+        for o, exact in ((oracle_fma, True), (oracle_ref, False)):
+            Xo, llo, _ = O.theta_forward(o, mid, dp, th[p, :npar], guides, cfg.FHN_X0, Wc[p])
+            if exact:
+                assert np.array_equal(Xc[p], Xo) and ll[p] == llo
+            else:
+                assert np.max(np.abs(Xc[p] - Xo)) <= XTOL * (1 + np.max(np.abs(Xo)))
+                assert abs(ll[p] - llo) <= LLREL * abs(llo) + LLABS
+    # pCN with the chains' own tables
+    rho = 0.9
+    acc0 = ens.acc
+    for it in range(2):
+        llc = ens.ll
+        ens.theta_pcn_step_(rho, seed, it)
+        Wp = ens.download(B.W, which=B.PROP); Xp = ens.download(B.X, which=B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
+        assert np.array_equal(flags.astype(bool), logu <= llp - llc)
+        for p in (0, 5, 33, 95):
+            guides, _ = oracle_left(oracle_fma, Pm, th[p], grids, obs_v, O.AUX_FHN_MATCHING, None)
+            mdl = O.make_model(mid, 2, dp, th[p, :npar])
+            llo, lu, Wo, Xo, _ = oracle_fma.pcn_propose(mdl, guides, cfg.FHN_X0, Wc[p], rho, seed, it, 500 + p)
+            assert np.array_equal(Wp[p], Wo) and np.array_equal(Xp[p], Xo), (it, p)
+            assert llp[p] == llo and logu[p] == lu
+        Wc = ens.download(B.W)
+        assert np.array_equal(ens.ll, np.where(flags.astype(bool), llp, llc))
+    assert ens.acc - acc0 > 0
+    # X of the chains that rejected is recomputed from their current W with their own tables
+    Xcur = ens.download(B.X)
+    for p in (0, 5, 33, 95):
+        guides, _ = oracle_left(oracle_fma, Pm, th[p], grids, obs_v, O.AUX_FHN_MATCHING, None)
+        Xo, llo, _ = O.theta_forward(oracle_fma, mid, dp, th[p, :npar], guides, cfg.FHN_X0, Wc[p])
+        assert np.array_equal(Xcur[p], Xo) and ens.ll[p] == llo
+    ens.close()
+
+
+def test_theta_param_step_vs_oracle(B, oracle_fma, oracle_ref):
+    import bridge_jl_b200.configs as cfg
+    P, n, S, seed = 128, 81, 4, 99
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, n, S, priors=PRIORS, offset=7000)
+    ens.theta_guided_euler_ll_()
+    Wc = ens.download(B.W)
+    npar = len(Pm.par()); mid = Pm.model_id
+    nacc = 0
+    for it in range(3):
+        thc = ens.theta(); llc = ens.ll; leftc = ens.theta_left(B.CUR)
+        ens.theta_param_step_(RW, seed, 100 + it)
+        tho = ens.theta(B.PROP); lefto = ens.theta_left(B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted.astype(bool)
+        Xp = ens.download(B.X, which=B.PROP)
+        # replay of the accept test from the kernel's own numbers (exact)
+        diff = (lefto[:, 7] - leftc[:, 7])
+        diff = diff + (llp - llc)
+        diff = diff + (((lefto[:, 8] - leftc[:, 8]) + lefto[:, 9]) - leftc[:, 9])
+        assert np.array_equal(flags, logu <= diff)
+        assert np.array_equal(ens.theta(), np.where(flags[:, None], tho, thc))
+        assert np.array_equal(ens.ll, np.where(flags, llp, llc))
+        assert np.array_equal(ens.theta_left(B.CUR), np.where(flags[:, None], lefto, leftc))
+        assert np.array_equal(ens.download(B.W), Wc)  # innovations are held fixed (bolus3.jl:306)
+        for p in (0, 17, 64, 127):
+            tp = O.theta_propose(oracle_fma, thc[p], RW, seed, 100 + it, 7000 + p)
+            gc, lc = oracle_left(oracle_fma, Pm, thc[p], grids, obs_v, O.AUX_FHN_MATCHING, PRIORS)
+            go, lo = oracle_left(oracle_fma, Pm, tp, grids, obs_v, O.AUX_FHN_MATCHING, PRIORS)
+            for o, exact in ((oracle_fma, True), (oracle_ref, False)):
+                assert np.array_equal(tp, O.theta_propose(o, thc[p], RW, seed, 100 + it, 7000 + p))
+                Xo, llo, _ = O.theta_forward(o, mid, dp, tp[:npar], go, cfg.FHN_X0, Wc[p])
+                _, llcur, _ = O.theta_forward(o, mid, dp, thc[p, :npar], gc, cfg.FHN_X0, Wc[p])
+                d_or = O.theta_diffll(lc, lo, llcur, llo)
+                lu = o.logu_q(seed, 100 + it, 7000 + p, O.Q_THETA_LOGU)
+                if exact:
+                    assert np.array_equal(tho[p], tp) and np.array_equal(Xp[p], Xo) and llp[p] == llo
+                    assert llc[p] == llcur and logu[p] == lu
+                    assert abs(diff[p] - d_or) <= 1e-12 * (1 + abs(d_or))
+                else:
+                    assert np.max(np.abs(Xp[p] - Xo)) <= XTOL * (1 + np.max(np.abs(Xo)))
+                    assert abs(llp[p] - llo) <= LLREL * abs(llo) + LLABS
+                if abs(lu - d_or) > 1e-5 * (1 + abs(llo) + abs(llcur)):  # decisions away from the boundary agree
+                    assert flags[p] == (lu <= d_or)
+        nacc += int(flags.sum())
+    assert ens.acc_theta == nacc and 0 < nacc < 3 * P
+    # the current path of every chain (rejected proposals recomputed with the tables of the CURRENT θ)
+    Xcur = ens.download(B.X); thf = ens.theta()
+    for p in (0, 17, 64, 127):
+        g, _ = oracle_left(oracle_fma, Pm, thf[p], grids, obs_v, O.AUX_FHN_MATCHING, PRIORS)
+        Xo, llo, _ = O.theta_forward(oracle_fma, mid, dp, thf[p, :npar], g, cfg.FHN_X0, Wc[p])
+        assert np.array_equal(Xcur[p], Xo) and ens.ll[p] == llo
+    # a pCN step after parameter steps uses the tables of the current θ
+    llc = ens.ll
+    ens.theta_pcn_step_(0.95, seed, 7)
+    Wp = ens.download(B.W, which=B.PROP)
+    for p in (0, 17, 64, 127):
+        g, _ = oracle_left(oracle_fma, Pm, thf[p], grids, obs_v, O.AUX_FHN_MATCHING, PRIORS)
+        mdl = O.make_model(mid, 2, dp, thf[p, :npar])
+        llo, lu, Wo, Xo, _ = oracle_fma.pcn_propose(mdl, g, cfg.FHN_X0, Wc[p], 0.95, seed, 7, 7000 + p)
+        assert np.array_equal(Wp[p], Wo) and ens.ll_prop[p] == llo
+    ens.close()
+
+
+def test_theta_equal_parameters_reproduce_shared_tables(B):
+    """All chains at the model's θ: the per-chain kernels must give what the shared-table kernels give."""
+    import bridge_jl_b200.configs as cfg
+    P, n, seed = 300, 129, 3
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, n, 4, spread=False)
+    Pm2, guides, x0, rho = cfg.fhn_config4(n)
+    ref = B.PathEnsemble(P, 4, n, 2, 1)
+    for s, g in enumerate(guides):
+        ref.set_grid(s, g.tt)
+    ref.set_start(x0)
+    ref.sample_(11, 0xFFFFFFF0)
+    assert np.array_equal(ref.download(B.W), ens.download(B.W))
+    ref.guided_euler_ll_(Pm2, guides)
+    ens.theta_guided_euler_ll_()
+    ν, H = ens.theta_tables(123)
+    for s, g in enumerate(guides):
+        assert np.array_equal(ν[s], g.ν) and np.array_equal(H[s], g.H)
+    assert np.array_equal(ref.ll, ens.ll) and np.array_equal(ref.download(B.X), ens.download(B.X))
+    for it in range(3):
+        ref.pcn_step_(Pm2, guides, rho, seed, it)
+        ens.theta_pcn_step_(rho, seed, it)
+        assert np.array_equal(ref.accepted, ens.accepted) and np.array_equal(ref.ll_prop, ens.ll_prop)
+        assert np.array_equal(ref.download(B.W, which=B.PROP), ens.download(B.W, which=B.PROP))
+        assert np.array_equal(ref.download(B.X, which=B.PROP), ens.download(B.X, which=B.PROP))
+    assert ref.acc == ens.acc
+    assert np.array_equal(ref.download(B.X), ens.download(B.X))
+    ref.close(); ens.close()
+
+
+def test_theta_rejects_impossible_parameters(B):
+    """σ° <= 0 under a Gamma prior has logπ = -Inf: never accepted; NaN log-likelihoods never accepted."""
+    P = 64
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, 41, 2, priors=PRIORS)
+    ens.theta_guided_euler_ll_()
+    th0 = ens.theta()
+    ens.theta_param_step_(np.array([0, 0, 0, 0, 5.0, 0, 0, 0]), 1, 0)  # huge steps in σ: about half go negative
+    tho = ens.theta(B.PROP); flags = ens.accepted.astype(bool)
+    assert (tho[:, 4] <= 0).any()
+    assert not flags[tho[:, 4] <= 0].any()
+    assert np.array_equal(ens.theta()[~flags], th0[~flags])
+    ens.close()
+
+
+def test_theta_errors(B):
+    import bridge_jl_b200.configs as cfg
+    ens = B.PathEnsemble(8, 1, 9, 3, 3)
+    with pytest.raises(B.BridgeError) as ei:
+        ens.theta_attach_(B.Lorenz((10.0, 28.0, 8 / 3), (1.0, 1.0, 1.0)), np.eye(3), np.eye(3), 1e-3, [[0, 0, 0]])
+    assert ei.value.status == -11  # BB_ERR_UNSUPPORTED
+    with pytest.raises(B.BridgeError):
+        ens.theta_guides_()  # nothing attached
+    ens.close()
+    ens = B.PathEnsemble(8, 1, 9, 2, 1)
+    ens.theta_attach_(B.FitzhughDiffusion(*cfg.FHN_PAR), cfg.FHN_L, cfg.FHN_SIGMA, cfg.FHN_EPS, [0.5])
+    with pytest.raises(B.BridgeError):
+        ens.theta_guides_()  # no grid set
+    with pytest.raises(B.BridgeError):
+        ens.theta_param_step_(np.array([1, 1, 1, 1, 1.0, 0, 0, 0]), 1, 0)  # more than 4 updated parameters
+    ens.close()
