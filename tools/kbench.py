@@ -38,6 +38,6 @@ for m in modes:
         ctx.synchronize()
         ts.append(ctx.last_kernel_ms)
     t = float(np.median(ts[3:]))
-    print(f"{os.environ.get('BB_LIB','default').split('/')[-1]:24s} {m:13s} P={P} ms={t:8.3f} steps/s={steps / t * 1e-3:.3e} "
+    print(f"{os.environ.get('BB_LIB','default').split('/')[-1]:24s} {m:13s} P={P} ms={t:8.3f} steps/s={steps / t * 1e3:.3e} "
           f"alg GB/s={steps * nbytes / t * 1e-6:7.0f} ({nbytes} B/step) frac={steps * nbytes / t * 1e-6 / 6546.6:.3f}", flush=True)
 ens.close()

@@ -26,3 +26,15 @@ for s in range(2):
     e3.set_grid(s, np.linspace(s, s + 1, 33))
 e3.set_start([1.0, 0.0, 0.0]); e3.sample_euler_(L3, 3, 0); e3.innovations_(L3)
 print("ok", float(np.sum(X)) != 0.0, ens.acc)
+# per-chain parameters: backward tables, forward, pCN, parameter step, X refresh (ragged: P = 333, N = 49)
+et = B.PathEnsemble(333, 3, n, 2, 1)
+for s, g in enumerate(guides):
+    et.set_grid(s, g.tt)
+et.set_start(x0)
+et.theta_attach_(Pm, cfg.FHN_L, cfg.FHN_SIGMA, cfg.FHN_EPS, (-1.0, -0.5, 0.5), priors={4: ("gamma", 2.0, 50.0)})
+et.sample_(1, 0)
+et.theta_guided_euler_ll_()
+et.theta_param_step_([0, 0, 0.02, 0.02, 0.01], 1, 10)
+et.theta_pcn_step_(rho, 1, 11)
+Xt = et.download(B.X)
+print("theta ok", et.acc_theta, et.acc, float(np.sum(Xt)) != 0.0)
