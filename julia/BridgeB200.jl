@@ -142,4 +142,39 @@ function solve!(::EulerMaruyama, Y::SamplePath{T}, u::T, W::SamplePath, P::Conti
     Y.tt .= W.tt; Y
 end
 
+# ---- per-chain parameters: the `updateparams` branch of partialbridge_bolus3.jl:248-365 (bb_theta_* of the header)
+struct BBThetaSpec   # == bb_theta_spec
+    m::Int32; aux_kind::Int32
+    L::NTuple{16,Float64}; Sigma::NTuple{16,Float64}; eps::Float64
+    v::NTuple{64,Float64}                      # v[s][0..3], row per segment
+    prior_kind::NTuple{8,Int32}; prior_a::NTuple{8,Float64}; prior_b::NTuple{8,Float64}
+end
+const AUXKIND = Dict(:fhn_matching => Int32(1), :fhn_linearised_end => Int32(2))
+function theta_attach!(E::PathEnsemble, P::ContinuousTimeProcess, L, Σ, ϵ, obs; aux = :fhn_matching, priors = Dict())
+    m, d = size(L)
+    Lr = zeros(16); Sr = zeros(16); vr = zeros(64); pk = zeros(Int32, 8); pa = zeros(8); pb = zeros(8)
+    for i in 1:m, j in 1:d; Lr[(i-1)*d + j] = L[i, j]; end        # row-major in the ABI
+    for i in 1:m, j in 1:m; Sr[(i-1)*m + j] = Σ[i, j]; end
+    for (s, v) in enumerate(obs), i in 1:m; vr[(s-1)*4 + i] = v[i]; end
+    for (k, (kind, a, b)) in priors; pk[k+1] = 1; pa[k+1] = a; pb[k+1] = b; end   # k: 0-based parameter index
+    spec = Ref(BBThetaSpec(m, AUXKIND[aux], Tuple(Lr), Tuple(Sr), ϵ, Tuple(vr), Tuple(pk), Tuple(pa), Tuple(pb)))
+    mdl = Ref(bbmodel(P))
+    check(ccall((:bb_theta_attach, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ref{BBThetaSpec}), E.h, mdl, spec)); E
+end
+theta_solve!(E::PathEnsemble; skip = 0, store_x = true) =   # backward ODEs of every chain + solve! + llikelihood
+    check(ccall((:bb_theta_guided_euler_ll, lib), Cint, (Ptr{Cvoid}, Int32, UInt32), E.h, skip, store_x ? 1 : 0))
+theta_pcn!(E::PathEnsemble, ρ, seed::UInt64, iter::Integer; skip = 0, store_x = true) =
+    check(ccall((:bb_theta_pcn_step, lib), Cint, (Ptr{Cvoid}, Float64, UInt64, UInt32, Int32, UInt32),
+                E.h, ρ, seed, iter, skip, store_x ? 1 : 0))
+function theta_param_step!(E::PathEnsemble, rw_sd, seed::UInt64, iter::Integer; skip = 0, store_x = true)
+    sd = zeros(8); sd[1:length(rw_sd)] .= rw_sd
+    check(ccall((:bb_theta_param_step, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, UInt64, UInt32, Int32, UInt32),
+                E.h, sd, seed, iter, skip, store_x ? 1 : 0))
+    acc = Ref{Int64}(0); check(ccall((:bb_theta_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, acc)); acc[]
+end
+function theta(E::PathEnsemble)   # param(P) of every chain: 8 x P (column per chain)
+    θ = Matrix{Float64}(undef, 8, E.P)
+    check(ccall((:bb_theta_get, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, E.P, θ)); θ
+end
+
 end # module
