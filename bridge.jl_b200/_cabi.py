@@ -29,6 +29,7 @@ W, X = 0, 1
 CUR, PROP = 0, 1
 F_LL, F_LL_PROP, F_LOGU, F_XEND, F_XEND_PROP = range(5)
 RUN_STORE_X, RUN_NO_LL = 1, 2
+SCHEME_EULER, SCHEME_STRATONOVICH, SCHEME_HEUN, SCHEME_SRK, SCHEME_MDB = range(5)
 
 
 class BridgeError(RuntimeError):
@@ -100,6 +101,7 @@ def _load():
         "bb_wiener_sample": (C.c_int, [vp, u64, u32]),
         "bb_euler": (C.c_int, [vp, C.POINTER(Model)]),
         "bb_sample_euler": (C.c_int, [vp, C.POINTER(Model), u64, u32]),
+        "bb_solve_scheme": (C.c_int, [vp, C.POINTER(Model), i32]),
         "bb_guide_create": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, pp]),
         "bb_guide_create_ncd": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, pp]),
         "bb_guide_destroy": (C.c_int, [vp]),

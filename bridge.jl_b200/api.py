@@ -91,6 +91,22 @@ class EulerMaruyama(SDESolver):  # src/euler.jl:17-21
 Euler = EulerMaruyama  # src/euler.jl:23
 
 
+class StratonovichEuler(SDESolver):  # src/euler.jl:26-31
+    scheme = K.SCHEME_STRATONOVICH
+
+
+class StochasticHeun(SDESolver):  # src/euler.jl:38-44
+    scheme = K.SCHEME_HEUN
+
+
+class StochasticRungeKutta(SDESolver):  # src/euler.jl:55-61
+    scheme = K.SCHEME_SRK
+
+
+class Mdb(SDESolver):  # src/euler.jl:46-52 (needs a classic proposal process: not on the accelerated path)
+    scheme = K.SCHEME_MDB
+
+
 class LeftRule:  # src/ode.jl:8
     pass
 
@@ -506,6 +522,11 @@ class PathEnsemble:
         m = P.cmodel()
         check(lib.bb_euler(self.h, C.byref(m)))
 
+    def solve_scheme_(self, P: ContinuousTimeProcess, scheme: int):
+        """solve! with StratonovichEuler / StochasticHeun / StochasticRungeKutta for a plain target (bb_solve_scheme)."""
+        m = P.cmodel()
+        check(lib.bb_solve_scheme(self.h, C.byref(m), scheme))
+
     def sample_euler_(self, P: ContinuousTimeProcess, seed: int, stream: int = 0):
         m = P.cmodel()
         check(lib.bb_sample_euler(self.h, C.byref(m), seed, stream))
@@ -874,9 +895,12 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
     """solve!(::EulerMaruyama, Y, u, W, P) -> Y                     src/euler.jl:135-152
     solve!(::Euler, Y, u, W, P°) -> Y.yy[N] (the end point)       src/euler.jl:247-268"""
     ctx = ctx or default_context()
-    if not isinstance(method, EulerMaruyama):
-        raise NotImplementedError("only EulerMaruyama()/Euler() is on the accelerated path")
     guided = _is_proposal(P)
+    scheme = getattr(method, "scheme", K.SCHEME_EULER)
+    if guided and scheme not in (K.SCHEME_EULER, K.SCHEME_STRATONOVICH):
+        # guided solve! exists for Euler and StratonovichEuler only (src/euler.jl:246-306); the latter equals the
+        # former for the registry's constant σ
+        raise BridgeError(K.ERR_UNSUPPORTED, lib.bb_strerror(K.ERR_UNSUPPORTED).decode())
     target = P.Target if guided else P
     if guided and W.tt is P.tt:
         raise BridgeError(K.ERR_TIMEAXIS, lib.bb_strerror(K.ERR_TIMEAXIS).decode())  # src/euler.jl:248
@@ -894,7 +918,12 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
         Y.tt[...] = P.tt  # tt[:] = P.tt  src/euler.jl:256
     else:
         e.set_grid(0, W.tt)
-        e.euler_(target)
+        if scheme == K.SCHEME_EULER:
+            e.euler_(target)
+        else:
+            if scheme == K.SCHEME_HEUN:  # yy[N] is not written by this scheme (src/euler.jl:188-196)
+                e.upload(K.X, Y._as2d())
+            e.solve_scheme_(target, scheme)
         Y.tt[...] = W.tt
     X = e.download(K.X)
     Y.yy[...] = X.reshape(Y.yy.shape)

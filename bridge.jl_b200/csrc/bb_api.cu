@@ -718,7 +718,7 @@ struct run_spec {
   int64_t p_begin = 0, p_end = -1; /* chain sub-range (default: all) */
 };
 
-/* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations! */
+/* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations!; 12 = StochasticHeun */
 static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, const run_spec& rs) {
   if (!e || !model) return BB_ERR_ARG;
   bb_ctx* c = e->ctx;
@@ -777,7 +777,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   }
   c->launches++;
   if (rs.rng == 1) e->x_maybe_stale = true;
-  else if (rs.rng < 10 && rs.store_x) e->x_maybe_stale = false;
+  else if ((rs.rng < 10 || rs.rng == 12) && rs.store_x) e->x_maybe_stale = false;
   return BB_OK;
 }
 
@@ -797,6 +797,24 @@ extern "C" int bb_wiener_sample(bb_ens* e, uint64_t seed, uint32_t stream) {
 extern "C" int bb_euler(bb_ens* e, const bb_model* model) {
   run_spec rs{0, true, false, true, 0, 0.0, 0, 0};
   return run_chain(e, model, nullptr, rs);
+}
+extern "C" int bb_solve_scheme(bb_ens* e, const bb_model* model, int32_t scheme) {
+  if (!e || !model) return BB_ERR_ARG;
+  switch (scheme) {
+    case BB_SCHEME_EULER:
+    case BB_SCHEME_STRATONOVICH: /* ½(σ + σ) = σ exactly for the registry's constant σ  (src/euler.jl:82-83) */
+      return bb_euler(e, model);
+    case BB_SCHEME_SRK: /* T <: Number only (src/euler.jl:330); its correction term is exactly 0 for constant σ */
+      if (model->d != 1) return BB_ERR_UNSUPPORTED;
+      return bb_euler(e, model);
+    case BB_SCHEME_HEUN: {
+      if (e->S != 1) return BB_ERR_UNSUPPORTED;
+      run_spec rs{12, true, false, true, 0, 0.0, 0, 0};
+      return run_chain(e, model, nullptr, rs);
+    }
+    case BB_SCHEME_MDB: return BB_ERR_UNSUPPORTED;
+    default: return BB_ERR_ARG;
+  }
 }
 extern "C" int bb_sample_euler(bb_ens* e, const bb_model* model, uint64_t seed, uint32_t stream) {
   run_spec rs{2, true, false, true, 0, 0.0, seed, stream};

@@ -66,6 +66,76 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
   if (MODE == 0) a.ll[p] = lltot;
 }
 
+/* solve!(StochasticHeun(), Y, u, W, P)  src/euler.jl:178-198 for a plain target, one segment:
+ *   y2 = y + b(y) dt;  y = y + 0.5 (b(y2) + b(y)) dt + sigma dw   for the steps 0 .. N-3 ("for i in 1:N-2 # fix me");
+ *   yy[N-1] = endpoint(y);  yy[N] keeps its old value, as in the reference. */
+template <class M>
+__global__ void __launch_bounds__(BB_THREADS) bb_heun_kernel(const __grid_constant__ bb_chain_args a) {
+  constexpr int D = M::D, DP = M::DP;
+  const long long P = a.P;
+  const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.p_end) return;
+  const int par = a.par[p], N = a.N;
+  const double* wr = a.W[par] + p * (a.nbuf * BB_TC * DP);
+  double* xw = a.X + p * (BB_TC * D);
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+  const double* tab = a.tab[0];
+  double y[D], wprev[DP], xlast[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + p];
+  { /* the last grid point is not written by this scheme: carry its old value through the row store */
+    const int jl = N - 1;
+    const double* q = a.X + ((long long)(jl / BB_TC) * P + p) * (BB_TC * D) + (jl % BB_TC) * D;
+#pragma unroll
+    for (int k = 0; k < D; k++) xlast[k] = q[k];
+  }
+  for (int c = 0; c < a.NC; c++) {
+    bb_rowout<D> xo;
+#pragma unroll 1
+    for (int h = 0; h < BB_TC / 4; h++) {
+      double w[4 * DP];
+#pragma unroll
+      for (int q = 0; q < DP; q++) bb_ld4(wr + 4 * h * DP + 4 * q, w + 4 * q);
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++) {
+        const int j = c * BB_TC + 4 * h + s4;
+        if (j >= 1 && j <= N - 2) {
+          const double dt = tab[2 * j];
+          double b1[D], b2[D], y2[D], hb[D], dw[DP];
+          M::b(a.model, y, b1);
+#pragma unroll
+          for (int k = 0; k < D; k++) y2[k] = fma(b1[k], dt, y[k]);
+          M::b(a.model, y2, b2);
+#pragma unroll
+          for (int k = 0; k < D; k++) hb[k] = 0.5 * (b2[k] + b1[k]);
+#pragma unroll
+          for (int k = 0; k < DP; k++) dw[k] = w[s4 * DP + k] - wprev[k];
+          bb_em_update<M>(a.model, hb, dt, dw, y);
+        }
+#pragma unroll
+        for (int k = 0; k < DP; k++) wprev[k] = w[s4 * DP + k];
+        double o[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) o[k] = (j == N - 1) ? xlast[k] : y[k];
+        xo.put(xw + 4 * h * D, s4, o, true);
+      }
+    }
+    wr += wstride;
+    xw += xstride;
+  }
+  a.xstale[p] = 0;
+  if (a.write_end) {
+#pragma unroll
+    for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
+  }
+}
+template <class M>
+static cudaError_t bb_heun_launch(const bb_chain_args& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
+  bb_heun_kernel<M><<<grid, BB_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <class M, int GK, int GM, int AUXM, int MODE>
 static cudaError_t bb_second_launch(const bb_chain_args& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
@@ -83,10 +153,11 @@ static bb_chain_launch_fn bb_lookup_second_guide(int auxm, int mode) {
   }
   return nullptr;
 }
-/* mode 0 = llikelihood (needs a guide), 1 = innovations (guide optional, needs d' = d) */
+/* mode 0 = llikelihood (needs a guide), 1 = innovations (guide optional, needs d' = d), 2 = StochasticHeun (no guide) */
 template <class M>
 static bb_chain_launch_fn bb_lookup_second(int gk, int gm, int auxc, int mode) {
   if (gk == 0) {
+    if (mode == 2) return &bb_heun_launch<M>;
     if constexpr (M::D == M::DP) {
       if (mode == 1) return &bb_second_launch<M, 0, 0, true, 1>;
     }

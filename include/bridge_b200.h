@@ -201,6 +201,18 @@ int bb_wiener_sample(bb_ens* ens, uint64_t seed, uint32_t stream);
  * s+1 continues from the end point of segment s.  src/euler.jl:135-152.
  */
 int bb_euler(bb_ens* ens, const bb_model* model);
+/* The reference's other SDE schemes for a plain (unguided) target, S = 1:
+ *   BB_SCHEME_EULER         solve!(EulerMaruyama(), ...)                          src/euler.jl:135-152  (= bb_euler)
+ *   BB_SCHEME_STRATONOVICH  solve!(StratonovichEuler(), ...)  src/euler.jl:68-88: y + b dt + ½(σ(y^E) + σ(y)) dw.  Every
+ *                           registry model has a constant σ, for which ½(σ + σ) = σ exactly: the Euler-Maruyama kernel.
+ *   BB_SCHEME_SRK           solve!(StochasticRungeKutta(), ...) src/euler.jl:330-356 (scalar processes): its correction
+ *                           ½(σ(ups) - σ(y))(dw² - δ)/√δ is exactly 0 for constant σ: the Euler-Maruyama kernel, d = 1.
+ *   BB_SCHEME_HEUN          solve!(StochasticHeun(), ...)     src/euler.jl:178-198: drift by Heun's rule; as in the
+ *                           reference the loop stops at N-2 and yy[N] is left untouched.
+ * Mdb (src/euler.jl:308-327) needs a proposal process with its own time axis (the classic BridgeProp family, out of
+ * scope): BB_ERR_UNSUPPORTED. */
+enum { BB_SCHEME_EULER = 0, BB_SCHEME_STRATONOVICH = 1, BB_SCHEME_HEUN = 2, BB_SCHEME_SRK = 3, BB_SCHEME_MDB = 4 };
+int bb_solve_scheme(bb_ens* ens, const bb_model* model, int32_t scheme);
 /* fused sample! + solve! (W and X are both written, W is never read) */
 int bb_sample_euler(bb_ens* ens, const bb_model* model, uint64_t seed, uint32_t stream);
 

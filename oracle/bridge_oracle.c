@@ -469,6 +469,29 @@ void bbo_euler(const bb_model* P, int N, const double* tt, const double* u, cons
   memcpy(X + (size_t)(N - 1) * d, y, sizeof(double) * d); /* endpoint(y,P) = y  src/euler.jl:65 */
 }
 
+/* solve!(StochasticHeun(), Y, u, W, P)   src/euler.jl:178-198
+ *   for i in 1:N-2 ("fix me" in the reference): yy[i] = y; B = b(t_i, y); y2 = y + B dt;
+ *       y = y + 0.5 (b(t_{i+1}, y2) + B) dt + sigma (w_{i+1} - w_i)
+ *   yy[N-1] = endpoint(y, P);  yy[N] is NOT written (X[N-1] keeps the caller's value). */
+void bbo_heun(const bb_model* P, int N, const double* tt, const double* u, const double* W,
+              double* X) {
+  int d = P->d, dp = P->dprime;
+  double y[DM], y2[DM], b[DM], b2[DM], hb[DM], dw[DM], S[DM2];
+  model_sigma(P, S);
+  memcpy(y, u, sizeof(double) * d);
+  for (int i = 0; i < N - 2; i++) {
+    memcpy(X + (size_t)i * d, y, sizeof(double) * d);
+    double dt = tt[i + 1] - tt[i];
+    model_b(P, tt[i], y, b);
+    for (int k = 0; k < d; k++) y2[k] = MA(b[k], dt, y[k]);
+    model_b(P, tt[i + 1], y2, b2);
+    for (int k = 0; k < d; k++) hb[k] = 0.5 * (b2[k] + b[k]);
+    for (int l = 0; l < dp; l++) dw[l] = W[(size_t)(i + 1) * dp + l] - W[(size_t)i * dp + l];
+    em_update(P, S, hb, dt, dw, y);
+  }
+  if (N >= 2) memcpy(X + (size_t)(N - 2) * d, y, sizeof(double) * d);
+}
+
 /* ======================================================================= auxiliary process access */
 static void aux_stage(const bb_aux* A, int i, int k, const double** B, const double** beta,
                       const double** a) {

@@ -179,6 +179,13 @@ class Oracle:
         self.lib.bbo_euler(C.byref(model), tt.size, _p(tt), _p(u), _p(W), _p(X))
         return X
 
+    def heun(self, model, tt, u, W, X0=None):
+        """solve!(StochasticHeun(), Y, u, W, P): the last point of Y is not written by the reference (X0 supplies it)."""
+        tt = _f64(tt); W = _f64(W).reshape(tt.size, model.dprime); u = np.atleast_1d(_f64(u))
+        X = np.zeros((tt.size, model.d)) if X0 is None else _f64(X0).reshape(tt.size, model.d).copy()
+        self.lib.bbo_heun(C.byref(model), tt.size, _p(tt), _p(u), _p(W), _p(X))
+        return X
+
     def guided_euler(self, model, guide: GuideHolder, u, W, store=True):
         W = _f64(W).reshape(guide.N, model.dprime); u = np.atleast_1d(_f64(u))
         X = np.zeros((guide.N, model.d)) if store else None

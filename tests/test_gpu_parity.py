@@ -861,3 +861,62 @@ def test_pooled_online_statistics(B, oracle_fma):
     assert np.all(lo <= mean) and np.all(mean <= hi)
     assert np.allclose(mean[0, 0], [-0.5, -0.6]) and np.allclose(cov[0, 0], 0.0, atol=1e-12)   # fixed start point
     ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- rank 4: other SDE schemes
+@pytest.mark.parametrize("name,mk,om,exact", MODELS, ids=[m[0] for m in MODELS])
+def test_stochastic_heun_vs_oracle(B, oracle_ref, oracle_fma, name, mk, om, exact):
+    """solve!(StochasticHeun(), Y, u, W, P)  src/euler.jl:178-198 incl. its quirk: the loop stops at N-2, yy[N-1] gets
+    the end point and yy[N] keeps the caller's value."""
+    Pm = mk(B)
+    d, dp = om.d, om.dprime
+    P, N = 70, 83
+    tt = warped(0.0, 0.7, N)
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal((P, d)) * 0.3
+    ens = B.PathEnsemble(P, 1, N, d, dp, double_buffer=False)
+    ens.set_grid(0, tt)
+    ens.set_start(u)
+    ens.sample_(seed=5, stream=1)
+    W = ens.download(B.W)
+    X0 = rng.standard_normal((P, 1, N, d))
+    ens.upload(B.X, X0)
+    ens.solve_scheme_(Pm, B.StochasticHeun.scheme)
+    X = ens.download(B.X)
+    assert np.array_equal(X[:, 0, -1], X0[:, 0, -1])  # last point untouched
+    for p in (0, 33, 69):
+        Xf = oracle_fma.heun(om, tt, u[p], W[p, 0], X0[p, 0])
+        Xr = oracle_ref.heun(om, tt, u[p], W[p, 0], X0[p, 0])
+        if exact:
+            assert np.array_equal(X[p, 0], Xf), (name, p)
+        assert close_x(X[p, 0], Xr), (name, p)
+    # StratonovichEuler (and StochasticRungeKutta for scalar processes) coincide with Euler-Maruyama for constant σ
+    ens.solve_scheme_(Pm, B.StratonovichEuler.scheme)
+    Xs = ens.download(B.X)
+    ens.euler_(Pm)
+    assert np.array_equal(Xs, ens.download(B.X))
+    if d == 1:
+        ens.solve_scheme_(Pm, B.StochasticRungeKutta.scheme)
+        assert np.array_equal(Xs, ens.download(B.X))
+    else:
+        with pytest.raises(B.BridgeError) as ei:
+            ens.solve_scheme_(Pm, B.StochasticRungeKutta.scheme)
+        assert ei.value.status == -11
+    with pytest.raises(B.BridgeError) as ei:
+        ens.solve_scheme_(Pm, B.Mdb.scheme)
+    assert ei.value.status == -11
+    ens.close()
+
+
+def test_schemes_through_solve(B, oracle_fma):
+    """solve(StochasticHeun(), u, W, P) / solve(StratonovichEuler(), ...) on SamplePaths (P = 1 plumbing)."""
+    tt = np.arange(0, 101) * 0.01
+    W = B.sample(tt, B.Wiener())
+    Pm = B.OrnsteinUhlenbeck(2.0, 0.7)
+    om = O.make_model(O.OU, 1, 1, [2.0, 0.7])
+    X = B.solve(B.StochasticHeun(), 0.1, W, Pm)
+    assert np.array_equal(X.yy, oracle_fma.heun(om, tt, [0.1], W.yy)[:, 0]) and X.yy[-1] == 0.0
+    Xs = B.solve(B.StratonovichEuler(), 0.1, W, Pm)
+    assert np.array_equal(Xs.yy, B.solve(B.Euler(), 0.1, W, Pm).yy)
+    Xk = B.solve(B.StochasticRungeKutta(), 0.1, W, Pm)
+    assert np.array_equal(Xk.yy, Xs.yy)

@@ -455,3 +455,23 @@ def test_nonconstdiff_llikelihood_terms(oracle_ref):
         extra += -0.5 * np.trace(Ad @ H) * dt + 0.5 * (r @ Ad @ r) * dt
     assert abs(extra) > 1e-3
     assert abs((ll1 - ll0) - extra) < 1e-10 * max(1.0, abs(extra))
+
+
+def test_stochastic_heun_linear_closed_form(oracle_ref):
+    """solve!(StochasticHeun(), ...) (src/euler.jl:178-198) for b = -βx, σ const: one step is
+    y (1 - β dt + β² dt²/2) + σ dw; the loop stops at N-2 and the last grid point is not written."""
+    beta, sig = 2.0, 0.7
+    m = O.make_model(O.OU, 1, 1, [beta, sig])
+    tt = np.linspace(0, 1, 41) ** 1.5
+    W = oracle_ref.wiener_sample(tt, 1, 9, 0, 3)
+    X0 = np.full((41, 1), 123.0)
+    X = oracle_ref.heun(m, tt, [0.4], W, X0)
+    y = 0.4
+    want = np.empty(40)
+    for i in range(39):
+        want[i] = y
+        dt = tt[i + 1] - tt[i]
+        y = y * (1 - beta * dt + 0.5 * beta * beta * dt * dt) + sig * (W[i + 1, 0] - W[i, 0])
+    want[39] = y
+    assert np.allclose(X[:40, 0], want, rtol=1e-13, atol=1e-15)
+    assert X[40, 0] == 123.0
