@@ -188,6 +188,28 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 3}
 
 
+def bind_near_gpu(torch, local):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned staging
+    buffers of the host-buffer leg are allocated on the GPU's NUMA node.  Returns the original mask (the CPU baseline
+    leg runs on ALL host cores and restores it first) or None if NVML is not usable."""
+    try:
+        import pynvml
+        orig = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        if not os.sched_getaffinity(0):
+            os.sched_setaffinity(0, orig)
+        return orig
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -202,6 +224,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    orig_affinity = bind_near_gpu(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -363,6 +386,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if orig_affinity is not None:
+            os.sched_setaffinity(0, orig_affinity)  # the CPU baseline uses every host core
         v, cores, sample, _, _, _ = cpu_run(n, args.cpu_seconds)
         cpu = {"value": v, "unit": "path-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
@@ -376,6 +401,8 @@ def main():
                        "chains_per_gpu": P, "segments": S, "grid_points": n,
                        "path_steps_per_step": world * steps_per_iter_rank,
                        "state_bytes_per_gpu": ens.nbytes, "l2": "working set >> 126 MB L2: no flush needed",
+                       "host_binding": ("rank threads bound to the GPU's NUMA-local CPUs (NVML) for the host-buffer leg"
+                                        if orig_affinity is not None else "none"),
                        "parallelism": f"chains sharded over {world} GPU(s), all-reduce of acc only"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "acc_rate": acc_rate,

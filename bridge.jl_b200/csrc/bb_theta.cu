@@ -13,11 +13,11 @@
  *                              tables, and the accept test (:340); the same kernel runs the pCN iteration
  *                              (test/partialbridgenuH.jl:176-191) for chains with their own tables.
  *
- * Layout: the tables are T [S][N][K][P] doubles, K = d + d*d (ν[i], H[i]), chain-minor, so that the 32 chains of a
+ * Layout: the tables are T [S][N][K][P (padded to 16)] doubles, K = d + d*d (ν[i], H[i]), chain-minor, so that the 32 chains of a
  * warp read/write 256 contiguous bytes per value (no staging needed); they are written once by the backward
- * kernel and read once by the forward kernel: 8K bytes per path-step each way.  Lanes 0..2K-1 of a warp prefetch
- * the 2K lines of the row BB_TPF steps ahead into L2; the record of the next step is loaded into registers while
- * the current step computes.  W / X keep the chunked layout of bb_chain.cuh (shared with the other kernels).
+ * kernel and read once by the forward kernel: 8K bytes per path-step each way.  The forward kernel moves a chain's
+ * rows through a shared-memory ring with 8-byte cp.async, BB_TDEPTH-1 steps ahead of their use; X° and W° leave as
+ * whole 128-byte lines.  W / X keep the chunked layout of bb_chain.cuh (shared with the other kernels).
  * The per-step arithmetic is bb_chain<...>::drift / bb_em_update / nuH_step, i.e. the same instruction sequence
  * as the shared-table kernels and the one-system constructors.
  */
@@ -30,12 +30,21 @@
 #include "bb_backward.cuh"
 #include "bb_host.h"
 
-#define BB_TPF 8 /* table rows prefetched ahead into L2 */
+#ifndef BB_TWPF
+#define BB_TWPF 1 /* W pieces are loaded into registers one group of 4 steps ahead */
+#endif
+#ifndef BB_TPAIR
+#define BB_TPAIR 1 /* table rows are copied 16 bytes (two chains) at a time, see t_issue */
+#endif
+#ifndef BB_TDEPTH
+#define BB_TDEPTH 4 /* table rows a chain keeps in flight / in shared memory */
+#endif
 
 struct bb_theta {
   bb_model model;
   bb_theta_spec spec;
   int K = 0, NL = 0;
+  long long PT = 0; /* chains per table row, padded to a multiple of 16 (whole 128-byte lines) */
   double* theta[2] = {nullptr, nullptr}; /* [BB_NTHETA][P]: current, last proposal */
   double* T = nullptr;                   /* [S][N][K][P] */
   double* left[2] = {nullptr, nullptr};  /* [NL][P]: ν(0), H⁺(0), C, logpdfnormal, trace term, log prior */
@@ -53,6 +62,7 @@ struct bb_theta_args {
   uint8_t *accepted, *xstale;
   unsigned long long *acc, *acc_theta;
   long long P, chain_offset;
+  long long PT; /* chains per table row, padded to whole 128-byte lines */
   int S, N, NC, nbuf, jll, start_bcast, store_x;
   const double* gridtab[BB_MAXSEG]; /* rows (dt, sqrt dt) */
   const double* tt;
@@ -144,7 +154,7 @@ __device__ __forceinline__ double theta_logu(const bb_philox_keys& k, uint32_t s
 template <class M, int AUXK, int MOBS>
 __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_constant__ bb_theta_args a) {
   constexpr int D = M::D, K = D + D * D, NTH = M::NTH;
-  const long long P = a.P;
+  const long long P = a.P, PT = a.PT;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const unsigned long long chain = (unsigned long long)(a.chain_offset + p);
@@ -186,20 +196,20 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
     theta_aux<M, AUXK>(m, a.spec.v[s][0], Bt, be);
     const aux_dev A{Bt, be, at, at, 1};
     if (minv<D>(Hp, Hc)) bad = true;
-    double* Trow = a.T + ((long long)s * N + (N - 1)) * K * P + p;
+    double* Trow = a.T + ((long long)s * N + (N - 1)) * K * PT + p;
 #pragma unroll
-    for (int k = 0; k < D; k++) Trow[(long long)k * P] = nu[k];
+    for (int k = 0; k < D; k++) Trow[(long long)k * PT] = nu[k];
 #pragma unroll
-    for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * P] = Hc[k];
+    for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * PT] = Hc[k];
     const double* tt = a.tt + (long long)s * N;
     for (int i = N - 2; i >= 0; i--) {
       const double dt = tt[i] - tt[i + 1];
       if (nuH_step<D>(BB_ODE_LYAP, A, i, dt, Hp, Hc, nu, Cc)) bad = true;
-      Trow -= (long long)K * P;
+      Trow -= (long long)K * PT;
 #pragma unroll
-      for (int k = 0; k < D; k++) Trow[(long long)k * P] = nu[k];
+      for (int k = 0; k < D; k++) Trow[(long long)k * PT] = nu[k];
 #pragma unroll
-      for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * P] = Hc[k];
+      for (int k = 0; k < D * D; k++) Trow[(long long)(D + k) * PT] = Hc[k];
     }
     double tr = Bt[0];
 #pragma unroll
@@ -264,33 +274,75 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
   double* xw = sx ? a.X + pc * (BB_TC * D) : nullptr;
   const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
 
+  /* X° (and W° of a pCN proposal) leave through shared memory as whole 128-byte lines written back to back:
+   * 32-byte stores that drip out while the chain computes cost 15-20 % of DRAM bandwidth (tools/membench.cu).
+   * Rows are XOR-swizzled by the chain index as in bb_chain.cuh (conflict-free 128-bit accesses). */
+  extern __shared__ __align__(128) unsigned char th_smem[];
+  constexpr bool XBUF = (D == 2);
+  constexpr int XWIN = 16 / D; /* steps per 128-byte window */
+  double* xbuf = reinterpret_cast<double*>(th_smem) + (size_t)threadIdx.x * 16;
+  double* wrow = reinterpret_cast<double*>(th_smem) + (size_t)BB_THREADS * 16 + (size_t)threadIdx.x * (BB_TC * DP);
+
   double y[D], wprev[DP], w2[DP];
 #pragma unroll
   for (int k = 0; k < D; k++) y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
   double lltot = 0.0;
 
-  /* the chain's table rows in the order they are used: g = s N + i, i = 0 .. N-2 */
+  /* The chain's table rows in the order they are used (g = s N + i, i = 0 .. N-2; row N-1 of a segment drives no
+   * step) travel through a BB_TDEPTH-deep shared-memory ring: every thread copies its own K values of a row with
+   * 8-byte cp.async (a warp's copies of one value are 256 contiguous bytes), BB_TDEPTH-1 steps before it reads them
+   * back, so no warp waits on a global load and no register is tied up.  (Register double-buffering + L2 prefetch
+   * left the kernel latency bound: long-scoreboard stalls of 11 warps per issue, 18 % of the lines fetched twice.) */
+  double* tring = reinterpret_cast<double*>(th_smem) + (size_t)BB_THREADS * 16 +
+                  (PCN ? (size_t)BB_THREADS * (BB_TC * DP) : 0) + threadIdx.x;
   const double* Tp = a.T + pc;
-  const long long rowstride = (long long)K * P;
-  const long long warp_p0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-  const long long grows = (long long)S * N;
-  auto prefetch_row = [&](long long g) {
-    /* lane l < 2K: line (l & 1) of value l >> 1 of row g (256 bytes per value and warp) */
-    if (lane < 2 * K && g < grows) {
-      const double* q = a.T + g * rowstride + (long long)(lane >> 1) * P + warp_p0 + (lane & 1) * 16;
-      if (warp_p0 + (lane & 1) * 16 < P) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    }
-  };
-  double Tn[K];
-  auto load_row = [&](long long g) {
+  const long long PT = a.PT;
+  const long long rowstride = (long long)K * PT;
+  const long long nrows = (long long)S * (N - 1); /* rows that drive a step */
+  const bool pair_ok = (p & ~1ll) < P; /* at least one chain of this lane pair exists (rows are padded to 16 chains) */
+  long long gi = 0;                                /* next row to request: global index and position in its segment */
+  int gi_i = 0;
+  long long gi_n = 0;
+  auto t_issue = [&]() { /* request the next row (if any); always commits a group */
+    if (gi_n < nrows) {
+      double* dst = tring + (size_t)(gi_n % BB_TDEPTH) * (K * BB_THREADS);
+      const double* src = Tp + gi * rowstride;
+#if BB_TPAIR
+      /* two neighbouring chains share the copies: the even lane moves the even values, the odd lane the odd ones,
+       * 16 bytes (both chains) at a time -> cp.async.cg (L2 only: the small L1 that remains next to the shared-memory
+       * carve-out stays with the time-grid table) and half the instructions */
+      if (pair_ok) {
 #pragma unroll
-    for (int k = 0; k < K; k++) Tn[k] = Tp[g * rowstride + (long long)k * P];
+        for (int k = 0; k < K; k += 2)
+          bb_cp_async16(dst + (k + (int)(threadIdx.x & 1)) * BB_THREADS - (threadIdx.x & 1),
+                        a.T + gi * rowstride + (long long)(k + (int)(threadIdx.x & 1)) * PT + (p & ~1ll));
+      }
+#else
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bb_smem_u32(dst + k * BB_THREADS)),
+                     "l"(src + (long long)k * PT)
+                     : "memory");
+#endif
+      gi_n++;
+      if (++gi_i == N - 1) { gi_i = 0; gi += 2; } else { gi += 1; }
+    }
+    bb_cp_async_commit();
   };
 #pragma unroll 1
-  for (int g = 0; g < BB_TPF; g++) prefetch_row(g);
-  load_row(0);
+  for (int g = 0; g < BB_TDEPTH - 1; g++) t_issue();
+  long long rcons = 0; /* rows consumed */
 
   double wq[4] = {0.0, 0.0, 0.0, 0.0};
+#if BB_TWPF
+  double wnx[DP][4]; /* the pieces of W of the next group of 4 steps */
+#pragma unroll
+  for (int i = 0; i < DP; i++) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) wnx[i][l] = 0.0;
+    if (act) bb_ld4(wr + 4 * i, wnx[i]);
+  }
+#endif
   for (int s = 0; s < S; s++) {
     const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
     const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
@@ -319,7 +371,18 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
             const int mm = s4 * DP + k;
             if ((mm & 3) == 0) {
               const int q = h * DP + (mm >> 2);
+#if BB_TWPF
+              /* the piece was requested one group of 4 steps ago; request the same piece of the next group now */
+#pragma unroll
+              for (int i = 0; i < 4; i++) wq[i] = wnx[mm >> 2][i];
+              {
+                const bool last = (s == S - 1) && (c == NC - 1) && (h == BB_TC / 4 - 1);
+                const double* nxt = (h == BB_TC / 4 - 1) ? wr + wstride + 4 * (mm >> 2) : wr + 4 * (q + DP);
+                if (act && !last) bb_ld4(nxt, wnx[mm >> 2]);
+              }
+#else
               if (act) bb_ld4(wr + 4 * q, wq);
+#endif
               if constexpr (PCN) {
                 float z[4];
                 bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
@@ -332,7 +395,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
                   if (jj != 0) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);
                   wq[i] = fma(a.rho2, w2[kk], a.rho * wq[i]);
                 }
-                if (act) bb_st4(ww + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+                bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
               }
             }
             wj[k] = wq[mm & 3];
@@ -344,12 +407,15 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
             double R[REC];
             R[0] = gt[2 * j];
             R[1] = 0.0;
+            bb_cp_async_wait<BB_TDEPTH - 2>(); /* this step's row has landed */
+#if BB_TPAIR
+            __syncwarp(); /* ... including the half the neighbouring lane copied */
+#endif
+            const double* Ts = tring + (size_t)(rcons % BB_TDEPTH) * (K * BB_THREADS);
 #pragma unroll
-            for (int k = 0; k < K; k++) R[2 + k] = Tn[k];
-            const long long g = (long long)s * N + (j - 1);
-            const long long gn = (j == N - 1) ? g + 2 : g + 1; /* row N-1 of a segment drives no step */
-            if (gn < grows - 1) load_row(gn);
-            prefetch_row(gn + BB_TPF - 1);
+            for (int k = 0; k < K; k++) R[2 + k] = Ts[k * BB_THREADS];
+            rcons++;
+            t_issue(); /* refill the stage read one step ago */
             double dw[DP], bd[D];
 #pragma unroll
             for (int k = 0; k < DP; k++) {
@@ -359,7 +425,35 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
             CH::drift(m, R, sc, y, R[0], j <= a.jll, som, bd);
             bb_em_update<M>(m, bd, R[0], dw, y);
           }
-          if (sx) xo.put(xw + 4 * h * D, s4, y, act);
+          if (sx) {
+            if constexpr (XBUF) {
+              const int ls = (4 * h + s4) % XWIN;
+              *reinterpret_cast<double2*>(xbuf + 2 * ((ls ^ threadIdx.x) & 7)) = make_double2(y[0], y[1]);
+            } else {
+              xo.put(xw + 4 * h * D, s4, y, act);
+            }
+          }
+        }
+        if constexpr (XBUF) {
+          if (sx && act && ((4 * h + 3) % XWIN) == XWIN - 1) { /* a 128-byte window of X° is complete */
+            double* xdst = xw + (4 * h + 4 - XWIN) * D;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              double v[4];
+              bb_lds4_swz(xbuf, 2 * q, threadIdx.x & 7, v);
+              bb_st4(xdst + 4 * q, v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      }
+      if constexpr (PCN) {
+        if (act) { /* the chain's row of W° is complete: write its 128 d' bytes back to back */
+#pragma unroll
+          for (int q = 0; q < NPIECE; q++) {
+            double v[4];
+            bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, v);
+            bb_st4(ww + 4 * q, v[0], v[1], v[2], v[3]);
+          }
         }
       }
       wr += wstride;
@@ -460,7 +554,7 @@ static int fill_args(bb_ens* e, bb_theta_args& a) {
   a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
   a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
   a.accepted = e->accepted; a.xstale = e->xstale; a.acc = e->acc; a.acc_theta = t->acc;
-  a.P = e->P; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC; a.nbuf = e->nbuf;
+  a.P = e->P; a.PT = t->PT; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC; a.nbuf = e->nbuf;
   for (int s = 0; s < e->S; s++) {
     if (!e->gridtab[s] || (int)e->tt[s].size() != e->N) return BB_ERR_ARG; /* bb_ens_set_grid first */
     a.gridtab[s] = e->gridtab[s];
@@ -540,7 +634,10 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
                                                         : lookup_forward<MFhnDiag>(t->spec.aux_kind, pcn);
   if (!fn) return BB_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((e->P + BB_THREADS - 1) / BB_THREADS);
-  fn<<<grid, BB_THREADS, 0, c->stream>>>(a);
+  const size_t smem = (size_t)BB_THREADS * 128 + (pcn ? (size_t)BB_THREADS * BB_TC * e->dp * 8 : 0) +
+                      (size_t)BB_TDEPTH * t->K * BB_THREADS * 8;
+  BB_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<grid, BB_THREADS, smem, c->stream>>>(a);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     bb_set_cuda_error(err, "bb_theta_forward_kernel launch");
@@ -596,7 +693,8 @@ extern "C" int bb_theta_attach(bb_ens* e, const bb_model* model, const bb_theta_
   const size_t P = (size_t)e->P;
   int rc = th_alloc(e, &t->theta[0], (size_t)BB_NTHETA * P);
   if (rc == BB_OK) rc = th_alloc(e, &t->theta[1], (size_t)BB_NTHETA * P);
-  if (rc == BB_OK) rc = th_alloc(e, &t->T, (size_t)e->S * e->N * t->K * P);
+  t->PT = (e->P + 15) & ~15ll;
+  if (rc == BB_OK) rc = th_alloc(e, &t->T, (size_t)e->S * e->N * t->K * (size_t)t->PT);
   if (rc == BB_OK) rc = th_alloc(e, &t->left[0], (size_t)t->NL * P);
   if (rc == BB_OK) rc = th_alloc(e, &t->left[1], (size_t)t->NL * P);
   if (rc == BB_OK) rc = th_alloc(e, &t->tt, (size_t)e->S * e->N);
@@ -672,7 +770,7 @@ extern "C" int bb_theta_get_tables(bb_ens* e, int64_t p, double* nu, double* H) 
   const int K = e->th->K, d = e->d;
   const size_t rows = (size_t)e->S * e->N;
   std::vector<double> h(rows * K);
-  BB_CUDA(cudaMemcpy2DAsync(h.data(), sizeof(double), e->th->T + p, sizeof(double) * e->P, sizeof(double), rows * K,
+  BB_CUDA(cudaMemcpy2DAsync(h.data(), sizeof(double), e->th->T + p, sizeof(double) * e->th->PT, sizeof(double), rows * K,
                             cudaMemcpyDeviceToHost, e->ctx->stream));
   BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
   for (size_t g = 0; g < rows; g++) {
