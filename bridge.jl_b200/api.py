@@ -308,6 +308,58 @@ class Lorenz(ContinuousTimeProcess):  # src/Models.jl:38-55
         return np.diag(self.p[3:6])
 
 
+class Landmarks(ContinuousTimeProcess):  # project_partialbridge/partialbridge_landmarks.jl:47,67-72,86-101
+    """n = 4 landmarks in the plane with Gaussian kernel parameter a, noise level σ on the momenta and mean reversion λ.
+    State: (q1, p1, ..., q4, p4) flattened (the script's fll(Vector{Point})), d = 16, d' = 8."""
+    model_id = K.LANDMARKS
+    d, dprime, n = 16, 8, 4
+
+    def __init__(self, a, σ, λ, n: int = 4):
+        if n != 4:
+            raise ValueError("the device registry holds the n = 4 instance (state SVector{16}, :51)")
+        self.a_, self.σ_, self.λ = float(a), float(σ), float(λ)
+
+    def par(self):
+        return [self.a_, self.σ_, self.λ]
+
+    def kernel(self, x):  # :47
+        return np.exp(-float(np.dot(x, x)) / (2 * self.a_)) / (2 * np.pi * self.a_)
+
+    def b(self, t, x):  # :90-101
+        x = np.asarray(x, dtype=np.float64).reshape(self.n, 2, 2)  # [landmark][q|p][coordinate]
+        out = np.zeros_like(x)
+        for i in range(self.n):
+            for j in range(self.n):
+                k = self.kernel(x[i, 0] - x[j, 0])
+                out[i, 0] += 0.5 * x[j, 1] * k
+                out[i, 1] += (-self.λ * 0.5 * x[j, 1] * k
+                              + 1 / (2 * self.a_) * np.dot(x[i, 1], x[j, 1]) * (x[i, 0] - x[j, 0]) * k)
+        return out.ravel()
+
+    def σ(self, t, x=None):
+        S = np.zeros((16, 8))
+        for i in range(self.n):
+            for k in range(2):
+                S[4 * i + 2 + k, 2 * i + k] = self.σ_
+        return S
+
+
+def LandmarksTilde(a, σ, λ, qT):  # partialbridge_landmarks.jl:75-81,126-146
+    """Auxiliary process of the landmarks bridge: the drift linearised with the positions frozen at the end
+    configuration qT [n, 2]:  B~[q(i),p(j)] = k(qT_i - qT_j)/2 I, B~[p(i),p(j)] = -λ k(qT_i - qT_j)/2 I, β~ = 0, a~ = a."""
+    P = Landmarks(a, σ, λ)
+    qT = np.asarray(qT, dtype=np.float64).reshape(P.n, 2)
+    B = np.zeros((16, 16))
+    for i in range(P.n):
+        for j in range(P.n):
+            k = P.kernel(qT[i] - qT[j])
+            for c in range(2):
+                B[4 * i + c, 4 * j + 2 + c] += 0.5 * 1.0 * k
+                B[4 * i + 2 + c, 4 * j + 2 + c] += -0.5 * 1.0 * P.λ * k
+    S = P.σ(0.0)
+    return LinearAux(B, np.zeros(16), S @ S.T)
+
+
 class LinearAux:
     """An auxiliary process given by B(t), β(t), a(t) (constants or callables), the protocol the
     guided proposals use (Bridge.B, Bridge.β, Bridge.a; partialbridge_fitzhugh.jl:99-116)."""

@@ -207,7 +207,8 @@ int bb_h_inv(int d, const double* A, double* Ai) {
 static bool model_shape_ok(const bb_model* m) {
   const int d = m->d, dp = m->dprime;
   switch (m->id) {
-    case BB_MODEL_WIENER: return d == dp && d >= 1 && d <= 3;
+    case BB_MODEL_WIENER: return d == dp && ((d >= 1 && d <= 3) || d == 8);
+    case BB_MODEL_LANDMARKS: return d == 16 && dp == 8;
     case BB_MODEL_OU: return d == 1 && dp == 1;
     case BB_MODEL_LINPRO: return d == dp && d >= 1 && d <= 3;
     case BB_MODEL_FHN_DIAG: return d == 2 && dp == 2;
@@ -237,6 +238,15 @@ static void model_sigma_host(const bb_model* P, double* S) {
 void bb_prepare_model(const bb_model* m, bb_model_dev* o) {
   memset(o, 0, sizeof(*o));
   memcpy(o->par, m->par, sizeof(o->par));
+  if (m->id == BB_MODEL_LANDMARKS) { /* partialbridge_landmarks.jl:47,96-98 (oracle model_b) */
+    const double a = m->par[0];
+    o->der[0] = 1.0 / ((2 * M_PI) * a);
+    o->der[1] = 1.0 / (2 * a);
+    o->der[2] = 0.0 + m->par[1] * m->par[1];
+    o->der[3] = (-m->par[2]) * 0.5;
+    return;
+  }
+  if (m->d > BB_MAXD) return; /* the d' = 8 Wiener process: nothing to derive */
   if (m->id == BB_MODEL_FHN_DIAG || m->id == BB_MODEL_FHN_HYPO) o->der[0] = 1.0 / m->par[0];
   double S[BB_MAXD * BB_MAXD];
   model_sigma_host(m, S);
@@ -253,7 +263,7 @@ void bb_prepare_model(const bb_model* m, bb_model_dev* o) {
   }
 }
 static bool model_sigma_invertible(const bb_model* m) {
-  if (m->d != m->dprime) return false;
+  if (m->d != m->dprime || m->d > BB_MAXD) return false;
   double S[BB_MAXD * BB_MAXD], Si[BB_MAXD * BB_MAXD];
   model_sigma_host(m, S);
   return bb_h_inv(m->d, S, Si) == 0;
@@ -275,7 +285,10 @@ static bb_chain_launch_fn lookup_second(const bb_model* m, int gk, int gm, int a
 }
 static bb_chain_launch_fn lookup_kernel(const bb_model* m, int gk, int gm, int auxc, int rng) {
   switch (m->id) {
-    case BB_MODEL_WIENER: return gk == 0 ? bb_lookup_wiener(m->d, rng) : nullptr;
+    case BB_MODEL_WIENER:
+      if (gk != 0) return nullptr;
+      return m->d > 3 ? bb_lookup_wiener_wide(m->d, rng) : bb_lookup_wiener(m->d, rng);
+    case BB_MODEL_LANDMARKS: return bb_lookup_landmarks(gk, gm, auxc, rng);
     case BB_MODEL_OU: return bb_lookup_ou(gk, gm, auxc, rng);
     case BB_MODEL_LINPRO:
       return m->d == 1 ? bb_lookup_linpro1(gk, gm, auxc, rng)
@@ -322,7 +335,7 @@ extern "C" int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32
   if (!out) return BB_ERR_ARG;
   *out = nullptr;
   if (!ctx) return BB_ERR_NODEVICE;
-  if (P <= 0 || S <= 0 || S > BB_MAXSEG || N < 2 || d < 1 || d > 3 || dprime < 1 || dprime > d) return BB_ERR_ARG;
+  if (P <= 0 || S <= 0 || S > BB_MAXSEG || N < 2 || d < 1 || d > BB_MAXD_WIDE || dprime < 1 || dprime > d) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(ctx->device));
   bb_ens* e = new (std::nothrow) bb_ens();
   if (!e) return BB_ERR_NOMEM;
@@ -602,7 +615,9 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
   if (!out) return BB_ERR_ARG;
   *out = nullptr;
   if (!ctx) return BB_ERR_NODEVICE;
-  if (!tt || !A || !b || !Bt || !betat || N < 2 || d < 1 || d > 3) return BB_ERR_ARG;
+  if (!tt || !A || !b || !Bt || !betat || N < 2 || d < 1 || d > BB_MAXD_WIDE) return BB_ERR_ARG;
+  /* wide models (d > 3): PartialBridgeνH tables with a constant auxiliary drift only */
+  if (d > 3 && (kind != BB_GUIDE_NUH || aux_const == 0 || Adiff)) return BB_ERR_UNSUPPORTED;
   if (kind != BB_GUIDE_NUH && kind != BB_GUIDE_HV && kind != BB_GUIDE_LMMU) return BB_ERR_ARG;
   if (kind == BB_GUIDE_LMMU) {
     if (!Mm || !v || m < 1 || m > d) return BB_ERR_ARG;
@@ -619,6 +634,10 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
             off_tr = off_be + d, off_ad = off_tr + 1;
   std::vector<double> tab;
   grid_rows(tt, N, NC, rec, tab);
+  if (d > 3) { /* B~, beta~ follow the rows (they do not fit the per-segment kernel constants): bb_wide.cuh */
+    tab.insert(tab.end(), Bt, Bt + (size_t)d * d);
+    tab.insert(tab.end(), betat, betat + d);
+  }
   for (int j = 1; j < N; j++) {
     const int i = j - 1;
     double* R = tab.data() + (size_t)j * rec;
@@ -675,7 +694,7 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
   }
   double segc[BB_SEGC];
   memset(segc, 0, sizeof(segc));
-  if (auxc) {
+  if (auxc && d <= 3) {
     memcpy(segc, Bt, sizeof(double) * d * d);
     memcpy(segc + d * d, betat, sizeof(double) * d);
   }

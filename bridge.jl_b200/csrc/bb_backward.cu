@@ -22,6 +22,13 @@
 #include "bb_backward.cuh"
 #include "bb_host.h"
 
+/* d > 3: block-parallel generic-d kernels (bb_backward_gen.cu); all pointers are device pointers */
+cudaError_t bb_gen_backward_nuH(cudaStream_t st, int method, int N, int d, const double* tt, const double* B,
+                                const double* beta, const double* a, const double* a_left, int is_const,
+                                const double* nu_end, const double* Hplus_end, double C0, double* nu, double* H,
+                                double* out_left, int* status);
+cudaError_t bb_gen_update_nuHC(cudaStream_t st, int d, int m, const double* in, double* out, int* status);
+
 namespace {
 using namespace bbk;
 
@@ -263,6 +270,12 @@ extern "C" int bb_update_nuHC(bb_ctx* ctx, int32_t d, int32_t m, const double* L
   int rc = pack_upload(ctx, pk, nout);
   if (rc) return rc;
   std::vector<double> out;
+  if (d > 3) {
+    if (d > BB_MAXD_WIDE) return BB_ERR_UNSUPPORTED;
+    rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
+      bb_gen_update_nuHC(ctx->stream, d, m, pk.dev.p, pk.dev.p + oout, st);
+    });
+  } else
   BB_DM_SWITCH(d, m, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
                  k_update_nuHC<D, M><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st);
                }));
@@ -324,6 +337,13 @@ extern "C" int bb_backward_nuH(bb_ctx* ctx, int32_t method, int32_t N, int32_t d
   double* dH = dnu + (size_t)N * d;
   double* dleft = dH + (size_t)N * d * d;
   std::vector<double> out;
+  if (d > 3) {
+    if (d > BB_MAXD_WIDE) return BB_ERR_UNSUPPORTED;
+    rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
+      bb_gen_backward_nuH(ctx->stream, method, N, d, D0 + ott, A.B, A.beta, A.a, A.a_left, A.is_const, D0 + one, D0 + ohe,
+                          C0, dnu, dH, dleft, st);
+    });
+  } else
   BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
                 k_backward_nuH<D><<<1, 1, 0, ctx->stream>>>(method, N, D0 + ott, A, D0 + one, D0 + ohe, C0, dnu, dH,
                                                           dleft, st);

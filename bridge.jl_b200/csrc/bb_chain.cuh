@@ -164,7 +164,7 @@ struct bb_chain {
       if constexpr (M::SPARSE) {
 #pragma unroll
         for (int k = 0; k < D; k++)
-          if (M::col(k) >= 0) bd[k] = fma(model.der[8 + k * D + k], r[k], bd[k]);
+          if (M::col(k) >= 0) bd[k] = fma(bb_adiag<M>(model, k), r[k], bd[k]);
       } else {
         double ar[D];
         bb_matvec<D, D>(model.der + 8, r, ar);

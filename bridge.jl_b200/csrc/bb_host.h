@@ -87,6 +87,8 @@ bb_chain_launch_fn bb_lookup_fhn_hypo(int gk, int gm, int auxc, int rng);
 bb_chain_launch_fn bb_lookup_intdiff(int gk, int gm, int auxc, int rng);
 bb_chain_launch_fn bb_lookup_nclar3(int gk, int gm, int auxc, int rng);
 bb_chain_launch_fn bb_lookup_lorenz(int gk, int gm, int auxc, int rng);
+bb_chain_launch_fn bb_lookup_landmarks(int gk, int gm, int auxc, int rng); /* bb_wide.cuh */
+bb_chain_launch_fn bb_lookup_wiener_wide(int d, int rng);
 
 bb_chain_launch_fn bb_lookup2_wiener(int d, int mode);
 bb_chain_launch_fn bb_lookup2_ou(int gk, int gm, int auxc, int mode);

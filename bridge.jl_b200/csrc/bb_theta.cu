@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
    * left the kernel latency bound: long-scoreboard stalls of 11 warps per issue, 18 % of the lines fetched twice.) */
   double* tring = reinterpret_cast<double*>(th_smem) + (size_t)BB_THREADS * 16 +
                   (PCN ? (size_t)BB_THREADS * (BB_TC * DP) : 0) + threadIdx.x;
+#if !BB_TPAIR
   const double* Tp = a.T + pc;
+#endif
   const long long PT = a.PT;
   const long long rowstride = (long long)K * PT;
   const long long nrows = (long long)S * (N - 1); /* rows that drive a step */
@@ -306,7 +308,6 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
   auto t_issue = [&]() { /* request the next row (if any); always commits a group */
     if (gi_n < nrows) {
       double* dst = tring + (size_t)(gi_n % BB_TDEPTH) * (K * BB_THREADS);
-      const double* src = Tp + gi * rowstride;
 #if BB_TPAIR
       /* two neighbouring chains share the copies: the even lane moves the even values, the odd lane the odd ones,
        * 16 bytes (both chains) at a time -> cp.async.cg (L2 only: the small L1 that remains next to the shared-memory
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
                         a.T + gi * rowstride + (long long)(k + (int)(threadIdx.x & 1)) * PT + (p & ~1ll));
       }
 #else
+      const double* src = Tp + gi * rowstride;
 #pragma unroll
       for (int k = 0; k < K; k++)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bb_smem_u32(dst + k * BB_THREADS)),

@@ -44,7 +44,8 @@ extern "C" {
 #endif
 
 #define BB_ABI_VERSION 1
-#define BB_MAXD 4   /* largest state dimension of the registry models */
+#define BB_MAXD 4   /* largest state dimension of the narrow registry models (and of bb_theta_spec) */
+#define BB_MAXD_WIDE 16 /* state dimension of the wide model (LANDMARKS); constructors accept d <= 16 */
 #define BB_NPAR 32  /* doubles in a model parameter block */
 
 /* ------------------------------------------------------------------ status */
@@ -84,6 +85,15 @@ int bb_abi_version(void);
  *   NCLAR3    d=3,d'=1; par={alpha,omega,sigma}; b=(x2,x3,-alpha sin(omega x3))
  *                                       project_partialbridge/partialbridge_nclar.jl:58-60
  *   LORENZ    d=d'=3; par={th1,th2,th3, s1,s2,s3}; sigma=diag(s)  src/Models.jl:38-55, test/euler.jl:49-50
+ *   LANDMARKS d=16,d'=8; par={a, sigma, lambda}: n = 4 landmarks in the plane, state (q1,p1,...,q4,p4) with
+ *             q_i, p_i in R^2 (the flattened Vector{Point} of the script), Gaussian kernel
+ *             k(x) = exp(-|x|^2/(2a))/(2 pi a), drift  dq_i = 1/2 sum_j p_j k(q_i-q_j),
+ *             dp_i = sum_j [-lambda/2 p_j + <p_i,p_j>(q_i-q_j)/(2a)] k(q_i-q_j), noise sigma dW on the momenta
+ *                                       project_partialbridge/partialbridge_landmarks.jl:47,86-101,111-118
+ *             (BASELINE config 5.  The reference script is an unfinished draft that does not run -- SURVEY 8d --
+ *             so parity for this model is against the oracle restatement of these lines only.)
+ *             "Wide" model: one segment-table kind (BB_GUIDE_NUH with a constant auxiliary drift), no second-pass
+ *             llikelihood / innovations, plain thread-per-chain kernels (csrc/bb_wide.cuh).
  */
 typedef enum {
   BB_MODEL_WIENER = 0,
@@ -94,7 +104,8 @@ typedef enum {
   BB_MODEL_INTDIFF = 5,
   BB_MODEL_NCLAR3 = 6,
   BB_MODEL_LORENZ = 7,
-  BB_MODEL_COUNT = 8
+  BB_MODEL_LANDMARKS = 8,
+  BB_MODEL_COUNT = 9
 } bb_model_id;
 
 typedef struct {

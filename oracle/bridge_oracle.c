@@ -388,6 +388,29 @@ static void model_b(const bb_model* P, double t, const double* x, double* b) {
       b[2] = x[0] * x[1] - p[2] * x[2];
 #endif
       break;
+    case BB_MODEL_LANDMARKS: { /* partialbridge_landmarks.jl:47 (kernel), :90-101 (b!), state = fll(Vector{Point}) */
+      const int n = 4;
+      const double a = p[0], lam = p[2];
+      const double c0 = 1.0 / ((2 * M_PI) * a); /* 1/(2*π*P.a)^(length(x)/2), length(x) = 2 */
+      const double c1 = 1.0 / (2 * a);
+      const double nlh = (-lam) * 0.5;
+      for (int i = 0; i < 4 * n; i++) b[i] = 0.0;
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+          const double *qi = x + 4 * i, *pi = x + 4 * i + 2, *qj = x + 4 * j, *pj = x + 4 * j + 2;
+          double dx = qi[0] - qj[0], dy = qi[1] - qj[1];
+          double nrm = sqrt(MA(dy, dy, dx * dx)); /* norm(x) */
+          double kij = c0 * exp(-(nrm * nrm) / (2 * a));
+          double dot = MA(pi[1], pj[1], pi[0] * pj[0]);
+          for (int k = 0; k < 2; k++) {
+            b[4 * i + k] += (0.5 * pj[k]) * kij;
+            double t1 = (nlh * pj[k]) * kij;
+            double t2 = ((c1 * dot) * (qi[k] - qj[k])) * kij;
+            b[4 * i + 2 + k] += t1 + t2;
+          }
+        }
+      break;
+    }
     default:
       for (int i = 0; i < P->d; i++) b[i] = NAN;
   }
@@ -406,6 +429,10 @@ static void model_sigma(const bb_model* P, double* S) {
     case BB_MODEL_INTDIFF: S[1] = p[0]; break;
     case BB_MODEL_NCLAR3: S[2] = p[2]; break;
     case BB_MODEL_LORENZ: S[0] = p[3]; S[4] = p[4]; S[8] = p[5]; break;
+    case BB_MODEL_LANDMARKS: /* noise on the momenta: component 4i+2+k <- column 2i+k  (partialbridge_landmarks.jl:111-118) */
+      for (int i = 0; i < 4; i++)
+        for (int k = 0; k < 2; k++) S[(4 * i + 2 + k) * dp + 2 * i + k] = p[1];
+      break;
   }
 }
 static int model_sigma_is_sparse(const bb_model* P) { return P->id != BB_MODEL_LINPRO; }

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 BB_NPAR = 32
 
 # model ids (include/bridge_b200.h)
-WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ = range(8)
+WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS = range(9)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
 ODE_R3, ODE_LYAP = 0, 1
 
