@@ -4,11 +4,15 @@
  *
  * Same operations and the same data layout as bb_chain.cuh (sample!, W° = rho W + sqrt(1-rho^2) W2, plain or guided
  * solve!, llikelihood, accept/reject; W [S][NC][P][nbuf][16][d'], X [S][NC][P][16][d]), but a plain design: one thread
- * per chain, 64 chains per CTA, the step tables read straight from global memory (every lane of a warp reads the
- * same address: one L1 transaction per value), no staging.  With d = 16 a chain already moves whole 128-byte lines
- * per step (X) and the ensembles of this configuration are small (1e4 chains = 2 warps per SM), so the kernel is
- * bound by the latency of its ~1000 dependent fp64 operations per step, not by bandwidth; the chunk pipeline of
- * bb_chain.cuh (256 chains x 16 steps x 8 d' bytes of staging per CTA) does not fit shared memory at d' = 8.
+ * per chain, 64 chains per CTA.  With d = 16 a chain already moves whole 128-byte lines per step (X) and the
+ * ensembles of this configuration are small (1e4 chains = 2 warps per SM), so the kernel is bound by the latency of
+ * its ~1000 fp64 operations per step, not by bandwidth; the chunk pipeline of bb_chain.cuh (256 chains x 16 steps x
+ * 8 d' bytes of staging per CTA) does not fit shared memory at d' = 8.
+ * The per-step table row (dt, sqrt dt, nu, H: 2 + d + d*d doubles, the same for every chain) is streamed through a
+ * BB_WIDE_RING-deep shared-memory ring: the CTA copies the row BB_WIDE_RING-1 steps ahead with 16-byte cp.async and
+ * reads the current one by broadcast LDS (read straight from global memory every value was an L2 round trip: with
+ * one or two warps per SM nothing is reused in L1 -- 10 ms per 1000 steps instead of ~2).  The constant auxiliary
+ * drift is copied to shared memory once.
  * The per-step arithmetic is bb_chain<...>::drift / bb_em_update: the oracle's operation order.
  * A constant auxiliary drift (B~ [d*d], beta~ [d]) does not fit the per-segment constants of bb_chain_args; it is
  * appended to the segment's table (after the NC*16 rows).
@@ -17,6 +21,7 @@
 #include "bb_chain.cuh"
 
 #define BB_WIDE_THREADS 64
+#define BB_WIDE_RING 4
 
 /* RNG: 0 read W, 1 pCN + X°, 2 fresh Wiener path, 3 pCN without X° (as bb_chain_kernel); GK = 0 or BB_GUIDE_NUH */
 template <class M, int GK, int RNG>
@@ -47,11 +52,37 @@ __global__ void __launch_bounds__(BB_WIDE_THREADS) bb_wide_kernel(const __grid_c
   double lltot = 0.0;
   double wq[4] = {0.0, 0.0, 0.0, 0.0};
 
+  /* shared memory: the ring of table rows, then B~, beta~ */
+  constexpr int NAUX = (GK != 0) ? D * D + D : 0;
+  constexpr int PIECES = REC / 2; /* 16-byte pieces per row */
+  __shared__ __align__(16) double ring[BB_WIDE_RING * REC + NAUX + 2];
+  double* sc_s = ring + BB_WIDE_RING * REC;
+  const int rows_per_seg = NC * BB_TC;
+  const int total_rows = S * rows_per_seg;
+  int issue_row = 0; /* next row (over all segments) to request */
+  auto row_issue = [&]() { /* the CTA requests one row; every thread commits a (possibly empty) group */
+    if (issue_row < total_rows) {
+      const double* src = a.tab[issue_row / rows_per_seg] + (size_t)(issue_row % rows_per_seg) * REC;
+      double* dst = ring + (issue_row % BB_WIDE_RING) * REC;
+      for (int q = threadIdx.x; q < PIECES; q += BB_WIDE_THREADS) bb_cp_async16(dst + 2 * q, src + 2 * q);
+    }
+    issue_row++;
+    bb_cp_async_commit();
+  };
+#pragma unroll 1
+  for (int r = 0; r < BB_WIDE_RING - 1; r++) row_issue();
+  int cons_row = 0;
+
   for (int s = 0; s < S; s++) {
     const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
     const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
     const double* tab = a.tab[s];
-    const double* sc = tab + (size_t)NC * BB_TC * REC; /* B~, beta~ (guided launches) */
+    if constexpr (GK != 0) { /* B~, beta~ of this segment (they follow the rows of its table) */
+      __syncthreads();
+      for (int q = threadIdx.x; q < NAUX; q += BB_WIDE_THREADS) sc_s[q] = tab[(size_t)NC * BB_TC * REC + q];
+      __syncthreads();
+    }
+    const double* sc = sc_s;
     double som = 0.0;
 #pragma unroll
     for (int k = 0; k < DP; k++) w2[k] = 0.0;
@@ -59,7 +90,12 @@ __global__ void __launch_bounds__(BB_WIDE_THREADS) bb_wide_kernel(const __grid_c
 #pragma unroll 1
       for (int slot = 0; slot < BB_TC; slot++) {
         const int j = c * BB_TC + slot;
-        const double* R = tab + (size_t)j * REC;
+        /* this step's row has landed for every thread of the CTA; the stage read one step ago is free again */
+        bb_cp_async_wait<BB_WIDE_RING - 2>();
+        __syncthreads();
+        const double* R = ring + (cons_row % BB_WIDE_RING) * REC;
+        cons_row++;
+        row_issue();
         double wj[DP];
 #pragma unroll
         for (int k = 0; k < DP; k++) {
@@ -76,7 +112,8 @@ __global__ void __launch_bounds__(BB_WIDE_THREADS) bb_wide_kernel(const __grid_c
               for (int i = 0; i < 4; i++) {
                 const int sl = (mm + i) / DP, kk = (mm + i) % DP;
                 const int jj = c * BB_TC + sl;
-                const double rootdt = tab[(size_t)jj * REC + 1];
+                /* a piece never leaves its grid point when d' is a multiple of 4: sqrt(dt) of the staged row */
+                const double rootdt = (DP % 4 == 0) ? R[1] : tab[(size_t)jj * REC + 1];
                 if constexpr (PCN) {
                   /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
                   if (jj != 0) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);

@@ -38,3 +38,19 @@ et.theta_param_step_([0, 0, 0.02, 0.02, 0.01], 1, 10)
 et.theta_pcn_step_(rho, 1, 11)
 Xt = et.download(B.X)
 print("theta ok", et.acc_theta, et.acc, float(np.sum(Xt)) != 0.0)
+# wide path: Landmarks d = 16, d' = 8 (constructors at d = 16, sample, guided Euler + ll, pCN with and without X; P = 70, N = 21)
+A_K, SIG, LAM = 0.5, 2.0, 0.5
+QT = np.array([[-0.6, -1.4], [1.5, -0.9], [0.8, 1.4], [-1.2, 0.7]])
+xl = np.array([-1.0, -1.0, 0.5, 0.1, 1.0, -1.2, -0.2, 0.4, 1.1, 0.9, -0.3, -0.3, -0.8, 1.0, 0.2, -0.5])
+Ll = np.zeros((8, 16))
+for i in range(4):
+    for c in range(2):
+        Ll[2 * i + c, 4 * i + c] = 1.0
+ttl = np.linspace(0.0, 1.0, 21)
+Pl = B.Landmarks(A_K, SIG, LAM); Ptl = B.LandmarksTilde(A_K, SIG, LAM, QT)
+Pol = B.PartialBridgeνH(ttl, Pl, Ptl, Ll, QT.ravel(), 1e-3, 1e-4 * np.eye(8))
+el = B.PathEnsemble(70, 1, 21, 16, 8)
+el.set_grid(0, ttl); el.set_start(xl); el.sample_(1, 0); el.guided_euler_ll_(Pl, [Pol])
+el.pcn_step_(Pl, [Pol], 0.9, 1, 0); el.pcn_step_(Pl, [Pol], 0.9, 1, 1, store_x=False)
+Xl = el.download(B.X)
+print("landmarks ok", el.acc, bool(np.all(np.isfinite(Xl))))
