@@ -586,6 +586,7 @@ class PathEnsemble:
     def guided_euler_ll_(self, P, guides, skip: int = 0, store_x: bool = True, ll: bool = True):
         m = P.cmodel()
         flags = (K.RUN_STORE_X if store_x else 0) | (0 if ll else K.RUN_NO_LL)
+        self._last = (P, list(guides))
         check(lib.bb_guided_euler_ll(self.h, C.byref(m), self._garr(guides), skip, flags))
 
     def pcn_step_host_(self, P, guides, ρ: float, seed: int, it: int, W, Wo, Xo=None, llo=None, accepted=None,

@@ -796,7 +796,9 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   }
   c->launches++;
   if (rs.rng == 1) e->x_maybe_stale = true;
-  else if ((rs.rng < 10 || rs.rng == 12) && rs.store_x) e->x_maybe_stale = false;
+  else if ((rs.rng < 10 || rs.rng == 12) && rs.store_x && !rs.only_stale) e->x_maybe_stale = false;
+  else if (rs.rng < 10 && !rs.store_x && e->X) e->x_maybe_stale = true; /* X no longer belongs to the chains' state */
+  if (rs.only_stale) e->x_maybe_stale = false;
   return BB_OK;
 }
 

@@ -510,7 +510,7 @@ struct bb_chain {
     } else {
       if (act) {
         if (a.do_ll) a.ll[p] = lltot;
-        if (sx(a)) a.xstale[p] = 0;
+        a.xstale[p] = sx(a) ? 0 : 1; /* a solve that does not store X leaves X behind the chain's current state */
         if (a.write_end) {
 #pragma unroll
           for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];

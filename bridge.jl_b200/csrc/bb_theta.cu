@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
     if (act) a.xstale[p] = 0;
   } else if (act) {
     a.ll[p] = lltot;
-    if (sx) a.xstale[p] = 0;
+    a.xstale[p] = sx ? 0 : 1;
 #pragma unroll
     for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
   }
@@ -646,8 +646,8 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
     return BB_ERR_CUDA;
   }
   c->launches++;
-  if (pcn || mode == 2) e->x_maybe_stale = true;
-  else if (store_x) e->x_maybe_stale = false; /* modes 0 and 3 leave X current for every chain */
+  if (pcn || mode == 2 || !store_x) e->x_maybe_stale = true;
+  else e->x_maybe_stale = false; /* modes 0 and 3 with X stored leave X current for every chain */
   return BB_OK;
 }
 

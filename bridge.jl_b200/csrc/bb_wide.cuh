@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(BB_WIDE_THREADS) bb_wide_kernel(const __grid_c
     if (lane == 0 && mk) atomicAdd(a.acc, (unsigned long long)__popc(mk));
   } else if (act) {
     if (a.do_ll) a.ll[p] = lltot;
-    if (sx) a.xstale[p] = 0;
+    a.xstale[p] = sx ? 0 : 1;
     if (a.write_end) {
 #pragma unroll
       for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];

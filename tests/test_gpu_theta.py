@@ -249,3 +249,36 @@ def test_theta_errors(B):
     with pytest.raises(B.BridgeError):
         ens.theta_param_step_(np.array([1, 1, 1, 1, 1.0, 0, 0, 0]), 1, 0)  # more than 4 updated parameters
     ens.close()
+
+
+@pytest.mark.parametrize("P,n,S,diag", [(37, 18, 1, False), (1, 33, 2, False), (259, 21, 3, True)])
+def test_theta_ragged_sizes_skip_and_no_x(B, oracle_fma, P, n, S, diag):
+    """Odd numbers of chains (a lane pair with one chain, a single chain), N not a multiple of 16, llikelihood with
+    skip > 0, proposals whose X° is not stored (recomputed on demand), the linearised auxiliary process."""
+    import bridge_jl_b200.configs as cfg
+    aux = O.AUX_FHN_LINEARISED_END
+    ens, Pm, grids, obs_v, th, dp = setup(B, P, n, S, aux_kind=aux, priors=PRIORS, diag=diag, offset=11)
+    skip, seed = 2, 8
+    npar = len(Pm.par()); mid = Pm.model_id
+    ens.theta_guided_euler_ll_(skip=skip, store_x=False)
+    Wc = ens.download(B.W); ll0 = ens.ll
+    chains = sorted({0, P // 2, P - 1})
+    for p in chains:
+        g, _ = oracle_left(oracle_fma, Pm, th[p], grids, obs_v, aux, PRIORS)
+        _, llo, _ = O.theta_forward(oracle_fma, mid, dp, th[p, :npar], g, cfg.FHN_X0, Wc[p], skip=skip)
+        assert ll0[p] == llo
+    ens.theta_param_step_(RW, seed, 50, skip=skip, store_x=False)
+    tho = ens.theta(B.PROP); flags = ens.accepted.astype(bool); llp = ens.ll_prop
+    for p in chains:
+        tp = O.theta_propose(oracle_fma, th[p], RW, seed, 50, 11 + p)
+        assert np.array_equal(tho[p], tp)
+        g, _ = oracle_left(oracle_fma, Pm, tp, grids, obs_v, aux, PRIORS)
+        _, llo, _ = O.theta_forward(oracle_fma, mid, dp, tp[:npar], g, cfg.FHN_X0, Wc[p], skip=skip)
+        assert llp[p] == llo
+    ens.theta_pcn_step_(0.8, seed, 51, skip=skip, store_x=False)
+    thf = ens.theta(); Wf = ens.download(B.W); Xf = ens.download(B.X)  # X is recomputed for every chain that needs it
+    for p in chains:
+        g, _ = oracle_left(oracle_fma, Pm, thf[p], grids, obs_v, aux, PRIORS)
+        Xo, llo, _ = O.theta_forward(oracle_fma, mid, dp, thf[p, :npar], g, cfg.FHN_X0, Wf[p], skip=skip)
+        assert np.array_equal(Xf[p], Xo) and ens.ll[p] == llo
+    ens.close()
