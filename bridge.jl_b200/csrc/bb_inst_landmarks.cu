@@ -1,9 +1,14 @@
 /* kernel instantiations for the wide models: Landmarks (d = 16, d' = 8) and the d' = 8 Wiener process that drives
  * it; see bb_wide.cuh */
+#include <stdlib.h>
+
 #include "bb_wide.cuh"
 bb_chain_launch_fn bb_lookup_landmarks(int gk, int gm, int auxc, int rng) {
   (void)gm;
-  return bb_lookup_wide<MLandmarks>(gk, auxc, rng);
+  const char* e = getenv("BB_WIDE_LANES");
+  if (e && atoi(e) == 1) return bb_lookup_wide<MLandmarks>(gk, auxc, rng);
+  bb_chain_launch_fn f = bb_lookup_landmarks4(gk, auxc, rng);
+  return f ? f : bb_lookup_wide<MLandmarks>(gk, auxc, rng); /* sample! + solve! fused (rng 2) stays one thread per chain */
 }
 bb_chain_launch_fn bb_lookup_wiener_wide(int d, int rng) {
   if (d == 8) return bb_lookup_wide<MWiener<8>>(0, 1, rng);

@@ -191,6 +191,38 @@ double bbo_logpdfnormal(int d, const double* x, const double* Sigma) {
   return -(n2 + 2 * sld + d * log(2 * M_PI)) / 2;
 }
 
+/* exp(x), x <= 0, of the landmarks kernel.  Reference arithmetic: libm exp (what Julia computes).  GPU order: the
+ * kernels' own exponential (bb_device.cuh bb_exp: +, *, fma, rint only), so that paths can be compared bit for bit. */
+static double bb_exp(double x) {
+#ifdef ORACLE_GPU_ORDER
+  const double kd = rint(x * 0x1.71547652b82fep+0);
+  double r = fma(-kd, 0x1.62e42fee00000p-1, x);
+  r = fma(-kd, 0x1.a39ef35793c76p-33, r);
+  double p = 0x1.6124613a86d09p-33;
+  p = fma(p, r, 0x1.1eed8eff8d898p-29);
+  p = fma(p, r, 0x1.ae64567f544e4p-26);
+  p = fma(p, r, 0x1.27e4fb7789f5cp-22);
+  p = fma(p, r, 0x1.71de3a556c734p-19);
+  p = fma(p, r, 0x1.a01a01a01a01ap-16);
+  p = fma(p, r, 0x1.a01a01a01a01ap-13);
+  p = fma(p, r, 0x1.6c16c16c16c17p-10);
+  p = fma(p, r, 0x1.1111111111111p-7);
+  p = fma(p, r, 0x1.5555555555555p-5);
+  p = fma(p, r, 0x1.5555555555555p-3);
+  p = fma(p, r, 0x1.0000000000000p-1);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  int k = (int)kd;
+  k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
+  union { uint64_t u; double d; } s;
+  s.u = (uint64_t)(k + 1023) << 52;
+  return x < -708.0 ? 0.0 : p * s.d;
+#else
+  return exp(x);
+#endif
+}
+double bbo_exp(double x) { return bb_exp(x); }
+
 /* ======================================================================= random numbers */
 /* Philox4x32-10, Random123 (Salmon et al. 2011), constants PHILOX_M4x32_0/1, PHILOX_W32_0/1 */
 void bbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
@@ -400,7 +432,7 @@ static void model_b(const bb_model* P, double t, const double* x, double* b) {
           const double *qi = x + 4 * i, *pi = x + 4 * i + 2, *qj = x + 4 * j, *pj = x + 4 * j + 2;
           double dx = qi[0] - qj[0], dy = qi[1] - qj[1];
           double nrm = sqrt(MA(dy, dy, dx * dx)); /* norm(x) */
-          double kij = c0 * exp(-(nrm * nrm) / (2 * a));
+          double kij = c0 * bb_exp(-(nrm * nrm) / (2 * a));
           double dot = MA(pi[1], pj[1], pi[0] * pj[0]);
           for (int k = 0; k < 2; k++) {
             b[4 * i + k] += (0.5 * pj[k]) * kij;

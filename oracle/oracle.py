@@ -137,6 +137,8 @@ class Oracle:
         L.bbo_normal.restype = C.c_double
         L.bbo_accept_logu.restype = C.c_double
         L.bbo_logu_q.restype = C.c_double
+        L.bbo_exp.restype = C.c_double
+        L.bbo_exp.argtypes = [C.c_double]
         L.bbo_llikelihood.restype = C.c_double
         L.bbo_pcn_propose.restype = C.c_double
         L.bbo_pcn_bench.restype = C.c_longlong
