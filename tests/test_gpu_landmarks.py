@@ -145,10 +145,21 @@ def test_landmarks_plain_euler_and_unsupported(B, oracle_fma):
     for p in (0, 69):
         Xo = oracle_fma.euler(om, tt, x0(), W[p, 0])
         assert np.array_equal(X[p, 0], Xo)
-    # positions carry no noise: q moves only through the drift
+    # fused sample! + solve! gives the same W and X
+    ens2 = B.PathEnsemble(P, 1, N, 16, 8, double_buffer=False)
+    ens2.set_grid(0, tt); ens2.set_start(x0()); ens2.sample_euler_(Pm, 2, 1)
+    assert np.array_equal(ens2.download(B.W), W) and np.array_equal(ens2.download(B.X), X)
+    ens2.close()
+    # not on the wide path: innovations! (sigma is 16 x 8), pooled statistics, second-pass llikelihood, other schemes
     with pytest.raises(B.BridgeError) as ei:
         ens.innovations_(Pm)
     assert ei.value.status in (-11, -12)
+    with pytest.raises(B.BridgeError) as ei:
+        ens.mc_update_()
+    assert ei.value.status == -11
+    with pytest.raises(B.BridgeError) as ei:
+        ens.solve_scheme_(Pm, B.StochasticHeun.scheme)
+    assert ei.value.status == -11
     ens.close()
 
 

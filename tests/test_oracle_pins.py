@@ -475,3 +475,88 @@ def test_stochastic_heun_linear_closed_form(oracle_ref):
     want[39] = y
     assert np.allclose(X[:40, 0], want, rtol=1e-13, atol=1e-15)
     assert X[40, 0] == 123.0
+
+
+def test_kernel_exponential_restatement_accuracy(oracle_fma, oracle_ref):
+    """bb_exp of the GPU-order build (the landmarks kernel's exponential: +, *, fma, rint only) against libm:
+    relative error < 3e-16 on the argument range of the Gaussian kernel; the reference build IS libm exp."""
+    import math
+    xs = -np.concatenate([np.linspace(0.0, 6.0, 4001), np.logspace(-14, 2.84, 4000)])
+    err = max(abs(oracle_fma.lib.bbo_exp(float(x)) - math.exp(x)) / math.exp(x) for x in xs)
+    assert err < 3e-16
+    assert oracle_fma.lib.bbo_exp(-0.0) == 1.0 and oracle_fma.lib.bbo_exp(-750.0) == 0.0
+    assert all(oracle_ref.lib.bbo_exp(float(x)) == math.exp(x) for x in xs[::97])
+
+
+def test_landmarks_drift_restatement(oracle_ref, oracle_fma):
+    """project_partialbridge/partialbridge_landmarks.jl:47,90-101: the oracle's drift against an independent NumPy
+    transcription; with the positions frozen at qT the position part of the drift is B~ x of :129-138 (the auxiliary
+    process is the drift's linearisation there)."""
+    a, sig, lam = 0.5, 2.0, 0.5
+    om = O.make_model(O.LANDMARKS, 16, 8, [a, sig, lam])
+
+    def kern(x):
+        return np.exp(-np.dot(x, x) / (2 * a)) / (2 * np.pi * a)
+
+    def drift(x):
+        x = x.reshape(4, 2, 2)
+        out = np.zeros_like(x)
+        for i in range(4):
+            for j in range(4):
+                k = kern(x[i, 0] - x[j, 0])
+                out[i, 0] += 0.5 * x[j, 1] * k
+                out[i, 1] += -lam * 0.5 * x[j, 1] * k + 1 / (2 * a) * np.dot(x[i, 1], x[j, 1]) * (x[i, 0] - x[j, 0]) * k
+        return out.ravel()
+
+    rng = np.random.default_rng(3)
+    for orc, tol in ((oracle_ref, 1e-14), (oracle_fma, 1e-14)):
+        for _ in range(4):
+            x = rng.standard_normal(16)
+            b = np.zeros(16)
+            orc.lib.bbo_model_b(O.C.byref(om), O.C.c_double(0.0), O._p(x), O._p(b))
+            assert np.allclose(b, drift(x), rtol=tol, atol=1e-15)
+    qT = rng.standard_normal((4, 2))
+    Bt = np.zeros((16, 16))
+    for i in range(4):
+        for j in range(4):
+            k = kern(qT[i] - qT[j])
+            for c in range(2):
+                Bt[4 * i + c, 4 * j + 2 + c] += 0.5 * k
+                Bt[4 * i + 2 + c, 4 * j + 2 + c] += -0.5 * lam * k
+    x = rng.standard_normal((4, 2, 2)); x[:, 0] = qT
+    assert np.allclose((Bt @ x.ravel()).reshape(4, 2, 2)[:, 0], drift(x.ravel()).reshape(4, 2, 2)[:, 0], rtol=1e-13)
+    # noise acts on the momenta only: a = sigma^2 on the p components
+    A = np.zeros((16, 16))
+    oracle_ref.lib.bbo_model_a(O.C.byref(om), O._p(A))
+    want = np.zeros(16); want[[2, 3, 6, 7, 10, 11, 14, 15]] = sig * sig
+    assert np.array_equal(A, np.diag(want))
+
+
+def test_theta_oracle_composition_matches_the_backward_chain(oracle_ref):
+    """oracle.theta_backward (per-chain parameter path) is the chain of partialbridge_bolus3.jl:162-180 that the shared
+    tables of config 4 are built with; with θ = the model's parameters both give the same tables."""
+    eps_, sdiag = 1e-3, 1e-10
+    par = (0.1, 0.0, 1.5, 0.8, 0.3)
+    L = np.array([[1.0, 0.0]]); Sig = np.array([[sdiag]])
+    obs_t, obs_v = (0.5, 1.0, 1.5), (-1.0, -0.5, 0.5)
+
+    def tau(t0, t1, n):
+        s = np.linspace(0.0, t1 - t0, n)
+        return t0 + s * (2.0 - s / (t1 - t0))
+
+    grids = [tau(a, b, 41) for a, b in zip((0.0,) + obs_t[:-1], obs_t)]
+    guides, left = O.theta_backward(oracle_ref, O.FHN_HYPO, par, grids, [-0.5, -0.6], L, Sig, eps_, obs_v,
+                                    O.AUX_FHN_MATCHING, {4: ("gamma", 1.0, 100.0)})
+    nu = np.zeros(2); Hp = np.eye(2) / eps_
+    nu, Hp = oracle_ref.gpupdate_nuH(nu, Hp, L, Sig, [obs_v[-1]])
+    for s in range(2, -1, -1):
+        Bt, bt = O.fhn_aux(O.AUX_FHN_MATCHING, par, obs_v[s])
+        nus, Hs, nu, Hp, _ = oracle_ref.backward_nuH(O.ODE_LYAP, grids[s], O.const_aux(Bt, bt, O.fhn_a(O.FHN_HYPO, par)),
+                                                     nu, Hp, 0.0)
+        assert np.array_equal(guides[s].A, Hs) and np.array_equal(guides[s].b, nus)
+        if s > 0:
+            nu, Hp = oracle_ref.gpupdate_nuH(nu, Hp, L, Sig, [obs_v[s - 1]])
+    assert np.array_equal(left["nu"], nu) and np.array_equal(left["Hp"], Hp)
+    assert left["lpn"] == oracle_ref.logpdfnormal(np.array([-0.5, -0.6]) - nu, Hp)
+    assert abs(left["lpri"] - (-np.log(100.0) - 0.3 / 100.0)) < 1e-15
+    assert abs(left["trsum"] - 1.5 * (1 / 0.1 - 1.0)) < 1e-12
