@@ -11,6 +11,6 @@ from .api import *  # noqa: F401,F403
 from .api import (Context, default_context, PathEnsemble, SamplePath, VSamplePath, samplepath, sample, sample_,
                   seed_, solve, solve_, bridge_, llikelihood, innovations_, pcn_, gpupdate, gpupdate_νH,
                   EulerMaruyama, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
-                  LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde,
+                  LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde, BolusDiffusion,
                   LinearAux, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,
                   PartialBridge, GuideTables)  # noqa: F401

@@ -21,7 +21,7 @@ OK, ERR_LENGTH, ERR_TIMEAXIS, ERR_STARTPOINT, ERR_DIM, ERR_ASSERT_M, ERR_MODEL, 
     ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE = (0, -1, -2, -3, -4, -5, -6, -7, -8, -9,
                                                                          -10, -11, -12, -13)
 # model ids
-WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS = range(9)
+WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS, BOLUS = range(10)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
 ODE_R3, ODE_LYAP = 0, 1
 ENS_DOUBLE_BUFFER, ENS_NO_X = 1, 2
@@ -47,7 +47,7 @@ class Model(C.Structure):
 
 
 BB_NTHETA, BB_MAXD, BB_MAXSEG = 8, 4, 16
-AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END = 1, 2
+AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END, AUX_BOLUS = 1, 2, 3
 PRIOR_FLAT, PRIOR_GAMMA = 0, 1
 
 

@@ -308,6 +308,30 @@ class Lorenz(ContinuousTimeProcess):  # src/Models.jl:38-55
         return np.diag(self.p[3:6])
 
 
+class BolusDiffusion(ContinuousTimeProcess):  # project_partialbridge/partialbridge_bolus3.jl:38-51 (`Diffusion`)
+    """dX1 = (α dose(t) - (λ+β) X1 + μ X2) dt + σ1 dW1,  dX2 = (λ X1 - μ X2) dt + σ1 dW2; σ2 enters the auxiliary process
+    only.  Its drift depends on t: it runs on the per-chain-parameter path (PathEnsemble.theta_*)."""
+    model_id = K.BOLUS
+    d = dprime = 2
+
+    def __init__(self, α, β, λ, μ, σ1, σ2):
+        self.p = [float(v) for v in (α, β, λ, μ, σ1, σ2)]
+
+    def par(self):
+        return self.p
+
+    @staticmethod
+    def dose(t):  # :73
+        return 2 * (t / 2) / (1 + (t / 2) ** 2)
+
+    def b(self, t, x):
+        α, β, λ, μ = self.p[:4]
+        return np.array([α * self.dose(t) - (λ + β) * x[0] + μ * x[1], λ * x[0] - μ * x[1]])
+
+    def σ(self, t, x=None):
+        return self.p[4] * np.eye(2)
+
+
 class Landmarks(ContinuousTimeProcess):  # project_partialbridge/partialbridge_landmarks.jl:47,67-72,86-101
     """n = 4 landmarks in the plane with Gaussian kernel parameter a, noise level σ on the momenta and mean reversion λ.
     State: (q1, p1, ..., q4, p4) flattened (the script's fll(Vector{Point})), d = 16, d' = 8."""

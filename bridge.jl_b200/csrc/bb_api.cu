@@ -209,6 +209,7 @@ static bool model_shape_ok(const bb_model* m) {
   switch (m->id) {
     case BB_MODEL_WIENER: return d == dp && ((d >= 1 && d <= 3) || d == 8);
     case BB_MODEL_LANDMARKS: return d == 16 && dp == 8;
+    case BB_MODEL_BOLUS: return d == 2 && dp == 2; /* per-chain-parameter path only: no shared-table kernel */
     case BB_MODEL_OU: return d == 1 && dp == 1;
     case BB_MODEL_LINPRO: return d == dp && d >= 1 && d <= 3;
     case BB_MODEL_FHN_DIAG: return d == 2 && dp == 2;
@@ -233,6 +234,7 @@ static void model_sigma_host(const bb_model* P, double* S) {
     case BB_MODEL_INTDIFF: S[1] = p[0]; break;
     case BB_MODEL_NCLAR3: S[2] = p[2]; break;
     case BB_MODEL_LORENZ: S[0] = p[3]; S[4] = p[4]; S[8] = p[5]; break;
+    case BB_MODEL_BOLUS: S[0] = p[4]; S[3] = p[4]; break;
   }
 }
 void bb_prepare_model(const bb_model* m, bb_model_dev* o) {

@@ -101,20 +101,39 @@ __device__ __forceinline__ void theta_model(const double* th, bb_model_dev& m) {
       m.der[8 + i * D + j] = (M::col(i) >= 0 && M::col(i) == M::col(j)) ? M::sig(m, i) * M::sig(m, j) : 0.0;
 }
 
-/* B~, beta~ of a segment from (θ, v): partialbridge_fitzhugh.jl:98-108 (x^2, x^3 are products, as Julia's literal_pow) */
+/* B~, beta~ of a segment from (θ, v) at time t: partialbridge_fitzhugh.jl:98-108 (x^2, x^3 are products, as Julia's
+ * literal_pow), partialbridge_bolus3.jl:66-67 */
 template <class M, int AUXK>
-__device__ __forceinline__ void theta_aux(const bb_model_dev& m, double v, double* Bt, double* be) {
-  static_assert(M::ID == BB_MODEL_FHN_DIAG || M::ID == BB_MODEL_FHN_HYPO, "auxiliary registry: FitzHugh-Nagumo");
-  const double eps = m.par[0], s = m.par[1], gam = m.par[2], beta = m.par[3];
-  const double ie = 1.0 / eps;
-  if (AUXK == BB_AUX_FHN_MATCHING) {
-    Bt[0] = ie; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
-    be[0] = s / eps - (v * v * v) / eps;
-    be[1] = beta;
+__device__ __forceinline__ void theta_aux(const bb_model_dev& m, double v, double t, double* Bt, double* be) {
+  if constexpr (AUXK == BB_AUX_BOLUS) {
+    static_assert(M::ID == BB_MODEL_BOLUS, "auxiliary registry: DiffusionAux belongs to the bolus model");
+    const double alpha = m.par[0], beta = m.par[1], lam = m.par[2], mu = m.par[3];
+    Bt[0] = -lam - beta; Bt[1] = mu; Bt[2] = lam; Bt[3] = -mu;
+    be[0] = alpha * bb_dose(t);
+    be[1] = 0.0;
   } else {
-    Bt[0] = ie - (3.0 * (v * v)) / eps; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
-    be[0] = s / eps + (2.0 * (v * v * v)) / eps;
-    be[1] = beta;
+    static_assert(M::ID == BB_MODEL_FHN_DIAG || M::ID == BB_MODEL_FHN_HYPO, "auxiliary registry: FitzHugh-Nagumo");
+    const double eps = m.par[0], s = m.par[1], gam = m.par[2], beta = m.par[3];
+    const double ie = 1.0 / eps;
+    if (AUXK == BB_AUX_FHN_MATCHING) {
+      Bt[0] = ie; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
+      be[0] = s / eps - (v * v * v) / eps;
+      be[1] = beta;
+    } else {
+      Bt[0] = ie - (3.0 * (v * v)) / eps; Bt[1] = -ie; Bt[2] = gam; Bt[3] = -1.0;
+      be[0] = s / eps + (2.0 * (v * v * v)) / eps;
+      be[1] = beta;
+    }
+  }
+}
+/* a~: the target's a for the FitzHugh-Nagumo pairs; diag(σ1², σ2²) for DiffusionAux (bolus3.jl:68,71) */
+template <class M, int AUXK>
+__device__ __forceinline__ void theta_aux_a(const bb_model_dev& m, double* at) {
+  if constexpr (AUXK == BB_AUX_BOLUS) {
+    at[0] = m.par[4] * m.par[4]; at[1] = 0.0; at[2] = 0.0; at[3] = m.par[5] * m.par[5];
+  } else {
+#pragma unroll
+    for (int k = 0; k < M::D * M::D; k++) at[k] = m.der[8 + k];
   }
 }
 
@@ -178,7 +197,9 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
   }
   bb_model_dev m;
   theta_model<M>(th, m);
-  const double* at = m.der + 8;
+  constexpr bool TDEP = (AUXK == BB_AUX_BOLUS); /* beta~ depends on t */
+  double at[D * D];
+  theta_aux_a<M, AUXK>(m, at);
   bool bad = false;
   double nu[D], Hp[D * D], Hc[D * D];
   /* νend = 0, Hend⁺ = I/ϵ, then the update with the last observation  (bolus3.jl:162-165) */
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
   double Cc = 0.0, trsum = 0.0;
   for (int s = S - 1; s >= 0; s--) {
     double Bt[D * D], be[D];
-    theta_aux<M, AUXK>(m, a.spec.v[s][0], Bt, be);
+    theta_aux<M, AUXK>(m, a.spec.v[s][0], 0.0, Bt, be);
     const aux_dev A{Bt, be, at, at, 1};
     if (minv<D>(Hp, Hc)) bad = true;
     double* Trow = a.T + ((long long)s * N + (N - 1)) * K * PT + p;
@@ -204,7 +225,22 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
     const double* tt = a.tt + (long long)s * N;
     for (int i = N - 2; i >= 0; i--) {
       const double dt = tt[i] - tt[i + 1];
-      if (nuH_step<D>(BB_ODE_LYAP, A, i, dt, Hp, Hc, nu, Cc)) bad = true;
+      if constexpr (TDEP) {
+        /* values at the Ralston stage times t, t + dt/2, t + 3dt/4 of the step that starts at t = tt[i+1]
+         * (src/ode.jl:44-49); B~ and a~ are constant, a~(tt[i]) = a~ */
+        double Bs[3][D * D], bs[3][D], as[3][D * D];
+        const double tq[3] = {tt[i + 1], tt[i + 1] + 0.5 * dt, tt[i + 1] + 0.75 * dt};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          theta_aux<M, AUXK>(m, a.spec.v[s][0], tq[q], Bs[q], bs[q]);
+#pragma unroll
+          for (int k = 0; k < D * D; k++) as[q][k] = at[k];
+        }
+        const aux_dev As{&Bs[0][0], &bs[0][0], &as[0][0], at, 0};
+        if (nuH_step<D>(BB_ODE_LYAP, As, 0, dt, Hp, Hc, nu, Cc)) bad = true;
+      } else {
+        if (nuH_step<D>(BB_ODE_LYAP, A, i, dt, Hp, Hc, nu, Cc)) bad = true;
+      }
       Trow -= (long long)K * PT;
 #pragma unroll
       for (int k = 0; k < D; k++) Trow[(long long)k * PT] = nu[k];
@@ -349,7 +385,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
     const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
     const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
     double sc[D * D + D];
-    theta_aux<M, AUXK>(m, a.spec.v[s][0], sc, sc + D * D);
+    theta_aux<M, AUXK>(m, a.spec.v[s][0], 0.0, sc, sc + D * D);
+    constexpr bool TDEP = (AUXK == BB_AUX_BOLUS);
+    const double* tts = a.tt + (long long)s * N;
     const double* gt = a.gridtab[s];
     double som = 0.0;
 #pragma unroll
@@ -423,6 +461,10 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
             for (int k = 0; k < DP; k++) {
               dw[k] = wj[k] - wprev[k];
               wprev[k] = wj[k];
+            }
+            if constexpr (TDEP) { /* b(tt[i], x) and b~(tt[i], x) at the left end of the step, i = j - 1 */
+              m.der[1] = m.par[0] * bb_dose(tts[j - 1]);
+              sc[D * D] = m.der[1];
             }
             CH::drift(m, R, sc, y, R[0], j <= a.jll, som, bd);
             bb_em_update<M>(m, bd, R[0], dw, y);
@@ -528,6 +570,12 @@ typedef void (*theta_kernel_fn)(const bb_theta_args);
 
 template <class M>
 static theta_kernel_fn lookup_backward(int auxk, int mobs) {
+  if constexpr (M::ID == BB_MODEL_BOLUS) {
+    if (auxk != BB_AUX_BOLUS) return nullptr;
+    if (mobs == 1) return &bb_theta_backward_kernel<M, BB_AUX_BOLUS, 1>;
+    if (mobs == 2) return &bb_theta_backward_kernel<M, BB_AUX_BOLUS, 2>;
+    return nullptr;
+  } else {
   if (auxk == BB_AUX_FHN_MATCHING) {
     if (mobs == 1) return &bb_theta_backward_kernel<M, BB_AUX_FHN_MATCHING, 1>;
     if (mobs == 2) return &bb_theta_backward_kernel<M, BB_AUX_FHN_MATCHING, 2>;
@@ -537,9 +585,14 @@ static theta_kernel_fn lookup_backward(int auxk, int mobs) {
     if (mobs == 2) return &bb_theta_backward_kernel<M, BB_AUX_FHN_LINEARISED_END, 2>;
   }
   return nullptr;
+  }
 }
 template <class M>
 static theta_kernel_fn lookup_forward(int auxk, bool pcn) {
+  if constexpr (M::ID == BB_MODEL_BOLUS) {
+    if (auxk != BB_AUX_BOLUS) return nullptr;
+    return pcn ? &bb_theta_forward_kernel<M, BB_AUX_BOLUS, true> : &bb_theta_forward_kernel<M, BB_AUX_BOLUS, false>;
+  } else {
   if (auxk == BB_AUX_FHN_MATCHING)
     return pcn ? &bb_theta_forward_kernel<M, BB_AUX_FHN_MATCHING, true>
                : &bb_theta_forward_kernel<M, BB_AUX_FHN_MATCHING, false>;
@@ -547,6 +600,7 @@ static theta_kernel_fn lookup_forward(int auxk, bool pcn) {
     return pcn ? &bb_theta_forward_kernel<M, BB_AUX_FHN_LINEARISED_END, true>
                : &bb_theta_forward_kernel<M, BB_AUX_FHN_LINEARISED_END, false>;
   return nullptr;
+  }
 }
 
 static int fill_args(bb_ens* e, bb_theta_args& a) {
@@ -599,8 +653,10 @@ static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd,
   if (rw_sd) memcpy(a.rw_sd, rw_sd, sizeof(a.rw_sd));
   bb_philox_key_schedule(seed, a.keys);
   a.stream = stream;
-  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO ? lookup_backward<MFhnHypo>(t->spec.aux_kind, t->spec.m)
-                                                        : lookup_backward<MFhnDiag>(t->spec.aux_kind, t->spec.m);
+  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO
+                           ? lookup_backward<MFhnHypo>(t->spec.aux_kind, t->spec.m)
+                           : (t->model.id == BB_MODEL_FHN_DIAG ? lookup_backward<MFhnDiag>(t->spec.aux_kind, t->spec.m)
+                                                               : lookup_backward<MBolus>(t->spec.aux_kind, t->spec.m));
   if (!fn) return BB_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((e->P + 127) / 128);
   fn<<<grid, 128, 0, c->stream>>>(a);
@@ -632,8 +688,10 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
   a.rho2 = sqrt(1 - rho * rho);
   bb_philox_key_schedule(seed, a.keys);
   a.stream = stream;
-  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO ? lookup_forward<MFhnHypo>(t->spec.aux_kind, pcn)
-                                                        : lookup_forward<MFhnDiag>(t->spec.aux_kind, pcn);
+  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO
+                           ? lookup_forward<MFhnHypo>(t->spec.aux_kind, pcn)
+                           : (t->model.id == BB_MODEL_FHN_DIAG ? lookup_forward<MFhnDiag>(t->spec.aux_kind, pcn)
+                                                               : lookup_forward<MBolus>(t->spec.aux_kind, pcn));
   if (!fn) return BB_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((e->P + BB_THREADS - 1) / BB_THREADS);
   const size_t smem = (size_t)BB_THREADS * 128 + (pcn ? (size_t)BB_THREADS * BB_TC * e->dp * 8 : 0) +
@@ -674,11 +732,14 @@ static int th_alloc(bb_ens* e, T** p, size_t count) {
 extern "C" int bb_theta_attach(bb_ens* e, const bb_model* model, const bb_theta_spec* spec) {
   if (!e || !model || !spec) return BB_ERR_ARG;
   if (e->th) return BB_ERR_ARG;
-  if (model->id != BB_MODEL_FHN_HYPO && model->id != BB_MODEL_FHN_DIAG) return BB_ERR_UNSUPPORTED;
+  if (model->id != BB_MODEL_FHN_HYPO && model->id != BB_MODEL_FHN_DIAG && model->id != BB_MODEL_BOLUS)
+    return BB_ERR_UNSUPPORTED;
   if (model->d != e->d || model->dprime != e->dp) return BB_ERR_MODEL;
   if (model->d != 2 || model->dprime != (model->id == BB_MODEL_FHN_HYPO ? 1 : 2)) return BB_ERR_MODEL;
   if (spec->m < 1 || spec->m > e->d) return BB_ERR_ASSERT_M;
-  if (spec->aux_kind != BB_AUX_FHN_MATCHING && spec->aux_kind != BB_AUX_FHN_LINEARISED_END) return BB_ERR_UNSUPPORTED;
+  if (model->id == BB_MODEL_BOLUS ? spec->aux_kind != BB_AUX_BOLUS
+                                  : (spec->aux_kind != BB_AUX_FHN_MATCHING && spec->aux_kind != BB_AUX_FHN_LINEARISED_END))
+    return BB_ERR_UNSUPPORTED;
   for (int k = 0; k < BB_NTHETA; k++) {
     if (spec->prior_kind[k] != BB_PRIOR_FLAT && spec->prior_kind[k] != BB_PRIOR_GAMMA) return BB_ERR_ARG;
     if (spec->prior_kind[k] == BB_PRIOR_GAMMA && !(spec->prior_a[k] > 0 && spec->prior_b[k] > 0)) return BB_ERR_ARG;

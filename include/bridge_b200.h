@@ -85,6 +85,10 @@ int bb_abi_version(void);
  *   NCLAR3    d=3,d'=1; par={alpha,omega,sigma}; b=(x2,x3,-alpha sin(omega x3))
  *                                       project_partialbridge/partialbridge_nclar.jl:58-60
  *   LORENZ    d=d'=3; par={th1,th2,th3, s1,s2,s3}; sigma=diag(s)  src/Models.jl:38-55, test/euler.jl:49-50
+ *   BOLUS     d=d'=2; par={alpha,beta,lambda,mu,sigma1,sigma2}; b=(alpha dose(t) - (lambda+beta)x1 + mu x2,
+ *             lambda x1 - mu x2), dose(t) = 2(t/2)/(1+(t/2)^2), sigma = sigma1 I   project_partialbridge/
+ *             partialbridge_bolus3.jl:38-51,73.  The drift depends on t: this model runs on the per-chain-parameter
+ *             path only (bb_theta_*, which is where the reference uses it); the shared-table kernels are autonomous.
  *   LANDMARKS d=16,d'=8; par={a, sigma, lambda}: n = 4 landmarks in the plane, state (q1,p1,...,q4,p4) with
  *             q_i, p_i in R^2 (the flattened Vector{Point} of the script), Gaussian kernel
  *             k(x) = exp(-|x|^2/(2a))/(2 pi a), drift  dq_i = 1/2 sum_j p_j k(q_i-q_j),
@@ -105,7 +109,8 @@ typedef enum {
   BB_MODEL_NCLAR3 = 6,
   BB_MODEL_LORENZ = 7,
   BB_MODEL_LANDMARKS = 8,
-  BB_MODEL_COUNT = 9
+  BB_MODEL_BOLUS = 9,
+  BB_MODEL_COUNT = 10
 } bb_model_id;
 
 typedef struct {
@@ -364,7 +369,9 @@ int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
 #define BB_NTHETA 8
 typedef enum {
   BB_AUX_FHN_MATCHING = 1,      /* B~ = [1/ϵ -1/ϵ; γ -1], β~ = (s/ϵ - v³/ϵ, β)           partialbridge_fitzhugh.jl:106-108 */
-  BB_AUX_FHN_LINEARISED_END = 2 /* B~ = [1/ϵ - 3v²/ϵ  -1/ϵ; γ -1], β~ = (s/ϵ + 2v³/ϵ, β)  partialbridge_fitzhugh.jl:98-100 */
+  BB_AUX_FHN_LINEARISED_END = 2,/* B~ = [1/ϵ - 3v²/ϵ  -1/ϵ; γ -1], β~ = (s/ϵ + 2v³/ϵ, β)  partialbridge_fitzhugh.jl:98-100 */
+  BB_AUX_BOLUS = 3              /* DiffusionAux: B~ = [-λ-β μ; λ -μ], β~(t) = (α dose(t), 0), a~ = diag(σ1², σ2²)  bolus3.jl:54-71
+                                   (time dependent: evaluated on the device at the Ralston stage times) */
 } bb_aux_kind;
 enum { BB_PRIOR_FLAT = 0, BB_PRIOR_GAMMA = 1 /* Gamma(shape a, scale b): logπ of bolus3.jl:237 */ };
 typedef struct {

@@ -149,7 +149,7 @@ struct BBThetaSpec   # == bb_theta_spec
     v::NTuple{64,Float64}                      # v[s][0..3], row per segment
     prior_kind::NTuple{8,Int32}; prior_a::NTuple{8,Float64}; prior_b::NTuple{8,Float64}
 end
-const AUXKIND = Dict(:fhn_matching => Int32(1), :fhn_linearised_end => Int32(2))
+const AUXKIND = Dict(:fhn_matching => Int32(1), :fhn_linearised_end => Int32(2), :bolus => Int32(3))
 function theta_attach!(E::PathEnsemble, P::ContinuousTimeProcess, L, Σ, ϵ, obs; aux = :fhn_matching, priors = Dict())
     m, d = size(L)
     Lr = zeros(16); Sr = zeros(16); vr = zeros(64); pk = zeros(Int32, 8); pa = zeros(8); pb = zeros(8)

@@ -420,6 +420,13 @@ static void model_b(const bb_model* P, double t, const double* x, double* b) {
       b[2] = x[0] * x[1] - p[2] * x[2];
 #endif
       break;
+    case BB_MODEL_BOLUS: { /* partialbridge_bolus3.jl:49,73  (α dose(t) - (λ+β) x1 + μ x2,  λ x1 - μ x2), dose(t) = 2(t/2)/(1+(t/2)^2) */
+      double u = t / 2;
+      double dose = (2 * u) / (1 + u * u);
+      b[0] = (p[0] * dose - (p[2] + p[1]) * x[0]) + p[3] * x[1];
+      b[1] = p[2] * x[0] - p[3] * x[1];
+      break;
+    }
     case BB_MODEL_LANDMARKS: { /* partialbridge_landmarks.jl:47 (kernel), :90-101 (b!), state = fll(Vector{Point}) */
       const int n = 4;
       const double a = p[0], lam = p[2];
@@ -461,6 +468,7 @@ static void model_sigma(const bb_model* P, double* S) {
     case BB_MODEL_INTDIFF: S[1] = p[0]; break;
     case BB_MODEL_NCLAR3: S[2] = p[2]; break;
     case BB_MODEL_LORENZ: S[0] = p[3]; S[4] = p[4]; S[8] = p[5]; break;
+    case BB_MODEL_BOLUS: S[0] = p[4]; S[3] = p[4]; break; /* σ = [σ1 0; 0 σ1]  bolus3.jl:50 */
     case BB_MODEL_LANDMARKS: /* noise on the momenta: component 4i+2+k <- column 2i+k  (partialbridge_landmarks.jl:111-118) */
       for (int i = 0; i < 4; i++)
         for (int k = 0; k < 2; k++) S[(4 * i + 2 + k) * dp + 2 * i + k] = p[1];

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 BB_NPAR = 32
 
 # model ids (include/bridge_b200.h)
-WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS = range(9)
+WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS, BOLUS = range(10)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
 ODE_R3, ODE_LYAP = 0, 1
 
@@ -314,7 +314,7 @@ def load(variant: str = "ref") -> Oracle:
 # the oracle's restatements of the reference functions it calls (partialbridgeνH / Lyap, gpupdate, solve!,
 # llikelihood, logpdfnormal).  Mirrors bb_theta.cu; the summation orders of the script-level quantities
 # (trace term, diffll) are the ones written here.
-AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END = 1, 2
+AUX_FHN_MATCHING, AUX_FHN_LINEARISED_END, AUX_BOLUS = 1, 2, 3
 Q_THETA_NORMALS, Q_THETA_LOGU = 0xFFFFFFFE, 0xFFFFFFFD
 
 
@@ -337,20 +337,42 @@ def fhn_a(model_id, par):
     return np.array([[float(par[4]) * float(par[4]), 0.0], [0.0, float(par[5]) * float(par[5])]])
 
 
+def dose(t):
+    """dose(t) = 2*(t/2)/(1+(t/2)^2)   partialbridge_bolus3.jl:73"""
+    u = t / 2
+    return (2 * u) / (1 + u * u)
+
+
+def bolus_aux(par):
+    """DiffusionAux of partialbridge_bolus3.jl:54-71: B~ (constant), beta~(t), a~ = diag(σ1², σ2²)."""
+    alpha, beta, lam, mu, s1, s2 = (float(x) for x in par[:6])
+    Bt = np.array([[-lam - beta, mu], [lam, -mu]])
+    at = np.array([[s1 * s1, 0.0], [0.0, s2 * s2]])
+    return Bt, (lambda t: np.array([alpha * dose(t), 0.0])), at
+
+
 def theta_backward(o: Oracle, model_id, par, grids, x0, L, Sigma, eps, obs_v, aux_kind, priors=None):
     """-> (guides [S], left dict): bolus3.jl:162-165, 276-291 for one θ."""
     S = len(grids)
     L = np.atleast_2d(_f64(L)); d = L.shape[1]
-    at = fhn_a(model_id, par)
     nu = np.zeros(d); Hp = np.eye(d) * (1.0 / eps)
     nu, Hp = o.gpupdate_nuH(nu, Hp, L, Sigma, np.atleast_1d(obs_v[S - 1]))
     guides = [None] * S
     Cc = 0.0; trsum = 0.0
     for s in range(S - 1, -1, -1):
-        Bt, bt = fhn_aux(aux_kind, par, float(np.atleast_1d(obs_v[s])[0]))
-        aux = const_aux(Bt, bt, at)
-        nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], aux, nu, Hp, Cc)
-        guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=Bt, betat=bt)
+        if aux_kind == AUX_BOLUS:
+            Bt, bf, at = bolus_aux(par)
+            aux = staged_aux(grids[s], lambda t: Bt, bf, lambda t: at)
+            nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], aux, nu, Hp, Cc)
+            n = len(grids[s])
+            guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=np.broadcast_to(Bt, (n, d, d)).copy(),
+                                    betat=np.stack([bf(t) for t in grids[s]]), aux_const=False)
+        else:
+            at = fhn_a(model_id, par)
+            Bt, bt = fhn_aux(aux_kind, par, float(np.atleast_1d(obs_v[s])[0]))
+            aux = const_aux(Bt, bt, at)
+            nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], aux, nu, Hp, Cc)
+            guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=Bt, betat=bt)
         tr = Bt[0, 0]
         for i in range(1, d):
             tr += Bt[i, i]

@@ -282,3 +282,91 @@ def test_theta_ragged_sizes_skip_and_no_x(B, oracle_fma, P, n, S, diag):
         Xo, llo, _ = O.theta_forward(oracle_fma, mid, dp, thf[p, :npar], g, cfg.FHN_X0, Wf[p], skip=skip)
         assert np.array_equal(Xf[p], Xo) and ens.ll[p] == llo
     ens.close()
+
+
+# ----------------------------------------------------------------------------------------------- the model of bolus3.jl itself
+BOLUS_PAR = (70.0 / 0.6, 8.0, 15.0 / (20 * 0.6), 1.5 * 15.0 / 15.0, 0.5, 0.2)  # α, β(init 8.0), λ, μ, σ1(init .5), σ2  :74-77,152-154
+BOLUS_L = np.array([[0.5, 0.5]])                                                 # :31
+BOLUS_PRIORS = {1: ("gamma", 1.0, 100.0), 4: ("gamma", 1.0, 100.0)}              # logπ, :237
+BOLUS_RW = np.array([0.0, 0.02, 0.0, 0.0, 0.02, 0.0, 0, 0])                      # propose(.02, P): β and σ1, :239-242,272
+
+
+def test_theta_bolus_model_parameter_update_vs_oracle(B, oracle_fma, oracle_ref):
+    """The parameter-update branch of partialbridge_bolus3.jl with ITS model: time-dependent drift α dose(t), auxiliary
+    process DiffusionAux (β~(t) evaluated at the Ralston stage times on the device, a~ = diag(σ1², σ2²) != a), L = [.5 .5],
+    Σ = 1e-4, ϵ = 1e-3, Gamma(1,100) priors on β and σ1, random-walk proposals of sd 0.02 on both."""
+    P, n, S, seed = 96, 61, 3, 12
+    obs_t = (0.8, 1.7, 2.5); obs_v = (4.0, 9.0, 12.0)
+    tcut = (0.0,) + obs_t
+    grids = []
+    for k in range(S):
+        s = np.linspace(0.0, tcut[k + 1] - tcut[k], n)
+        grids.append(tcut[k] + s * (2 - s / (tcut[k + 1] - tcut[k])))  # τ(t, T0, Tend), :157
+    x0 = np.array([0.5, 0.2])
+    Pm = B.BolusDiffusion(*BOLUS_PAR)
+    ens = B.PathEnsemble(P, S, n, 2, 2, chain_offset=40)
+    for s_, g in enumerate(grids):
+        ens.set_grid(s_, g)
+    ens.set_start(x0)
+    ens.theta_attach_(Pm, BOLUS_L, 1e-4 * np.eye(1), 1e-3, obs_v, aux_kind=O.AUX_BOLUS, priors=BOLUS_PRIORS)
+    th = ens.theta()
+    rng = np.random.default_rng(2)
+    th[:, 1] += 0.5 * rng.standard_normal(P); th[:, 4] *= np.exp(0.1 * rng.standard_normal(P))
+    ens.set_theta(th)
+    ens.sample_(seed, 0xFFFFFFF0)
+    ens.theta_guided_euler_ll_()
+    Wc = ens.download(B.W); Xc = ens.download(B.X); llc = ens.ll; leftc = ens.theta_left()
+
+    def orc_left(o, par):
+        return O.theta_backward(o, O.BOLUS, par[:6], grids, x0, BOLUS_L, 1e-4 * np.eye(1), 1e-3, obs_v, O.AUX_BOLUS,
+                                BOLUS_PRIORS)
+
+    chains = (0, 31, 32, 95)
+    for p in chains:
+        g, lo = orc_left(oracle_fma, th[p])
+        ν, H = ens.theta_tables(p)
+        for s_ in range(S):
+            assert np.array_equal(ν[s_], g[s_].b) and np.array_equal(H[s_], g[s_].A), (p, s_)
+        assert np.array_equal(leftc[p, 0:2], lo["nu"]) and np.array_equal(leftc[p, 2:6].reshape(2, 2), lo["Hp"])
+        assert leftc[p, 6] == lo["C"] and leftc[p, 8] == lo["trsum"]
+        assert abs(leftc[p, 7] - lo["lpn"]) <= 1e-13 * abs(lo["lpn"]) and abs(leftc[p, 9] - lo["lpri"]) <= 1e-13
+        for o, exact in ((oracle_fma, True), (oracle_ref, False)):
+            Xo, llo, _ = O.theta_forward(o, O.BOLUS, 2, th[p, :6], g, x0, Wc[p])
+            if exact:
+                assert np.array_equal(Xc[p], Xo) and llc[p] == llo
+            else:
+                assert np.max(np.abs(Xc[p] - Xo)) <= XTOL * (1 + np.max(np.abs(Xo)))
+                assert abs(llc[p] - llo) <= LLREL * abs(llo) + LLABS
+    nacc = 0
+    for it in range(3):
+        thc = ens.theta(); llc = ens.ll; leftc = ens.theta_left(B.CUR)
+        ens.theta_param_step_(BOLUS_RW, seed, 200 + it)
+        tho = ens.theta(B.PROP); lefto = ens.theta_left(B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted.astype(bool)
+        diff = (lefto[:, 7] - leftc[:, 7]) + (llp - llc)
+        diff = diff + (((lefto[:, 8] - leftc[:, 8]) + lefto[:, 9]) - leftc[:, 9])
+        assert np.array_equal(flags, logu <= diff)
+        Xp = ens.download(B.X, which=B.PROP)
+        for p in chains:
+            tp = O.theta_propose(oracle_fma, thc[p], BOLUS_RW, seed, 200 + it, 40 + p)
+            assert np.array_equal(tho[p], tp)
+            g, lo = orc_left(oracle_fma, tp)
+            Xo, llo, _ = O.theta_forward(oracle_fma, O.BOLUS, 2, tp[:6], g, x0, Wc[p])
+            assert np.array_equal(Xp[p], Xo) and llp[p] == llo
+            assert logu[p] == oracle_fma.logu_q(seed, 200 + it, 40 + p, O.Q_THETA_LOGU)
+        nacc += int(flags.sum())
+    assert ens.acc_theta == nacc and 0 < nacc < 3 * P
+    # pCN with the tables of the chains' current parameters (ρ = 0 in the script, :28: an independence sampler)
+    thf = ens.theta(); llc = ens.ll
+    ens.theta_pcn_step_(0.0, seed, 300)
+    Wp = ens.download(B.W, which=B.PROP)
+    for p in chains:
+        g, _ = orc_left(oracle_fma, thf[p])
+        mdl = O.make_model(O.BOLUS, 2, 2, thf[p, :6])
+        llo, lu, Wo, Xo, _ = oracle_fma.pcn_propose(mdl, g, x0, Wc[p], 0.0, seed, 300, 40 + p)
+        assert np.array_equal(Wp[p], Wo) and ens.ll_prop[p] == llo and ens.logu[p] == lu
+    # this model is not on the shared-table path (its drift depends on t)
+    with pytest.raises(B.BridgeError) as ei:
+        ens.euler_(Pm)
+    assert ei.value.status == -11
+    ens.close()
