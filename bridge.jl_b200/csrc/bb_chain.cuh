@@ -520,8 +520,15 @@ struct bb_chain {
   }
 };
 
+/* Resident CTAs per SM the kernel is compiled for.  With d' >= 2 the staging of the driving path alone takes
+ * 2 x 256 x 128 d' bytes >= 128 KB of shared memory, so only ONE CTA fits an SM anyway: compiling those kernels for two
+ * (a 128-register cap) bought nothing and made them spill 70-420 bytes per thread (config 3, LinPro d = 3:
+ * 2.75 ms -> 0.83 ms for guided Euler + ll once the cap is lifted). */
+template <class M>
+constexpr int bb_min_ctas() { return M::DP >= 2 ? 1 : BB_MINB; }
+
 template <class M, int GK, int GM, int AUXM, int RNG>
-__global__ void __launch_bounds__(BB_THREADS, BB_MINB) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
+__global__ void __launch_bounds__(BB_THREADS, bb_min_ctas<M>()) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
   bb_chain<M, GK, GM, AUXM, RNG>::run(a);
 }
 
