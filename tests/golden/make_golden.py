@@ -95,9 +95,82 @@ def main():
     Xi, _ = orc.guided_euler(omi, ogi, [2.0, 1.0], Wi)
     np.savez(os.path.join(OUT, "oracle_intdiff_partialbridge.npz"), tt=ttp, L=Lt, M=Mt, mu=mut, v=np.array([2.5]),
              Bt=aux["B"], bt=aux["beta"], W=Wi, X=Xi, ll=orc.llikelihood(omi, ogi, Xi))
+    make_theta_and_landmarks(orc)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+BOLUS_PAR = [70.0 / 0.6, 8.0, 15.0 / (20 * 0.6), 1.5, 0.5, 0.2]
+BOLUS_PRIORS = {1: ("gamma", 1.0, 100.0), 4: ("gamma", 1.0, 100.0)}
+BOLUS_RW = [0.0, 0.02, 0.0, 0.0, 0.02, 0.0, 0.0, 0.0]
+LM_PAR = [0.5, 2.0, 0.5]
+LM_QT = np.array([[-0.6, -1.4], [1.5, -0.9], [0.8, 1.4], [-1.2, 0.7]])
+LM_X0 = np.array([-1.0, -1.0, 0.5, 0.1, 1.0, -1.2, -0.2, 0.4, 1.1, 0.9, -0.3, -0.3, -0.8, 1.0, 0.2, -0.5])
+
+
+def make_theta_and_landmarks(orc):
+    """Per-chain parameter step of partialbridge_bolus3.jl with its own model, and the landmarks bridge (config 5)."""
+    # ---- bolus model: two chains, one parameter proposal each (reference arithmetic)
+    n, S, seed, it = 41, 2, 21, 5
+    tcut = (0.0, 0.8, 1.7); obs_v = [4.0, 9.0]
+    grids = [warped(tcut[k], tcut[k + 1], n) for k in range(S)]
+    x0 = np.array([0.5, 0.2]); L = np.array([[0.5, 0.5]]); Sg = 1e-2 * np.eye(1)
+    # (the script's own Σ = 1e-4, ϵ = 1e-3 make the backward recursion ill-conditioned in rounding: tables computed with and
+    #  without fused multiply-adds agree to 4e-4 only; Σ = 1e-2, ϵ = 0.1 agree to 1e-8, which is what a frozen fixture needs)
+    EPSB = 0.1
+    chains = [3, 250]
+    th = np.array([BOLUS_PAR + [0.0, 0.0], [BOLUS_PAR[0], 7.1, BOLUS_PAR[2], BOLUS_PAR[3], 0.62, 0.2, 0.0, 0.0]])
+    out = dict(grids=np.stack(grids), x0=x0, L=L, Sigma=Sg, eps=EPSB, obs_v=np.array(obs_v), chains=np.array(chains),
+               theta=th, rw=np.array(BOLUS_RW), seed=seed, it=it)
+    W = []; thp = []; left_c = []; left_o = []; Xo = []; llo = []; llc = []; logu = []
+    for k, c in enumerate(chains):
+        Wk = np.stack([orc.wiener_sample(grids[s], 2, seed, 0xFFFFFFF0, c * S + s) for s in range(S)])
+        gc, lc = O.theta_backward(orc, O.BOLUS, th[k, :6], grids, x0, L, Sg, EPSB, obs_v, O.AUX_BOLUS, BOLUS_PRIORS)
+        _, ll0, _ = O.theta_forward(orc, O.BOLUS, 2, th[k, :6], gc, x0, Wk)
+        tp = O.theta_propose(orc, th[k], BOLUS_RW, seed, it, c)
+        go, lo = O.theta_backward(orc, O.BOLUS, tp[:6], grids, x0, L, Sg, EPSB, obs_v, O.AUX_BOLUS, BOLUS_PRIORS)
+        X1, ll1, _ = O.theta_forward(orc, O.BOLUS, 2, tp[:6], go, x0, Wk)
+        W.append(Wk); thp.append(tp); Xo.append(X1); llo.append(ll1); llc.append(ll0)
+        left_c.append([lc["lpn"], lc["trsum"], lc["lpri"]]); left_o.append([lo["lpn"], lo["trsum"], lo["lpri"]])
+        logu.append(orc.logu_q(seed, it, c, O.Q_THETA_LOGU))
+    out.update(W=np.stack(W), theta_prop=np.stack(thp), Xo=np.stack(Xo), llo=np.array(llo), llc=np.array(llc),
+               left_c=np.array(left_c), left_o=np.array(left_o), logu=np.array(logu))
+    np.savez(os.path.join(OUT, "oracle_bolus_theta_step.npz"), **out)
+    # ---- landmarks: PartialBridgeνH tables at d = 16, two guided paths with log-likelihood, one pCN proposal
+    N = 33
+    tt = warped(0.0, 1.0, N)
+    Lm = np.zeros((8, 16))
+    for i in range(4):
+        for c2 in range(2):
+            Lm[2 * i + c2, 4 * i + c2] = 1.0
+    a, sig, lam = LM_PAR
+    Bt = np.zeros((16, 16))
+    for i in range(4):
+        for j in range(4):
+            dq = LM_QT[i] - LM_QT[j]
+            kk = np.exp(-np.dot(dq, dq) / (2 * a)) / (2 * np.pi * a)
+            for c2 in range(2):
+                Bt[4 * i + c2, 4 * j + 2 + c2] += 0.5 * kk
+                Bt[4 * i + 2 + c2, 4 * j + 2 + c2] += -0.5 * lam * kk
+    at = np.zeros((16, 16))
+    for k in (2, 3, 6, 7, 10, 11, 14, 15):
+        at[k, k] = sig * sig
+    nu, Hp, C0 = orc.update_nuHC(Lm, 1e-4 * np.eye(8), LM_QT.ravel(), 1e-3)
+    nus, Hs, _, _, Cc = orc.backward_nuH(O.ODE_R3, tt, O.const_aux(Bt, np.zeros(16), at), nu, Hp, C0)
+    om = O.make_model(O.LANDMARKS, 16, 8, LM_PAR)
+    og = O.GuideHolder(O.GUIDE_NUH, tt, Hs, nus, Bt=Bt, betat=np.zeros(16))
+    chains = [0, 41]
+    Wl = np.stack([orc.wiener_sample(tt, 8, 9, 0xFFFFFFF0, c) for c in chains])
+    Xl = []; lll = []; Wo = []; Xo = []; llo = []; lu = []
+    for k, c in enumerate(chains):
+        X, _ = orc.guided_euler(om, og, LM_X0, Wl[k])
+        Xl.append(X); lll.append(orc.llikelihood(om, og, X))
+        l1, u1, W1, X1, _ = orc.pcn_propose(om, [og], LM_X0, Wl[k][None], 0.9, 9, 2, c)
+        Wo.append(W1[0]); Xo.append(X1[0]); llo.append(l1); lu.append(u1)
+    np.savez(os.path.join(OUT, "oracle_landmarks_bridge.npz"), tt=tt, par=np.array(LM_PAR), qT=LM_QT, x0=LM_X0, L=Lm,
+             Bt=Bt, at=at, nu=nus, H=Hs, C=Cc, chains=np.array(chains), W=Wl, X=np.stack(Xl), ll=np.array(lll),
+             Wo=np.stack(Wo), Xo=np.stack(Xo), llo=np.array(llo), logu=np.array(lu), rho=0.9, seed=9, it=2)
 
 
 if __name__ == "__main__":

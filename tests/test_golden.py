@@ -91,3 +91,83 @@ def test_gpu_reproduces_golden():
     ens.set_start([2.0, 1.0]); ens.upload(B.W, h["W"][None, None]); ens.guided_euler_ll_(Pi, [Gi])
     assert xt(ens.download(B.X)[0, 0], h["X"]) and lt(ens.ll[0], float(h["ll"]))
     ens.close()
+
+
+BOLUS_PRIORS = {1: ("gamma", 1.0, 100.0), 4: ("gamma", 1.0, 100.0)}
+
+
+def test_oracle_reproduces_theta_and_landmarks_golden(oracle_ref):
+    f = load("oracle_bolus_theta_step.npz")
+    grids = list(f["grids"]); S = len(grids)
+    for k, c in enumerate(f["chains"]):
+        c = int(c)
+        for s in range(S):
+            assert np.array_equal(oracle_ref.wiener_sample(grids[s], 2, int(f["seed"]), 0xFFFFFFF0, c * S + s), f["W"][k, s])
+        tp = O.theta_propose(oracle_ref, f["theta"][k], f["rw"], int(f["seed"]), int(f["it"]), c)
+        assert np.array_equal(tp, f["theta_prop"][k])
+        go, lo = O.theta_backward(oracle_ref, O.BOLUS, tp[:6], grids, f["x0"], f["L"], f["Sigma"], float(f["eps"]),
+                                  list(f["obs_v"]), O.AUX_BOLUS, BOLUS_PRIORS)
+        X, ll, _ = O.theta_forward(oracle_ref, O.BOLUS, 2, tp[:6], go, f["x0"], f["W"][k])
+        assert np.array_equal(X, f["Xo"][k]) and ll == f["llo"][k]
+        assert [lo["lpn"], lo["trsum"], lo["lpri"]] == list(f["left_o"][k])
+        assert oracle_ref.logu_q(int(f["seed"]), int(f["it"]), c, O.Q_THETA_LOGU) == f["logu"][k]
+    g = load("oracle_landmarks_bridge.npz")
+    om = O.make_model(O.LANDMARKS, 16, 8, g["par"])
+    nu, Hp, C0 = oracle_ref.update_nuHC(g["L"], 1e-4 * np.eye(8), g["qT"].ravel(), 1e-3)
+    nus, Hs, _, _, Cc = oracle_ref.backward_nuH(O.ODE_R3, g["tt"], O.const_aux(g["Bt"], np.zeros(16), g["at"]), nu, Hp, C0)
+    assert np.array_equal(nus, g["nu"]) and np.array_equal(Hs, g["H"]) and Cc == float(g["C"])
+    og = O.GuideHolder(O.GUIDE_NUH, g["tt"], g["H"], g["nu"], Bt=g["Bt"], betat=np.zeros(16))
+    for k, c in enumerate(g["chains"]):
+        X, _ = oracle_ref.guided_euler(om, og, g["x0"], g["W"][k])
+        assert np.array_equal(X, g["X"][k]) and oracle_ref.llikelihood(om, og, X) == g["ll"][k]
+        llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(om, [og], g["x0"], g["W"][k][None], float(g["rho"]), int(g["seed"]),
+                                                    int(g["it"]), int(c))
+        assert np.array_equal(Wo[0], g["Wo"][k]) and np.array_equal(Xo[0], g["Xo"][k]) and llo == g["llo"][k]
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_theta_and_landmarks_golden():
+    """The fixtures are in REFERENCE arithmetic (no fma, libm exp).  The bolus fixture uses Σ = 1e-2, ϵ = 0.1, for which
+    the backward recursion is well conditioned (tables with and without fma agree to 1e-8; with the script's Σ = 1e-4,
+    ϵ = 1e-3 only to 4e-4), and the device builds its own tables: paths to 1e-6, ll to 1e-5.  The landmarks run uses the
+    fixture's tables and is compared to the parity tolerance."""
+    import bridge_jl_b200 as B
+    K = B.api.K
+    f = load("oracle_bolus_theta_step.npz")
+    grids = list(f["grids"]); S, n = len(grids), len(grids[0])
+    Pm = B.BolusDiffusion(*f["theta"][0, :6])
+    for k, c in enumerate(f["chains"]):
+        ens = B.PathEnsemble(1, S, n, 2, 2, chain_offset=int(c))
+        for s in range(S):
+            ens.set_grid(s, grids[s])
+        ens.set_start(f["x0"])
+        ens.theta_attach_(Pm, f["L"], f["Sigma"], float(f["eps"]), f["obs_v"], aux_kind=K.AUX_BOLUS, priors=BOLUS_PRIORS)
+        ens.set_theta(f["theta"][k][None])
+        ens.sample_(int(f["seed"]), 0xFFFFFFF0)
+        assert np.max(np.abs(ens.download(B.W)[0] - f["W"][k])) <= 1e-10 * (1 + np.max(np.abs(f["W"][k])))
+        ens.theta_guided_euler_ll_()
+        assert abs(ens.ll[0] - f["llc"][k]) <= 1e-5 * abs(f["llc"][k]) + 1e-6, (ens.ll[0], f["llc"][k])
+        ens.theta_param_step_(f["rw"], int(f["seed"]), int(f["it"]))
+        assert np.array_equal(ens.theta(B.PROP)[0], f["theta_prop"][k]) and ens.logu[0] == f["logu"][k]
+        Xo = ens.download(B.X, which=B.PROP)[0]
+        assert np.max(np.abs(Xo - f["Xo"][k])) <= 1e-6 * (1 + np.max(np.abs(f["Xo"][k])))
+        assert abs(ens.ll_prop[0] - f["llo"][k]) <= 1e-5 * abs(f["llo"][k]) + 1e-6
+        left = ens.theta_left(B.PROP)[0]
+        assert np.allclose(left[7:10], f["left_o"][k], rtol=1e-5, atol=1e-9)  # logpdfnormal amplifies the table rounding
+        ens.close()
+    g = load("oracle_landmarks_bridge.npz")
+    Pl = B.Landmarks(*g["par"])
+    Gl = B.GuideTables(K.GUIDE_NUH, g["tt"], Pl, g["H"], g["nu"], g["Bt"], np.zeros(16))
+    N = len(g["tt"])
+    for k, c in enumerate(g["chains"]):
+        ens = B.PathEnsemble(1, 1, N, 16, 8, chain_offset=int(c))
+        ens.set_grid(0, g["tt"]); ens.set_start(g["x0"]); ens.sample_(int(g["seed"]), 0xFFFFFFF0)
+        ens.guided_euler_ll_(Pl, [Gl])
+        X = ens.download(B.X)[0, 0]
+        assert np.max(np.abs(X - g["X"][k])) <= 1e-9 * (1 + np.max(np.abs(g["X"][k])))
+        assert abs(ens.ll[0] - g["ll"][k]) <= 1e-6 * abs(g["ll"][k]) + 1e-9
+        ens.pcn_step_(Pl, [Gl], float(g["rho"]), int(g["seed"]), int(g["it"]))
+        assert np.max(np.abs(ens.download(B.W, which=B.PROP)[0, 0] - g["Wo"][k])) <= 1e-10 * (1 + np.max(np.abs(g["Wo"][k])))
+        assert np.max(np.abs(ens.download(B.X, which=B.PROP)[0, 0] - g["Xo"][k])) <= 1e-9 * (1 + np.max(np.abs(g["Xo"][k])))
+        assert abs(ens.ll_prop[0] - g["llo"][k]) <= 1e-6 * abs(g["llo"][k]) + 1e-9 and ens.logu[0] == g["logu"][k]
+        ens.close()
