@@ -225,6 +225,22 @@ __device__ __forceinline__ void bb_st2(double* p, double a, double b) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+/* one row of a 16-column mat-vec from shared memory with 128-bit loads (the row is 16-byte aligned); the summation
+ * order is bb_matvec's */
+__device__ __forceinline__ double bb_rowdot16(const double* row, const double* x) {
+  const double2* r2 = reinterpret_cast<const double2*>(row);
+  double2 v = r2[0];
+  double s = v.x * x[0];
+  s = fma(v.y, x[1], s);
+#pragma unroll
+  for (int l = 1; l < 8; l++) {
+    v = r2[l];
+    s = fma(v.x, x[2 * l], s);
+    s = fma(v.y, x[2 * l + 1], s);
+  }
+  return s;
+}
+
 template <int GK, int RNG>
 __global__ void __launch_bounds__(BB_W4_THREADS) bb_wide4_kernel(const __grid_constant__ bb_chain_args a) {
   using M = MLandmarks;
@@ -377,15 +393,18 @@ __global__ void __launch_bounds__(BB_W4_THREADS) bb_wide4_kernel(const __grid_co
             /* r rows 4g .. 4g+3 of H (nu - x);  b~ rows of B~ x + beta~;  <b - b~, r> through the four lanes in order */
             double e[D], rg[4];
 #pragma unroll
-            for (int k = 0; k < D; k++) e[k] = R[OFF_C + k] - y[k];
+            for (int k = 0; k < D; k += 2) {
+              const double2 nu2 = *reinterpret_cast<const double2*>(R + OFF_C + k);
+              e[k] = nu2.x - y[k];
+              e[k + 1] = nu2.y - y[k + 1];
+            }
 #pragma unroll
-            for (int k = 0; k < 4; k++) bb_matvec<1, D>(R + OFF_A2 + (4 * g + k) * D + 2 * g, e, rg + k);
+            for (int k = 0; k < 4; k++) rg[k] = bb_rowdot16(R + OFF_A2 + (4 * g + k) * D + 2 * g, e);
             if (j <= a.jll) {
               double ee[4];
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                double bt;
-                bb_matvec<1, D>(sc_s + (4 * g + k) * D + 2 * g, y, &bt);
+                const double bt = bb_rowdot16(sc_s + (4 * g + k) * D + 2 * g, y);
                 ee[k] = bg[k] - (bt + sc_s[D * D + 8 + 4 * g + k]);
               }
               double sdot = 0.0;
