@@ -317,6 +317,9 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
   constexpr bool XBUF = (D == 2);
   constexpr int XWIN = 16 / D; /* steps per 128-byte window */
   double* xbuf = reinterpret_cast<double*>(th_smem) + (size_t)threadIdx.x * 16;
+  /* W° rows are completed in shared memory only for scalar noise: with d' = 2 the 64 KB they need would leave room
+   * for ONE CTA per SM (8 warps); their pieces are stored directly instead and two CTAs fit */
+  constexpr bool WBUF = PCN && (DP == 1);
   double* wrow = reinterpret_cast<double*>(th_smem) + (size_t)BB_THREADS * 16 + (size_t)threadIdx.x * (BB_TC * DP);
 
   double y[D], wprev[DP], w2[DP];
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
    * back, so no warp waits on a global load and no register is tied up.  (Register double-buffering + L2 prefetch
    * left the kernel latency bound: long-scoreboard stalls of 11 warps per issue, 18 % of the lines fetched twice.) */
   double* tring = reinterpret_cast<double*>(th_smem) + (size_t)BB_THREADS * 16 +
-                  (PCN ? (size_t)BB_THREADS * (BB_TC * DP) : 0) + threadIdx.x;
+                  (WBUF ? (size_t)BB_THREADS * (BB_TC * DP) : 0) + threadIdx.x;
 #if !BB_TPAIR
   const double* Tp = a.T + pc;
 #endif
@@ -435,7 +438,8 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
                   if (jj != 0) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);
                   wq[i] = fma(a.rho2, w2[kk], a.rho * wq[i]);
                 }
-                bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+                if constexpr (WBUF) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+                else if (act) bb_st4(ww + 4 * q, wq[0], wq[1], wq[2], wq[3]);
               }
             }
             wj[k] = wq[mm & 3];
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
           }
         }
       }
-      if constexpr (PCN) {
+      if constexpr (WBUF) {
         if (act) { /* the chain's row of W° is complete: write its 128 d' bytes back to back */
 #pragma unroll
           for (int q = 0; q < NPIECE; q++) {
@@ -694,7 +698,7 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
                                                                : lookup_forward<MBolus>(t->spec.aux_kind, pcn));
   if (!fn) return BB_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((e->P + BB_THREADS - 1) / BB_THREADS);
-  const size_t smem = (size_t)BB_THREADS * 128 + (pcn ? (size_t)BB_THREADS * BB_TC * e->dp * 8 : 0) +
+  const size_t smem = (size_t)BB_THREADS * 128 + ((pcn && e->dp == 1) ? (size_t)BB_THREADS * BB_TC * e->dp * 8 : 0) +
                       (size_t)BB_TDEPTH * t->K * BB_THREADS * 8;
   BB_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fn<<<grid, BB_THREADS, smem, c->stream>>>(a);

@@ -8,12 +8,13 @@ import bridge_jl_b200 as B
 import bridge_jl_b200.configs as cfg
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 250000
+DIAG = len(sys.argv) > 2 and sys.argv[2] == "diag"  # the d' = 2 model (src/Models.jl:18-19) instead of the hypoelliptic one
 ctx = B.default_context()
 ctx.set_timing(True)
 n, S = 1001, 4
 grids = cfg.fhn_segment_grids(n)
-Pm = B.FitzhughDiffusion(*cfg.FHN_PAR)
-ens = B.PathEnsemble(P, S, n, 2, 1)
+Pm = B.FitzHughNagumo(*cfg.FHN_PAR[:4], 0.3, 0.3) if DIAG else B.FitzhughDiffusion(*cfg.FHN_PAR)
+ens = B.PathEnsemble(P, S, n, 2, 2 if DIAG else 1)
 for s, g in enumerate(grids):
     ens.set_grid(s, g)
 ens.set_start(cfg.FHN_X0)
@@ -28,12 +29,13 @@ ens.theta_guided_euler_ll_()
 print("device bytes: %.1f GB" % (ens.nbytes / 1e9), flush=True)
 steps = P * S * (n - 1)
 RW = [0, 0, 0.01, 0.01, 0.005]
-# algorithmic bytes per path-step: tables 48 (d + d*d doubles), W 8, X 16
+# algorithmic bytes per path-step: tables 48 (d + d*d doubles), W 8 d', X 16
+w = 16 if DIAG else 8
 calls = {
     "backward (tables of θ)": (lambda it: ens.theta_guides_(), 48),
-    "forward guided Euler+ll": (lambda it: (ens.set_theta(th[:1]), ens.theta_guides_(), ens.theta_guided_euler_ll_())[-1], 72),
-    "pCN, own tables": (lambda it: ens.theta_pcn_step_(cfg.FHN_RHO, 4, it), 80),
-    "parameter step (backward + forward)": (lambda it: ens.theta_param_step_(RW, 4, 1000 + it), 120),
+    "forward guided Euler+ll": (lambda it: (ens.set_theta(th[:1]), ens.theta_guides_(), ens.theta_guided_euler_ll_())[-1], 64 + w),
+    "pCN, own tables": (lambda it: ens.theta_pcn_step_(cfg.FHN_RHO, 4, it), 64 + 2 * w),
+    "parameter step (backward + forward)": (lambda it: ens.theta_param_step_(RW, 4, 1000 + it), 112 + w),
 }
 for name, (fn, nbytes) in calls.items():
     ts = []
