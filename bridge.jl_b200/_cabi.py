@@ -55,7 +55,8 @@ class ThetaSpec(C.Structure):  # bb_theta_spec
     _fields_ = [("m", C.c_int32), ("aux_kind", C.c_int32), ("L", C.c_double * (BB_MAXD * BB_MAXD)),
                 ("Sigma", C.c_double * (BB_MAXD * BB_MAXD)), ("eps", C.c_double),
                 ("v", (C.c_double * BB_MAXD) * BB_MAXSEG), ("prior_kind", C.c_int32 * BB_NTHETA),
-                ("prior_a", C.c_double * BB_NTHETA), ("prior_b", C.c_double * BB_NTHETA)]
+                ("prior_a", C.c_double * BB_NTHETA), ("prior_b", C.c_double * BB_NTHETA),
+                ("start_sd", C.c_double), ("start_dir", C.c_double * BB_MAXD)]
 
 
 class Aux(C.Structure):
@@ -125,6 +126,7 @@ def _load():
         "bb_theta_attach": (C.c_int, [vp, C.POINTER(Model), C.POINTER(ThetaSpec)]),
         "bb_theta_set": (C.c_int, [vp, i64, i64, vp]),
         "bb_theta_get": (C.c_int, [vp, C.c_int, i64, i64, vp]),
+        "bb_theta_get_start": (C.c_int, [vp, C.c_int, i64, i64, vp]),
         "bb_theta_guides": (C.c_int, [vp]),
         "bb_theta_get_left": (C.c_int, [vp, C.c_int, i64, i64, vp]),
         "bb_theta_get_tables": (C.c_int, [vp, i64, vp, vp]),

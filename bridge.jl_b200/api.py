@@ -674,7 +674,7 @@ class PathEnsemble:
 
     # ---- per-chain parameters: the `updateparams` branch of partialbridge_bolus3.jl:248-365 for P chains
     def theta_attach_(self, P: ContinuousTimeProcess, L, Σ, ϵ: float, obs_v, aux_kind: int = K.AUX_FHN_MATCHING,
-                      priors=None):
+                      priors=None, start_sd: float = 0.0, start_dir=None):
         """Give every chain its own copy θ_p of P's parameters (all chains start at P's) and its own guiding tables.
         L (m x d), Σ (m x m), ϵ: observation scheme and H⁺ = I/ϵ right of the last observation (bolus3.jl:162-165);
         obs_v[s]: observation at the right end of segment s; priors: {index: ("gamma", shape, scale)} (logπ, :237)."""
@@ -695,9 +695,18 @@ class PathEnsemble:
             if pr[0] != "gamma":
                 raise ValueError("priors: ('gamma', shape, scale)")
             sp.prior_kind[k], sp.prior_a[k], sp.prior_b[k] = K.PRIOR_GAMMA, float(pr[1]), float(pr[2])
+        if start_sd:  # joint random walk on the starting point in parameter steps (bolus3.jl:311-318)
+            sp.start_sd = float(start_sd)
+            for k, v in enumerate(f64(start_dir).ravel()):
+                sp.start_dir[k] = float(v)
         mdl = P.cmodel()
         check(lib.bb_theta_attach(self.h, C.byref(mdl), C.byref(sp)))
         self._theta = True
+
+    def theta_start(self, which=K.CUR):
+        out = np.empty((self.P, self.d))
+        check(lib.bb_theta_get_start(self.h, which, 0, self.P, ptr(out)))
+        return out
 
     def set_theta(self, θ, p0: int = 0):
         θ = f64(θ).reshape(-1, K.BB_NTHETA)

@@ -49,6 +49,7 @@ struct bb_theta {
   double* T = nullptr;                   /* [S][N][K][P] */
   double* left[2] = {nullptr, nullptr};  /* [NL][P]: ν(0), H⁺(0), C, logpdfnormal, trace term, log prior */
   double* tt = nullptr;                  /* [S][N] */
+  double* startprop = nullptr;           /* [d][P]: x0° of the last parameter proposal (start moves only) */
   unsigned long long* acc = nullptr;
   int tstate = 0; /* 0: T invalid; 1: T belongs to the current θ; 2: T belongs to the last proposal */
 };
@@ -57,7 +58,8 @@ struct bb_theta_args {
   double* W[2];
   double* X;
   uint8_t* par;
-  const double* start;
+  double* start;
+  double* startprop; /* x0° (start moves) */
   double *ll, *llprop, *logu, *xend, *xendprop;
   uint8_t *accepted, *xstale;
   unsigned long long *acc, *acc_theta;
@@ -195,6 +197,25 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
       a.theta[1][(long long)k * P + p] = th[k];
     }
   }
+  /* starting point this pass refers to: x0, or the proposal x0° (bolus3.jl:311-318) */
+  double xs[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) xs[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + p];
+  if (a.propose && a.spec.start_sd != 0.0) {
+    float z[4];
+    bb_normal_quad(a.keys, a.stream, (uint32_t)chain, (uint32_t)(chain >> 32), 0xFFFFFFFEu, z);
+    uint32_t o[4];
+    bb_philox4x32_10(0xFFFFFFFCu, a.stream, (uint32_t)chain, (uint32_t)(chain >> 32), a.keys, o);
+    if (o[0] & 1u) {
+#pragma unroll
+      for (int k = 0; k < D; k++) xs[k] = xs[k] + (a.spec.start_sd * (double)z[3]) * a.spec.start_dir[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) a.startprop[(long long)k * P + p] = xs[k];
+  } else if (a.which == 1 && a.spec.start_sd != 0.0) {
+#pragma unroll
+    for (int k = 0; k < D; k++) xs[k] = a.startprop[(long long)k * P + p];
+  }
   bb_model_dev m;
   theta_model<M>(th, m);
   constexpr bool TDEP = (AUXK == BB_AUX_BOLUS); /* beta~ depends on t */
@@ -257,7 +278,7 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
   /* left end: ν(0), H⁺(0), C, logpdfnormal(x0 - ν(0), symmetrize(H⁺(0)))  (bolus3.jl:319), trace term, logπ(θ) */
   double x[D];
 #pragma unroll
-  for (int k = 0; k < D; k++) x[k] = (a.start_bcast ? a.start[k] : a.start[(long long)k * P + p]) - nu[k];
+  for (int k = 0; k < D; k++) x[k] = xs[k] - nu[k];
   double lpn = logpdfnormal_dev<D>(x, Hp, a.log2pi);
   if (bad) lpn = nan("");
   double lpri = 0.0;
@@ -324,7 +345,10 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
 
   double y[D], wprev[DP], w2[DP];
 #pragma unroll
-  for (int k = 0; k < D; k++) y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
+  for (int k = 0; k < D; k++)
+    y[k] = (!PCN && a.mode == 2 && a.spec.start_sd != 0.0)
+               ? a.startprop[(long long)k * P + pc]
+               : (a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc]);
   double lltot = 0.0;
 
   /* The chain's table rows in the order they are used (g = s N + i, i = 0 .. N-2; row N-1 of a segment drives no
@@ -556,6 +580,10 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
         for (int k = 0; k < NTH; k++) a.theta[0][(long long)k * P + p] = th[k];
 #pragma unroll
         for (int k = 0; k < K + 4; k++) a.left[0][(long long)k * P + p] = Lo[(long long)k * P];
+        if (a.spec.start_sd != 0.0) {
+#pragma unroll
+          for (int k = 0; k < D; k++) a.start[(long long)k * P + p] = a.startprop[(long long)k * P + p];
+        }
       }
     }
     const unsigned mk = __ballot_sync(0xFFFFFFFFu, ok);
@@ -611,7 +639,7 @@ static int fill_args(bb_ens* e, bb_theta_args& a) {
   bb_theta* t = e->th;
   memset(&a, 0, sizeof(a));
   a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X = e->X;
-  a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast;
+  a.par = e->par; a.start = e->start; a.start_bcast = e->start_bcast; a.startprop = t->startprop;
   a.ll = e->ll; a.llprop = e->llprop; a.logu = e->logu; a.xend = e->xend; a.xendprop = e->xendprop;
   a.accepted = e->accepted; a.xstale = e->xstale; a.acc = e->acc; a.acc_theta = t->acc;
   a.P = e->P; a.PT = t->PT; a.chain_offset = e->chain_offset; a.S = e->S; a.N = e->N; a.NC = e->NC; a.nbuf = e->nbuf;
@@ -718,7 +746,7 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
 void bb_theta_free(bb_ens* e) {
   bb_theta* t = e->th;
   if (!t) return;
-  void* ptrs[] = {t->theta[0], t->theta[1], t->T, t->left[0], t->left[1], t->tt, t->acc};
+  void* ptrs[] = {t->theta[0], t->theta[1], t->T, t->left[0], t->left[1], t->tt, t->acc, t->startprop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;
@@ -744,6 +772,7 @@ extern "C" int bb_theta_attach(bb_ens* e, const bb_model* model, const bb_theta_
   if (model->id == BB_MODEL_BOLUS ? spec->aux_kind != BB_AUX_BOLUS
                                   : (spec->aux_kind != BB_AUX_FHN_MATCHING && spec->aux_kind != BB_AUX_FHN_LINEARISED_END))
     return BB_ERR_UNSUPPORTED;
+  if (!(spec->start_sd >= 0.0)) return BB_ERR_ARG;
   for (int k = 0; k < BB_NTHETA; k++) {
     if (spec->prior_kind[k] != BB_PRIOR_FLAT && spec->prior_kind[k] != BB_PRIOR_GAMMA) return BB_ERR_ARG;
     if (spec->prior_kind[k] == BB_PRIOR_GAMMA && !(spec->prior_a[k] > 0 && spec->prior_b[k] > 0)) return BB_ERR_ARG;
@@ -766,6 +795,7 @@ extern "C" int bb_theta_attach(bb_ens* e, const bb_model* model, const bb_theta_
   if (rc == BB_OK) rc = th_alloc(e, &t->left[1], (size_t)t->NL * P);
   if (rc == BB_OK) rc = th_alloc(e, &t->tt, (size_t)e->S * e->N);
   if (rc == BB_OK) rc = th_alloc(e, &t->acc, 1);
+  if (rc == BB_OK && spec->start_sd != 0.0) rc = th_alloc(e, &t->startprop, (size_t)d * P);
   if (rc != BB_OK) {
     bb_theta_free(e);
     return rc;
@@ -803,6 +833,30 @@ extern "C" int bb_theta_get(bb_ens* e, int which, int64_t p0, int64_t np, double
   BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
   for (int64_t p = 0; p < np; p++)
     for (int k = 0; k < BB_NTHETA; k++) theta[(size_t)p * BB_NTHETA + k] = h[(size_t)k * np + p];
+  return BB_OK;
+}
+
+extern "C" int bb_theta_get_start(bb_ens* e, int which, int64_t p0, int64_t np, double* x0) {
+  if (!e || !e->th || !x0 || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  if (which != BB_CUR && which != BB_PROP) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int d = e->d;
+  if (which == BB_CUR && e->start_bcast) {
+    std::vector<double> u(d);
+    BB_CUDA(cudaMemcpyAsync(u.data(), e->start, sizeof(double) * d, cudaMemcpyDeviceToHost, e->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    for (int64_t p = 0; p < np; p++) memcpy(x0 + (size_t)p * d, u.data(), sizeof(double) * d);
+    return BB_OK;
+  }
+  const double* src = which == BB_CUR ? e->start : e->th->startprop;
+  if (!src) return BB_ERR_ARG;
+  std::vector<double> h((size_t)np * d);
+  for (int k = 0; k < d; k++)
+    BB_CUDA(cudaMemcpyAsync(h.data() + (size_t)k * np, src + (size_t)k * e->P + p0, sizeof(double) * np,
+                            cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  for (int64_t p = 0; p < np; p++)
+    for (int k = 0; k < d; k++) x0[(size_t)p * d + k] = h[(size_t)k * np + p];
   return BB_OK;
 }
 
@@ -882,8 +936,9 @@ extern "C" int bb_theta_param_step(bb_ens* e, const double* rw_sd, uint64_t seed
     if (!(rw_sd[k] >= 0.0)) return BB_ERR_ARG;
     if (rw_sd[k] != 0.0) nz++;
   }
-  if (nz > 4) return BB_ERR_ARG;
+  if (nz > (e->th->spec.start_sd != 0.0 ? 3 : 4)) return BB_ERR_ARG; /* normal 3 of the quad drives the start move */
   BB_CUDA(cudaSetDevice(e->ctx->device));
+  if (e->th->spec.start_sd != 0.0 && e->start_bcast) return BB_ERR_STARTPOINT; /* per-chain starting points: bb_ens_set_start(..., broadcast = 0) */
   bb_time_begin(e->ctx);
   int rc = BB_OK;
   /* the left-end values of the current θ (logpdfnormal, trace term, prior) enter the accept test */

@@ -363,8 +363,9 @@ int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
  * The guiding tables of ALL chains are built on the device (one thread per chain) into a table array
  * T [S][N][d+d*d][P] (ν[i], H[i] per grid point, chain-minor: warp accesses are contiguous), so that no
  * θ-proposal round-trips to the host.  The auxiliary process follows from (θ, v_s) by a closed registry
- * (bb_aux_kind), for the same reason the target models do.  The starting point is not updated (the script's
- * random-walk on x0 is specific to its L = [.5 .5]).
+ * (bb_aux_kind), for the same reason the target models do.  The script's joint random walk on the starting point
+ * (:311-318) is available through start_sd / start_dir of bb_theta_spec; its blocked segment updates (klow..kup) are not:
+ * all segments are updated together.
  */
 #define BB_NTHETA 8
 typedef enum {
@@ -383,6 +384,12 @@ typedef struct {
   double v[16][BB_MAXD];             /* v[s][0..m-1]: observation at the right end of segment s */
   int32_t prior_kind[BB_NTHETA];
   double prior_a[BB_NTHETA], prior_b[BB_NTHETA];
+  /* joint update of the starting point in a parameter step (bolus3.jl:311-318): with probability 1/2
+   * x0° = x0 + start_sd * u * start_dir, u ~ N(0,1) (the script: 0.1 * (u, -u)); start_sd = 0 switches it off.
+   * Random numbers: u is normal 3 of the proposal quad (so at most 3 parameters are updated), the coin is bit 0 of
+   * word 0 of Philox counter (0xFFFFFFFC, iter, chain). */
+  double start_sd;
+  double start_dir[BB_MAXD];
 } bb_theta_spec;
 
 /* allocate θ (all chains start at model->par), the table array T and the per-chain left-end values */
@@ -390,6 +397,8 @@ int bb_theta_attach(bb_ens* ens, const bb_model* model, const bb_theta_spec* spe
 /* theta: [np][BB_NTHETA] */
 int bb_theta_set(bb_ens* ens, int64_t p0, int64_t np, const double* theta);
 int bb_theta_get(bb_ens* ens, int which /* BB_CUR | BB_PROP */, int64_t p0, int64_t np, double* theta);
+/* starting points of the chains (current) or of the last parameter proposal: x0 [np][d] */
+int bb_theta_get_start(bb_ens* ens, int which, int64_t p0, int64_t np, double* x0);
 /* backward pass for the CURRENT θ of every chain -> T, left-end values */
 int bb_theta_guides(bb_ens* ens);
 /* left-end values of the last backward pass: out [np][d + d*d + 4] = ν(0), H⁺(0), C,

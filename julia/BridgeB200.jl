@@ -148,16 +148,18 @@ struct BBThetaSpec   # == bb_theta_spec
     L::NTuple{16,Float64}; Sigma::NTuple{16,Float64}; eps::Float64
     v::NTuple{64,Float64}                      # v[s][0..3], row per segment
     prior_kind::NTuple{8,Int32}; prior_a::NTuple{8,Float64}; prior_b::NTuple{8,Float64}
+    start_sd::Float64; start_dir::NTuple{4,Float64}   # joint start-point random walk, bolus3.jl:311-318 (0 = off)
 end
 const AUXKIND = Dict(:fhn_matching => Int32(1), :fhn_linearised_end => Int32(2), :bolus => Int32(3))
-function theta_attach!(E::PathEnsemble, P::ContinuousTimeProcess, L, Σ, ϵ, obs; aux = :fhn_matching, priors = Dict())
+function theta_attach!(E::PathEnsemble, P::ContinuousTimeProcess, L, Σ, ϵ, obs; aux = :fhn_matching, priors = Dict(),
+                       start_sd = 0.0, start_dir = (0.0, 0.0, 0.0, 0.0))
     m, d = size(L)
     Lr = zeros(16); Sr = zeros(16); vr = zeros(64); pk = zeros(Int32, 8); pa = zeros(8); pb = zeros(8)
     for i in 1:m, j in 1:d; Lr[(i-1)*d + j] = L[i, j]; end        # row-major in the ABI
     for i in 1:m, j in 1:m; Sr[(i-1)*m + j] = Σ[i, j]; end
     for (s, v) in enumerate(obs), i in 1:m; vr[(s-1)*4 + i] = v[i]; end
     for (k, (kind, a, b)) in priors; pk[k+1] = 1; pa[k+1] = a; pb[k+1] = b; end   # k: 0-based parameter index
-    spec = Ref(BBThetaSpec(m, AUXKIND[aux], Tuple(Lr), Tuple(Sr), ϵ, Tuple(vr), Tuple(pk), Tuple(pa), Tuple(pb)))
+    spec = Ref(BBThetaSpec(m, AUXKIND[aux], Tuple(Lr), Tuple(Sr), ϵ, Tuple(vr), Tuple(pk), Tuple(pa), Tuple(pb), start_sd, Tuple(Float64.(start_dir))))
     mdl = Ref(bbmodel(P))
     check(ccall((:bb_theta_attach, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ref{BBThetaSpec}), E.h, mdl, spec)); E
 end

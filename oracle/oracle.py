@@ -418,6 +418,20 @@ def theta_propose(o: Oracle, par, rw_sd, seed, it, chain):
     return par
 
 
+Q_THETA_COIN = 0xFFFFFFFC
+
+
+def theta_propose_start(o: Oracle, x0, sd, direction, seed, it, chain):
+    """Joint start-point proposal of a parameter step (bolus3.jl:311-318): with probability 1/2 (bit 0 of word 0 of the
+    Philox counter (0xFFFFFFFC, it, chain)) x0° = x0 + (sd u) dir, u = normal 3 of the proposal quad."""
+    x0 = np.array(x0, dtype=np.float64)
+    coin = int(o.philox([Q_THETA_COIN, it, chain & 0xFFFFFFFF, chain >> 32], [seed & 0xFFFFFFFF, seed >> 32])[0]) & 1
+    if coin:
+        u = o.normal(seed, it, chain, 4 * Q_THETA_NORMALS + 3)
+        x0 = x0 + (sd * u) * np.asarray(direction, dtype=np.float64)
+    return x0
+
+
 def theta_diffll(left_c, left_o, ll_c, ll_o):
     """diffll of bolus3.jl:319,331-336 in the kernel's summation order."""
     diff = left_o["lpn"] - left_c["lpn"]

@@ -370,3 +370,64 @@ def test_theta_bolus_model_parameter_update_vs_oracle(B, oracle_fma, oracle_ref)
         ens.euler_(Pm)
     assert ei.value.status == -11
     ens.close()
+
+
+def test_theta_joint_start_point_update(B, oracle_fma):
+    """bolus3.jl:311-318: in a parameter step the starting point is proposed jointly with probability 1/2,
+    x0° = x0 + 0.1 (u, -u); logpdfnormal(x0° - ν°(0), H⁺°(0)) - logpdfnormal(x0 - ν(0), H⁺(0)) enters diffll (:319)."""
+    P, n, S, seed = 64, 41, 2, 31
+    obs_t = (0.8, 1.7); obs_v = (4.0, 9.0)
+    tcut = (0.0,) + obs_t
+    grids = []
+    for k in range(S):
+        s = np.linspace(0.0, tcut[k + 1] - tcut[k], n)
+        grids.append(tcut[k] + s * (2 - s / (tcut[k + 1] - tcut[k])))
+    rng = np.random.default_rng(4)
+    x0 = np.array([0.5, 0.2]) + 0.05 * rng.standard_normal((P, 2))
+    Pm = B.BolusDiffusion(*BOLUS_PAR)
+    ens = B.PathEnsemble(P, S, n, 2, 2, chain_offset=900)
+    for s_, g in enumerate(grids):
+        ens.set_grid(s_, g)
+    ens.set_start(x0)
+    ens.theta_attach_(Pm, BOLUS_L, 1e-2 * np.eye(1), 0.1, obs_v, aux_kind=O.AUX_BOLUS, priors=BOLUS_PRIORS,
+                      start_sd=0.1, start_dir=[1.0, -1.0])
+    ens.sample_(seed, 0xFFFFFFF0)
+    ens.theta_guided_euler_ll_()
+    Wc = ens.download(B.W)
+    moved = 0
+    for it in range(2):
+        thc = ens.theta(); llc = ens.ll; leftc = ens.theta_left(B.CUR); x0c = ens.theta_start(B.CUR)
+        ens.theta_param_step_(BOLUS_RW, seed, 70 + it)
+        tho = ens.theta(B.PROP); lefto = ens.theta_left(B.PROP); x0o = ens.theta_start(B.PROP)
+        llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted.astype(bool)
+        diff = (lefto[:, 7] - leftc[:, 7]) + (llp - llc)
+        diff = diff + (((lefto[:, 8] - leftc[:, 8]) + lefto[:, 9]) - leftc[:, 9])
+        assert np.array_equal(flags, logu <= diff)
+        assert np.array_equal(ens.theta_start(B.CUR), np.where(flags[:, None], x0o, x0c))
+        Xp = ens.download(B.X, which=B.PROP)
+        assert np.array_equal(Xp[:, 0, 0], x0o)  # the proposal path starts at x0°
+        for p in (0, 13, 63):
+            xs = O.theta_propose_start(oracle_fma, x0c[p], 0.1, [1.0, -1.0], seed, 70 + it, 900 + p)
+            assert np.array_equal(x0o[p], xs)
+            tp = O.theta_propose(oracle_fma, thc[p], BOLUS_RW, seed, 70 + it, 900 + p)
+            g, lo = O.theta_backward(oracle_fma, O.BOLUS, tp[:6], grids, xs, BOLUS_L, 1e-2 * np.eye(1), 0.1, obs_v,
+                                     O.AUX_BOLUS, BOLUS_PRIORS)
+            Xo, llo, _ = O.theta_forward(oracle_fma, O.BOLUS, 2, tp[:6], g, xs, Wc[p])
+            assert np.array_equal(Xp[p], Xo) and llp[p] == llo
+            assert abs(lefto[p, 7] - lo["lpn"]) <= 1e-13 * abs(lo["lpn"])
+        moved += int(np.sum(np.any(x0o != x0c, axis=1)))
+    assert 0.25 * 2 * P < moved < 0.75 * 2 * P  # about half of the proposals move the starting point
+    # current paths start at the chains' current starting points
+    Xc = ens.download(B.X)
+    assert np.array_equal(Xc[:, 0, 0], ens.theta_start(B.CUR))
+    # a broadcast starting point cannot be moved per chain
+    e2 = B.PathEnsemble(4, S, n, 2, 2)
+    for s_, g in enumerate(grids):
+        e2.set_grid(s_, g)
+    e2.set_start([0.5, 0.2])
+    e2.theta_attach_(Pm, BOLUS_L, 1e-2 * np.eye(1), 0.1, obs_v, aux_kind=O.AUX_BOLUS, start_sd=0.1, start_dir=[1.0, -1.0])
+    e2.sample_(1, 0); e2.theta_guided_euler_ll_()
+    with pytest.raises(B.BridgeError) as ei:
+        e2.theta_param_step_(BOLUS_RW, 1, 0)
+    assert ei.value.status == -3
+    e2.close(); ens.close()
