@@ -1078,3 +1078,22 @@ def pcn_(ens: PathEnsemble, P, guides, ρ: float, iterations: int, seed: int, fi
         if callback is not None:
             callback(it, ens)
     return ens.acc
+
+
+def theta_mcmc_(ens: PathEnsemble, ρ: float, rw_sd, iterations: int, seed: int, first_iter: int = 0, skip: int = 0,
+                store_x: bool = True, param_prob: float = 0.5, callback: Optional[Callable] = None):
+    """The outer loop of project_partialbridge/partialbridge_bolus3.jl:248-365 for all chains of an ensemble with
+    per-chain parameters (theta_attach_): every iteration is, with probability `param_prob` (`updateparams = rand(Bool)`,
+    :259), a parameter update with the innovations held fixed, otherwise a pCN update of the paths (all segments together).
+    The coin is common to all chains (one launch per iteration) and comes from the host RNG seeded with `seed`; the two
+    step kinds use disjoint Philox counters, so `it` can be shared.  Returns (accepted pCN proposals, accepted parameter
+    proposals), summed over chains."""
+    rng = np.random.default_rng(seed)
+    for it in range(first_iter, first_iter + iterations):
+        if rng.random() < param_prob:
+            ens.theta_param_step_(rw_sd, seed, it, skip, store_x)
+        else:
+            ens.theta_pcn_step_(ρ, seed, it, skip, store_x)
+        if callback is not None:
+            callback(it, ens)
+    return ens.acc, ens.acc_theta

@@ -431,3 +431,37 @@ def test_theta_joint_start_point_update(B, oracle_fma):
         e2.theta_param_step_(BOLUS_RW, 1, 0)
     assert ei.value.status == -3
     e2.close(); ens.close()
+
+
+def test_theta_mcmc_loop_recovers_plausible_parameters(B):
+    """The outer loop of bolus3.jl:248-365 (parameter updates and pCN updates alternating at random) runs for many
+    chains at once; a statistical smoke check: chains move, both kinds of proposals are accepted at sane rates, the
+    log-likelihoods stay finite, θ stays in the support of its priors."""
+    P, n, S = 512, 41, 3
+    obs_t = (0.8, 1.7, 2.5); obs_v = (4.0, 9.0, 12.0)
+    tcut = (0.0,) + obs_t
+    grids = []
+    for k in range(S):
+        s = np.linspace(0.0, tcut[k + 1] - tcut[k], n)
+        grids.append(tcut[k] + s * (2 - s / (tcut[k + 1] - tcut[k])))
+    Pm = B.BolusDiffusion(*BOLUS_PAR)
+    ens = B.PathEnsemble(P, S, n, 2, 2)
+    for s_, g in enumerate(grids):
+        ens.set_grid(s_, g)
+    ens.set_start(np.tile([0.5, 0.2], (P, 1)))
+    ens.theta_attach_(Pm, BOLUS_L, 1e-2 * np.eye(1), 0.1, obs_v, aux_kind=O.AUX_BOLUS, priors=BOLUS_PRIORS,
+                      start_sd=0.1, start_dir=[1.0, -1.0])
+    ens.sample_(5, 0xFFFFFFF0)
+    ens.theta_guided_euler_ll_()
+    th0 = ens.theta()
+    seen = []
+    acc, acct = B.theta_mcmc_(ens, 0.7, BOLUS_RW, 40, 5, callback=lambda it, e: seen.append(it))
+    assert seen == list(range(40))
+    th = ens.theta()
+    assert np.all(np.isfinite(ens.ll)) and np.all(th[:, 1] > 0) and np.all(th[:, 4] > 0)
+    assert np.array_equal(th[:, [0, 2, 3, 5]], th0[:, [0, 2, 3, 5]])  # only β and σ1 are updated
+    assert np.std(th[:, 1]) > 0.01 and np.std(th[:, 4]) > 0.005       # chains have moved apart
+    assert 0 < acc and 0 < acct
+    X = ens.download(B.X)
+    assert np.all(np.isfinite(X))
+    ens.close()
