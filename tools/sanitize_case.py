@@ -54,3 +54,15 @@ el.set_grid(0, ttl); el.set_start(xl); el.sample_(1, 0); el.guided_euler_ll_(Pl,
 el.pcn_step_(Pl, [Pol], 0.9, 1, 0); el.pcn_step_(Pl, [Pol], 0.9, 1, 1, store_x=False)
 Xl = el.download(B.X)
 print("landmarks ok", el.acc, bool(np.all(np.isfinite(Xl))))
+# the bolus model of partialbridge_bolus3.jl on the per-chain path: time-dependent auxiliary drift, joint start-point move
+Pb = B.BolusDiffusion(70.0 / 0.6, 8.0, 1.25, 1.5, 0.5, 0.2)
+gb = [np.linspace(0.0, 0.8, 27), np.linspace(0.8, 1.7, 27)]
+eb = B.PathEnsemble(101, 2, 27, 2, 2)
+for s, g in enumerate(gb):
+    eb.set_grid(s, g)
+eb.set_start(np.tile([0.5, 0.2], (101, 1)))
+eb.theta_attach_(Pb, [[0.5, 0.5]], 1e-2 * np.eye(1), 0.1, (4.0, 9.0), aux_kind=3, priors={1: ("gamma", 1.0, 100.0)},
+                 start_sd=0.1, start_dir=[1.0, -1.0])
+eb.sample_(2, 0); eb.theta_guided_euler_ll_()
+B.theta_mcmc_(eb, 0.5, [0, 0.02, 0, 0, 0.02], 4, 3)
+print("bolus ok", eb.acc, eb.acc_theta, bool(np.all(np.isfinite(eb.download(B.X)))))
