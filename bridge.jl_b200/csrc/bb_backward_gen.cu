@@ -303,14 +303,9 @@ cudaError_t bb_gen_backward_nuH(cudaStream_t st, int method, int N, int d, const
                                 const double* beta, const double* a, const double* a_left, int is_const,
                                 const double* nu_end, const double* Hplus_end, double C0, double* nu, double* H,
                                 double* out_left, int* status) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_backward_nuH_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gshared));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_update_nuHC_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gshared));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  /* the attribute is per device; the working set (sizeof(gshared) ~ 21 KB) is below the default limit anyway */
+  cudaError_t e = cudaFuncSetAttribute(k_backward_nuH_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gshared));
+  if (e != cudaSuccess) return e;
   gaux A{B, beta, a, a_left, is_const};
   k_backward_nuH_gen<<<1, GT, sizeof(gshared), st>>>(method, N, d, tt, A, nu_end, Hplus_end, C0, nu, H, out_left, status);
   return cudaGetLastError();
