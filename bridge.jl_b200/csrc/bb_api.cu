@@ -72,6 +72,9 @@ extern "C" int bb_ctx_destroy(bb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->stage) cudaFree(c->stage);
+  for (auto& kv : c->pool_size) cudaFree(kv.first); /* recycled buffers, free or still lent out to live guides */
+  c->pool_size.clear();
+  c->pool_free.clear();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -122,6 +125,33 @@ void bb_time_end(bb_ctx* c) {
     cudaEventRecord(c->ev1, c->stream);
     c->ev_valid = true;
   }
+}
+
+/* ---- recycled small device buffers */
+static const size_t BB_POOL_MAX_BLOCK = (size_t)32 << 20; /* larger requests are not kept */
+cudaError_t bb_pool_alloc(bb_ctx* c, size_t bytes, void** out) {
+  const size_t want = (bytes + 4095) & ~(size_t)4095;
+  for (size_t i = 0; i < c->pool_free.size(); i++) {
+    if (c->pool_free[i].first >= want && c->pool_free[i].first <= 2 * want) {
+      *out = c->pool_free[i].second;
+      c->pool_free.erase(c->pool_free.begin() + i);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, want);
+  if (e == cudaSuccess) c->pool_size[*out] = want;
+  return e;
+}
+void bb_pool_release(bb_ctx* c, void* p) {
+  if (!p) return;
+  auto it = c->pool_size.find(p);
+  if (it == c->pool_size.end()) { cudaFree(p); return; }
+  if (it->second > BB_POOL_MAX_BLOCK || c->pool_free.size() >= 64) {
+    cudaFree(p);
+    c->pool_size.erase(it);
+    return;
+  }
+  c->pool_free.push_back({it->second, p});
 }
 
 static int ctx_stage(bb_ctx* c, size_t bytes) {
@@ -588,8 +618,8 @@ extern "C" int64_t bb_ens_bytes(bb_ens* e) { return e ? e->bytes : -1; }
 extern "C" int bb_guide_destroy(bb_guide* g) {
   if (!g) return BB_ERR_ARG;
   cudaSetDevice(g->ctx->device);
-  cudaStreamSynchronize(g->ctx->stream);
-  if (g->tab) cudaFree(g->tab);
+  cudaStreamSynchronize(g->ctx->stream); /* no launch of this context still reads the table */
+  bb_pool_release(g->ctx, g->tab);
   delete g;
   return BB_OK;
 }
@@ -715,7 +745,7 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
   g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxm; g->NC = NC; g->rec = rec;
   g->tt.assign(tt, tt + N);
   memcpy(g->segc, segc, sizeof(segc));
-  cudaError_t e1 = cudaMalloc(&g->tab, tab.size() * sizeof(double));
+  cudaError_t e1 = bb_pool_alloc(ctx, tab.size() * sizeof(double), (void**)&g->tab);
   if (e1 != cudaSuccess) {
     bb_set_cuda_error(e1, "cudaMalloc(guide)");
     bb_guide_destroy(g);

@@ -174,9 +174,10 @@ __global__ void k_gpupdate(const double* in, double* out, int* status) {
 }
 
 /* ---------------------------------------------------------------- host plumbing */
-struct dev_buf {
+struct dev_buf { /* work space from the context's recycled buffers */
   double* p = nullptr;
-  ~dev_buf() { if (p) cudaFree(p); }
+  bb_ctx* ctx = nullptr;
+  ~dev_buf() { if (p) bb_pool_release(ctx, p); }
 };
 struct dev_pack {
   /* one device allocation holding several host arrays back to back */
@@ -195,7 +196,8 @@ struct dev_pack {
 
 static int pack_upload(bb_ctx* ctx, dev_pack& pk, size_t extra_out) {
   const size_t n = pk.host.size() + extra_out + 2;
-  BB_CUDA(cudaMalloc(&pk.dev.p, n * sizeof(double)));
+  pk.dev.ctx = ctx;
+  BB_CUDA(bb_pool_alloc(ctx, n * sizeof(double), (void**)&pk.dev.p));
   BB_CUDA(cudaMemcpyAsync(pk.dev.p, pk.host.data(), pk.host.size() * sizeof(double), cudaMemcpyHostToDevice,
                           ctx->stream));
   BB_CUDA(cudaMemsetAsync(pk.dev.p + pk.host.size(), 0, (extra_out + 2) * sizeof(double), ctx->stream));

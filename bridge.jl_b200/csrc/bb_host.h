@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bridge_b200.h"
@@ -23,6 +24,10 @@ struct bb_ctx {
   /* staging for host <-> device transposes */
   double* stage = nullptr;
   size_t stage_bytes = 0;
+  /* small device buffers (constructor work space, guiding tables) are recycled instead of cudaMalloc / cudaFree per
+   * call: cudaFree synchronises the whole device, which serialised table rebuilds with the running path kernel */
+  std::vector<std::pair<size_t, void*>> pool_free;
+  std::unordered_map<void*, size_t> pool_size;
   /* host-buffer pipeline (bb_pcn_step_host) */
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -63,6 +68,9 @@ struct bb_ens {
 };
 
 void bb_theta_free(bb_ens* e); /* bb_theta.cu */
+/* recycled small device buffers of a context (bb_api.cu) */
+cudaError_t bb_pool_alloc(bb_ctx* c, size_t bytes, void** out);
+void bb_pool_release(bb_ctx* c, void* p);
 
 /* thread-local error text for bb_last_cuda_error */
 void bb_set_cuda_error(cudaError_t e, const char* where);
