@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(BB_W4_THREADS) bb_wide4_kernel(const __grid_co
   const int S = a.S, N = a.N, NC = a.NC;
   const bool sx = RNG == 1 ? true : (RNG == 3 ? false : a.store_x != 0);
   const bb_model_dev& m = a.model;
-  const double c0 = m.der[0], c1 = m.der[1], akk = m.der[2], nlh = m.der[3], twoa = 2 * m.par[0], sig = m.par[1];
+  const double c0 = m.der[0], c1 = m.der[1], akk = m.der[2], nlh = m.der[3], sig = m.par[1];
 
   const int par = a.par[pc];
   const int wbuf = PCN ? 1 - par : par;
@@ -370,9 +370,8 @@ __global__ void __launch_bounds__(BB_W4_THREADS) bb_wide4_kernel(const __grid_co
             const double ax = __shfl_sync(0xFFFFFFFFu, yo[0], (g + 1) & 3, 4), ay = __shfl_sync(0xFFFFFFFFu, yo[1], (g + 1) & 3, 4);
             const double bx = __shfl_sync(0xFFFFFFFFu, yo[0], (g + 2) & 3, 4), by = __shfl_sync(0xFFFFFFFFu, yo[1], (g + 2) & 3, 4);
             const double dxa = yo[0] - ax, dya = yo[1] - ay, dxb = yo[0] - bx, dyb = yo[1] - by;
-            const double na = sqrt(fma(dya, dya, dxa * dxa)), nb = sqrt(fma(dyb, dyb, dxb * dxb));
-            kA = c0 * bb_exp(-(na * na) / twoa);
-            kB = c0 * bb_exp(-(nb * nb) / twoa);
+            kA = c0 * bb_exp(-(fma(dya, dya, dxa * dxa) * c1));
+            kB = c0 * bb_exp(-(fma(dyb, dyb, dxb * dxb) * c1));
             kC = __shfl_sync(0xFFFFFFFFu, kA, (g + 3) & 3, 4);
           }
           double bg[4] = {0.0, 0.0, 0.0, 0.0};

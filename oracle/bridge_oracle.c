@@ -438,8 +438,12 @@ static void model_b(const bb_model* P, double t, const double* x, double* b) {
         for (int j = 0; j < n; j++) {
           const double *qi = x + 4 * i, *pi = x + 4 * i + 2, *qj = x + 4 * j, *pj = x + 4 * j + 2;
           double dx = qi[0] - qj[0], dy = qi[1] - qj[1];
-          double nrm = sqrt(MA(dy, dy, dx * dx)); /* norm(x) */
+#ifdef ORACLE_GPU_ORDER
+          double kij = c0 * bb_exp(-(fma(dy, dy, dx * dx) * c1)); /* |x|^2 directly, product with 1/(2a): as the kernels */
+#else
+          double nrm = sqrt(dy * dy + dx * dx); /* norm(x) */
           double kij = c0 * bb_exp(-(nrm * nrm) / (2 * a));
+#endif
           double dot = MA(pi[1], pj[1], pi[0] * pj[0]);
           for (int k = 0; k < 2; k++) {
             b[4 * i + k] += (0.5 * pj[k]) * kij;
