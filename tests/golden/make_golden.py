@@ -19,6 +19,15 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def savez(path, **arrays):
+    """np.savez, but an existing file with identical contents is left alone (zip timestamps would dirty the work tree)."""
+    if os.path.exists(path):
+        old = np.load(path)
+        if set(old.files) == set(arrays) and all(np.array_equal(old[k], np.asarray(v)) for k, v in arrays.items()):
+            return
+    np.savez(path, **arrays)
 FHN_PAR = [0.1, 0.0, 1.5, 0.8, 0.3]
 
 
@@ -31,7 +40,7 @@ def main():
     O.build()
     orc = O.load("ref")
     # ---- the reference's own golden vector
-    np.savez(os.path.join(OUT, "reference_docs_ou.npz"),
+    savez(os.path.join(OUT, "reference_docs_ou.npz"),
              tt=np.arange(11) * 0.1,
              W=np.array([0.0, 0.0940107, 0.214935, 0.0259463, 0.0226432, -0.24268, -0.144298, 0.581472, -0.135443,
                          0.0321464, 0.168574]),
@@ -65,7 +74,7 @@ def main():
             Xc[k, s], start = orc.guided_euler(om, og[s], start, Wc[k, s])
             llc[k] += orc.llikelihood(om, og[s], Xc[k, s])
         llo[k], logu[k], Wo[k], Xo[k], _ = orc.pcn_propose(om, og, x0, Wc[k], rho, seed, 3, c)
-    np.savez(os.path.join(OUT, "oracle_fhn_nuH_pcn.npz"), grids=np.stack(grids), nu=np.stack([t[0] for t in tabs]),
+    savez(os.path.join(OUT, "oracle_fhn_nuH_pcn.npz"), grids=np.stack(grids), nu=np.stack([t[0] for t in tabs]),
              H=np.stack([t[1] for t in tabs]), Bt=np.stack([t[2] for t in tabs]), bt=np.stack([t[3] for t in tabs]),
              par=np.array(FHN_PAR), x0=x0, chains=np.array(chains), seed=seed, rho=rho, it=3, W=Wc, X=Xc, ll=llc,
              Wo=Wo, Xo=Xo, llo=llo, logu=logu)
@@ -83,7 +92,7 @@ def main():
     for c in range(3):
         X3[c], _ = orc.guided_euler(om3, og3, np.zeros(3), W3[c])
         ll3[c] = orc.llikelihood(om3, og3, X3[c])
-    np.savez(os.path.join(OUT, "oracle_linpro3_guidedbridge.npz"), tt=tt, B1=B1, sigma=sig, v=v3, Hdia=Hd, V=V, W=W3,
+    savez(os.path.join(OUT, "oracle_linpro3_guidedbridge.npz"), tt=tt, B1=B1, sigma=sig, v=v3, Hdia=Hd, V=V, W=W3,
              X=X3, ll=ll3)
     # ---- IntegratedDiffusion, PartialBridge (L, M, mu) on the grid of test/partialparam.jl (first 201 points)
     ttp = np.arange(201) / 1000
@@ -93,7 +102,7 @@ def main():
     ogi = O.GuideHolder(O.GUIDE_LMMU, ttp, Lt, mut, Mm=Mt, v=[2.5], Bt=aux["B"], betat=aux["beta"], m=1)
     Wi = orc.wiener_sample(ttp, 1, 1, 0, 0)
     Xi, _ = orc.guided_euler(omi, ogi, [2.0, 1.0], Wi)
-    np.savez(os.path.join(OUT, "oracle_intdiff_partialbridge.npz"), tt=ttp, L=Lt, M=Mt, mu=mut, v=np.array([2.5]),
+    savez(os.path.join(OUT, "oracle_intdiff_partialbridge.npz"), tt=ttp, L=Lt, M=Mt, mu=mut, v=np.array([2.5]),
              Bt=aux["B"], bt=aux["beta"], W=Wi, X=Xi, ll=orc.llikelihood(omi, ogi, Xi))
     make_theta_and_landmarks(orc)
     for f in sorted(os.listdir(OUT)):
@@ -136,7 +145,7 @@ def make_theta_and_landmarks(orc):
         logu.append(orc.logu_q(seed, it, c, O.Q_THETA_LOGU))
     out.update(W=np.stack(W), theta_prop=np.stack(thp), Xo=np.stack(Xo), llo=np.array(llo), llc=np.array(llc),
                left_c=np.array(left_c), left_o=np.array(left_o), logu=np.array(logu))
-    np.savez(os.path.join(OUT, "oracle_bolus_theta_step.npz"), **out)
+    savez(os.path.join(OUT, "oracle_bolus_theta_step.npz"), **out)
     # ---- landmarks: PartialBridgeνH tables at d = 16, two guided paths with log-likelihood, one pCN proposal
     N = 33
     tt = warped(0.0, 1.0, N)
@@ -168,7 +177,7 @@ def make_theta_and_landmarks(orc):
         Xl.append(X); lll.append(orc.llikelihood(om, og, X))
         l1, u1, W1, X1, _ = orc.pcn_propose(om, [og], LM_X0, Wl[k][None], 0.9, 9, 2, c)
         Wo.append(W1[0]); Xo.append(X1[0]); llo.append(l1); lu.append(u1)
-    np.savez(os.path.join(OUT, "oracle_landmarks_bridge.npz"), tt=tt, par=np.array(LM_PAR), qT=LM_QT, x0=LM_X0, L=Lm,
+    savez(os.path.join(OUT, "oracle_landmarks_bridge.npz"), tt=tt, par=np.array(LM_PAR), qT=LM_QT, x0=LM_X0, L=Lm,
              Bt=Bt, at=at, nu=nus, H=Hs, C=Cc, chains=np.array(chains), W=Wl, X=np.stack(Xl), ll=np.array(lll),
              Wo=np.stack(Wo), Xo=np.stack(Xo), llo=np.array(llo), logu=np.array(lu), rho=0.9, seed=9, it=2)
 
