@@ -73,12 +73,12 @@ setgrid!(E::PathEnsemble, seg, tt::Vector{Float64}) =
 setstart!(E::PathEnsemble, u::SVector) = (v = collect(u);
     check(ccall((:bb_ens_set_start, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), E.h, v, length(v), 1)))
 
-# ---- guiding tables: the constructors of Bridge.jl have already run the backward ODE on the host, or use
-#      bb_backward_nuH / bb_backward_HV / bb_backward_LMmu to run it on the device (same R3 / Lyapunov schemes)
 # per-chain starting points: X0 is d x P (one column per chain), the ABI wants [P][d] -- the same bytes
 setstart!(E::PathEnsemble, X0::Matrix{Float64}) =
     check(ccall((:bb_ens_set_start, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), E.h, X0, length(X0), 0))
 
+# ---- guiding tables: the constructors of Bridge.jl have already run the backward ODE on the host, or use
+#      bb_backward_nuH / bb_backward_HV / bb_backward_LMmu to run it on the device (same R3 / Lyapunov schemes)
 mutable struct Guide
     h::Ptr{Cvoid}
 end
