@@ -431,6 +431,7 @@ extern "C" int bb_ens_set_grid(bb_ens* e, int32_t seg, const double* tt, int32_t
                           e->ctx->stream));
   BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
   e->tt[seg].assign(tt, tt + n);
+  bb_theta_invalidate(e);
   return BB_OK;
 }
 extern "C" int bb_ens_get_grid(bb_ens* e, int32_t seg, double* tt, int32_t n) {
@@ -442,6 +443,7 @@ extern "C" int bb_ens_get_grid(bb_ens* e, int32_t seg, double* tt, int32_t n) {
 
 extern "C" int bb_ens_set_start(bb_ens* e, const double* u, int32_t n_u, int32_t broadcast) {
   if (!e || !u) return BB_ERR_ARG;
+  bb_theta_invalidate(e); /* the left-end Gaussian term of the per-chain path depends on x0 */
   BB_CUDA(cudaSetDevice(e->ctx->device));
   const int d = e->d;
   if (broadcast) {

@@ -68,6 +68,7 @@ struct bb_ens {
 };
 
 void bb_theta_free(bb_ens* e); /* bb_theta.cu */
+void bb_theta_invalidate(bb_ens* e); /* grids or starting points changed: tables / left-end values must be rebuilt */
 /* recycled small device buffers of a context (bb_api.cu) */
 cudaError_t bb_pool_alloc(bb_ctx* c, size_t bytes, void** out);
 void bb_pool_release(bb_ctx* c, void* p);

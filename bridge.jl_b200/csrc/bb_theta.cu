@@ -743,6 +743,10 @@ static int run_forward(bb_ens* e, bool pcn, int which, int mode, int skip, bool 
 
 }  // namespace
 
+void bb_theta_invalidate(bb_ens* e) {
+  if (e->th) e->th->tstate = 0;
+}
+
 void bb_theta_free(bb_ens* e) {
   bb_theta* t = e->th;
   if (!t) return;
