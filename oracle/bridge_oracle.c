@@ -1241,6 +1241,121 @@ long long bbo_pcn_bench(const bb_model* Pm, const bbo_guide* const* G, int S, lo
   return acc;
 }
 
+/* ======================================================================= CPU baseline of the parameter-update step
+ * (timing only: tools/cpu_theta_baseline.py).  The `updateparams` branch of partialbridge_bolus3.jl:268-355 for P
+ * independent chains of the hypoelliptic FitzHugh-Nagumo model with the "matching" auxiliary process
+ * (partialbridge_fitzhugh.jl:44-46,106-108), flat priors, fixed starting point; OpenMP over chains.  Per chain and
+ * iteration: propose θ°, backward chain (gpupdate + Lyapunov step per segment), solve! + llikelihood with W fixed,
+ * logpdfnormal / trace terms, accept.  Returns the number of accepted proposals. */
+static void theta_fhn_backward(const double* par, int S, int N, const double* grids, const double* x0, const double* L,
+                               double Sigma, double eps, const double* obs_v, double* nu_t, double* H_t,
+                               double* lpn, double* trsum) {
+  double nu[2] = {0, 0}, Hp[4] = {1.0 / eps, 0, 0, 1.0 / eps}, C = 0.0;
+  double at[4] = {0, 0, 0, par[4] * par[4]};
+  bbo_gpupdate_nuH(2, 1, nu, Hp, L, &Sigma, &obs_v[S - 1]);
+  *trsum = 0.0;
+  for (int s = S - 1; s >= 0; s--) {
+    double ie = 1.0 / par[0], v = obs_v[s];
+    double Bt[4] = {ie, -ie, par[2], -1.0}, bt[2] = {par[1] / par[0] - (v * v * v) / par[0], par[3]};
+    bb_aux A = {2, 1, Bt, bt, at, NULL};
+    double nul[2], Hpl[4];
+    bbo_backward_nuH(BB_ODE_LYAP, N, 2, grids + (size_t)s * N, &A, nu, Hp, C, nu_t + (size_t)s * N * 2,
+                     H_t + (size_t)s * N * 4, nul, Hpl, &C);
+    memcpy(nu, nul, sizeof(nu)); memcpy(Hp, Hpl, sizeof(Hp));
+    *trsum += (grids[(size_t)s * N + N - 1] - grids[(size_t)s * N]) * (Bt[0] + Bt[3]);
+    if (s > 0) bbo_gpupdate_nuH(2, 1, nu, Hp, L, &Sigma, &obs_v[s - 1]);
+  }
+  double x[2] = {x0[0] - nu[0], x0[1] - nu[1]};
+  *lpn = bbo_logpdfnormal(2, x, Hp);
+}
+static double theta_fhn_forward(const double* par, int S, int N, const double* grids, const double* x0, const double* obs_v,
+                                const double* nu_t, const double* H_t, const double* W, double* X) {
+  bb_model P;
+  memset(&P, 0, sizeof(P));
+  P.id = BB_MODEL_FHN_HYPO; P.d = 2; P.dprime = 1;
+  memcpy(P.par, par, sizeof(double) * 5);
+  double start[2] = {x0[0], x0[1]}, end[2], ll = 0.0;
+  for (int s = 0; s < S; s++) {
+    double ie = 1.0 / par[0], v = obs_v[s];
+    double Bt[4] = {ie, -ie, par[2], -1.0}, bt[2] = {par[1] / par[0] - (v * v * v) / par[0], par[3]};
+    bbo_guide G;
+    memset(&G, 0, sizeof(G));
+    G.kind = BB_GUIDE_NUH; G.N = N; G.d = 2; G.tt = grids + (size_t)s * N; G.A = H_t + (size_t)s * N * 4;
+    G.b = nu_t + (size_t)s * N * 2; G.Bt = Bt; G.betat = bt; G.aux_const = 1; G.adiff_const = 1;
+    bbo_guided_euler(&P, &G, start, W + (size_t)s * N, X + (size_t)s * N * 2, end);
+    ll += bbo_llikelihood(&P, &G, X + (size_t)s * N * 2, 0);
+    start[0] = end[0]; start[1] = end[1];
+  }
+  return ll;
+}
+long long bbo_theta_param_bench(const double* par0, int S, int N, const double* grids, const double* x0, const double* L,
+                                double Sigma, double eps, const double* obs_v, const double* rw_sd, long long P,
+                                uint64_t seed, int iters, int nthreads, double* seconds) {
+  size_t wsz = (size_t)S * N;
+  double* W = (double*)calloc((size_t)P * wsz, sizeof(double));
+  double* th = (double*)calloc((size_t)P * 5, sizeof(double));
+  double* ll = (double*)calloc((size_t)P, sizeof(double));
+  double* lp = (double*)calloc((size_t)P * 2, sizeof(double));
+  long long acc = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    double* nu_t = (double*)malloc(sizeof(double) * wsz * 2);
+    double* H_t = (double*)malloc(sizeof(double) * wsz * 4);
+    double* X = (double*)malloc(sizeof(double) * wsz * 2);
+#pragma omp for schedule(static)
+    for (long long c = 0; c < P; c++) {
+      memcpy(th + c * 5, par0, sizeof(double) * 5);
+      for (int s = 0; s < S; s++)
+        bbo_wiener_sample(N, 1, grids + (size_t)s * N, seed, 0xFFFFFFFEu, (uint64_t)c * S + s, W + c * wsz + (size_t)s * N);
+      theta_fhn_backward(th + c * 5, S, N, grids, x0, L, Sigma, eps, obs_v, nu_t, H_t, &lp[2 * c], &lp[2 * c + 1]);
+      ll[c] = theta_fhn_forward(th + c * 5, S, N, grids, x0, obs_v, nu_t, H_t, W + c * wsz, X);
+    }
+    free(nu_t); free(H_t); free(X);
+  }
+  double t0 = 0, t1 = 0;
+#ifdef _OPENMP
+  t0 = omp_get_wtime();
+#endif
+  for (int it = 0; it < iters; it++) {
+#pragma omp parallel reduction(+ : acc)
+    {
+      double* nu_t = (double*)malloc(sizeof(double) * wsz * 2);
+      double* H_t = (double*)malloc(sizeof(double) * wsz * 4);
+      double* X = (double*)malloc(sizeof(double) * wsz * 2);
+#pragma omp for schedule(static)
+      for (long long c = 0; c < P; c++) {
+        double tp[5], z[4], lpn, trs;
+        bbo_normal_quad(seed, (uint32_t)it, (uint64_t)c, 0xFFFFFFFEu, z);
+        int n = 0;
+        for (int k = 0; k < 5; k++) {
+          tp[k] = th[c * 5 + k];
+          if (rw_sd[k] != 0.0) tp[k] = tp[k] + rw_sd[k] * z[n++ & 3];
+        }
+        theta_fhn_backward(tp, S, N, grids, x0, L, Sigma, eps, obs_v, nu_t, H_t, &lpn, &trs);
+        double llo = theta_fhn_forward(tp, S, N, grids, x0, obs_v, nu_t, H_t, W + c * wsz, X);
+        double diff = lpn - lp[2 * c];
+        diff += llo - ll[c];
+        diff += trs - lp[2 * c + 1];
+        if (bbo_logu_q(seed, (uint32_t)it, (uint64_t)c, 0xFFFFFFFDu) <= diff) {
+          memcpy(th + c * 5, tp, sizeof(tp));
+          ll[c] = llo; lp[2 * c] = lpn; lp[2 * c + 1] = trs;
+          acc += 1;
+        }
+      }
+      free(nu_t); free(H_t); free(X);
+    }
+  }
+#ifdef _OPENMP
+  t1 = omp_get_wtime();
+#endif
+  if (seconds) *seconds = t1 - t0;
+  free(W); free(th); free(ll); free(lp);
+  return acc;
+}
+
 int bbo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
