@@ -560,3 +560,30 @@ def test_theta_oracle_composition_matches_the_backward_chain(oracle_ref):
     assert left["lpn"] == oracle_ref.logpdfnormal(np.array([-0.5, -0.6]) - nu, Hp)
     assert abs(left["lpri"] - (-np.log(100.0) - 0.3 / 100.0)) < 1e-15
     assert abs(left["trsum"] - 1.5 * (1 / 0.1 - 1.0)) < 1e-12
+
+
+def test_logpdfnormal_and_gamma_prior_against_scipy(oracle_ref):
+    """logpdfnormal(x, Σ) (src/gaussian.jl:66-75) against scipy's multivariate normal; the Gamma(shape, scale) log-density of
+    logπ (bolus3.jl:237, Distributions.Gamma) as restated in oracle.theta_backward against scipy.stats.gamma."""
+    from scipy.stats import gamma, multivariate_normal
+    rng = np.random.default_rng(7)
+    for d in (1, 2, 3):
+        A = rng.standard_normal((d, d))
+        S = A @ A.T + 0.3 * np.eye(d)
+        x = rng.standard_normal(d)
+        want = multivariate_normal(mean=np.zeros(d), cov=S).logpdf(x)
+        assert abs(oracle_ref.logpdfnormal(x, S) - want) <= 1e-12 * (1 + abs(want))
+    # symmetrisation: an asymmetric input is used as (Σ + Σ')/2  (Bridge.symmetrize, bolus3.jl:319)
+    S = np.array([[2.0, 0.3], [0.1, 1.0]])
+    x = np.array([0.4, -0.7])
+    assert abs(oracle_ref.logpdfnormal(x, S) - multivariate_normal(cov=0.5 * (S + S.T)).logpdf(x)) < 1e-12
+    grids = [np.linspace(0.0, 0.5, 9)]
+    for (a, b, xval) in ((1.0, 100.0, 0.3), (2.0, 50.0, 0.7), (3.5, 2.0, 1.9)):
+        par = [0.1, 0.0, 1.5, 0.8, xval]
+        _, left = O.theta_backward(oracle_ref, O.FHN_HYPO, par, grids, [-0.5, -0.6], np.array([[1.0, 0.0]]),
+                                   np.array([[1e-2]]), 0.1, [0.5], O.AUX_FHN_MATCHING, {4: ("gamma", a, b)})
+        assert abs(left["lpri"] - gamma(a, scale=b).logpdf(xval)) < 1e-12
+    _, left = O.theta_backward(oracle_ref, O.FHN_HYPO, [0.1, 0.0, 1.5, 0.8, -0.2], grids, [-0.5, -0.6],
+                               np.array([[1.0, 0.0]]), np.array([[1e-2]]), 0.1, [0.5], O.AUX_FHN_MATCHING,
+                               {4: ("gamma", 1.0, 100.0)})
+    assert left["lpri"] == -np.inf  # outside the support: never accepted
