@@ -6,10 +6,10 @@ directory, whose own name is not a Python identifier).  Contents:
     _cabi   ctypes binding of the C ABI
     api     host-side mirror of the reference interface (SamplePath, solve, llikelihood, ...)
 """
-from ._cabi import (BridgeError, CUR, PROP, W, X, SYMBOLS, LIB_PATH)  # noqa: F401
+from ._cabi import (BridgeError, CUR, PROP, W, X, SYMBOLS, LIB_PATH, ARITH_REFERENCE, ARITH_FUSED)  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (Context, default_context, PathEnsemble, SamplePath, VSamplePath, samplepath, sample, sample_,
-                  seed_, solve, solve_, bridge_, llikelihood, innovations_, pcn_, theta_mcmc_, gpupdate, gpupdate_νH,
+                  seed_, solve, solve_, bridge_, llikelihood, lptilde, innovations_, pcn_, theta_mcmc_, gpupdate, gpupdate_νH,
                   EulerMaruyama, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
                   LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde, BolusDiffusion,
                   LinearAux, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,

@@ -29,6 +29,7 @@ W, X = 0, 1
 CUR, PROP = 0, 1
 F_LL, F_LL_PROP, F_LOGU, F_XEND, F_XEND_PROP = range(5)
 RUN_STORE_X, RUN_NO_LL = 1, 2
+ARITH_REFERENCE, ARITH_FUSED = 0, 1
 SCHEME_EULER, SCHEME_STRATONOVICH, SCHEME_HEUN, SCHEME_SRK, SCHEME_MDB = range(5)
 
 
@@ -84,6 +85,7 @@ def _load():
         "bb_ctx_launch_count": (i64, [vp]),
         "bb_ctx_set_timing": (C.c_int, [vp, C.c_int]),
         "bb_ctx_last_kernel_ms": (dbl, [vp]),
+        "bb_ctx_set_arith": (C.c_int, [vp, C.c_int]),
         "bb_ens_create": (C.c_int, [vp, i64, i32, i32, i32, i32, u32, pp]),
         "bb_ens_destroy": (C.c_int, [vp]),
         "bb_ens_set_chain_offset": (C.c_int, [vp, i64]),
@@ -114,6 +116,8 @@ def _load():
         "bb_backward_FH": (C.c_int, [vp, i32, i32, vp, C.POINTER(Aux), vp, vp, dbl, vp, vp, C.POINTER(dbl)]),
         "bb_backward_HV": (C.c_int, [vp, i32, i32, vp, C.POINTER(Aux), vp, vp, vp, vp]),
         "bb_backward_LMmu": (C.c_int, [vp, i32, i32, i32, vp, C.POINTER(Aux), vp, vp, vp, vp, vp]),
+        "bb_lptilde_nuH": (C.c_int, [vp, i32, vp, vp, dbl, vp, C.POINTER(dbl)]),
+        "bb_lptilde_HV": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, C.POINTER(dbl)]),
         "bb_guided_euler_ll": (C.c_int, [vp, C.POINTER(Model), pp, i32, u32]),
         "bb_llikelihood": (C.c_int, [vp, C.POINTER(Model), pp, i32]),
         "bb_innovations": (C.c_int, [vp, C.POINTER(Model), pp]),

@@ -52,6 +52,11 @@ class Context:
     def set_timing(self, on: bool):
         check(lib.bb_ctx_set_timing(self.h, 1 if on else 0))
 
+    def set_arith(self, arith: int):
+        """Rounding order of the shared-table constructors: K.ARITH_REFERENCE (default, bit-identical to the CPU
+        restatement in reference arithmetic) or K.ARITH_FUSED (the per-chain kernels' explicit fused multiply-adds)."""
+        check(lib.bb_ctx_set_arith(self.h, arith))
+
     @property
     def last_kernel_ms(self) -> float:
         return lib.bb_ctx_last_kernel_ms(self.h)
@@ -388,8 +393,9 @@ class LinearAux:
     """An auxiliary process given by B(t), β(t), a(t) (constants or callables), the protocol the
     guided proposals use (Bridge.B, Bridge.β, Bridge.a; partialbridge_fitzhugh.jl:99-116)."""
 
-    def __init__(self, B, β, a):
+    def __init__(self, B, β, a, constdiff: bool = True):
         self._B, self._β, self._a = B, β, a
+        self.constdiff = constdiff  # Bridge.constdiff(::Aux): the scripts' auxiliary processes all declare `true`
         self.is_const = not (callable(B) or callable(β) or callable(a))
         B0 = np.atleast_2d(f64(B(0.0) if callable(B) else B))
         self.d = B0.shape[0]
@@ -773,25 +779,26 @@ class _Proposal:
         A, b = f64(A), f64(b)
         Mm = None if Mm is None else f64(Mm)
         v = None if v is None else f64(v)
-        # constdiff(P°) = constdiff(Target) && constdiff(Pt) and a == a~ (src/partialbridge.jl:63): if the auxiliary
-        # diffusion differs from the target's, the extra log-likelihood terms of src/partialbridge.jl:79-84 apply
-        a_t = np.atleast_2d(f64(self.Target.a(self.tt[0], None)))
-        if const:
-            Ad = a_t - np.atleast_2d(f64(self.Pt.a(self.tt[0])))
-            ad_const = 1
-        else:
-            Ad = np.stack([a_t - np.atleast_2d(f64(self.Pt.a(t))) for t in self.tt])
-            ad_const = 0
-        if np.any(Ad != 0.0):
+        # constdiff(P°) = constdiff(Target) && constdiff(Pt)  (src/partialbridge.jl:64, guip.jl:199, a TRAIT of the two
+        # processes, not a comparison of a and a~): only if it is false do the extra log-likelihood terms of
+        # src/partialbridge.jl:79-84 apply.  A pair such as Diffusion / DiffusionAux of partialbridge_bolus3.jl:54,70
+        # (both constdiff = true, σ1 != σ2) runs WITHOUT them in the reference, and so it does here.
+        self.constdiff = bool(getattr(self.Target, "constdiff", True)) and bool(getattr(self.Pt, "constdiff", True))
+        if not self.constdiff:
+            a_t = np.atleast_2d(f64(self.Target.a(self.tt[0], None)))
+            if const:
+                Ad = a_t - np.atleast_2d(f64(self.Pt.a(self.tt[0])))
+                ad_const = 1
+            else:
+                Ad = np.stack([a_t - np.atleast_2d(f64(self.Pt.a(t))) for t in self.tt])
+                ad_const = 0
             Ad = f64(Ad)
             check(lib.bb_guide_create_ncd(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt),
                                           ptr(A), ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, ptr(Ad), ad_const,
                                           C.byref(h)))
-            self.constdiff = False
         else:
             check(lib.bb_guide_create(self.ctx.h, self.kind, len(self.tt), self.Target.d, self.m, ptr(self.tt), ptr(A),
                                       ptr(b), ptr(Mm), ptr(v), ptr(Bt), ptr(bt), const, C.byref(h)))
-            self.constdiff = True
         self._guide = h
 
     def __del__(self):
@@ -935,6 +942,33 @@ def gpupdate_νH(ν, Hp, L, Σ, v, ctx=None):
     Σ = np.atleast_2d(f64(Σ)); v = np.atleast_1d(f64(v))
     check(lib.bb_gpupdate_nuH(ctx.h, d, m, ptr(ν), ptr(Hp), ptr(L), ptr(Σ), ptr(v)))
     return ν, Hp
+
+
+def lptilde(a, b, ctx=None) -> float:
+    """lptilde(P::GuidedBridge, u)   src/guip.jl:206   (proposal first)
+    lptilde(x, P::PartialBridgeνH)  src/partialbridgenuH.jl:169 (point first), in the form the reference tests:
+    -0.5 (x'H[1]x - 2x'H[1]ν[1]) - C  (test/partialbridgenuH.jl:124)."""
+    Po, x = (a, b) if _is_proposal(a) else (b, a)
+    ctx = ctx or Po.ctx
+    x = np.atleast_1d(f64(x)); d = Po.Target.d
+    out = C.c_double(0)
+    if isinstance(Po, PartialBridgeνH):
+        check(lib.bb_lptilde_nuH(ctx.h, d, ptr(f64(Po.ν[0])), ptr(f64(Po.H[0])), float(Po.C), ptr(x), C.byref(out)))
+    elif isinstance(Po, GuidedBridge):
+        tt = Po.tt
+        if getattr(Po.Pt, "is_const", False):
+            tr, const = f64([np.trace(np.atleast_2d(Po.Pt.B(tt[0])))]), 1
+        else:  # tr B~ at the forward Ralston stage times of every interval (src/ode.jl:44-49,178-184)
+            tr = np.empty((len(tt) - 1, 3)); const = 0
+            for i in range(len(tt) - 1):
+                h = tt[i + 1] - tt[i]
+                for k, c in enumerate((0.0, 0.5, 0.75)):
+                    tr[i, k] = np.trace(np.atleast_2d(Po.Pt.B(tt[i] + c * h)))
+        check(lib.bb_lptilde_HV(ctx.h, len(tt), d, ptr(tt), ptr(tr), const, ptr(f64(Po.V[0])), ptr(f64(Po.Hdia[0])),
+                                ptr(x), C.byref(out)))
+    else:
+        raise BridgeError(K.ERR_UNSUPPORTED, "lptilde: GuidedBridge or PartialBridgeνH")
+    return out.value
 
 
 # ----------------------------------------------------------------------------------------------- reference calls

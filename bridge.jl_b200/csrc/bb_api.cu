@@ -60,15 +60,25 @@ extern "C" int bb_ctx_create(int device, bb_ctx** out) {
   bb_ctx* c = new (std::nothrow) bb_ctx();
   if (!c) return BB_ERR_NOMEM;
   c->device = device;
-  BB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  BB_CUDA(cudaEventCreate(&c->ev0));
-  BB_CUDA(cudaEventCreate(&c->ev1));
-  BB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev1);
+  if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (ce != cudaSuccess) {
+    bb_set_cuda_error(ce, "bb_ctx_create");
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ce == cudaErrorMemoryAllocation ? BB_ERR_NOMEM : BB_ERR_CUDA;
+  }
   *out = c;
   return BB_OK;
 }
 extern "C" int bb_ctx_destroy(bb_ctx* c) {
   if (!c) return BB_ERR_ARG;
+  /* guides and ensembles keep a pointer to their context (and guides borrow its recycled buffers): destroy them first */
+  if (c->live > 0) return BB_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->stage) cudaFree(c->stage);
@@ -107,6 +117,11 @@ extern "C" int bb_ctx_set_timing(bb_ctx* c, int on) {
   if (!c) return BB_ERR_ARG;
   c->timing = on != 0;
   c->ev_valid = false;
+  return BB_OK;
+}
+extern "C" int bb_ctx_set_arith(bb_ctx* c, int arith) {
+  if (!c || (arith != BB_ARITH_REFERENCE && arith != BB_ARITH_FUSED)) return BB_ERR_ARG;
+  c->arith = arith;
   return BB_OK;
 }
 extern "C" double bb_ctx_last_kernel_ms(bb_ctx* c) {
@@ -350,6 +365,7 @@ extern "C" int bb_ens_destroy(bb_ens* e) {
     if (p) cudaFree(p);
   for (double* g : e->gridtab)
     if (g) cudaFree(g);
+  e->ctx->live--;
   delete e;
   return BB_OK;
 }
@@ -372,6 +388,7 @@ extern "C" int bb_ens_create(bb_ctx* ctx, int64_t P, int32_t S, int32_t N, int32
   bb_ens* e = new (std::nothrow) bb_ens();
   if (!e) return BB_ERR_NOMEM;
   e->ctx = ctx; e->P = P; e->S = S; e->N = N; e->d = d; e->dp = dprime; e->flags = flags;
+  ctx->live++;
   e->NC = (N + BB_TC - 1) / BB_TC;
   const int nbuf = (flags & BB_ENS_DOUBLE_BUFFER) ? 2 : 1;
   const size_t rows = (size_t)ens_rows(e);
@@ -450,9 +467,10 @@ extern "C" int bb_ens_set_start(bb_ens* e, const double* u, int32_t n_u, int32_t
     if (n_u != d) return BB_ERR_STARTPOINT;
     if (!e->start_bcast) {
       BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+      double* fresh = nullptr;
+      BB_CUDA(cudaMalloc(&fresh, sizeof(double) * d)); /* on failure the old per-chain array stays valid */
       cudaFree(e->start);
-      e->start = nullptr;
-      BB_CUDA(cudaMalloc(&e->start, sizeof(double) * d));
+      e->start = fresh;
       e->start_bcast = 1;
     }
     BB_CUDA(cudaMemcpyAsync(e->start, u, sizeof(double) * d, cudaMemcpyHostToDevice, e->ctx->stream));
@@ -465,9 +483,10 @@ extern "C" int bb_ens_set_start(bb_ens* e, const double* u, int32_t n_u, int32_t
     for (int k = 0; k < d; k++) t[(size_t)k * e->P + p] = u[(size_t)p * d + k];
   if (e->start_bcast) {
     BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    double* fresh = nullptr;
+    BB_CUDA(cudaMalloc(&fresh, sizeof(double) * e->P * d)); /* on failure the broadcast point stays valid */
     cudaFree(e->start);
-    e->start = nullptr;
-    BB_CUDA(cudaMalloc(&e->start, sizeof(double) * e->P * d));
+    e->start = fresh;
     e->bytes += (int64_t)(sizeof(double) * e->P * d);
     e->start_bcast = 0;
   }
@@ -550,7 +569,14 @@ static int ens_transfer(bb_ens* e, int what, int which, int64_t p0, int64_t np, 
   return BB_OK;
 }
 extern "C" int bb_ens_upload(bb_ens* e, int what, int which, int64_t p0, int64_t np, const double* host) {
-  return ens_transfer(e, what, which, p0, np, const_cast<double*>(host), true);
+  const int rc = ens_transfer(e, what, which, p0, np, const_cast<double*>(host), true);
+  if (rc == BB_OK && what == BB_X && np > 0) {
+    /* a path supplied by the caller IS the chains' path now: it must not be recomputed from W by a later refresh
+     * (sample! followed by llikelihood on an uploaded X would otherwise evaluate a different path) */
+    BB_CUDA(cudaMemsetAsync(e->xstale + p0, 0, (size_t)np, e->ctx->stream));
+    if (p0 == 0 && np == e->P) e->x_maybe_stale = false;
+  }
+  return rc;
 }
 extern "C" int bb_ens_download(bb_ens* e, int what, int which, int64_t p0, int64_t np, double* host) {
   return ens_transfer(e, what, which, p0, np, host, false);
@@ -622,6 +648,7 @@ extern "C" int bb_guide_destroy(bb_guide* g) {
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream); /* no launch of this context still reads the table */
   bb_pool_release(g->ctx, g->tab);
+  g->ctx->live--;
   delete g;
   return BB_OK;
 }
@@ -745,6 +772,7 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
   bb_guide* g = new (std::nothrow) bb_guide();
   if (!g) return BB_ERR_NOMEM;
   g->ctx = ctx; g->kind = kind; g->N = N; g->d = d; g->m = m; g->auxc = auxm; g->NC = NC; g->rec = rec;
+  ctx->live++;
   g->tt.assign(tt, tt + N);
   memcpy(g->segc, segc, sizeof(segc));
   cudaError_t e1 = bb_pool_alloc(ctx, tab.size() * sizeof(double), (void**)&g->tab);
@@ -753,8 +781,13 @@ static int guide_create_impl(bb_ctx* ctx, int32_t kind, int32_t N, int32_t d, in
     bb_guide_destroy(g);
     return BB_ERR_NOMEM;
   }
-  BB_CUDA(cudaMemcpyAsync(g->tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  BB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaError_t e2 = cudaMemcpyAsync(g->tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+  if (e2 != cudaSuccess) {
+    bb_set_cuda_error(e2, "guide table upload");
+    bb_guide_destroy(g);
+    return BB_ERR_CUDA;
+  }
   *out = g;
   return BB_OK;
 }

@@ -12,7 +12,9 @@
  * Each call integrates ONE d x d system over the N grid points: O(N d^3) strictly sequential work,
  * done by a single thread with the state in registers (the path kernels spend P*N steps for every
  * one of these).  The auxiliary process arrives as values at the Ralston stage times (bb_aux).
- * Operation order is the oracle's (ORACLE_GPU_ORDER build), see bb_device.cuh.
+ * Operation order is the oracle's: reference arithmetic by default (bit-identical to liboracle_ref.so), explicit
+ * fused multiply-adds with BB_ARITH_FUSED (liboracle_fma.so); see bb_ctx_set_arith.  d > 3 (bb_backward_gen.cu) is
+ * fused order only.
  */
 #include <math.h>
 #include <string.h>
@@ -22,6 +24,25 @@
 #include "bb_backward.cuh"
 #include "bb_host.h"
 
+/* the kernels in both arithmetic flavours: bbk:: (explicit fma, the per-chain kernels' rounding order) and bbk_ref::
+ * (reference arithmetic, bit-identical to liboracle_ref.so); bb_ctx::arith selects, see bb_ctx_set_arith */
+#define BBK_NS bbk
+#include "bb_backward_kernels.inc"
+#undef BBK_NS
+#define BBK_NS bbk_ref
+#define BBK_MA(a, b, c) (((a) * (b)) + (c))
+#include "bb_backward_body.inc"
+#include "bb_backward_kernels.inc"
+#undef BBK_NS
+#undef BBK_MA
+
+/* runs the launch statement with the kernels of the flavour the context asks for */
+#define BB_ARITH_LAUNCH(ctx, ...)                                  \
+  do {                                                             \
+    if ((ctx)->arith == BB_ARITH_FUSED) { using namespace bbk; __VA_ARGS__; } \
+    else { using namespace bbk_ref; __VA_ARGS__; }                 \
+  } while (0)
+
 /* d > 3: block-parallel generic-d kernels (bb_backward_gen.cu); all pointers are device pointers */
 cudaError_t bb_gen_backward_nuH(cudaStream_t st, int method, int N, int d, const double* tt, const double* B,
                                 const double* beta, const double* a, const double* a_left, int is_const,
@@ -30,148 +51,7 @@ cudaError_t bb_gen_backward_nuH(cudaStream_t st, int method, int N, int d, const
 cudaError_t bb_gen_update_nuHC(cudaStream_t st, int d, int m, const double* in, double* out, int* status);
 
 namespace {
-using namespace bbk;
-
-/* ---- partialbridgeodeνH!  (R3: partialbridgenuH.jl:21-55; Lyap: :86-103) */
-template <int d>
-__global__ void k_backward_nuH(int method, int N, const double* __restrict__ tt, aux_dev A,
-                               const double* nu_end, const double* Hplus_end, double C0, double* nu, double* H,
-                               double* out_left /* nu_left[d], Hplus_left[d*d], C */, int* status) {
-  double Hp[d * d], Hc[d * d], v[d];
-  for (int q = 0; q < d * d; q++) Hp[q] = Hplus_end[q];
-  for (int q = 0; q < d; q++) v[q] = nu_end[q];
-  if (minv<d>(Hp, Hc)) { *status = BB_ERR_SINGULAR; return; }
-  for (int q = 0; q < d * d; q++) H[(size_t)(N - 1) * d * d + q] = Hc[q];
-  for (int q = 0; q < d; q++) nu[(size_t)(N - 1) * d + q] = v[q];
-  double Cc = C0;
-  for (int i = N - 2; i >= 0; i--) {
-    const double dt = tt[i] - tt[i + 1];
-    if (nuH_step<d>(method, A, i, dt, Hp, Hc, v, Cc)) { *status = BB_ERR_SINGULAR; return; }
-    for (int q = 0; q < d; q++) nu[(size_t)i * d + q] = v[q];
-    for (int q = 0; q < d * d; q++) H[(size_t)i * d * d + q] = Hc[q];
-  }
-  for (int q = 0; q < d; q++) out_left[q] = v[q];
-  for (int q = 0; q < d * d; q++) out_left[d + q] = Hp[q];
-  out_left[d + d * d] = Cc;
-  *status = BB_OK;
-}
-
-/* ---- partialbridgeodeHνH!  partialbridgenuH.jl:64-81 */
-template <int d>
-__global__ void k_backward_FH(int N, const double* __restrict__ tt, aux_dev A, const double* F_end,
-                              const double* H_end, double C0, double* F, double* H, double* out_C, int* status) {
-  double Hc[d * d], Fc[d];
-  for (int q = 0; q < d * d; q++) Hc[q] = H_end[q];
-  for (int q = 0; q < d; q++) Fc[q] = F_end[q];
-  for (int q = 0; q < d * d; q++) H[(size_t)(N - 1) * d * d + q] = Hc[q];
-  for (int q = 0; q < d; q++) F[(size_t)(N - 1) * d + q] = Fc[q];
-  double Cc = C0;
-  for (int i = N - 2; i >= 0; i--) {
-    const double dt = tt[i] - tt[i + 1];
-    aux_at<d> s0(A, i, 0);
-    double aF[d];
-    mvec<d, d>(s0.a, Fc, aF);
-    Cc += (vdot<d>(s0.beta, Fc) * dt + 0.5 * vdot<d>(Fc, aF) * dt) - 0.5 * trprod<d>(Hc, s0.a) * dt;
-    r3_step<d * d>(rhs_dH<d>{A, i}, Hc, dt);
-    r3_step<d>(rhs_dF<d>{A, i, Hc}, Fc, dt);
-    for (int q = 0; q < d; q++) F[(size_t)i * d + q] = Fc[q];
-    for (int q = 0; q < d * d; q++) H[(size_t)i * d * d + q] = Hc[q];
-  }
-  *out_C = Cc;
-  *status = BB_OK;
-}
-
-/* ---- gpHinv! / gpV!  guip.jl:172-180 */
-template <int d>
-__global__ void k_backward_HV(int N, const double* __restrict__ tt, aux_dev A, const double* v,
-                              const double* hdia_end, double* Hdia, double* V, int* status) {
-  double K[d * d], Vc[d];
-  for (int q = 0; q < d * d; q++) K[q] = hdia_end ? hdia_end[q] : 0.0;
-  for (int q = 0; q < d; q++) Vc[q] = v[q];
-  for (int q = 0; q < d * d; q++) Hdia[(size_t)(N - 1) * d * d + q] = K[q];
-  for (int q = 0; q < d; q++) V[(size_t)(N - 1) * d + q] = Vc[q];
-  for (int i = N - 2; i >= 0; i--) {
-    const double dt = tt[i] - tt[i + 1];
-    r3_step<d * d>(rhs_dHinv<d>{A, i}, K, dt);
-    r3_step<d>(rhs_btilde<d>{A, i}, Vc, dt);
-    for (int q = 0; q < d * d; q++) Hdia[(size_t)i * d * d + q] = K[q];
-    for (int q = 0; q < d; q++) V[(size_t)i * d + q] = Vc[q];
-  }
-  *status = BB_OK;
-}
-
-/* ---- partialbridgeode!  partialbridge.jl:1-22 */
-template <int d, int m>
-__global__ void k_backward_LMmu(int N, const double* __restrict__ tt, aux_dev A, const double* L,
-                                const double* Sigma, double* Lt, double* Mt, double* mut, int* status) {
-  double Lc[m * d], Mp[m * m], Mi[m * m], mu[m];
-  for (int q = 0; q < m * d; q++) Lc[q] = L[q];
-  for (int q = 0; q < m * m; q++) Mp[q] = Sigma[q];
-  for (int q = 0; q < m; q++) mu[q] = 0.0;
-  if (minv<m>(Mp, Mi)) { *status = BB_ERR_SINGULAR; return; }
-  for (int q = 0; q < m * d; q++) Lt[(size_t)(N - 1) * m * d + q] = Lc[q];
-  for (int q = 0; q < m * m; q++) Mt[(size_t)(N - 1) * m * m + q] = Mi[q];
-  for (int q = 0; q < m; q++) mut[(size_t)(N - 1) * m + q] = mu[q];
-  for (int i = N - 2; i >= 0; i--) {
-    const double dt = tt[i] - tt[i + 1];
-    r3_step<m * d>(rhs_dL<d, m>{A, i}, Lc, dt);
-    r3_step<m * m>(rhs_dMplus<d, m>{A, i, Lc}, Mp, dt);
-    r3_step<m>(rhs_dmu<d, m>{A, i, Lc}, mu, dt);
-    if (minv<m>(Mp, Mi)) { *status = BB_ERR_SINGULAR; return; }
-    for (int q = 0; q < m * d; q++) Lt[(size_t)i * m * d + q] = Lc[q];
-    for (int q = 0; q < m * m; q++) Mt[(size_t)i * m * m + q] = Mi[q];
-    for (int q = 0; q < m; q++) mut[(size_t)i * m + q] = mu[q];
-  }
-  *status = BB_OK;
-}
-
-/* ---- updateνH⁺C  partialbridgenuH.jl:1-17.  io: in = L[m*d], Sigma[m*m], v[m], eps ; out = nu[d], Hplus[d*d], C */
-template <int d, int m>
-__global__ void k_update_nuHC(const double* in, double* out, int* status) {
-  const double *L = in, *Sigma = in + m * d, *v = Sigma + m * m;
-  const double eps = v[m];
-  double Si[m * m], Lt[d * m], LtSi[d * m], H[d * d], Hplus[d * d], Siv[m], nu[d];
-  if (minv<m>(Sigma, Si)) { *status = BB_ERR_SINGULAR; return; }
-  mtr<m, d>(L, Lt);
-  mmul<d, m, m>(Lt, Si, LtSi);
-  mmul<d, m, d>(LtSi, L, H);
-  for (int i = 0; i < d; i++) H[i * d + i] += eps;
-  if (minv<d>(H, Hplus)) { *status = BB_ERR_SINGULAR; return; }
-  double HpLt[d * m], HpLtSi[d * m];
-  mmul<d, d, m>(Hplus, Lt, HpLt);
-  mmul<d, m, m>(HpLt, Si, HpLtSi);
-  mvec<d, m>(HpLtSi, v, nu);
-  mvec<m, m>(Si, v, Siv);
-  double c = 0.0;
-  c += 0.5 * vdot<m>(v, Siv);
-  double ld;
-  if (m == 1) ld = log(Sigma[0]);
-  else {
-    double Lc[m * m];
-    if (chol_lower<m>(Sigma, Lc)) { *status = BB_ERR_SINGULAR; return; }
-    ld = 0;
-    for (int i = 0; i < m; i++) ld += 2 * log(Lc[i * m + i]);
-  }
-  c += m / 2.0 * log(2 * 3.14159265358979323846) + 0.5 * ld;
-  for (int q = 0; q < d; q++) out[q] = nu[q];
-  for (int q = 0; q < d * d; q++) out[d + q] = Hplus[q];
-  out[d + d * d] = c;
-  *status = BB_OK;
-}
-
-/* ---- observation update  Z = I - H⁺L'(Σ + LH⁺L')⁻¹L;  ν <- Z H⁺L'Σ⁻¹v + Zν;  H⁺ <- Z H⁺
- * io: in = nu[d], Hplus[d*d], L[m*d], Sigma[m*m], v[m]; out = nu[d], Hplus[d*d] */
-template <int d, int m>
-__global__ void k_gpupdate(const double* in, double* out, int* status) {
-  double nu[d], Hplus[d * d];
-  const double *L = in + d + d * d, *Sigma = L + m * d, *v = Sigma + m * m;
-  for (int q = 0; q < d; q++) nu[q] = in[q];
-  for (int q = 0; q < d * d; q++) Hplus[q] = in[d + q];
-  if (gpupdate_dev<d, m>(nu, Hplus, L, Sigma, v)) { *status = BB_ERR_SINGULAR; return; }
-  for (int q = 0; q < d; q++) out[q] = nu[q];
-  for (int q = 0; q < d * d; q++) out[d + q] = Hplus[q];
-  *status = BB_OK;
-}
+using bbk_common::aux_dev;
 
 /* ---------------------------------------------------------------- host plumbing */
 struct dev_buf { /* work space from the context's recycled buffers */
@@ -263,6 +143,7 @@ static int run_small(bb_ctx* ctx, dev_pack& pk, size_t oout, size_t nout, std::v
 extern "C" int bb_update_nuHC(bb_ctx* ctx, int32_t d, int32_t m, const double* L, const double* Sigma,
                               const double* v, double eps, double* nu, double* Hplus, double* C) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!L || !Sigma || !v || !nu || !Hplus || !C) return BB_ERR_ARG;
   if (m < 1 || m > d) return BB_ERR_ASSERT_M;
   BB_CUDA(cudaSetDevice(ctx->device));
@@ -279,7 +160,7 @@ extern "C" int bb_update_nuHC(bb_ctx* ctx, int32_t d, int32_t m, const double* L
     });
   } else
   BB_DM_SWITCH(d, m, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                 k_update_nuHC<D, M><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st);
+                 BB_ARITH_LAUNCH(ctx, k_update_nuHC<D, M><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st));
                }));
   if (rc) return rc;
   memcpy(nu, out.data(), sizeof(double) * d);
@@ -291,6 +172,7 @@ extern "C" int bb_update_nuHC(bb_ctx* ctx, int32_t d, int32_t m, const double* L
 static int gpupdate_impl(bb_ctx* ctx, int d, int m, double* nu, double* Hplus, const double* L,
                          const double* Sigma, const double* v) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!L || !Sigma || !v || !nu || !Hplus) return BB_ERR_ARG;
   if (m < 1 || m > d) return BB_ERR_ASSERT_M;
   BB_CUDA(cudaSetDevice(ctx->device));
@@ -301,7 +183,7 @@ static int gpupdate_impl(bb_ctx* ctx, int d, int m, double* nu, double* Hplus, c
   if (rc) return rc;
   std::vector<double> out;
   BB_DM_SWITCH(d, m, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                 k_gpupdate<D, M><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st);
+                 BB_ARITH_LAUNCH(ctx, k_gpupdate<D, M><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st));
                }));
   if (rc) return rc;
   memcpy(nu, out.data(), sizeof(double) * d);
@@ -321,6 +203,7 @@ extern "C" int bb_backward_nuH(bb_ctx* ctx, int32_t method, int32_t N, int32_t d
                                const bb_aux* aux, const double* nu_end, const double* Hplus_end, double C0,
                                double* nu, double* H, double* nu_left, double* Hplus_left, double* C) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!tt || !nu_end || !Hplus_end || !nu || !H || N < 2) return BB_ERR_ARG;
   if (method != BB_ODE_R3 && method != BB_ODE_LYAP) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(ctx->device));
@@ -347,8 +230,8 @@ extern "C" int bb_backward_nuH(bb_ctx* ctx, int32_t method, int32_t N, int32_t d
     });
   } else
   BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                k_backward_nuH<D><<<1, 1, 0, ctx->stream>>>(method, N, D0 + ott, A, D0 + one, D0 + ohe, C0, dnu, dH,
-                                                          dleft, st);
+                BB_ARITH_LAUNCH(ctx, k_backward_nuH<D><<<1, 1, 0, ctx->stream>>>(method, N, D0 + ott, A, D0 + one, D0 + ohe, C0, dnu, dH,
+                                                          dleft, st));
               }));
   if (rc) return rc;
   memcpy(nu, out.data(), sizeof(double) * N * d);
@@ -364,6 +247,7 @@ extern "C" int bb_backward_FH(bb_ctx* ctx, int32_t N, int32_t d, const double* t
                               const double* F_end, const double* H_end, double C0, double* F, double* H,
                               double* C) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!tt || !F_end || !H_end || !F || !H || !C || N < 2) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(ctx->device));
   dev_pack pk;
@@ -382,7 +266,7 @@ extern "C" int bb_backward_FH(bb_ctx* ctx, int32_t N, int32_t d, const double* t
   double* dC = dH + (size_t)N * d * d;
   std::vector<double> out;
   BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                k_backward_FH<D><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + ofe, D0 + ohe, C0, dF, dH, dC, st);
+                BB_ARITH_LAUNCH(ctx, k_backward_FH<D><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + ofe, D0 + ohe, C0, dF, dH, dC, st));
               }));
   if (rc) return rc;
   memcpy(F, out.data(), sizeof(double) * N * d);
@@ -394,6 +278,7 @@ extern "C" int bb_backward_FH(bb_ctx* ctx, int32_t N, int32_t d, const double* t
 extern "C" int bb_backward_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const bb_aux* aux,
                               const double* v, const double* hdia_end, double* Hdia, double* V) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!tt || !v || !Hdia || !V || N < 2) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(ctx->device));
   dev_pack pk;
@@ -412,8 +297,8 @@ extern "C" int bb_backward_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* t
   double* dV = dHd + (size_t)N * d * d;
   std::vector<double> out;
   BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                k_backward_HV<D><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + ov, hdia_end ? D0 + ohe : nullptr, dHd,
-                                                         dV, st);
+                BB_ARITH_LAUNCH(ctx, k_backward_HV<D><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + ov, hdia_end ? D0 + ohe : nullptr, dHd,
+                                                         dV, st));
               }));
   if (rc) return rc;
   memcpy(Hdia, out.data(), sizeof(double) * N * d * d);
@@ -425,6 +310,7 @@ extern "C" int bb_backward_LMmu(bb_ctx* ctx, int32_t N, int32_t d, int32_t m, co
                                 const bb_aux* aux, const double* L, const double* Sigma, double* Lt, double* Mt,
                                 double* mut) {
   if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
   if (!tt || !L || !Sigma || !Lt || !Mt || !mut || N < 2) return BB_ERR_ARG;
   if (m < 1 || m > d) return BB_ERR_ASSERT_M;
   BB_CUDA(cudaSetDevice(ctx->device));
@@ -444,11 +330,57 @@ extern "C" int bb_backward_LMmu(bb_ctx* ctx, int32_t N, int32_t d, int32_t m, co
   double* dmu = dM + (size_t)N * m * m;
   std::vector<double> out;
   BB_DM_SWITCH(d, m, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
-                 k_backward_LMmu<D, M><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + oL, D0 + oS, dL, dM, dmu, st);
+                 BB_ARITH_LAUNCH(ctx, k_backward_LMmu<D, M><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, A, D0 + oL, D0 + oS, dL, dM, dmu, st));
                }));
   if (rc) return rc;
   memcpy(Lt, out.data(), sizeof(double) * N * m * d);
   memcpy(Mt, out.data() + (size_t)N * m * d, sizeof(double) * N * m * m);
   memcpy(mut, out.data() + (size_t)N * (m * d + m * m), sizeof(double) * N * m);
+  return BB_OK;
+}
+
+/* lptilde: see the kernels in bb_backward_kernels.inc */
+extern "C" int bb_lptilde_nuH(bb_ctx* ctx, int32_t d, const double* nu0, const double* H0, double C, const double* x,
+                              double* out) {
+  if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
+  if (!nu0 || !H0 || !x || !out) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  dev_pack pk;
+  pk.add(nu0, d); pk.add(H0, d * d); pk.add(&C, 1); pk.add(x, d);
+  const size_t oout = pk.host.size();
+  int rc = pack_upload(ctx, pk, 1);
+  if (rc) return rc;
+  std::vector<double> o;
+  BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, 1, o, [&](int* st) {
+                BB_ARITH_LAUNCH(ctx, k_lptilde_nuH<D><<<1, 1, 0, ctx->stream>>>(pk.dev.p, pk.dev.p + oout, st));
+              }));
+  if (rc) return rc;
+  *out = o[0];
+  return BB_OK;
+}
+extern "C" int bb_lptilde_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const double* trB, int32_t trB_const,
+                             const double* V0, const double* Hdia0, const double* u, double* out) {
+  if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
+  if (!tt || !trB || !V0 || !Hdia0 || !u || !out || N < 2) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  dev_pack pk;
+  const size_t ott = pk.add(tt, N);
+  const size_t otr = pk.add(trB, trB_const ? 1 : (size_t)(N - 1) * 3);
+  const size_t oin = pk.add(V0, d);
+  pk.add(Hdia0, d * d); pk.add(u, d);
+  const size_t oout = pk.host.size();
+  int rc = pack_upload(ctx, pk, 1);
+  if (rc) return rc;
+  double* D0 = pk.dev.p;
+  std::vector<double> o;
+  const double log2pi = log(2 * M_PI);
+  BB_D_SWITCH(d, rc = run_small(ctx, pk, oout, 1, o, [&](int* st) {
+                BB_ARITH_LAUNCH(ctx, k_lptilde_HV<D><<<1, 1, 0, ctx->stream>>>(N, D0 + ott, D0 + otr, trB_const, D0 + oin,
+                                                                             log2pi, D0 + oout, st));
+              }));
+  if (rc) return rc;
+  *out = o[0];
   return BB_OK;
 }

@@ -31,6 +31,8 @@
  * geometry or on how chains are sharded over GPUs.
  */
 #pragma once
+#include <atomic>
+
 #include "bb_device.cuh"
 
 struct bb_chain_args {
@@ -546,14 +548,16 @@ typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   const size_t smem = bb_chain_smem<M, GK, GM, AUXM, RNG>(a.S);
-  static unsigned long long attr_done = 0; /* per instantiation: bit i = set on device i (the attribute is per device) */
+  /* per instantiation: bit i = attribute set on device i (it is per device).  Atomic: contexts of different host
+   * threads launch concurrently; setting the attribute twice is harmless.  Devices >= 64 always set it. */
+  static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
+  if (dev >= 64 || !((attr_done.load(std::memory_order_acquire) >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(bb_chain_kernel<M, GK, GM, AUXM, RNG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done |= 1ull << (dev & 63);
+    if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
   }
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_chain_kernel<M, GK, GM, AUXM, RNG><<<grid, BB_THREADS, smem, st>>>(a);

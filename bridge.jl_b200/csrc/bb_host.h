@@ -21,6 +21,8 @@ struct bb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int sm_count = 0;
+  int live = 0;  /* ensembles + guides created on this context and not yet destroyed (bb_ctx_destroy refuses while > 0) */
+  int arith = 0; /* BB_ARITH_REFERENCE / BB_ARITH_FUSED: rounding order of the shared-table constructors */
   /* staging for host <-> device transposes */
   double* stage = nullptr;
   size_t stage_bytes = 0;

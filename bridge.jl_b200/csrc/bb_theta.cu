@@ -139,32 +139,6 @@ __device__ __forceinline__ void theta_aux_a(const bb_model_dev& m, double* at) {
   }
 }
 
-/* logpdfnormal(x, Σ)  src/gaussian.jl:66-75 (oracle bbo_logpdfnormal) */
-template <int d>
-__device__ __forceinline__ double logpdfnormal_dev(const double* x, const double* Sigma, double log2pi) {
-  if constexpr (d == 1) {
-    return -(x[0] * x[0] / Sigma[0] + log(Sigma[0]) + log2pi) / 2;
-  } else {
-    double Ssym[d * d], S[d * d], y[d];
-#pragma unroll
-    for (int i = 0; i < d; i++)
-#pragma unroll
-      for (int j = 0; j < d; j++) Ssym[i * d + j] = 0.5 * (Sigma[i * d + j] + Sigma[j * d + i]);
-    if (chol_lower<d>(Ssym, S)) return nan("");
-    double n2 = 0, sld = 0;
-#pragma unroll
-    for (int i = 0; i < d; i++) {
-      double t = x[i];
-#pragma unroll
-      for (int k = 0; k < i; k++) t -= S[i * d + k] * y[k];
-      y[i] = t / S[i * d + i];
-      n2 += y[i] * y[i];
-      sld += log(S[i * d + i]);
-    }
-    return -(n2 + 2 * sld + d * log2pi) / 2;
-  }
-}
-
 __device__ __forceinline__ double theta_logu(const bb_philox_keys& k, uint32_t stream, uint64_t chain) {
   uint32_t o[4];
   bb_philox4x32_10(0xFFFFFFFDu, stream, (uint32_t)chain, (uint32_t)(chain >> 32), k, o);

@@ -158,6 +158,17 @@ int64_t bb_ctx_launch_count(bb_ctx* ctx);
  * events on the context's stream; valid after bb_ctx_synchronize */
 int bb_ctx_set_timing(bb_ctx* ctx, int enabled);
 double bb_ctx_last_kernel_ms(bb_ctx* ctx);
+/* Rounding order of the shared-table proposal constructors (bb_update_nuHC, bb_gpupdate_*, bb_backward_*, d <= 3):
+ *   BB_ARITH_REFERENCE (default)  plain products and sums, nothing fused: the operations the reference performs
+ *                                 (Julia does not contract a*b+c; StaticArrays' unrolled products), so the tables are
+ *                                 bit-identical to the CPU restatement in reference arithmetic (liboracle_ref.so).
+ *                                 The backward recursions are ill-conditioned at the scripts' settings (Σ = 1e-10,
+ *                                 ϵ = 1e-3): fused and unfused tables differ by 4e-8 relative, which moves ll by 2e-6.
+ *   BB_ARITH_FUSED                explicit fused multiply-adds, the rounding order of the per-chain-parameter
+ *                                 kernels (bb_theta_*), where the fp64 pipe is the limit; with it the shared-table
+ *                                 constructors reproduce the per-chain tables bit for bit. */
+enum { BB_ARITH_REFERENCE = 0, BB_ARITH_FUSED = 1 };
+int bb_ctx_set_arith(bb_ctx* ctx, int arith);
 
 /* ------------------------------------------------------------------ ensemble
  * P chains, each a concatenation of S segments of N grid points (N-1 Euler steps);
@@ -296,6 +307,18 @@ int bb_backward_LMmu(bb_ctx* ctx, int32_t N, int32_t d, int32_t m, const double*
                      const bb_aux* aux, const double* L, const double* Sigma,
                      double* Lt, double* Mt, double* mut);
 
+/* lptilde: log of the auxiliary process' transition density at the left end of a proposal (the p~ of every importance
+ * weight exp(ll) p~/p, test/guip.jl:245-274).
+ *   bb_lptilde_nuH   lptilde(x, P::PartialBridgeνH) = -1/2 (x'H[1]x - 2x'H[1]ν[1]) - C, the formula the reference TESTS
+ *                    (test/partialbridgenuH.jl:124; src/partialbridgenuH.jl:169 itself has a typo and does not run).
+ *   bb_lptilde_HV    lptilde(P::GuidedBridge, u) = logpdfnormal(V[1] - u, H♢[1]) - traceB(tt, Pt)   src/guip.jl:203-206,
+ *                    src/gaussian.jl:66-75; traceB = forward Ralston integral of tr B~(t) (src/ode.jl:178-184): trB holds
+ *                    tr B~ at the stage times tt[i], tt[i]+h/2, tt[i]+3h/4 of every interval ([(N-1)*3]) or, with
+ *                    trB_const != 0, the one constant value. */
+int bb_lptilde_nuH(bb_ctx* ctx, int32_t d, const double* nu0, const double* H0, double C, const double* x, double* out);
+int bb_lptilde_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const double* trB, int32_t trB_const,
+                  const double* V0, const double* Hdia0, const double* u, double* out);
+
 /* ------------------------------------------------------------------ a11-a13: guided Euler + Girsanov ll
  * solve!(Euler(), X, u, W, P°) fused with llikelihood(LeftRule(), X, P°; skip):
  * X_cur <- guided Euler path driven by W_cur, ll_cur <- sum over segments of the log-likelihood,
@@ -377,7 +400,9 @@ typedef enum {
 enum { BB_PRIOR_FLAT = 0, BB_PRIOR_GAMMA = 1 /* Gamma(shape a, scale b): logπ of bolus3.jl:237 */ };
 typedef struct {
   int32_t m;                         /* rows of L */
-  int32_t aux_kind;                  /* bb_aux_kind; a~ = a(θ) of the target (constdiff pairs) */
+  int32_t aux_kind;                  /* bb_aux_kind.  Every registry pair declares constdiff = true (bolus3.jl:54,70;
+                                        partialbridge_fitzhugh.jl:46,113), so no a != a~ terms enter ll -- also for
+                                        BB_AUX_BOLUS, whose a~ = diag(σ1², σ2²) differs from a = σ1² I, as in the reference */
   double L[BB_MAXD * BB_MAXD];       /* m x d, row-major */
   double Sigma[BB_MAXD * BB_MAXD];   /* m x m */
   double eps;                        /* H⁺ = I/eps right of the last observation */

@@ -943,6 +943,35 @@ int bbo_backward_LMmu(int N, int d, int m, const double* tt, const bb_aux* A, co
   return 0;
 }
 
+/* lptilde(x, P::PartialBridgeνH) in the form the reference tests: -0.5*(x'*H[1]*x - 2*x'*H[1]*ν[1]) - C
+ * (test/partialbridgenuH.jl:124; src/partialbridgenuH.jl:169 has a typo -- P.ν instead of P.ν[1] -- and does not run) */
+double bbo_lptilde_nuH(int d, const double* nu0, const double* H0, double C, const double* x) {
+  double Hx[DM], Hnu[DM];
+  mat_vec(d, d, H0, x, Hx);
+  mat_vec(d, d, H0, nu0, Hnu);
+  return -0.5 * (vdot(d, x, Hx) - 2 * vdot(d, x, Hnu)) - C;
+}
+/* lptilde(P::GuidedBridge, u) = logpdfnormal(P.V[1] - u, P.H♢[1]) - traceB(P.tt, P.Pt)   src/guip.jl:203-206
+ * traceB(tt, P) = solve(R3(), _traceB, tt, 0.0, P), _traceB(t, x, P) = tr(B(t, P))         src/ode.jl:178-184
+ * trB: tr B at the stage times tt[i], tt[i] + h/2, tt[i] + 3h/4 of every forward interval, or one constant */
+typedef struct { const double* trB; int is_const; int i; } trace_ctx;
+static void rhs_trace(void* c_, int st, const double* y, double* k) {
+  (void)y;
+  trace_ctx* c = (trace_ctx*)c_;
+  k[0] = c->is_const ? c->trB[0] : c->trB[3 * c->i + st];
+}
+double bbo_lptilde_HV(int N, int d, const double* tt, const double* trB, int trB_const, const double* V0,
+                      const double* Hdia0, const double* u) {
+  double y = 0.0, e[DM];
+  trace_ctx c = {trB, trB_const, 0};
+  for (int i = 0; i < N - 1; i++) {
+    c.i = i;
+    r3_step(1, rhs_trace, &c, &y, tt[i + 1] - tt[i]);
+  }
+  for (int q = 0; q < d; q++) e[q] = V0[q] - u[q];
+  return bbo_logpdfnormal(d, e, Hdia0) - y;
+}
+
 /* ======================================================================= guided proposal (forward) */
 typedef struct {
   int32_t kind, N, d, m;

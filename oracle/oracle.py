@@ -140,6 +140,8 @@ class Oracle:
         L.bbo_exp.restype = C.c_double
         L.bbo_exp.argtypes = [C.c_double]
         L.bbo_llikelihood.restype = C.c_double
+        L.bbo_lptilde_nuH.restype = C.c_double
+        L.bbo_lptilde_HV.restype = C.c_double
         L.bbo_pcn_propose.restype = C.c_double
         L.bbo_pcn_bench.restype = C.c_longlong
         assert L.bbo_gpu_order() == (1 if variant == "fma" else 0)
@@ -274,6 +276,17 @@ class Oracle:
                                         _p(Mt), _p(mut))
         assert rc == 0, rc
         return Lt, Mt, mut
+
+    def lptilde_nuH(self, nu0, H0, Cc, x):
+        nu0 = np.atleast_1d(_f64(nu0)); H0 = np.atleast_2d(_f64(H0)); x = np.atleast_1d(_f64(x))
+        return self.lib.bbo_lptilde_nuH(nu0.size, _p(nu0), _p(H0), C.c_double(Cc), _p(x))
+
+    def lptilde_HV(self, tt, trB, V0, Hdia0, u):
+        """trB: a scalar (constant tr B) or [(N-1), 3] values at the forward Ralston stage times."""
+        tt = _f64(tt); V0 = np.atleast_1d(_f64(V0)); H0 = np.atleast_2d(_f64(Hdia0)); u = np.atleast_1d(_f64(u))
+        const = 1 if np.ndim(trB) == 0 else 0
+        trB = np.atleast_1d(_f64(trB))
+        return self.lib.bbo_lptilde_HV(tt.size, V0.size, _p(tt), _p(trB), const, _p(V0), _p(H0), _p(u))
 
     # ---- pCN
     def pcn_propose(self, model, guides, u, Wc, rho, seed, it, chain, skip=0):

@@ -195,7 +195,14 @@ def test_theta_equal_parameters_reproduce_shared_tables(B):
     import bridge_jl_b200.configs as cfg
     P, n, seed = 300, 129, 3
     ens, Pm, grids, obs_v, th, dp = setup(B, P, n, 4, spread=False)
-    Pm2, guides, x0, rho = cfg.fhn_config4(n)
+    # the per-chain kernels compute in fused order (fp64-pipe bound); the shared-table constructors match them bit for
+    # bit in that order (their default is reference arithmetic)
+    ctx = B.default_context()
+    ctx.set_arith(B.api.K.ARITH_FUSED)
+    try:
+        Pm2, guides, x0, rho = cfg.fhn_config4(n)
+    finally:
+        ctx.set_arith(B.api.K.ARITH_REFERENCE)
     ref = B.PathEnsemble(P, 4, n, 2, 1)
     for s, g in enumerate(guides):
         ref.set_grid(s, g.tt)

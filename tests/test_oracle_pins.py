@@ -366,6 +366,66 @@ def test_guidedbridge_importance_weights_unbiased(oracle_ref):
     assert z < 3.5, (w.mean(), z)
 
 
+def test_partialbridge_nuH_importance_weights_unbiased(oracle_ref):
+    """E[exp(ll) p~/p] = 1 for PartialBridgeνH (the z-score check of test/guip.jl:245-274 carried over to the proposal
+    north_star names), with p~ = exp(lptilde(x0, P°)) in the form of test/partialbridgenuH.jl:124.  Target and
+    auxiliary are 2-d LinPro processes with a PARTIAL observation v = L X_T + N(0, Σ), L = [1 0], so that
+    p = N(v; L m_T, L K_T L' + Σ) is a closed-form Gaussian (src/linpro.jl:98-134).  ϵ = 1e-5 (the reference tests'
+    value, test/partialparam.jl) keeps the extra factor exp(-ϵ|x_T|²/2) of the regularised terminal condition
+    (src/partialbridgenuH.jl:4) at 1 - O(1e-5); a much smaller ϵ makes H⁺ = O(1/ϵ) too stiff for the explicit R3 step
+    (lptilde off by 0.1 at ϵ = 1e-9, N = 801 -- the conditioning issue behind test/partialbridgenuH.jl:121's @test_broken)."""
+    from scipy.linalg import expm, solve_continuous_lyapunov
+    T, n, m = 1.0, 801, 4000
+    s = np.linspace(0, T, n)
+    tt = s * (2 - s / T)
+    sig = np.array([[0.6, 0.0], [0.2, 0.5]])
+    a = sig @ sig.T
+    Bp = np.array([[-0.5, 0.4], [-0.3, -0.8]]); mup = np.array([0.2, -0.1])    # target
+    Bt = np.array([[-0.9, 0.1], [0.0, -0.6]]); mut = np.array([0.0, 0.1])      # auxiliary
+    L = np.array([[1.0, 0.0]]); Sig = np.array([[0.05]]); v = np.array([0.4]); eps = 1e-5
+    x0 = np.array([0.3, -0.2])
+    P = O.linpro_model(Bp, mup, sig)
+    aux = O.const_aux(Bt, -Bt @ mut, a)
+    nuT, HpT, C0 = oracle_ref.update_nuHC(L, Sig, v, eps)
+    nu, H, _, _, Cc = oracle_ref.backward_nuH(O.ODE_R3, tt, aux, nuT, HpT, C0)
+    G = O.GuideHolder(O.GUIDE_NUH, tt, H, nu, Bt=Bt, betat=-Bt @ mut)
+
+    def logp(B, mu):
+        Phi = expm(B * T)
+        Kinf = solve_continuous_lyapunov(B, -a)
+        K = Kinf - Phi @ Kinf @ Phi.T
+        mean = (L @ (Phi @ (x0 - mu) + mu))[0]
+        var = (L @ K @ L.T + Sig)[0, 0]
+        return -0.5 * (v[0] - mean) ** 2 / var - 0.5 * np.log(2 * np.pi * var)
+
+    lpt = oracle_ref.lptilde_nuH(nu[0], H[0], Cc, x0)
+    # lptilde equals the closed-form log-density of the auxiliary process up to the discretisation of C (a first-order
+    # sum, src/partialbridgenuH.jl:46: 2.2e-3 here, 2.2e-4 at N = 8001); test/partialbridgenuH.jl:127 asks |LP - LP2| < 0.01
+    assert abs(lpt - logp(Bt, mut)) < 5e-3, (lpt, logp(Bt, mut))
+    w = np.empty(m)
+    for k in range(m):
+        W = oracle_ref.wiener_sample(tt, 2, 77, 0, k)
+        X, _ = oracle_ref.guided_euler(P, G, x0, W)
+        w[k] = np.exp(oracle_ref.llikelihood(P, G, X) + lpt - logp(Bp, mup))
+    z = abs(w.mean() - 1) * np.sqrt(m) / w.std()
+    assert z < 3.5, (w.mean(), w.std(), z)
+
+
+def test_lptilde_guidedbridge_matches_closed_form(oracle_ref):
+    """test/VHK.jl:63-65: lptilde(GP, u) equals lp(t, u, T, v, Pt) of the linear auxiliary process to 1e-5
+    (1-d LinPro(-β, μ, σ), the setup of test/VHK.jl:12-27 with N = 200)."""
+    β, μ, σ, T, u, v = 0.8, 0.2, np.sqrt(0.7), 2.0, 0.5, 0.1
+    tt = np.linspace(0.0, T, 2001)
+    Hd, V = oracle_ref.backward_HV(tt, O.const_aux([[-β]], [β * μ], [[σ * σ]]), [v])
+    mean = np.exp(-β * T) * (u - μ) + μ
+    var = σ * σ / (2 * β) * (1 - np.exp(-2 * β * T))
+    lp = -0.5 * (v - mean) ** 2 / var - 0.5 * np.log(2 * np.pi * var)
+    assert abs(oracle_ref.lptilde_HV(tt, -β, V[0], Hd[0], [u]) - lp) < 1e-5
+    # time-dependent trace through the staged values: the same constant, tabulated
+    tr = np.full((len(tt) - 1, 3), -β)
+    assert abs(oracle_ref.lptilde_HV(tt, tr, V[0], Hd[0], [u]) - lp) < 1e-5
+
+
 # --------------------------------------------------------------------------- pCN
 def test_pcn_smoke_acceptance(oracle_ref):
     """test/partialbridge.jl:133 `1 < acc < iterations` on the partialparam setup (rho = 0.9)."""

@@ -75,13 +75,23 @@ def test_two_rank_gloo_allreduce_matches_single_process(oracle_ref):
 
 
 def test_streams_do_not_depend_on_sharding(oracle_ref):
-    """Chain 1000 gets the same Wiener path whether it is local chain 1000 of one rank or local chain 0 of the rank
-    whose offset is 1000 (the kernels add bb_ens_set_chain_offset to the local index; tests/test_gpu_parity.py checks
-    the device side of the same statement)."""
+    """The Philox row of (chain, segment) is (chain_offset + local index) * S + segment with chain_offset =
+    shard_chains(...)[0] (bb_ens_set_chain_offset): for every world size the ranks' rows tile the single-process
+    rows exactly -- same ids, each once -- so every chain draws the same noise however the chains are sharded
+    (tests/test_gpu_parity.py checks the device side: chain_offset enters the kernels' counters)."""
+    from bridge_jl_b200.sharding import shard_chains
+    total, S = 1003, 4
+    one = [(c * S + seg) for c in range(total) for seg in range(S)]
+    for world in (2, 3, 8):
+        rows = []
+        for r in range(world):
+            first, count = shard_chains(total, r, world)
+            rows += [((first + loc) * S + seg) for loc in range(count) for seg in range(S)]
+        assert rows == one
+    # and the rows of different chains are different streams
     tt = np.linspace(0, 1, 33)
-    S, seg = 4, 2
-    a = oracle_ref.wiener_sample(tt, 1, 4, 9, (0 + 1000) * S + seg)
-    b = oracle_ref.wiener_sample(tt, 1, 4, 9, (1000 + 0) * S + seg)
+    first, count = shard_chains(total, 5, 8)
+    a = oracle_ref.wiener_sample(tt, 1, 4, 9, (first + 0) * S + 2)
+    b = oracle_ref.wiener_sample(tt, 1, 4, 9, shard_chains(total, 0, 1)[0] * S + first * S + 2)
     assert np.array_equal(a, b)
-    c = oracle_ref.wiener_sample(tt, 1, 4, 9, 1001 * S + seg)
-    assert not np.array_equal(a, c)
+    assert not np.array_equal(a, oracle_ref.wiener_sample(tt, 1, 4, 9, (first + 1) * S + 2))
