@@ -18,8 +18,9 @@ LIB_PATH = os.environ.get("BB_LIB") or os.path.join(_HERE, "lib", "libbridge_b20
 BB_NPAR = 32
 # status codes
 OK, ERR_LENGTH, ERR_TIMEAXIS, ERR_STARTPOINT, ERR_DIM, ERR_ASSERT_M, ERR_MODEL, ERR_ARG, ERR_CUDA, \
-    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE = (0, -1, -2, -3, -4, -5, -6, -7, -8, -9,
-                                                                         -10, -11, -12, -13)
+    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE, ERR_COMM = (0, -1, -2, -3, -4, -5, -6, -7, -8,
+                                                                                   -9, -10, -11, -12, -13, -14)
+NCCL_ID_BYTES = 128
 # model ids
 WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS, BOLUS = range(10)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
@@ -140,6 +141,17 @@ def _load():
         "bb_theta_refresh_x": (C.c_int, [vp]),
         "bb_theta_get_acc": (C.c_int, [vp, C.POINTER(i64)]),
         "bb_theta_acc_device_ptr": (vp, [vp]),
+        "bb_comm_unique_id": (C.c_int, [vp]),
+        "bb_comm_create": (C.c_int, [vp, i32, i32, vp, pp]),
+        "bb_comm_adopt": (C.c_int, [vp, vp, i32, i32, pp]),
+        "bb_comm_destroy": (C.c_int, [vp]),
+        "bb_comm_rank": (C.c_int, [vp]),
+        "bb_comm_size": (C.c_int, [vp]),
+        "bb_comm_last_error": (C.c_char_p, []),
+        "bb_allreduce_acc": (C.c_int, [vp, vp]),
+        "bb_allreduce_theta_acc": (C.c_int, [vp, vp]),
+        "bb_comm_get_acc": (C.c_int, [vp, C.POINTER(i64)]),
+        "bb_comm_synchronize": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -156,6 +168,10 @@ def check(status: int) -> None:
         text = lib.bb_strerror(status).decode()
         if status == ERR_CUDA or status == ERR_NOMEM:
             text += ": " + lib.bb_last_cuda_error().decode()
+        if status == ERR_COMM or status == ERR_UNSUPPORTED:
+            extra = lib.bb_comm_last_error().decode()
+            if extra:
+                text += ": " + extra
         raise BridgeError(status, text)
 
 

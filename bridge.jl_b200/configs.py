@@ -72,3 +72,27 @@ def linpro_config3(n: int = 1001, ctx=None):
     Pt = B.LinPro(LIN3_B2, np.zeros(3), LIN3_SIG)
     tt = np.linspace(0.0, 1.0, n)
     return P, B.GuidedBridge(tt, P, Pt, LIN3_V, ctx=ctx), np.zeros(3)
+
+
+# ---- config 5: Landmarks d = 16 (n = 4 landmarks in the plane), noise on the momenta (d' = 8)
+# project_partialbridge/partialbridge_landmarks.jl:47,86-101,111-146 is an unfinished draft: the numbers
+# below are this repository's choice and are recorded in BASELINE.md
+LM_A, LM_SIGMA, LM_LAMBDA = 0.5, 2.0, 0.5
+LM_Q0 = np.array([[-1.0, -1.0], [1.0, -1.2], [1.1, 0.9], [-0.8, 1.0]])
+LM_P0 = np.array([[0.5, 0.1], [-0.2, 0.4], [-0.3, -0.3], [0.2, -0.5]])
+LM_QT = np.array([[-0.6, -1.4], [1.5, -0.9], [0.8, 1.4], [-1.2, 0.7]])
+LM_EPS, LM_OBS_VAR, LM_RHO = 1e-3, 1e-4, 0.9
+
+
+def landmarks_config5(n: int = 1001, ctx=None, T: float = 1.0):
+    """Target, PartialBridgeνH towards the observed end positions qT (positions observed, momenta free), start."""
+    x0 = np.concatenate([np.concatenate([LM_Q0[i], LM_P0[i]]) for i in range(4)])
+    L = np.zeros((8, 16))
+    for i in range(4):
+        for c in range(2):
+            L[2 * i + c, 4 * i + c] = 1.0
+    tt = tau_grid(0.0, T, n)
+    Pm = B.Landmarks(LM_A, LM_SIGMA, LM_LAMBDA)
+    Pt = B.LandmarksTilde(LM_A, LM_SIGMA, LM_LAMBDA, LM_QT)
+    Po = B.PartialBridgeνH(tt, Pm, Pt, L, LM_QT.ravel(), LM_EPS, LM_OBS_VAR * np.eye(8), ctx=ctx)
+    return Pm, Po, x0

@@ -35,6 +35,7 @@ extern "C" const char* bb_strerror(int status) {
     case BB_ERR_UNSUPPORTED: return "combination of model, guide and dimensions is not instantiated";
     case BB_ERR_SINGULAR: return "singular matrix";
     case BB_ERR_STALE: return "X holds rejected proposals for some chains: call bb_ens_refresh_x first";
+    case BB_ERR_COMM: return "NCCL error (see bb_comm_last_error)";
     default: return "unknown status";
   }
 }

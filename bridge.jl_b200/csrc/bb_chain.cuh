@@ -192,23 +192,71 @@ struct bb_chain {
     bb_em_update<M>(a.model, bd, dt, dw, st.y);
   }
 
+  /* The 4 d' driving values of group h (4 grid points) of chunk c -> out[4 d'] (element m = slot m / d', component
+   * m % d'): fetch the d' pieces of W from the staged row (unless the path is sampled afresh), turn them into the values
+   * that drive the Euler steps (pCN: W° = rho W + sqrt(1-rho^2) W2; sampling: W itself) and put them back (staged row,
+   * or a direct 256-bit store).  None of this depends on the state y. */
+  template <bool GENERIC>
+  static __device__ __forceinline__ void gen_group(const bb_chain_args& a, const double* __restrict__ rec, state& st,
+                                                   double* wq, double* wrow, double* wout_row, int c, int h,
+                                                   uint32_t row_lo, uint32_t row_hi, bool wact, double* out) {
+    constexpr int NPIECE = BB_TC * DP / 4; /* pieces of 4 doubles per chunk row */
+#pragma unroll
+    for (int pp = 0; pp < DP; pp++) {
+      const int q = h * DP + pp, m = 4 * pp;
+      if constexpr (RNG != 2) bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+      if constexpr (RNG != 0) {
+        float z[4];
+        bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP; /* slot / component of element i */
+          const bool first = GENERIC && (c * BB_TC + sl == 0);
+          const double rootdt = rec[sl * REC + 1];
+          if constexpr (PCN) {
+            /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
+            if (!first) st.w2[kk] = fma(rootdt, (double)z[i], st.w2[kk]);
+            wq[i] = fma(a.rho2, st.w2[kk], a.rho * wq[i]);
+          } else {
+            /* W[j] = W[j-1] + sqrt(dt) xi, W[0] kept   (src/wiener.jl:50-58); w2 carries W[j-1] */
+            st.w2[kk] = first ? wq[i] : fma(rootdt, (double)z[i], st.w2[kk]);
+            wq[i] = st.w2[kk];
+          }
+        }
+        /* memory-bound launches (X° stored too) complete the W° row in the staged row and write it as a whole
+         * line at the end of the chunk; compute-bound ones store the piece directly */
+        if (BB_WFLUSH && sx(a)) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+        else if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) out[m + i] = wq[i];
+    }
+  }
+
   /* One chunk of BB_TC grid points.  GENERIC = false is the steady state: every slot is a full step that
    * enters the log-likelihood; GENERIC = true also handles j = 0 (no step), j >= N (padding), steps that
    * `skip` excludes from the log-likelihood and the GuidedBridge end-point rule.
-   * The chain's row of the driving path (8 d' doubles) is already in shared memory (`wrow`, brought there by
-   * a per-chain TMA bulk copy issued BB_WSTAGES-1 chunks earlier) and is consumed in pieces of 4 doubles. */
+   * The chain's row of the driving path (16 d' doubles) is already in shared memory (`wrow`, requested BB_WSTAGES-1
+   * chunks earlier).  SOFTWARE PIPELINE: a chain has two instruction streams per group of 4 steps -- the noise stream
+   * (Philox, Box-Muller, the running sum W2, W°; ~half of the instructions, independent of y) and the dependent fp64
+   * chain of the Euler steps.  The loop body holds the noise of group h+1 next to the steps of group h, so that the
+   * compiler interleaves the two and a warp has twice the independent work in flight (the kernel is latency bound when
+   * a GPU holds few chains: the strong-scaling share of BASELINE config 4 is 6.6 warps per SM). */
   template <bool GENERIC>
   static __device__ __forceinline__ void chunk(const bb_chain_args& a, const double* __restrict__ rec,
                                                const double* __restrict__ sc, state& st, double* wq,
                                                double* wrow, double* wout_row, double* xout_row, double* xbuf,
                                                int c, uint32_t row_lo, uint32_t row_hi, bool wact, bool xact) {
-    constexpr int NPIECE = BB_TC * DP / 4; /* pieces of 4 doubles per chunk row */
+    constexpr int NPIECE = BB_TC * DP / 4;
     bb_rowout<D> xo;
     const int N = a.N;
+    double wg[4 * DP], wn[4 * DP];
+    gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, 0, row_lo, row_hi, wact, wg);
     /* groups of 4 grid points: the body is unrolled over one group only, which bounds code size and the
      * registers the scheduler spends on hoisted shared-memory loads */
 #pragma unroll 1
     for (int h = 0; h < BB_TC / 4; h++) {
+      if (h + 1 < BB_TC / 4) gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, h + 1, row_lo, row_hi, wact, wn);
 #pragma unroll
       for (int s4 = 0; s4 < 4; s4++) {
         const int slot = 4 * h + s4;
@@ -216,40 +264,7 @@ struct bb_chain {
         const double* R = rec + slot * REC;
         double wj[DP];
 #pragma unroll
-        for (int k = 0; k < DP; k++) {
-          const int m = s4 * DP + k; /* element within the half-chunk (compile time) */
-          if ((m & 3) == 0) {
-            /* ---- piece q = 4 consecutive values of the driving path: fetch W (unless it is sampled afresh),
-             * turn it into the values that drive the Euler steps, and write those back in one 256-bit store.
-             * None of this depends on the state y, so it overlaps the dependent fp64 chain of the steps. */
-            const int q = h * DP + (m >> 2);
-            if constexpr (RNG != 2) bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
-            if constexpr (RNG != 0) {
-              float z[4];
-              bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP; /* slot / component of element i */
-                const bool first = GENERIC && (c * BB_TC + sl == 0);
-                const double rootdt = rec[sl * REC + 1];
-                if constexpr (PCN) {
-                  /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
-                  if (!first) st.w2[kk] = fma(rootdt, (double)z[i], st.w2[kk]);
-                  wq[i] = fma(a.rho2, st.w2[kk], a.rho * wq[i]);
-                } else {
-                  /* W[j] = W[j-1] + sqrt(dt) xi, W[0] kept   (src/wiener.jl:50-58); w2 carries W[j-1] */
-                  st.w2[kk] = first ? wq[i] : fma(rootdt, (double)z[i], st.w2[kk]);
-                  wq[i] = st.w2[kk];
-                }
-              }
-              /* memory-bound launches (X° stored too) complete the W° row in the staged row and write it as a whole
-               * line at the end of the chunk; compute-bound ones store the piece directly */
-              if (BB_WFLUSH && sx(a)) bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
-              else if (wact) bb_st4(wout_row + 4 * q, wq[0], wq[1], wq[2], wq[3]);
-            }
-          }
-          wj[k] = wq[m & 3];
-        }
+        for (int k = 0; k < DP; k++) wj[k] = wg[s4 * DP + k];
         if (GENERIC && j == 0) {
 #pragma unroll
           for (int k = 0; k < DP; k++) st.wprev[k] = wj[k];
@@ -273,6 +288,8 @@ struct bb_chain {
           xo.put(xout_row + 4 * h * D, s4, st.y, xact);
         }
       }
+#pragma unroll
+      for (int i = 0; i < 4 * DP; i++) wg[i] = wn[i];
       if constexpr (XBUF) {
         /* a 128-byte window of X° is complete: write it back to back (whole line) */
         if (((4 * h + 3) % XWIN) == XWIN - 1 && xact) {

@@ -63,7 +63,8 @@ typedef enum {
   BB_ERR_NODEVICE = -10,   /* no CUDA device: the library has no CPU path */
   BB_ERR_UNSUPPORTED = -11,/* combination not instantiated (model x guide x dims) */
   BB_ERR_SINGULAR = -12,   /* singular matrix in a backward solve / update */
-  BB_ERR_STALE = -13       /* X holds rejected proposals; bb_ens_refresh_x recomputes the current paths */
+  BB_ERR_STALE = -13,      /* X holds rejected proposals; bb_ens_refresh_x recomputes the current paths */
+  BB_ERR_COMM = -14        /* an NCCL call failed; see bb_comm_last_error */
 } bb_status;
 
 const char* bb_strerror(int status);
@@ -445,6 +446,33 @@ int bb_theta_refresh_x(bb_ens* ens);
 /* accepted parameter proposals since attach, summed over this ensemble's chains */
 int bb_theta_get_acc(bb_ens* ens, int64_t* acc);
 void* bb_theta_acc_device_ptr(bb_ens* ens);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * Chains are independent: rank r owns a contiguous block of GLOBAL chain ids (bb_ens_set_chain_offset; the random
+ * streams are keyed by global chain id, so results do not depend on the number of GPUs) and all segments of a chain stay
+ * on one GPU.  The only exchange is the acceptance statistic -- the reference's `acc += 1` (test/partialbridgenuH.jl:189)
+ * -- one all-reduce(sum) of an int64.  It runs on the communicator's own stream behind an event: the compute stream gets
+ * an 8-byte snapshot copy and nothing else, so the next iteration's kernel is never delayed.
+ * One process (or host task) per GPU; NCCL is bound at run time (dlopen of libnccl.so.2, BB_NCCL_LIB overrides).
+ *   rank 0: bb_comm_unique_id(id), ship the 128 bytes to the other ranks by any means (a file, MPI, torch.distributed);
+ *   all ranks: bb_comm_create(ctx, nranks, rank, id, &comm)   [collective: ncclCommInitRank]
+ *   or, for a host that already owns an ncclComm_t: bb_comm_adopt. */
+#define BB_NCCL_ID_BYTES 128
+typedef struct bb_comm bb_comm;
+int bb_comm_unique_id(uint8_t* id /* [BB_NCCL_ID_BYTES] */);
+int bb_comm_create(bb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id, bb_comm** out);
+int bb_comm_adopt(bb_ctx* ctx, void* nccl_comm /* ncclComm_t */, int32_t nranks, int32_t rank, bb_comm** out);
+int bb_comm_destroy(bb_comm* comm);
+int bb_comm_rank(bb_comm* comm);
+int bb_comm_size(bb_comm* comm);
+const char* bb_comm_last_error(void);
+/* start the all-reduce of the ensemble's acceptance counter as it stands after the calls issued so far (asynchronous) */
+int bb_allreduce_acc(bb_ens* ens, bb_comm* comm);
+/* the same for the counter of accepted parameter proposals (bb_theta_param_step) */
+int bb_allreduce_theta_acc(bb_ens* ens, bb_comm* comm);
+/* global sum delivered by the most recent bb_allreduce_*acc on this communicator (waits for that all-reduce only) */
+int bb_comm_get_acc(bb_comm* comm, int64_t* acc_global);
+int bb_comm_synchronize(bb_comm* comm);
 
 #ifdef __cplusplus
 }

@@ -1270,6 +1270,178 @@ long long bbo_pcn_bench(const bb_model* Pm, const bbo_guide* const* G, int S, lo
   return acc;
 }
 
+/* ======================================================================= tuned CPU baseline driver (bench.py only)
+ * The SAME algorithm and pass structure as bbo_pcn_bench / the reference loop (sample!(W2), Wo .= ρW + √(1-ρ²)W2,
+ * solve!(Euler(), Xo, x0, Wo, Po), llikelihood(LeftRule(), Xo, Po), accept with a buffer swap), written the way Julia
+ * specialises it for this workload -- FitzHugh-Nagumo hypoelliptic target (SVector{2}, scalar Wiener), PartialBridgeνH
+ * with a constant auxiliary drift: no generic-d loops or DM-sized temporaries, model constants hoisted, every Philox
+ * call yields its four normals (the generic driver uses one of four), the normals of a segment drawn in a batch
+ * (vectorisable).  Operation ORDER is that of the generic code, so in the contraction-free builds the two drivers
+ * agree bit for bit (tests/test_oracle_pins.py); the timed `fast` build may contract differently. */
+static inline void bm_pair(uint32_t wu, uint32_t wa, float* z0, float* z1) { /* bb_box_muller without the switch */
+  float rad = sqrtf(-2.0f * bb_logf(bb_unif(wu)));
+  float t = (float)(int32_t)wa * 0x1p-31f;
+  float q = rintf(t * 2.0f);
+  float r = fmaf(q, -0.5f, t);
+  float s2 = r * r;
+  float ps = -0x1.2d9b7cp-1f;
+  ps = fmaf(ps, s2, 0x1.465ec4p+1f);
+  ps = fmaf(ps, s2, -0x1.4abbbap+2f);
+  ps = fmaf(ps, s2, 0x1.921fb6p+1f);
+  float sr = ps * r;
+  float pc = 0x1.d9c326p-3f;
+  pc = fmaf(pc, s2, -0x1.55c57ap+0f);
+  pc = fmaf(pc, s2, 0x1.03c1dcp+2f);
+  pc = fmaf(pc, s2, -0x1.3bd3ccp+2f);
+  float cr = fmaf(pc, s2, 1.0f);
+  int qi = ((int)q) & 3;
+  float a = (qi & 1) ? cr : sr, b = (qi & 1) ? sr : cr;
+  *z0 = rad * ((qi & 2) ? -a : a);
+  *z1 = rad * ((qi == 1 || qi == 2) ? -b : b);
+}
+/* normals 0 .. 4*nq-1 of row `row` (quads 0 .. nq-1), as bbo_normal_quad gives them */
+static void normals_batch(uint64_t seed, uint32_t stream, uint64_t row, int nq, float* z) {
+  const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32), r0 = (uint32_t)row, r1 = (uint32_t)(row >> 32);
+#pragma omp simd
+  for (int q = 0; q < nq; q++) {
+    uint32_t c0 = (uint32_t)q, c1 = stream, c2 = r0, c3 = r1, k0 = s0, k1 = s1;
+    for (int r = 0; r < 10; r++) {
+      uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+      uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    bm_pair(c0, c1, &z[4 * q], &z[4 * q + 1]);
+    bm_pair(c2, c3, &z[4 * q + 2], &z[4 * q + 3]);
+  }
+}
+typedef struct { double eps, s, gam, beta, sig, a11; } fhn_const;
+static inline void fhn_b(const fhn_const* c, double x1, double x2, double* b0, double* b1) { /* model_b, FHN_HYPO */
+  double cc = x1 * x1, u = x1 - x2;
+#ifdef ORACLE_GPU_ORDER
+  u = fma(-cc, x1, u);
+  *b0 = (u + c->s) * (1.0 / c->eps);
+#else
+  u = u - cc * x1;
+  *b0 = (u + c->s) / c->eps;
+#endif
+  *b1 = MA(c->gam, x1, -x2) + c->beta;
+}
+/* one pCN proposal of one chain: returns ll°, writes W° and X° */
+static double fhn_tuned_propose(const fhn_const* c, const bbo_guide* const* G, int S, const double* u, const double* Wc,
+                                double rho, double rho2, uint64_t seed, uint32_t iter, uint64_t chain, double* Wo,
+                                double* Xo, float* z) {
+  double y0 = u[0], y1 = u[1], ll = 0.0;
+  for (int s = 0; s < S; s++) {
+    const int N = G[s]->N;
+    const double* restrict tt = G[s]->tt;
+    const double* restrict H = G[s]->A;
+    const double* restrict nu = G[s]->b;
+    const double* Bt = G[s]->Bt; const double* be = G[s]->betat;
+    const double* restrict wc = Wc + (size_t)s * N;
+    double* restrict wo = Wo + (size_t)s * N;
+    double* restrict xo = Xo + (size_t)s * N * 2;
+    /* sample!(W2, Wiener()); Wo.yy .= ρ*W.yy + sqrt(1-ρ^2)*W2.yy */
+    normals_batch(seed, iter, chain * (uint64_t)S + s, (N + 3) >> 2, z);
+    double w2 = 0.0;
+    wo[0] = MA(rho2, w2, rho * wc[0]);
+    for (int j = 1; j < N; j++) {
+      w2 = MA(sqrt(tt[j] - tt[j - 1]), (double)z[j], w2);
+      wo[j] = MA(rho2, w2, rho * wc[j]);
+    }
+    /* solve!(Euler(), Xo, x0, Wo, Po)   src/euler.jl:247-268 with _b = b + a*H[i]*(ν[i] - x) */
+    for (int i = 0; i < N - 1; i++) {
+      xo[2 * i] = y0; xo[2 * i + 1] = y1;
+      double b0, b1;
+      fhn_b(c, y0, y1, &b0, &b1);
+      const double e0 = nu[2 * i] - y0, e1 = nu[2 * i + 1] - y1;
+      const double r0 = MA(H[4 * i + 1], e1, H[4 * i] * e0), r1 = MA(H[4 * i + 3], e1, H[4 * i + 2] * e0);
+      b0 = MA(0.0, r0, b0);
+      b1 = MA(c->a11, r1, b1);
+      const double dt = tt[i + 1] - tt[i], dw = wo[i + 1] - wo[i];
+      y0 = MA(b0, dt, y0) + 0.0 * dw;
+      y1 = MA(c->sig, dw, MA(b1, dt, y1));
+    }
+    xo[2 * (N - 1)] = y0; xo[2 * (N - 1) + 1] = y1;
+    /* llikelihood(LeftRule(), Xo, Po)   src/partialbridgenuH.jl:171-189 */
+    double som = 0.0;
+    for (int i = 0; i < N - 1; i++) {
+      const double x0 = xo[2 * i], x1 = xo[2 * i + 1];
+      const double e0 = nu[2 * i] - x0, e1 = nu[2 * i + 1] - x1;
+      const double r0 = MA(H[4 * i + 1], e1, H[4 * i] * e0), r1 = MA(H[4 * i + 3], e1, H[4 * i + 2] * e0);
+      double b0, b1;
+      fhn_b(c, x0, x1, &b0, &b1);
+      const double bt0 = MA(Bt[1], x1, Bt[0] * x0), bt1 = MA(Bt[3], x1, Bt[2] * x0);
+      const double d0 = b0 - (bt0 + be[0]), d1 = b1 - (bt1 + be[1]);
+      som = MA(MA(d1, r1, d0 * r0), tt[i + 1] - tt[i], som);
+    }
+    ll += som;
+  }
+  return ll;
+}
+long long bbo_pcn_bench_fhn_tuned(const bb_model* Pm, const bbo_guide* const* G, int S, long long P, const double* u,
+                                  double rho, uint64_t seed, int iters, int nthreads, double* seconds,
+                                  double* ll_out) {
+  if (Pm->id != BB_MODEL_FHN_HYPO) return -1;
+  for (int s = 0; s < S; s++)
+    if (G[s]->kind != BB_GUIDE_NUH || !G[s]->aux_const || G[s]->Adiff || G[s]->N != G[0]->N) return -1;
+  const int N = G[0]->N;
+  const fhn_const c = {Pm->par[0], Pm->par[1], Pm->par[2], Pm->par[3], Pm->par[4], 0.0 + Pm->par[4] * Pm->par[4]};
+  const double rho2 = sqrt(1 - rho * rho);
+  size_t wsz = (size_t)S * N, xsz = (size_t)S * N * 2;
+  double* W = (double*)calloc((size_t)P * 2 * wsz, sizeof(double));
+  double* X = (double*)calloc((size_t)P * 2 * xsz, sizeof(double));
+  double* ll = (double*)calloc((size_t)P, sizeof(double));
+  unsigned char* par = (unsigned char*)calloc((size_t)P, 1);
+  long long acc = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+  for (long long ch = 0; ch < P; ch++) { /* initial state exactly as bbo_pcn_bench */
+    double start[2] = {u[0], u[1]}, end[2], l = 0;
+    for (int s = 0; s < S; s++) {
+      double* w = W + ((size_t)ch * 2) * wsz + (size_t)s * N;
+      double* x = X + ((size_t)ch * 2) * xsz + (size_t)s * N * 2;
+      bbo_wiener_sample(N, 1, G[s]->tt, seed, 0xFFFFFFFEu, (uint64_t)ch * S + s, w);
+      bbo_guided_euler(Pm, G[s], start, w, x, end);
+      l += bbo_llikelihood(Pm, G[s], x, 0);
+      start[0] = end[0]; start[1] = end[1];
+    }
+    ll[ch] = l;
+  }
+  double t0 = 0, t1 = 0;
+#ifdef _OPENMP
+  t0 = omp_get_wtime();
+#endif
+#pragma omp parallel reduction(+ : acc)
+  {
+    float* z = (float*)malloc(sizeof(float) * (size_t)(N + 8));
+    for (int it = 0; it < iters; it++) {
+#pragma omp for schedule(static)
+      for (long long ch = 0; ch < P; ch++) {
+        const int p = par[ch];
+        const double llo = fhn_tuned_propose(&c, G, S, u, W + ((size_t)ch * 2 + p) * wsz, rho, rho2, seed, (uint32_t)it,
+                                             (uint64_t)ch, W + ((size_t)ch * 2 + (1 - p)) * wsz,
+                                             X + ((size_t)ch * 2 + (1 - p)) * xsz, z);
+        if (bbo_accept_logu(seed, (uint32_t)it, (uint64_t)ch) <= llo - ll[ch]) {
+          par[ch] = (unsigned char)(1 - p);
+          ll[ch] = llo;
+          acc += 1;
+        }
+      }
+    }
+    free(z);
+  }
+#ifdef _OPENMP
+  t1 = omp_get_wtime();
+#endif
+  if (seconds) *seconds = t1 - t0;
+  if (ll_out) memcpy(ll_out, ll, sizeof(double) * (size_t)P);
+  free(W); free(X); free(ll); free(par);
+  return acc;
+}
+
 /* ======================================================================= CPU baseline of the parameter-update step
  * (timing only: tools/cpu_theta_baseline.py).  The `updateparams` branch of partialbridge_bolus3.jl:268-355 for P
  * independent chains of the hypoelliptic FitzHugh-Nagumo model with the "matching" auxiliary process

@@ -50,6 +50,21 @@ def build(force: bool = False) -> None:
     subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
 
 
+def rebuild_fast_native() -> None:
+    """liboracle_fast.so is compiled with -march=native: rebuild it on the host that is about to TIME it (the built
+    .so travels with the repository snapshot and may come from another CPU model).  Once per process."""
+    global _fast_rebuilt
+    if _fast_rebuilt:
+        return
+    subprocess.run(["make", "-C", _HERE, "-B", os.path.join(_HERE, "liboracle_fast.so")], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    _fast_rebuilt = True
+    _cache.pop("fast", None)
+
+
+_fast_rebuilt = False
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -144,6 +159,7 @@ class Oracle:
         L.bbo_lptilde_HV.restype = C.c_double
         L.bbo_pcn_propose.restype = C.c_double
         L.bbo_pcn_bench.restype = C.c_longlong
+        L.bbo_pcn_bench_fhn_tuned.restype = C.c_longlong
         assert L.bbo_gpu_order() == (1 if variant == "fma" else 0)
 
     # ---- rng
@@ -307,6 +323,17 @@ class Oracle:
         acc = self.lib.bbo_pcn_bench(C.byref(model), garr, S, C.c_longlong(P), _p(u),
                                      C.c_double(rho), C.c_uint64(seed), C.c_int(iters),
                                      C.c_int(skip), C.c_int(nthreads), C.byref(secs), _p(ll))
+        return acc, secs.value, ll
+
+    def pcn_bench_fhn_tuned(self, model, guides, P, u, rho, seed, iters, nthreads=0):
+        """The same iteration as pcn_bench, specialised for the FitzHugh-Nagumo / PartialBridgeνH workload (bench.py)."""
+        S = len(guides)
+        garr = (C.POINTER(Guide) * S)(*[C.pointer(g.c) for g in guides])
+        u = np.atleast_1d(_f64(u)); secs = C.c_double(0); ll = np.zeros(P)
+        acc = self.lib.bbo_pcn_bench_fhn_tuned(C.byref(model), garr, S, C.c_longlong(P), _p(u), C.c_double(rho),
+                                               C.c_uint64(seed), C.c_int(iters), C.c_int(nthreads), C.byref(secs),
+                                               _p(ll))
+        assert acc >= 0, "bbo_pcn_bench_fhn_tuned: unsupported workload"
         return acc, secs.value, ll
 
     def max_threads(self):

@@ -542,15 +542,6 @@ def test_config4_end_to_end_vs_reference_arithmetic(B, oracle_ref, oracle_fma):
             worst_x = max(worst_x, float(np.max(np.abs(X[p, s] - Xo))))
         worst_ll = max(worst_ll, abs(ll[p] - llo) / abs(llo))
     assert worst_ll <= 1e-9 and worst_x <= 1e-9, (worst_ll, worst_x)  # measured: ~1e-13 / ~1e-12
-    # one pCN iteration of the benchmarked step
-    ens.pcn_step_(Pm, guides, rho, seed, 0)
-    llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
-    flips = 0
-    for p in range(P):
-        llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(om, og, x0, W[p], rho, seed, 0, p)
-        assert lu == logu[p] and abs(llp[p] - llo) <= 1e-9 * abs(llo)
-        flips += int(bool(flags[p]) != (lu <= llo - ll[p]))
-    assert flips == 0
     # what the fused-order tables would have cost (the reason for the reference-arithmetic default)
     ctx = B.default_context()
     try:
@@ -564,6 +555,17 @@ def test_config4_end_to_end_vs_reference_arithmetic(B, oracle_ref, oracle_fma):
         assert 1e-8 < dfused < 1e-4, dfused  # ~2e-6: above 1e-6
     finally:
         ctx.set_arith(K.ARITH_REFERENCE)
+    ens.guided_euler_ll_(Pm, guides)
+    assert np.array_equal(ens.ll, ll)
+    # one pCN iteration of the benchmarked step
+    ens.pcn_step_(Pm, guides, rho, seed, 0)
+    llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted
+    flips = 0
+    for p in range(P):
+        llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(om, og, x0, W[p], rho, seed, 0, p)
+        assert lu == logu[p] and abs(llp[p] - llo) <= 1e-9 * abs(llo)
+        flips += int(bool(flags[p]) != (lu <= llo - ll[p]))
+    assert flips == 0
     print(f"config-4 end to end vs reference arithmetic: max rel dll {worst_ll:.2e}, max |dX| {worst_x:.2e}; "
           f"fused-order tables would move ll by {dfused:.2e}")
     ens.close()

@@ -467,6 +467,28 @@ def test_pcn_bench_driver_matches_stepwise(oracle_ref):
     assert 0 <= acc <= 20 and secs >= 0
 
 
+def test_tuned_baseline_driver_is_the_same_algorithm(oracle_ref, oracle_fma):
+    """bench.py's CPU baseline runs a driver specialised for the FitzHugh-Nagumo / PartialBridgeνH workload (inlined
+    2-d arithmetic, batched normals, every Philox call fully used).  In the contraction-free builds it must reproduce the
+    generic restatement BIT FOR BIT: same acceptance count, same final log-likelihoods."""
+    T = 0.5
+    s = np.linspace(0, T, 97)
+    P = O.make_model(O.FHN_HYPO, 2, 1, [0.1, 0.0, 1.5, 0.8, 0.3])
+    for orc in (oracle_ref, oracle_fma):
+        guides = []
+        nu, Hp = np.zeros(2), np.eye(2) / 1e-3
+        nu, Hp = orc.gpupdate_nuH(nu, Hp, [[1.0, 0.0]], [[1e-4]], [-0.5])
+        for t0, v in ((0.5, -0.5), (0.0, -1.0)):
+            tt = t0 + s * (2 - s / T)
+            Bt = np.array([[10.0, -10.0], [1.5, -1.0]]); bet = np.array([0.0 - v ** 3 / 0.1, 0.8])
+            nut, Ht, nu, Hp, _ = orc.backward_nuH(O.ODE_LYAP, tt, O.const_aux(Bt, bet, [[0.0, 0.0], [0.0, 0.09]]), nu, Hp)
+            guides.insert(0, O.GuideHolder(O.GUIDE_NUH, tt, Ht, nut, Bt=Bt, betat=bet))
+            nu, Hp = orc.gpupdate_nuH(nu, Hp, [[1.0, 0.0]], [[1e-4]], [-1.0])
+        a1, _, l1 = orc.pcn_bench(P, guides, 24, [-0.5, -0.6], 0.95, 11, 5, nthreads=2)
+        a2, _, l2 = orc.pcn_bench_fhn_tuned(P, guides, 24, [-0.5, -0.6], 0.95, 11, 5, nthreads=2)
+        assert a1 == a2 and np.array_equal(l1, l2) and 0 < a1 < 24 * 5
+
+
 # --------------------------------------------------------------------------- the two oracle builds
 def test_ref_and_fma_builds_agree_to_rounding(oracle_ref, oracle_fma):
     """Contraction sensitivity of the FHN hypoelliptic bridge: reference arithmetic vs the kernels'
