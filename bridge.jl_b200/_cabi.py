@@ -31,6 +31,7 @@ CUR, PROP = 0, 1
 F_LL, F_LL_PROP, F_LOGU, F_XEND, F_XEND_PROP = range(5)
 RUN_STORE_X, RUN_NO_LL = 1, 2
 ARITH_REFERENCE, ARITH_FUSED = 0, 1
+PCN_AUTO, PCN_ONE_THREAD, PCN_WARP_SPECIALISED = 0, 1, 2
 SCHEME_EULER, SCHEME_STRATONOVICH, SCHEME_HEUN, SCHEME_SRK, SCHEME_MDB = range(5)
 
 
@@ -87,6 +88,7 @@ def _load():
         "bb_ctx_set_timing": (C.c_int, [vp, C.c_int]),
         "bb_ctx_last_kernel_ms": (dbl, [vp]),
         "bb_ctx_set_arith": (C.c_int, [vp, C.c_int]),
+        "bb_ctx_set_pcn_kernel": (C.c_int, [vp, C.c_int]),
         "bb_ens_create": (C.c_int, [vp, i64, i32, i32, i32, i32, u32, pp]),
         "bb_ens_destroy": (C.c_int, [vp]),
         "bb_ens_set_chain_offset": (C.c_int, [vp, i64]),

@@ -57,6 +57,10 @@ class Context:
         restatement in reference arithmetic) or K.ARITH_FUSED (the per-chain kernels' explicit fused multiply-adds)."""
         check(lib.bb_ctx_set_arith(self.h, arith))
 
+    def set_pcn_kernel(self, mode: int):
+        """K.PCN_AUTO (default) / K.PCN_ONE_THREAD / K.PCN_WARP_SPECIALISED: which kernel runs pcn_step_ (same results)."""
+        check(lib.bb_ctx_set_pcn_kernel(self.h, mode))
+
     @property
     def last_kernel_ms(self) -> float:
         return lib.bb_ctx_last_kernel_ms(self.h)

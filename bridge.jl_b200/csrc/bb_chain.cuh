@@ -250,13 +250,20 @@ struct bb_chain {
     constexpr int NPIECE = BB_TC * DP / 4;
     bb_rowout<D> xo;
     const int N = a.N;
+    /* pipelined where the launch is memory bound (paths stored); the compute-bound pCN without X° (RNG 3) keeps the
+     * noise of a group next to its own steps (measured: 4.3 ms vs 5.0 ms pipelined at 2.5e5 chains) */
+    constexpr bool PIPE = (RNG != 3);
     double wg[4 * DP], wn[4 * DP];
-    gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, 0, row_lo, row_hi, wact, wg);
+    if constexpr (PIPE) gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, 0, row_lo, row_hi, wact, wg);
     /* groups of 4 grid points: the body is unrolled over one group only, which bounds code size and the
      * registers the scheduler spends on hoisted shared-memory loads */
 #pragma unroll 1
     for (int h = 0; h < BB_TC / 4; h++) {
-      if (h + 1 < BB_TC / 4) gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, h + 1, row_lo, row_hi, wact, wn);
+      if constexpr (PIPE) {
+        if (h + 1 < BB_TC / 4) gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, h + 1, row_lo, row_hi, wact, wn);
+      } else {
+        gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, h, row_lo, row_hi, wact, wg);
+      }
 #pragma unroll
       for (int s4 = 0; s4 < 4; s4++) {
         const int slot = 4 * h + s4;
@@ -288,8 +295,10 @@ struct bb_chain {
           xo.put(xout_row + 4 * h * D, s4, st.y, xact);
         }
       }
+      if constexpr (PIPE) {
 #pragma unroll
-      for (int i = 0; i < 4 * DP; i++) wg[i] = wn[i];
+        for (int i = 0; i < 4 * DP; i++) wg[i] = wn[i];
+      }
       if constexpr (XBUF) {
         /* a 128-byte window of X° is complete: write it back to back (whole line) */
         if (((4 * h + 3) % XWIN) == XWIN - 1 && xact) {
@@ -581,6 +590,9 @@ static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <class M, int GK, int GM, int AUXM, int RNG>
+static cudaError_t bb_chain_ws_launch(const bb_chain_args& a, cudaStream_t st); /* bb_chain_ws.cuh */
+
 template <class M, int GK, int GM>
 static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
   if (rng == 0) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 0>
@@ -589,6 +601,11 @@ static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
                                  : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 1> : &bb_chain_launch<M, GK, GM, 2, 1>);
   if (rng == 3) return auxm == 1 ? &bb_chain_launch<M, GK, GM, 1, 3>
                                  : (auxm == 0 ? &bb_chain_launch<M, GK, GM, 0, 3> : &bb_chain_launch<M, GK, GM, 2, 3>);
+  /* 5: pCN with X° stored (mode 1) as the warp-specialised kernel (bb_chain_ws.cuh), scalar-noise models */
+  if constexpr (M::DP == 1) {
+    if (rng == 5) return auxm == 1 ? &bb_chain_ws_launch<M, GK, GM, 1, 1>
+                                   : (auxm == 0 ? &bb_chain_ws_launch<M, GK, GM, 0, 1> : &bb_chain_ws_launch<M, GK, GM, 2, 1>);
+  }
   return nullptr;
 }
 template <class M>
@@ -611,3 +628,5 @@ static bb_chain_launch_fn bb_lookup_model(int gk, int gm, int auxc, int rng) {
   }
   return nullptr;
 }
+
+#include "bb_chain_ws.cuh" /* the warp-specialised pCN kernel (defined in terms of bb_chain) */

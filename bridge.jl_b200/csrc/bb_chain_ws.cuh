@@ -1,0 +1,342 @@
+/*
+ * bb_chain_ws.cuh -- the pCN iteration as a WARP-SPECIALISED kernel: two threads per chain.
+ *
+ * One pCN step of a chain is two instruction streams of about equal length:
+ *   noise     sample!(W2, Wiener()) and Wo.yy .= rho*W.yy + sqrt(1-rho^2)*W2.yy   (src/wiener.jl:50-58,
+ *             test/partialbridgenuH.jl:178): Philox4x32-10, float32 Box-Muller, the running sum W2, W° -- INT / FP32 /
+ *             a few fp64 operations, independent of the chain's state;
+ *   dynamics  solve!(Euler(), Xo, x0, Wo, Po) + llikelihood(LeftRule(), Xo, Po)    (src/euler.jl:247-268,
+ *             src/partialbridgenuH.jl:171-189): the dependent fp64 chain of the guided Euler steps.
+ * In bb_chain_kernel one thread runs both, and a warp is stalled on fixed-latency dependencies most of the time
+ * (ncu: 52-58 % of the issue slots used, `wait` the top stall): at full size the memory system hides it, at the
+ * strong-scaling share of a GPU (31 250 chains = 6.6 warps per SM) nothing does.  Here the upper half of a CTA's warps
+ * are NOISE warps and the lower half DYNAMICS warps; warp pair k serves the same 32 chains.  The noise warp brings the
+ * chains' rows of W into shared memory (cp.async, BB_WS_PF chunks ahead), turns them into W° in place, hands the row to
+ * its dynamics warp through an mbarrier (full / empty per ring slot, BB_WS_WST slots) and writes the finished row back as
+ * whole 128-byte lines; the dynamics warp consumes the row, steps the chain and writes X°.  Twice the warps, each with
+ * half the instructions: the data, the arithmetic and every rounding are those of bb_chain_kernel (bit-identical
+ * results; the GPU tests run both).
+ *
+ * Measured (B200, FitzHugh-Nagumo config 4, profiles/r02_ws_ab.txt): 31 250 chains 0.929 -> 0.880 ms; 250 000 chains
+ * 5.93 ms either way (memory bound); without X° and for d' >= 2 the one-thread kernel is faster.  The library therefore
+ * launches this kernel for scalar-noise models with X° stored when the ensemble is SMALL (fewer than 2 CTAs of 128
+ * chains per SM), and bb_chain_kernel otherwise.  What still limits the small case is the dynamics warp itself: a
+ * serial chain of ~32 dependent fp64 operations per step at ~8 cycles each (no-noise experiment: 0.82 ms).
+ */
+#pragma once
+#include "bb_chain.cuh"
+
+#ifndef BB_WS_WST
+#define BB_WS_WST 4     /* slots of the W ring of a warp pair */
+#endif
+#ifndef BB_WS_PF
+#define BB_WS_PF 2      /* chunks the noise warp requests its rows ahead (a chunk of noise work is shorter than the DRAM latency) */
+#endif
+#define BB_WS_MAXPAIR 4 /* warp pairs per CTA (256 threads) */
+
+template <class M, int GK, int GM, int AUXM, int RNG>
+struct bb_chain_ws {
+  static_assert(RNG == 1 || RNG == 3, "pCN modes only");
+  using Dyn = bb_chain<M, GK, GM, AUXM, 0>; /* the dynamics warp runs the read-W chunk of the one-thread kernel */
+  static constexpr int D = M::D, DP = M::DP, REC = Dyn::REC;
+  static constexpr bool SX = (RNG == 1);
+  static constexpr int WROWP = BB_TC * DP, NPIECE = BB_TC * DP / 4;
+  /* mbarriers: table ring full / empty, then W ring full / empty per (pair, slot); padded to whole 128-byte lines */
+  static constexpr int BAR_BYTES = ((2 * BB_STAGES + 2 * BB_WS_MAXPAIR * BB_WS_WST) * 8 + 127) / 128 * 128;
+
+  static __host__ __device__ constexpr size_t smem_bytes(int nt) {
+    return (size_t)BB_STAGES * BB_TSTAGE * BB_TC * REC * 8 + BAR_BYTES +
+           (size_t)BB_WS_WST * (nt / 2) * WROWP * 8 + (Dyn::XBUF ? (size_t)(nt / 2) * 128 : 0);
+  }
+
+  /* W° of one chunk: every piece of the chain's staged row is replaced in place (pieces in time order: the running
+   * sum W2 is sequential) */
+  template <bool FIRST>
+  static __device__ __forceinline__ void noise_chunk(const bb_chain_args& a, const double* __restrict__ rec, double* w2,
+                                                     double* wrow, int c, uint32_t row_lo, uint32_t row_hi) {
+#pragma unroll 1
+    for (int h = 0; h < BB_TC / 4; h++) {
+#pragma unroll
+      for (int pp = 0; pp < DP; pp++) {
+        const int q = h * DP + pp, m = 4 * pp;
+        double wq[4];
+        bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+        float z[4];
+        bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int sl = 4 * h + (m + i) / DP, kk = (m + i) % DP;
+          const bool first = FIRST && (sl == 0);
+          const double rootdt = rec[sl * REC + 1];
+          /* W2[j] = W2[j-1] + sqrt(dt) xi ;  W°[j] = rho W[j] + sqrt(1-rho^2) W2[j] */
+          if (!first) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);
+          wq[i] = fma(a.rho2, w2[kk], a.rho * wq[i]);
+        }
+        bb_sts4_swz(wrow, 2 * q, threadIdx.x & 7, wq);
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void run(const bb_chain_args& a) {
+    constexpr uint32_t CHUNK_DOUBLES = BB_TC * REC;
+    constexpr uint32_t STAGE_DOUBLES = BB_TSTAGE * CHUNK_DOUBLES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NW = blockDim.x >> 5, NPAIR = NW >> 1, CH = blockDim.x >> 1;
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BB_STAGES * STAGE_DOUBLES);
+    uint64_t* empty = full + BB_STAGES;
+    uint64_t* wfull = empty + BB_STAGES;                  /* [pair][slot] */
+    uint64_t* wempty = wfull + BB_WS_MAXPAIR * BB_WS_WST;
+    double* wstage = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(full) + BAR_BYTES);
+    double* xbuf_all = wstage + (size_t)BB_WS_WST * CH * WROWP;
+
+    const int S = a.S, NC = a.NC;
+    const int NST = (NC + BB_TSTAGE - 1) / BB_TSTAGE;
+    const int T = S * NST;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool noise = warp >= NPAIR;
+    const int pair = noise ? warp - NPAIR : warp;
+    const int ci = pair * 32 + lane; /* chain of this thread within the CTA */
+
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < BB_STAGES; i++) {
+        bb_mbar_init(&full[i], 1);
+        bb_mbar_init(&empty[i], NW);
+      }
+      for (int i = 0; i < BB_WS_MAXPAIR * BB_WS_WST; i++) {
+        bb_mbar_init(&wfull[i], 1);
+        bb_mbar_init(&wempty[i], 1);
+      }
+      bb_mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long P = a.P;
+    const long long p = a.p_begin + (long long)blockIdx.x * CH + ci;
+    const long long pc = p < a.p_end ? p : a.p_end - 1;
+    const bool act = p < a.p_end && (!a.only || a.only[pc] != 0);
+    const int par = a.par[pc];
+    const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
+    const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+    const int TW = S * NC;
+    uint64_t* my_full = wfull + pair * BB_WS_WST;
+    uint64_t* my_empty = wempty + pair * BB_WS_WST;
+    double* wslot = wstage + (size_t)ci * WROWP; /* + slot * CH * WROWP */
+
+    /* table ring: thread 0 produces (1-D TMA bulk copies), every warp of the CTA consumes */
+    int issued = 0, iseg = 0, ist_in_seg = 0;
+    int stage = 0, gs = 0;
+    bool tab_ready = false;
+    uint32_t phase = 0;
+    const double* rec = ring;
+    auto tab_acquire = [&](int c) {
+      if ((c % BB_TSTAGE) == 0) {
+        if (threadIdx.x == 0) {
+          while (issued < T && issued <= gs + BB_LOOKAHEAD) {
+            const int ist = issued % BB_STAGES;
+            if (issued >= BB_STAGES) bb_mbar_wait(&empty[ist], ((issued / BB_STAGES) - 1) & 1);
+            const int c0 = ist_in_seg * BB_TSTAGE;
+            const int nch = (NC - c0 < BB_TSTAGE) ? NC - c0 : BB_TSTAGE;
+            const uint32_t bytes = (uint32_t)nch * CHUNK_DOUBLES * 8;
+            bb_mbar_expect_tx(&full[ist], bytes);
+            bb_tma_load_1d(ring + ist * STAGE_DOUBLES, a.tab[iseg] + (size_t)c0 * CHUNK_DOUBLES, bytes, &full[ist]);
+            issued++;
+            if (++ist_in_seg == NST) { ist_in_seg = 0; iseg++; }
+          }
+        }
+        __syncwarp();
+        if (!tab_ready) bb_mbar_wait(&full[stage], phase);
+        rec = ring + stage * STAGE_DOUBLES;
+      }
+    };
+    auto tab_probe = [&](int c) { /* non-blocking look at the next stage, one chunk before it is needed */
+      if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
+        const int nst = (stage + 1 == BB_STAGES) ? 0 : stage + 1;
+        const uint32_t nph = (stage + 1 == BB_STAGES) ? phase ^ 1 : phase;
+        tab_ready = (gs + 1 < T) ? bb_mbar_test(&full[nst], nph) : true;
+      }
+    };
+    auto tab_release = [&](int c) {
+      rec += CHUNK_DOUBLES;
+      if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
+        __syncwarp();
+        if (lane == 0) bb_mbar_arrive(&empty[stage]);
+        if (++stage == BB_STAGES) { stage = 0; phase ^= 1; }
+        gs++;
+      }
+    };
+
+    if (noise) {
+      /* ================================================================== NOISE warp */
+      /* cooperative copy of the warp's 32 rows, mapping as in bb_chain::run: one cp.async instruction requests whole
+       * 128 d'-byte rows (whole L2 lines even though neighbouring chains read different buffers) */
+      constexpr int NCP = BB_TC * DP / 2;
+      const unsigned amask = __ballot_sync(0xFFFFFFFFu, act);
+      const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
+      const long long warp_p0 = a.p_begin + (long long)blockIdx.x * CH + pair * 32;
+      const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP);
+      constexpr bool COOP_FAST = (32 % NCP == 0);
+      constexpr int CPI = COOP_FAST ? 32 / NCP : 1;
+      const uint32_t l_cw = (uint32_t)lane / NCP, l_pc = (uint32_t)lane % NCP;
+      uint32_t parbits = 0, actbits = 0;
+#pragma unroll
+      for (int r = 0; r < NCP; r++) {
+        const uint32_t cw = COOP_FAST ? CPI * r + l_cw : (32u * r + lane) / NCP;
+        parbits |= ((pmask >> cw) & 1u) << r;
+        actbits |= ((amask >> cw) & 1u) << r;
+      }
+      const uint32_t src_l = l_cw * wrow_d + 2 * l_pc;
+      constexpr int NSW = COOP_FAST ? (8 / CPI > 0 ? 8 / CPI : 1) : 1;
+      uint32_t dsw[NSW];
+#pragma unroll
+      for (int i = 0; i < NSW; i++) {
+        const uint32_t cw = CPI * i + l_cw;
+        dsw[i] = (pair * 32 + l_cw) * WROWP + 2 * ((l_pc & ~7u) | ((l_pc ^ cw) & 7u));
+      }
+      const double* wsrc = a.W[0] + warp_p0 * wrow_d;
+      auto w_issue = [&](int gc) {
+        if (gc < TW) {
+          double* dst = wstage + (size_t)(gc % BB_WS_WST) * CH * WROWP;
+          if constexpr (COOP_FAST) {
+            const double* src = wsrc + (long long)gc * wstride + src_l;
+#pragma unroll
+            for (int r = 0; r < NCP; r++) {
+              const uint32_t poff = ((parbits >> r) & 1u) * (uint32_t)(BB_TC * DP);
+              if ((actbits >> r) & 1u)
+                bb_cp_async16(dst + dsw[r % NSW] + r * (CPI * WROWP), src + (r * CPI * wrow_d + poff));
+            }
+          } else {
+            const double* src = wsrc + (long long)gc * wstride;
+#pragma unroll
+            for (int r = 0; r < NCP; r++) {
+              const uint32_t t = 32u * r + lane, cw = t / NCP, piece = t % NCP;
+              if ((amask >> cw) & 1u)
+                bb_cp_async16(dst + (pair * 32 + cw) * WROWP + 2 * ((piece & ~7u) | ((piece ^ cw) & 7u)),
+                              src + (cw * wrow_d + ((pmask >> cw) & 1u) * (BB_TC * DP) + 2 * piece));
+            }
+          }
+        }
+        bb_cp_async_commit();
+      };
+      /* the proposal goes to the buffer the chain does NOT read from */
+      double* ww = a.W[1 - par] + pc * (a.nbuf * BB_TC * DP);
+      double w2[DP];
+#pragma unroll 1
+      for (int i = 0; i < BB_WS_PF; i++) w_issue(i);
+      int g = 0;
+      for (int s = 0; s < S; s++) {
+        const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
+        const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
+#pragma unroll
+        for (int k = 0; k < DP; k++) w2[k] = 0.0;
+        for (int c = 0; c < NC; c++, g++) {
+          tab_acquire(c);
+          /* request the rows of chunk g+PF: their slot was last used by chunk g+PF-WST, which the dynamics warp must have
+           * consumed and this warp must have written back (program order + the warp barrier) */
+          __syncwarp();
+          if (g + BB_WS_PF < TW && g + BB_WS_PF >= BB_WS_WST)
+            bb_mbar_wait(&my_empty[(g + BB_WS_PF) % BB_WS_WST], (((g + BB_WS_PF) / BB_WS_WST) - 1) & 1);
+          w_issue(g + BB_WS_PF);
+          bb_cp_async_wait<BB_WS_PF>(); /* chunk g has landed (everything but the newest PF groups) */
+          __syncwarp();
+          tab_probe(c);
+          double* wrow = wslot + (size_t)(g % BB_WS_WST) * CH * WROWP;
+          if (c == 0) noise_chunk<true>(a, rec, w2, wrow, c, row_lo, row_hi);
+          else noise_chunk<false>(a, rec, w2, wrow, c, row_lo, row_hi);
+          __syncwarp();
+          if (lane == 0) bb_mbar_arrive(&my_full[g % BB_WS_WST]); /* release: the dynamics warp may read the row */
+          if (act) { /* the chain's row of W° is complete: write its 128 d' bytes back to back (whole lines) */
+#pragma unroll
+            for (int q = 0; q < NPIECE; q++) {
+              double v[4];
+              bb_lds4_swz(wrow, 2 * q, threadIdx.x & 7, v);
+              bb_st4(ww + 4 * q, v[0], v[1], v[2], v[3]);
+            }
+          }
+          ww += wstride;
+          tab_release(c);
+        }
+      }
+      return;
+    }
+
+    /* ==================================================================== DYNAMICS warp */
+    typename Dyn::state st;
+#pragma unroll
+    for (int k = 0; k < D; k++) st.y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
+    st.som = 0.0;
+    double lltot = 0.0;
+    const bool xact = act && SX;
+    double* xw = SX ? a.X + pc * (BB_TC * D) : nullptr;
+    double* xbuf = xbuf_all + (size_t)ci * 16;
+    double wq[4] = {0.0, 0.0, 0.0, 0.0};
+    int g = 0;
+    for (int s = 0; s < S; s++) {
+      const double* sc = a.segc[s];
+      st.som = 0.0;
+      for (int c = 0; c < NC; c++, g++) {
+        tab_acquire(c);
+        bb_mbar_wait(&my_full[g % BB_WS_WST], (g / BB_WS_WST) & 1); /* acquire: W° of chunk g is in the slot */
+        tab_probe(c);
+        double* wrow = wslot + (size_t)(g % BB_WS_WST) * CH * WROWP;
+        const bool generic = (c == 0) || (c == NC - 1) || (c * BB_TC + BB_TC - 1 > a.jll);
+        if (generic)
+          Dyn::template chunk<true>(a, rec, sc, st, wq, wrow, nullptr, xw, xbuf, c, 0u, 0u, false, xact);
+        else
+          Dyn::template chunk<false>(a, rec, sc, st, wq, wrow, nullptr, xw, xbuf, c, 0u, 0u, false, xact);
+        __syncwarp();
+        if (lane == 0) bb_mbar_arrive(&my_empty[g % BB_WS_WST]);
+        xw += xstride;
+        tab_release(c);
+      }
+      lltot += st.som;
+    }
+    /* ---- per-chain epilogue: accept iff log(U) <= ll° - ll   (test/partialbridgenuH.jl:183) */
+    const double logu = bb_accept_logu(a.keys, a.stream, chain);
+    const double llc = a.ll[pc];
+    const bool ok = act && (logu <= lltot - llc);
+    if (act) {
+      a.llprop[p] = lltot;
+      a.logu[p] = logu;
+      a.accepted[p] = ok ? 1 : 0;
+      a.xstale[p] = SX ? (ok ? 0 : 1) : (uint8_t)(a.xstale[p] | (ok ? 1 : 0));
+#pragma unroll
+      for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = st.y[k];
+      if (ok) {
+        a.ll[p] = lltot;
+        a.par[p] = (uint8_t)(1 - par);
+#pragma unroll
+        for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = st.y[k];
+      }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+    if (lane == 0 && m) atomicAdd(a.acc, (unsigned long long)__popc(m));
+  }
+};
+
+template <class M, int GK, int GM, int AUXM, int RNG>
+__global__ void __launch_bounds__(BB_THREADS, bb_min_ctas<M>()) bb_chain_ws_kernel(const __grid_constant__ bb_chain_args a) {
+  bb_chain_ws<M, GK, GM, AUXM, RNG>::run(a);
+}
+
+/* CTA size: 256 threads (128 chains) when that still gives every SM two CTAs, else 128 threads (64 chains) so that a
+ * small ensemble -- the strong-scaling share of a GPU -- spreads over all SMs */
+template <class M, int GK, int GM, int AUXM, int RNG>
+static cudaError_t bb_chain_ws_launch(const bb_chain_args& a, cudaStream_t st) {
+  using K = bb_chain_ws<M, GK, GM, AUXM, RNG>;
+  static std::atomic<unsigned long long> attr_done{0};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 64 || !((attr_done.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(bb_chain_ws_kernel<M, GK, GM, AUXM, RNG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::smem_bytes(BB_THREADS));
+    if (e != cudaSuccess) return e;
+    if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+  const long long n = a.p_end - a.p_begin;
+  const int nt = (n + 127) / 128 >= 2ll * sms ? 256 : 128;
+  const unsigned grid = (unsigned)((n + nt / 2 - 1) / (nt / 2));
+  bb_chain_ws_kernel<M, GK, GM, AUXM, RNG><<<grid, nt, K::smem_bytes(nt), st>>>(a);
+  return cudaGetLastError();
+}

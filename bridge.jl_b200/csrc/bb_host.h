@@ -22,6 +22,7 @@ struct bb_ctx {
   bool ev_valid = false;
   int sm_count = 0;
   int live = 0;  /* ensembles + guides created on this context and not yet destroyed (bb_ctx_destroy refuses while > 0) */
+  int pcn_kernel = 0; /* BB_PCN_AUTO / BB_PCN_ONE_THREAD / BB_PCN_WARP_SPECIALISED */
   int arith = 0; /* BB_ARITH_REFERENCE / BB_ARITH_FUSED: rounding order of the shared-table constructors */
   /* staging for host <-> device transposes */
   double* stage = nullptr;

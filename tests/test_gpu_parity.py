@@ -382,6 +382,59 @@ def test_pcn_replay_bit_exact(B, oracle_fma):
     ens.close()
 
 
+@pytest.mark.parametrize("model", ["fhn", "intdiff"])
+def test_pcn_kernels_agree_bit_for_bit(B, model):
+    """bb_pcn_step has two kernels for scalar-noise models with X° stored -- one thread per chain, and the
+    warp-specialised one (noise warps + dynamics warps) the library picks for small ensembles.  Same seeds, same state:
+    W°, X°, ll°, log U, flags, surviving state and acceptance counter must be identical, over several iterations, for a
+    ragged ensemble size, a skip and a tabulated auxiliary drift."""
+    K = B.api.K
+    ctx = B.default_context()
+    N, P, S = 83, 333, 3
+    grids = [warped(0.5 * s, 0.5 * (s + 1), N) for s in range(S)]
+    if model == "fhn":
+        Pm = B.FitzhughDiffusion(*FHN_PAR)
+        obs = (-1.0, -0.5, 0.5)
+        ν, Hp = np.zeros(2), np.eye(2) / 1e-3
+        ν, Hp = B.gpupdate_νH(ν, Hp, [[1.0, 0.0]], [[1e-4]], [obs[-1]])
+        guides = [None] * S
+        for i in range(S - 1, -1, -1):
+            Bt, bt, at = fhn_aux(obs[i])
+            guides[i], ν, Hp, _ = B.partialbridgeνH(grids[i], Pm, B.LinearAux(Bt, bt, at), ν, Hp)
+            if i > 0:
+                ν, Hp = B.gpupdate_νH(ν, Hp, [[1.0, 0.0]], [[1e-4]], [obs[i - 1]])
+        x0, skip = [-0.5, -0.6], 0
+    else:  # time-dependent auxiliary process (tabulated B~, beta~) and a skip
+        Pm = B.IntegratedDiffusion(0.7)
+        Pt = B.LinearAux(lambda t: np.array([[0.0, 1.0], [0.0, -1.0 - 0.1 * t]]), lambda t: np.array([0.0, 0.5]),
+                         lambda t: np.array([[0.0, 0.0], [0.0, 0.49]]))
+        guides = [B.PartialBridgeνH(g, Pm, Pt, [[1.0, 0.0]], [2.5 - 0.2 * s], 1e-3, [[0.1]]) for s, g in enumerate(grids)]
+        x0, skip = [2.0, 1.0], 2
+    out = {}
+    try:
+        for mode in (K.PCN_ONE_THREAD, K.PCN_WARP_SPECIALISED):
+            ctx.set_pcn_kernel(mode)
+            ens = B.PathEnsemble(P, S, N, 2, 1, chain_offset=77)
+            for s in range(S):
+                ens.set_grid(s, grids[s])
+            ens.set_start(x0); ens.sample_(9, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides, skip=skip)
+            rec = []
+            for it in range(4):
+                ens.pcn_step_(Pm, guides, 0.9, 9, it, skip=skip)
+                rec.append((ens.download(B.W, which=B.PROP), ens.download(B.X, which=B.PROP), ens.ll_prop, ens.logu,
+                            ens.accepted, ens.ll, ens.xend_prop))
+            rec.append((ens.download(B.W), ens.download(B.X), ens.acc))
+            out[mode] = rec
+            ens.close()
+    finally:
+        ctx.set_pcn_kernel(K.PCN_AUTO)
+    a, b = out[K.PCN_ONE_THREAD], out[K.PCN_WARP_SPECIALISED]
+    for ra, rb in zip(a, b):
+        for xa, xb in zip(ra, rb):
+            assert np.array_equal(xa, xb)
+    assert 0 < a[-1][2] < 4 * P
+
+
 def test_pcn_against_reference_arithmetic(B, oracle_ref):
     """The same iteration against the reference arithmetic (no fma): ll° within 1e-6 relative, decisions
     replayed from the kernel's own ll values are exact, flips against the oracle's ll are counted."""
