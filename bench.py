@@ -383,7 +383,10 @@ def main():
     steps_all = allsum(steps_rank)
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.time()
+    while not sampler.lines and time.time() - t_wait < 5.0:  # nvidia-smi takes a moment to deliver its first sample
+        time.sleep(0.05)
+    time.sleep(0.2)
     barrier()
     launches0 = ctx.launch_count
     acc0 = ens.acc
