@@ -325,6 +325,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
+    # libraries (NCCL's version banner, ...) write to fd 1: keep the real stdout for the ONE JSON line, send the rest
+    # to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -485,17 +490,19 @@ def main():
         barrier()
         e0.record(stream)
         nres = args.e2e_steps * 2
+        Pm2, chain, _, _ = cfg.fhn_config4_chain(n, ctx=ctx)
         for _ in range(nres):
-            Pm2, guides2, _, _ = cfg.fhn_config4(n, ctx=ctx)  # backward ODEs + table upload every step
-            ens.pcn_step_(Pm2, guides2, rho, 4, it); it += 1
+            cfg.fhn_config4_chain(n, ctx=ctx, chain=chain)  # the backward pass of all 4 segments: one launch, in place
+            ens.pcn_step_(Pm2, chain.segments, rho, 4, it); it += 1
             _ = ens.ll_prop, ens.accepted, ens.acc
         e1.record(stream)
         barrier()
         ems = allmax(e0.elapsed_time(e1))
         e2e["resident"] = {"value": steps_all * nres / (ems * 1e-3),
                            "unit": "path-steps/s", "d2h_bytes_per_step": P * 9 + 8, "steps": nres,
-                           "what": "chain state stays in HBM (PathEnsemble); per step: rebuild + upload the 4 guide "
-                                   "tables, bb_pcn_step, read back ll°, accept flags, acc"}
+                           "what": "chain state stays in HBM (PathEnsemble); per step: rebuild the 4 guide tables on the "
+                                   "device (bb_guides_chain_nuH, one launch, in place), bb_pcn_step, read back ll°, "
+                                   "accept flags, acc"}
     elif not args.no_e2e:
         # configs 2 / 3 / 5 through the public API with host arrays: W up (pinned), step, X and ll down
         k_w, k_x = ens.dprime, ens.d
@@ -550,7 +557,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "acc_rate": acc_rate,
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if comm:
         comm.close()
     ens.close()

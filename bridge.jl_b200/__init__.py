@@ -13,4 +13,4 @@ from .api import (Context, default_context, PathEnsemble, SamplePath, VSamplePat
                   EulerMaruyama, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
                   LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde, BolusDiffusion,
                   LinearAux, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,
-                  PartialBridge, GuideTables)  # noqa: F401
+                  PartialBridge, GuideTables, PartialBridgeνHChain)  # noqa: F401

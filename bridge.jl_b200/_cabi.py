@@ -119,6 +119,9 @@ def _load():
         "bb_backward_FH": (C.c_int, [vp, i32, i32, vp, C.POINTER(Aux), vp, vp, dbl, vp, vp, C.POINTER(dbl)]),
         "bb_backward_HV": (C.c_int, [vp, i32, i32, vp, C.POINTER(Aux), vp, vp, vp, vp]),
         "bb_backward_LMmu": (C.c_int, [vp, i32, i32, i32, vp, C.POINTER(Aux), vp, vp, vp, vp, vp]),
+        "bb_guides_chain_nuH": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, C.POINTER(Aux), vp, vp, vp, dbl, pp, vp, vp,
+                                          C.POINTER(dbl)]),
+        "bb_guide_download_nuH": (C.c_int, [vp, vp, vp]),
         "bb_lptilde_nuH": (C.c_int, [vp, i32, vp, vp, dbl, vp, C.POINTER(dbl)]),
         "bb_lptilde_HV": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, C.POINTER(dbl)]),
         "bb_guided_euler_ll": (C.c_int, [vp, C.POINTER(Model), pp, i32, u32]),

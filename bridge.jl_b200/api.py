@@ -887,6 +887,82 @@ def partialbridgeνH(tt, P, Pt, νend, Hendp, ctx=None):
 partialbridgenuH = partialbridgeνH
 
 
+class _ChainSegment(_Proposal):
+    """One segment of a PartialBridgeνHChain: a PartialBridgeνH whose tables live on the device only; ν and H are read
+    back on first use (values at grid points 0 .. N-2; the terminal values are not kept by the path kernels: NaN)."""
+    kind = K.GUIDE_NUH
+    constdiff = True
+
+    def __init__(self, ctx, tt, P, Pt, handle):
+        self.ctx, self.tt, self.Target, self.Pt, self._guide = ctx, tt, P, Pt, handle
+        self._tab = None
+
+    def _fetch(self):
+        if self._tab is None:
+            N, d = len(self.tt), self.Target.d
+            ν = np.empty((N, d)); H = np.empty((N, d, d))
+            check(lib.bb_guide_download_nuH(self._guide, ptr(ν), ptr(H)))
+            self._tab = (ν, H)
+        return self._tab
+
+    @property
+    def ν(self):
+        return self._fetch()[0]
+
+    @property
+    def H(self):
+        return self._fetch()[1]
+
+
+class PartialBridgeνHChain:
+    """The backward pass of a chain of segments -- the script loop of partialbridge_bolus3.jl:162-180 -- as ONE device
+    launch (bb_guides_chain_nuH): ν = 0, H⁺ = I/ϵ right of the last observation, gpupdate with vs[-1], then for every
+    segment from right to left `partialbridgeνH` (Lyapunov step) and the observation update.  The guiding tables are
+    written where the path kernels read them; `update_` re-runs the pass in place for new auxiliary processes /
+    observations (a parameter update of the sampler) without any table traffic to or from the host.
+    `segments` are proposals usable wherever a PartialBridgeνH is (guided_euler_ll_, pcn_step_, ...)."""
+
+    def __init__(self, grids, P, Pts, L, Σ, vs, ϵ, method=Lyap, ctx=None):
+        self.ctx = ctx or default_context()
+        self.Target = P
+        self.tt = f64(np.stack([f64(g) for g in grids]))
+        self.S, self.N = self.tt.shape
+        self.L = np.atleast_2d(f64(L)); self.m, self.d = self.L.shape
+        self.Σ = np.atleast_2d(f64(Σ)); self.ϵ = float(ϵ)
+        self.method = K.ODE_LYAP if method in (Lyap, K.ODE_LYAP) or isinstance(method, Lyap) else K.ODE_R3
+        self._handles = (C.c_void_p * self.S)()
+        self.segments: List[_ChainSegment] = []
+        self.update_(Pts, vs)
+
+    def update_(self, Pts, vs):
+        vs = f64(np.asarray(vs, dtype=np.float64).reshape(self.S, self.m))
+        auxs = [_AuxC(Pt, self.tt[s]) for s, Pt in enumerate(Pts)]
+        if any(not a.c.is_const for a in auxs):
+            raise BridgeError(K.ERR_UNSUPPORTED, "PartialBridgeνHChain: constant auxiliary processes (one per segment)")
+        arr = (K.Aux * self.S)(*[a.c for a in auxs])
+        νl = np.zeros(self.d); Hl = np.zeros((self.d, self.d)); Cc = C.c_double(0)
+        check(lib.bb_guides_chain_nuH(self.ctx.h, self.method, self.S, self.N, self.d, self.m, ptr(self.tt), arr,
+                                      ptr(self.L), ptr(self.Σ), ptr(vs), self.ϵ, self._handles, ptr(νl), ptr(Hl),
+                                      C.byref(Cc)))
+        if not self.segments:
+            self.segments = [_ChainSegment(self.ctx, self.tt[s], self.Target, Pts[s], C.c_void_p(self._handles[s]))
+                             for s in range(self.S)]
+        else:
+            for s, seg in enumerate(self.segments):
+                seg.Pt, seg._tab = Pts[s], None
+        self.ν_left, self.Hplus_left, self.C = νl, Hl, Cc.value
+        return self
+
+    def __iter__(self):
+        return iter(self.segments)
+
+    def __len__(self):
+        return self.S
+
+    def __getitem__(self, s):
+        return self.segments[s]
+
+
 class GuidedBridge(_Proposal):
     """GuidedBridge(tt, P, Pt, v[, h♢])  src/guip.jl:172-180; fields Target, Pt, tt, H♢, V."""
     kind = K.GUIDE_HV

@@ -60,6 +60,18 @@ def fhn_config4(n: int = 1001, ctx=None, obs_t=FHN_OBS_T, obs_v=FHN_OBS_V):
     return P, guides, FHN_X0.copy(), FHN_RHO
 
 
+def fhn_config4_chain(n: int = 1001, ctx=None, obs_t=FHN_OBS_T, obs_v=FHN_OBS_V, chain=None):
+    """The same proposals as fhn_config4 through the single-launch backward chain (tables stay on the device);
+    `chain` = an existing PartialBridgeνHChain to update in place."""
+    P = B.FitzhughDiffusion(*FHN_PAR)
+    Pts = [B.LinearAux(*fhn_matching_aux(v)) for v in obs_v]
+    if chain is None:
+        chain = B.PartialBridgeνHChain(fhn_segment_grids(n, obs_t), P, Pts, FHN_L, FHN_SIGMA, obs_v, FHN_EPS, ctx=ctx)
+    else:
+        chain.update_(Pts, obs_v)
+    return P, chain, FHN_X0.copy(), FHN_RHO
+
+
 # ---- config 3
 LIN3_B1 = -np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]])
 LIN3_B2 = -np.eye(3)

@@ -384,3 +384,83 @@ extern "C" int bb_lptilde_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt
   *out = o[0];
   return BB_OK;
 }
+
+/* ---- one launch for the backward pass of a whole chain of segments; tables written in place on the device */
+extern "C" int bb_guides_chain_nuH(bb_ctx* ctx, int32_t method, int32_t S, int32_t N, int32_t d, int32_t m,
+                                   const double* tt, const bb_aux* aux, const double* L, const double* Sigma,
+                                   const double* v, double eps, bb_guide** guides, double* nu_left,
+                                   double* Hplus_left, double* C) {
+  if (!ctx) return BB_ERR_NODEVICE;
+  if (d < 1) return BB_ERR_ARG;
+  if (!tt || !aux || !L || !Sigma || !v || !guides || S < 1 || S > BB_MAXSEG || N < 2) return BB_ERR_ARG;
+  if (method != BB_ODE_R3 && method != BB_ODE_LYAP) return BB_ERR_ARG;
+  if (m < 1 || m > d) return BB_ERR_ASSERT_M;
+  if (d > 3) return BB_ERR_UNSUPPORTED;
+  for (int s = 0; s < S; s++)
+    if (aux[s].d != d || !aux[s].is_const || !aux[s].B || !aux[s].beta || !aux[s].a) return BB_ERR_UNSUPPORTED;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  /* guides that do not exist yet are created (time grid rows, auxiliary drift); existing ones must match */
+  std::vector<double> zero((size_t)N * d * d, 0.0);
+  for (int s = 0; s < S; s++) {
+    if (!guides[s]) {
+      int rc = bb_guide_create(ctx, BB_GUIDE_NUH, N, d, 0, tt + (size_t)s * N, zero.data(), zero.data(), nullptr, nullptr,
+                               aux[s].B, aux[s].beta, 1, &guides[s]);
+      if (rc) return rc;
+    } else {
+      bb_guide* g = guides[s];
+      if (g->ctx != ctx || g->kind != BB_GUIDE_NUH || g->N != N || g->d != d || g->auxc != 1) return BB_ERR_ARG;
+      memcpy(g->segc, aux[s].B, sizeof(double) * d * d);          /* the auxiliary drift of this parameter value */
+      memcpy(g->segc + d * d, aux[s].beta, sizeof(double) * d);
+      g->tt.assign(tt + (size_t)s * N, tt + (size_t)(s + 1) * N);
+    }
+  }
+  dev_pack pk;
+  const size_t ott = pk.add(tt, (size_t)S * N);
+  const size_t oin = pk.add(L, m * d);
+  pk.add(Sigma, m * m); pk.add(&eps, 1);
+  for (int s = 0; s < S; s++) {
+    pk.add(v + (size_t)s * m, m); pk.add(aux[s].B, d * d); pk.add(aux[s].beta, d); pk.add(aux[s].a, d * d);
+  }
+  const size_t nout = d + d * d + 1, oout = pk.host.size();
+  int rc = pack_upload(ctx, pk, nout);
+  if (rc) return rc;
+  double* D0 = pk.dev.p;
+  bbk_ref::chain_tabs T;
+  bbk::chain_tabs Tf;
+  memset(&T, 0, sizeof(T)); memset(&Tf, 0, sizeof(Tf));
+  for (int s = 0; s < S; s++) { T.tab[s] = guides[s]->tab; Tf.tab[s] = guides[s]->tab; }
+  const int rec = guides[0]->rec;
+  std::vector<double> out;
+  BB_DM_SWITCH(d, m, rc = run_small(ctx, pk, oout, nout, out, [&](int* st) {
+                 if (ctx->arith == BB_ARITH_FUSED)
+                   bbk::k_chain_nuH<D, M><<<1, 1, 0, ctx->stream>>>(method, S, N, rec, D0 + ott, D0 + oin, Tf, D0 + oout, st);
+                 else
+                   bbk_ref::k_chain_nuH<D, M><<<1, 1, 0, ctx->stream>>>(method, S, N, rec, D0 + ott, D0 + oin, T, D0 + oout, st);
+               }));
+  if (rc) return rc;
+  if (nu_left) memcpy(nu_left, out.data(), sizeof(double) * d);
+  if (Hplus_left) memcpy(Hplus_left, out.data() + d, sizeof(double) * d * d);
+  if (C) *C = out[d + d * d];
+  return BB_OK;
+}
+
+/* ν[N][d], H[N][d][d] (NUH) / V, H♢⁻¹ ... as the path kernels hold them: values on the grid read back from the device
+ * table of a guide (rows 1 .. N-1 carry the values at grid points 0 .. N-2; the terminal values are not stored) */
+extern "C" int bb_guide_download_nuH(bb_guide* g, double* nu, double* H) {
+  if (!g || !nu || !H) return BB_ERR_ARG;
+  if (g->kind != BB_GUIDE_NUH) return BB_ERR_UNSUPPORTED;
+  bb_ctx* ctx = g->ctx;
+  BB_CUDA(cudaSetDevice(ctx->device));
+  const int N = g->N, d = g->d, rec = g->rec;
+  std::vector<double> tab((size_t)N * rec);
+  BB_CUDA(cudaMemcpyAsync(tab.data(), g->tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < N - 1; i++) {
+    const double* R = tab.data() + (size_t)(i + 1) * rec;
+    memcpy(nu + (size_t)i * d, R + 2, sizeof(double) * d);
+    memcpy(H + (size_t)i * d * d, R + 2 + d, sizeof(double) * d * d);
+  }
+  for (int q = 0; q < d; q++) nu[(size_t)(N - 1) * d + q] = NAN;
+  for (int q = 0; q < d * d; q++) H[(size_t)(N - 1) * d * d + q] = NAN;
+  return BB_OK;
+}

@@ -313,6 +313,19 @@ int bb_backward_LMmu(bb_ctx* ctx, int32_t N, int32_t d, int32_t m, const double*
                      const bb_aux* aux, const double* L, const double* Sigma,
                      double* Lt, double* Mt, double* mut);
 
+/* The backward pass of a CHAIN of S PartialBridgeνH segments in ONE launch (the script loop of
+ * partialbridge_bolus3.jl:162-180: ν = 0, H⁺ = I/ϵ right of the last observation; gpupdate with v[S-1]; for s = S-1 .. 0:
+ * partialbridgeνH over tt[s] -- `method` BB_ODE_LYAP as the script, or BB_ODE_R3 -- and, for s > 0, gpupdate with v[s-1]).
+ * The tables are written in place on the device, where the path kernels read them: guides[s] is updated if it exists
+ * (same N, d, kind NUH, constant auxiliary drift) or created if NULL.  Nothing returns to the host but the left-end
+ * values -- this is what a sampler that re-proposes parameters calls between two bb_pcn_step launches.
+ * aux[s]: the constant auxiliary process of segment s; v [S][m]; tt [S][N].  d <= 3.
+ * bb_guide_download_nuH reads ν[i], H[i] (i < N-1; the terminal values are not kept: NaN) back from a guide. */
+int bb_guides_chain_nuH(bb_ctx* ctx, int32_t method, int32_t S, int32_t N, int32_t d, int32_t m, const double* tt,
+                        const bb_aux* aux, const double* L, const double* Sigma, const double* v, double eps,
+                        bb_guide** guides, double* nu_left, double* Hplus_left, double* C);
+int bb_guide_download_nuH(bb_guide* g, double* nu, double* H);
+
 /* lptilde: log of the auxiliary process' transition density at the left end of a proposal (the p~ of every importance
  * weight exp(ll) p~/p, test/guip.jl:245-274).
  *   bb_lptilde_nuH   lptilde(x, P::PartialBridgeνH) = -1/2 (x'H[1]x - 2x'H[1]ν[1]) - C, the formula the reference TESTS

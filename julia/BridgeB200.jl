@@ -2,21 +2,31 @@
 # own generic functions for the data-parallel hot path.  Host code stays Julia; see include/bridge_b200.h for the ABI
 # and INTEGRATION.md for how a maintainer wires it in.
 #
-# STATUS: written against the header; NOT executed (no Julia runtime exists in the build environment).  The Python
-# binding bridge.jl_b200/_cabi.py makes exactly the same calls and IS tested on the GPU (tests/test_gpu_parity.py).
+# STATUS: written against the header; NOT executed (no Julia runtime exists in the build environment).  Every `ccall`
+# below is checked mechanically against include/bridge_b200.h by tools/check_shim.py (function name, arity, argument
+# classes and widths, and the byte layout of the mirrored structs BBModel / BBAux / BBThetaSpec against gcc's
+# sizeof/offsetof); tests/test_cabi.py runs that check.  The Python binding bridge.jl_b200/_cabi.py makes the same
+# calls and IS tested on the GPU (tests/test_gpu_*.py).
 #
-# What it adds (methods only; no Bridge.jl source is modified):
-#   PathEnsemble            device-resident container of P chains x S segments (replaces P*S (W, X) SamplePath pairs)
-#   Bridge.sample!(E, Wiener())                         -> bb_wiener_sample          (src/wiener.jl:50-58)
-#   Bridge.solve!(EulerMaruyama(), E, u, P)             -> bb_euler                  (src/euler.jl:135-152)
-#   Bridge.solve!(Euler(), E, u, Po::Vector{<:Guide})   -> bb_guided_euler_ll        (src/euler.jl:247-268)
-#   Bridge.llikelihood(LeftRule(), E, Po; skip)         -> bb_llikelihood / fused    (src/partialbridgenuH.jl:171-189)
-#   pcn!(E, P, Po, rho, seed, iter)                     -> bb_pcn_step               (test/partialbridgenuH.jl:176-191)
-#   solve!/llikelihood on plain SamplePath (P = 1 plumbing) go through a one-chain ensemble.
+# Two layers:
+#  (1) the reference's OWN signatures on SamplePath (one path per call), so that example/ and project_partialbridge/
+#      scripts run unchanged after `using BridgeB200`:
+#        sample!(W, Wiener{T}())                                   src/wiener.jl:24-58
+#        solve!(EulerMaruyama(), Y, u, W, P)                        src/euler.jl:135-152   (registry targets)
+#        solve!(Euler(), Y, u, W, P°) -> Y.yy[end]                  src/euler.jl:246-268   (P° ∈ GuidedBridge | PartialBridge | PartialBridgeνH)
+#        llikelihood(LeftRule(), X, P°; skip = 0)                   src/partialbridgenuH.jl:171, guip.jl:429, partialbridge.jl:67
+#        bridge!(Y, W, P°), bridge!(X, x0, W, P°)                   src/deprecated.jl:16-17, project/partialbridge.jl:63
+#        innovations!(EulerMaruyama(), W, Y, P)                     src/euler.jl:357-376
+#        lptilde(x, P°::PartialBridgeνH), lptilde(P°::GuidedBridge, u)
+#      They are more specific than Bridge's methods, so dispatch prefers them; `BridgeB200.enable!(false)` hands every
+#      call back to Bridge's CPU methods (`invoke`).  A process P is on the device iff `bbmodel(P)` is defined for it.
+#  (2) PathEnsemble: P chains x S segments resident in HBM -- what a many-chain sampler uses instead of P*S
+#      SamplePath pairs: sample!, solve!, llikelihood, pcn!, theta_* (per-chain parameters), Communicator (multi-GPU).
 module BridgeB200
 
 using Bridge, StaticArrays, LinearAlgebra
-import Bridge: sample!, solve!, llikelihood, EulerMaruyama, Euler, LeftRule, SamplePath, Wiener, ContinuousTimeProcess
+import Bridge: sample!, solve!, llikelihood, bridge!, innovations!, lptilde, EulerMaruyama, Euler, LeftRule, SamplePath,
+               Wiener, ContinuousTimeProcess, GuidedBridge, PartialBridge, PartialBridgeνH
 
 const lib = get(ENV, "BRIDGE_B200_LIB", joinpath(@__DIR__, "..", "bridge.jl_b200", "lib", "libbridge_b200.so"))
 
@@ -28,9 +38,15 @@ function check(st::Cint)
     st == -5 && throw(AssertionError("m == length(v)"))                      # src/partialbridgenuH.jl:3
     if st == -8 || st == -9
         msg *= ": " * unsafe_string(ccall((:bb_last_cuda_error, lib), Cstring, ()))
+    elseif st == -14
+        msg *= ": " * unsafe_string(ccall((:bb_comm_last_error, lib), Cstring, ()))
     end
     error(msg)   # "Y and W differ in length." / "Time axis mismatch ..." / "Starting point has wrong length."
 end
+
+const ENABLED = Ref(true)
+"""`enable!(false)`: every overloaded Bridge call falls back to Bridge's own CPU method."""
+enable!(on::Bool = true) = (ENABLED[] = on)
 
 # ---- registry models (bb_model): the device cannot call Julia closures
 struct BBModel
@@ -38,27 +54,36 @@ struct BBModel
     par::NTuple{32,Float64}
 end
 pad32(v) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 32)
+rowmajor(A::AbstractMatrix) = collect(vec(permutedims(A)))
 bbmodel(::Wiener{Float64}) = BBModel(0, 1, 1, 0, pad32(()))
 bbmodel(::Wiener{SVector{d,Float64}}) where {d} = BBModel(0, d, d, 0, pad32(()))
-bbmodel(P::Bridge.LinPro) = (d = size(P.B, 1); BBModel(2, d, d, 0, pad32(vcat(vec(P.B'), P.μ, vec(P.σ')))))   # row-major
+bbmodel(P::Bridge.LinPro) = (d = size(P.B, 1); BBModel(2, d, d, 0, pad32(vcat(rowmajor(P.B), P.μ, rowmajor(P.σ)))))
 bbmodel(P::Bridge.Models.FitzHughNagumo) = BBModel(3, 2, 2, 0, pad32((P.ϵ, P.s, P.γ, P.β, P.σ1, P.σ2)))        # src/Models.jl:9-20
+bbmodel(P::Bridge.Models.Lorenz) = BBModel(7, 3, 3, 0, pad32(vcat(collect(P.θ), diag(Matrix(P.σ)))))           # src/Models.jl:38-55
 # user structs opt in by defining bbmodel(P), e.g. for project_partialbridge/partialbridge_fitzhugh.jl:36-46
 #   BridgeB200.bbmodel(P::FitzhughDiffusion) = BridgeB200.BBModel(4, 2, 1, 0, BridgeB200.pad32((P.ϵ, P.s, P.γ, P.β, P.σ)))
+# ids: include/bridge_b200.h bb_model_id (OU 1, INTDIFF 5, NCLAR3 6, LANDMARKS 8, BOLUS 9)
+ondevice(P) = ENABLED[] && hasmethod(bbmodel, Tuple{typeof(P)})
 
-# ---- context / ensemble handles
+# ---- context: one per process by default (device = LOCAL_RANK), no extra argument anywhere
 mutable struct Context
     h::Ptr{Cvoid}
-    function Context(device::Integer = 0)
+    function Context(device::Integer = parse(Int, get(ENV, "LOCAL_RANK", "0")))
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:bb_ctx_create, lib), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r))
-        c = new(r[]); finalizer(c -> ccall((:bb_ctx_destroy, lib), Cint, (Ptr{Cvoid},), c.h), c); c
+        new(r[])   # never destroyed before its ensembles/guides: bb_ctx_destroy refuses while any is alive
     end
 end
+const DEFAULT_CTX = Ref{Union{Nothing,Context}}(nothing)
+default_context() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Context()); DEFAULT_CTX[]::Context)
+synchronize(ctx::Context = default_context()) = check(ccall((:bb_ctx_synchronize, lib), Cint, (Ptr{Cvoid},), ctx.h))
+"""0: reference arithmetic in the shared-table constructors (default), 1: fused multiply-adds"""
+set_arith!(a::Integer, ctx::Context = default_context()) = check(ccall((:bb_ctx_set_arith, lib), Cint, (Ptr{Cvoid}, Cint), ctx.h, a))
 
 mutable struct PathEnsemble
     h::Ptr{Cvoid}; ctx::Context
     P::Int; S::Int; N::Int; d::Int; dprime::Int
-    function PathEnsemble(ctx::Context, P, S, N, d, dprime; double_buffer = true, store_x = true, chain_offset = 0)
+    function PathEnsemble(P, S, N, d, dprime; ctx::Context = default_context(), double_buffer = true, store_x = true, chain_offset = 0)
         flags = UInt32((double_buffer ? 1 : 0) | (store_x ? 0 : 2))
         r = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:bb_ens_create, lib), Cint, (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Int32, UInt32, Ref{Ptr{Cvoid}}),
@@ -70,33 +95,113 @@ mutable struct PathEnsemble
 end
 setgrid!(E::PathEnsemble, seg, tt::Vector{Float64}) =
     check(ccall((:bb_ens_set_grid, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32), E.h, seg - 1, tt, length(tt)))
-setstart!(E::PathEnsemble, u::SVector) = (v = collect(u);
+setstart!(E::PathEnsemble, u::Number) = setstart!(E, SVector{1,Float64}(u))
+setstart!(E::PathEnsemble, u::AbstractVector) = (v = collect(Float64, u);
     check(ccall((:bb_ens_set_start, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), E.h, v, length(v), 1)))
-
 # per-chain starting points: X0 is d x P (one column per chain), the ABI wants [P][d] -- the same bytes
 setstart!(E::PathEnsemble, X0::Matrix{Float64}) =
     check(ccall((:bb_ens_set_start, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), E.h, X0, length(X0), 0))
+upload!(E::PathEnsemble, what::Integer, A::Array{Float64}; which = 0, p0 = 0, np = E.P) =   # A: [k, N, S, np] == [np][S][N][k]
+    check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, what, which, p0, np, A))
+download!(A::Array{Float64}, E::PathEnsemble, what::Integer; which = 0, p0 = 0, np = E.P) =
+    (check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, what, which, p0, np, A)); A)
+function getf64(E::PathEnsemble, field::Integer, width = 1)     # BB_F_LL 0, LL_PROP 1, LOGU 2, XEND 3, XEND_PROP 4
+    out = Array{Float64}(undef, width, E.P)
+    check(ccall((:bb_ens_get_f64, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), E.h, field, 0, E.P, out)); out
+end
+function accepted(E::PathEnsemble)
+    a = Vector{UInt8}(undef, E.P)
+    check(ccall((:bb_ens_get_accepted, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{UInt8}), E.h, 0, E.P, a)); a
+end
+acc(E::PathEnsemble) = (r = Ref{Int64}(0); check(ccall((:bb_ens_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, r)); r[])
 
-# ---- guiding tables: the constructors of Bridge.jl have already run the backward ODE on the host, or use
-#      bb_backward_nuH / bb_backward_HV / bb_backward_LMmu to run it on the device (same R3 / Lyapunov schemes)
+# ---- auxiliary process as values (bb_aux): constants, or values at the Ralston stage times of every interval
+struct BBAux
+    d::Int32; is_const::Int32
+    B::Ptr{Float64}; beta::Ptr{Float64}; a::Ptr{Float64}; a_left::Ptr{Float64}
+end
+struct AuxValues   # keeps the arrays alive
+    B::Vector{Float64}; β::Vector{Float64}; a::Vector{Float64}; al::Vector{Float64}; isconst::Bool; d::Int
+end
+isconstaux(Pt) = Pt isa Bridge.LinPro   # every other auxiliary process is sampled on the grid
+function AuxValues(Pt, tt)
+    d = size(Bridge.B(tt[1], Pt), 1)
+    if isconstaux(Pt)
+        return AuxValues(rowmajor(Bridge.B(tt[1], Pt)), collect(Float64, Bridge.β(tt[1], Pt)), rowmajor(Matrix(Bridge.a(tt[1], Pt))), Float64[], true, d)
+    end
+    Bs = Float64[]; βs = Float64[]; as = Float64[]; al = Float64[]
+    for i in 1:length(tt)-1                     # backward step over [tt[i], tt[i+1]]: t = tt[i+1], h = tt[i]-tt[i+1]  (src/ode.jl:44-49,92-95)
+        t, h = tt[i+1], tt[i] - tt[i+1]
+        for c in (0.0, 1/2, 3/4)
+            s = t + c*h
+            append!(Bs, rowmajor(Bridge.B(s, Pt))); append!(βs, collect(Float64, Bridge.β(s, Pt))); append!(as, rowmajor(Matrix(Bridge.a(s, Pt))))
+        end
+        append!(al, rowmajor(Matrix(Bridge.a(tt[i], Pt))))
+    end
+    AuxValues(Bs, βs, as, al, false, d)
+end
+bbaux(A::AuxValues) = BBAux(A.d, A.isconst ? 1 : 0, pointer(A.B), pointer(A.β), pointer(A.a), A.isconst ? Ptr{Float64}(C_NULL) : pointer(A.al))
+
+# ---- guiding tables of one segment on the device (bb_guide), built from the reference's own proposal structs
 mutable struct Guide
     h::Ptr{Cvoid}
 end
-rowmajor(A::AbstractMatrix) = collect(vec(permutedims(A)))
-function Guide(ctx::Context, Po::Bridge.PartialBridgeνH)           # fields Target, Pt, tt, ν, H, C  (src/partialbridgenuH.jl:122-130)
-    d = length(Po.ν[1]); N = length(Po.tt)
-    H = reduce(vcat, rowmajor.(Po.H)); ν = reduce(vcat, collect.(Po.ν))
-    Bt = reduce(vcat, [rowmajor(Bridge.B(t, Po.Pt)) for t in Po.tt]); βt = reduce(vcat, [collect(Bridge.β(t, Po.Pt)) for t in Po.tt])
+function newguide(ctx, kind, N, d, m, tt, A, b, Mm, v, Bt, βt, auxconst)
     r = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve H ν Bt βt check(ccall((:bb_guide_create, lib), Cint,
+    GC.@preserve tt A b Mm v Bt βt check(ccall((:bb_guide_create, lib), Cint,
         (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
-        ctx.h, 1, N, d, 0, Po.tt, H, ν, C_NULL, C_NULL, Bt, βt, 0, r))
+        ctx.h, kind, N, d, m, tt, A, b, Mm === nothing ? C_NULL : Mm, v === nothing ? C_NULL : v, Bt, βt, auxconst ? 1 : 0, r))
     g = Guide(r[]); finalizer(g -> ccall((:bb_guide_destroy, lib), Cint, (Ptr{Cvoid},), g.h), g); g
 end
-# GuidedBridge (kind 2: A = H♢, b = V) and PartialBridge (kind 3: A = L, b = μ, Mm = M, v) are built the same way.
+function auxongrid(Pt, tt)   # B̃(tt[i]), β̃(tt[i]) for llikelihood (b̃ = B̃x + β̃, src/partialbridgenuH.jl:176)
+    isconstaux(Pt) && return rowmajor(Bridge.B(tt[1], Pt)), collect(Float64, Bridge.β(tt[1], Pt)), true
+    reduce(vcat, [rowmajor(Bridge.B(t, Pt)) for t in tt]), reduce(vcat, [collect(Float64, Bridge.β(t, Pt)) for t in tt]), false
+end
+flat(v::Vector{<:SVector}) = collect(reinterpret(Float64, v))
+flat(v::Vector{<:SMatrix}) = reduce(vcat, rowmajor.(v))
+flat(v::Vector{Float64}) = v
+function Guide(Po::PartialBridgeνH; ctx::Context = default_context())   # fields Target, Pt, tt, ν, H, C  (src/partialbridgenuH.jl:122-130)
+    Bt, βt, c = auxongrid(Po.Pt, Po.tt)
+    newguide(ctx, 1, length(Po.tt), length(Po.ν[1]), 0, Po.tt, flat(Po.H), flat(Po.ν), nothing, nothing, Bt, βt, c)
+end
+function Guide(Po::GuidedBridge; ctx::Context = default_context())      # fields Target, Pt, tt, H♢, V  (src/guip.jl:165-170)
+    Bt, βt, c = auxongrid(Po.Pt, Po.tt)
+    newguide(ctx, 2, length(Po.tt), length(Po.V[1]), 0, Po.tt, flat(Po.H♢), flat(Po.V), nothing, nothing, Bt, βt, c)
+end
+function Guide(Po::PartialBridge; ctx::Context = default_context())     # fields Target, Pt, tt, v, L, M, μ  (src/partialbridge.jl:33-41)
+    Bt, βt, c = auxongrid(Po.Pt, Po.tt)
+    m, d = size(Po.L[1])
+    newguide(ctx, 3, length(Po.tt), d, m, Po.tt, flat(Po.L), flat(Po.μ), flat(Po.M), collect(Float64, Po.v), Bt, βt, c)
+end
+const Proposal = Union{GuidedBridge,PartialBridge,PartialBridgeνH}
+const GUIDES = IdDict{Any,Guide}()    # one device table per proposal object (uploaded on first use)
+guide_for(Po::Proposal) = get!(() -> Guide(Po), GUIDES, Po)
+forget!(Po::Proposal) = delete!(GUIDES, Po)
 
-# ---- the methods added to Bridge's generic functions
+# ---- backward ODEs on the device (the constructors' work; same R3 / Lyapunov schemes, reference arithmetic)
+"""`partialbridgeνH(tt, Pt, νend, Hend⁺)` on the device -> (ν [d, N], H [d, d, N] row-major per matrix, ν(tt[1]), H⁺(tt[1]), C)
+(src/partialbridgenuH.jl:86-103,148-155; `method` 0 = R3, 1 = Lyap)."""
+function backward_nuH(tt::Vector{Float64}, Pt, νend, Hendp; method = 1, C0 = 0.0, ctx::Context = default_context())
+    A = AuxValues(Pt, tt); N, d = length(tt), A.d
+    ν = Matrix{Float64}(undef, d, N); H = Array{Float64}(undef, d, d, N)
+    νl = Vector{Float64}(undef, d); Hl = Matrix{Float64}(undef, d, d); C = Ref{Float64}(0.0)
+    νe = collect(Float64, νend); He = rowmajor(Matrix(Hendp)); aux = Ref(bbaux(A))
+    GC.@preserve A νe He check(ccall((:bb_backward_nuH, lib), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ref{BBAux}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+        ctx.h, method, N, d, tt, aux, νe, He, C0, ν, H, νl, Hl, C))
+    ν, H, νl, permutedims(Hl), C[]
+end
+"""Observation update of (ν, H⁺) between segments (partialbridge_bolus3.jl:128-137), in place."""
+function gpupdate_nuH!(ν::Vector{Float64}, Hp::Matrix{Float64}, L, Σ, v; ctx::Context = default_context())
+    m, d = size(L); Hr = rowmajor(Hp); Lr = rowmajor(Matrix(L)); Sr = rowmajor(Matrix(Σ)); vv = collect(Float64, v)
+    check(ccall((:bb_gpupdate_nuH, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx.h, d, m, ν, Hr, Lr, Sr, vv))
+    Hp .= permutedims(reshape(Hr, d, d)); ν, Hp
+end
+
+# ---- (2) ensemble methods added to Bridge's generic functions
 function sample!(E::PathEnsemble, ::Wiener; seed::UInt64 = UInt64(0), stream::UInt32 = UInt32(0))
     check(ccall((:bb_wiener_sample, lib), Cint, (Ptr{Cvoid}, UInt64, UInt32), E.h, seed, stream)); E
 end
@@ -104,46 +209,168 @@ function solve!(::EulerMaruyama, E::PathEnsemble, u, P::ContinuousTimeProcess)
     setstart!(E, u); m = Ref(bbmodel(P))
     check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, m)); E
 end
-function solve!(::EulerMaruyama, E::PathEnsemble, u, P::ContinuousTimeProcess, guides::Vector{Guide}; skip = 0, store_x = true)
+function solve!(::EulerMaruyama, E::PathEnsemble, u, P::ContinuousTimeProcess, guides::Vector{Guide}; skip = 0, store_x = true, ll = true)
     setstart!(E, u); m = Ref(bbmodel(P)); hs = [g.h for g in guides]
     GC.@preserve guides check(ccall((:bb_guided_euler_ll, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32, UInt32),
-                                    E.h, m, hs, skip, store_x ? 1 : 0))
-    E   # end points: bb_ens_get_f64(E, BB_F_XEND, ...)
+                                    E.h, m, hs, skip, (store_x ? 1 : 0) | (ll ? 0 : 2)))
+    E   # end points: getf64(E, 3, E.d)
 end
 function llikelihood(::LeftRule, E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}; skip = 0)
     m = Ref(bbmodel(P)); hs = [g.h for g in guides]
     GC.@preserve guides check(ccall((:bb_llikelihood, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32), E.h, m, hs, skip))
-    ll = Vector{Float64}(undef, E.P)
-    check(ccall((:bb_ens_get_f64, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, E.P, ll)); ll
+    vec(getf64(E, 0))
 end
 """One pCN / MH update of every chain: the body of `for iter in 1:iterations` in test/partialbridgenuH.jl:176-191."""
 function pcn!(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}, ρ, seed::UInt64, iter::Integer; skip = 0, store_x = true)
     m = Ref(bbmodel(P)); hs = [g.h for g in guides]
     GC.@preserve guides check(ccall((:bb_pcn_step, lib), Cint,
         (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Float64, UInt64, UInt32, Int32, UInt32), E.h, m, hs, ρ, seed, iter, skip, store_x ? 1 : 0))
-    acc = Ref{Int64}(0); check(ccall((:bb_ens_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, acc)); acc[]
+    acc(E)
 end
-
 """Current paths of all chains as an array [d, N, S, P] (refreshes the chains whose last proposal was rejected)."""
 function download_x(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide})
     m = Ref(bbmodel(P)); hs = [g.h for g in guides]
     GC.@preserve guides check(ccall((:bb_ens_refresh_x, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}), E.h, m, hs))
-    X = Array{Float64}(undef, E.d, E.N, E.S, E.P)   # column-major == the ABI's [P][S][N][d]
-    check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, E.P, X)); X
+    download!(Array{Float64}(undef, E.d, E.N, E.S, E.P), E, 1)   # column-major == the ABI's [P][S][N][d]
 end
 
-# ---- P = 1 plumbing: the reference's own signatures on SamplePath (a one-chain ensemble per call)
-function solve!(::EulerMaruyama, Y::SamplePath{T}, u::T, W::SamplePath, P::ContinuousTimeProcess{T}, ctx::Context) where {T}
+# ---- multi-GPU: one Julia process (or task) per GPU; the acceptance counter is the only exchange (SURVEY 8e)
+mutable struct Communicator
+    h::Ptr{Cvoid}
+end
+function unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:bb_comm_unique_id, lib), Cint, (Ptr{UInt8},), id)); id
+end
+"""All ranks call this with the 128 bytes rank 0 got from `unique_id()` (ship them with MPI, a file, Distributed, ...)."""
+function Communicator(nranks::Integer, rank::Integer, id::Vector{UInt8}; ctx::Context = default_context())
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bb_comm_create, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}), ctx.h, nranks, rank, id, r))
+    c = Communicator(r[]); finalizer(c -> ccall((:bb_comm_destroy, lib), Cint, (Ptr{Cvoid},), c.h), c); c
+end
+"""Start the all-reduce of the acceptance counter (asynchronous, NCCL on its own stream); `acc(comm)` fetches the sum."""
+allreduce_acc!(E::PathEnsemble, c::Communicator) = check(ccall((:bb_allreduce_acc, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), E.h, c.h))
+acc(c::Communicator) = (r = Ref{Int64}(0); check(ccall((:bb_comm_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), c.h, r)); r[])
+
+# ---- (1) the reference's own signatures on SamplePath: a cached one-chain ensemble per (N, d, d')
+const SMALL = Dict{NTuple{3,Int},PathEnsemble}()
+small(N, d, dp) = get!(() -> PathEnsemble(1, 1, N, d, dp; double_buffer = false), SMALL, (N, d, dp))
+dimof(::Type{Float64}) = 1
+dimof(::Type{SVector{d,Float64}}) where {d} = d
+asf64(yy::Vector{Float64}) = yy
+asf64(yy::Vector{SVector{d,Float64}}) where {d} = reinterpret(Float64, yy)   # same bytes as the ABI's [N][d]
+const RNG = Ref((UInt64(0), UInt32(0)))
+"""`seed!(s)`: seeds the Philox streams `sample!` draws from (the device cannot reproduce Julia's own RNG streams)."""
+seed!(s::Integer) = (RNG[] = (UInt64(s), UInt32(0)))
+
+function sample!(W::SamplePath{T}, P::Wiener{T}, y1 = W.yy[1]) where {T<:Union{Float64,SVector}}
+    ENABLED[] || return invoke(sample!, Tuple{SamplePath{T},Wiener{T},Any}, W, P, y1)
+    dp = dimof(T); E = small(length(W.tt), dp, dp)
+    W.yy[1] = y1
+    setgrid!(E, 1, W.tt)
+    w = asf64(W.yy)
+    GC.@preserve W begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+        seed, stream = RNG[]; RNG[] = (seed, stream + UInt32(1))
+        check(ccall((:bb_wiener_sample, lib), Cint, (Ptr{Cvoid}, UInt64, UInt32), E.h, seed, stream))
+        check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+    end
+    W
+end
+
+function solve!(s::EulerMaruyama, Y::SamplePath{T}, u::T, W::SamplePath, P::ContinuousTimeProcess{T}) where {T}
+    ondevice(P) || return invoke(solve!, Tuple{EulerMaruyama,Any,T,SamplePath,Bridge.ProcessOrCoefficients}, s, Y, u, W, P)
     N = length(W); N != length(Y) && error("Y and W differ in length.")
-    d = length(u); dp = length(W.yy[1])
-    E = PathEnsemble(ctx, 1, 1, N, d, dp; double_buffer = false)
-    setgrid!(E, 1, W.tt); setstart!(E, SVector{d}(u...))
-    w = reinterpret(Float64, W.yy)
-    check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
-    m = Ref(bbmodel(P)); check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, m))
-    x = reinterpret(Float64, Y.yy)
-    check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
-    Y.tt .= W.tt; Y
+    m = bbmodel(P); E = small(N, Int(m.d), Int(m.dprime))
+    setgrid!(E, 1, W.tt); setstart!(E, u)
+    w = asf64(W.yy); x = asf64(Y.yy); mr = Ref(m)
+    GC.@preserve W Y begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+        check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, mr))
+        check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+    end
+    Y.tt[:] = W.tt
+    Y
+end
+
+"""solve!(Euler(), Y, u, W, P°) -> Y.yy[end]   (src/euler.jl:247-268; tt[:] = P.tt, end point rule of GuidedBridge)"""
+function solve!(s::EulerMaruyama, Y::SamplePath, u, W::SamplePath, Po::Proposal)
+    ondevice(Po.Target) || return invoke(solve!, Tuple{EulerMaruyama,Any,Any,SamplePath,Proposal}, s, Y, u, W, Po)
+    W.tt === Po.tt && error("Time axis mismatch between bridge P and driving W.")          # src/euler.jl:248
+    N = length(W); (N != length(Y) || N != length(Po.tt)) && error("Y and W differ in length.")   # :251
+    m = bbmodel(Po.Target); E = small(N, Int(m.d), Int(m.dprime)); g = guide_for(Po)
+    setstart!(E, u)
+    w = asf64(W.yy); x = asf64(Y.yy); mr = Ref(m); hs = [g.h]
+    GC.@preserve W Y g begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+        check(ccall((:bb_guided_euler_ll, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32, UInt32), E.h, mr, hs, 0, 1 | 2))
+        check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+    end
+    Y.tt[:] = Po.tt
+    Y.yy[end]
+end
+
+"""llikelihood(LeftRule(), X, P°; skip = 0) -> Float64"""
+function llikelihood(r::LeftRule, X::SamplePath, Po::Proposal; skip = 0)
+    ondevice(Po.Target) || return invoke(llikelihood, Tuple{LeftRule,SamplePath,typeof(Po)}, r, X, Po; skip = skip)
+    N = length(X); N != length(Po.tt) && error("Y and W differ in length.")
+    m = bbmodel(Po.Target); E = small(N, Int(m.d), Int(m.dprime)); g = guide_for(Po)
+    x = asf64(X.yy); mr = Ref(m); hs = [g.h]; ll = Ref{Float64}(0.0)
+    GC.@preserve X g begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+        check(ccall((:bb_llikelihood, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32), E.h, mr, hs, skip))
+        check(ccall((:bb_ens_get_f64, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ref{Float64}), E.h, 0, 0, 1, ll))
+    end
+    ll[]
+end
+
+# bridge!(Y, W, P°) (src/deprecated.jl:16-17) and the 4-argument form older scripts use (project/partialbridge.jl:63,65,87)
+bridge!(Y::SamplePath, W::SamplePath, Po::Proposal) = (solve!(Euler(), Y, Y.yy[1], W, Po); Y)
+bridge!(X::SamplePath, x0, W::SamplePath, Po::Proposal) = (solve!(Euler(), X, x0, W, Po); X)
+
+"""innovations!(EulerMaruyama(), W, Y, P) -> W   (src/euler.jl:357-376; P a registry target or a proposal; d' = d)"""
+function innovations!(s::EulerMaruyama, W::SamplePath, Y::SamplePath, P)
+    target = P isa Proposal ? P.Target : P
+    ondevice(target) || return invoke(innovations!, Tuple{EulerMaruyama,Any,Any,Any}, s, W, Y, P)
+    N = length(Y); N != length(W) && error("Y and W differ in length.")
+    m = bbmodel(target); E = small(N, Int(m.d), Int(m.dprime))
+    x = asf64(Y.yy); w = asf64(W.yy); mr = Ref(m)
+    hs = P isa Proposal ? [guide_for(P).h] : Ptr{Cvoid}[]
+    P isa Proposal || setgrid!(E, 1, Y.tt)
+    GC.@preserve W Y begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+        check(ccall((:bb_innovations, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}), E.h, mr, isempty(hs) ? C_NULL : hs))
+        check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
+    end
+    W.tt[:] = Y.tt
+    W
+end
+
+"""lptilde(x, P°::PartialBridgeνH) in the form the reference tests (test/partialbridgenuH.jl:124; the method in
+src/partialbridgenuH.jl:169 has a typo and does not run)"""
+function lptilde(x, Po::PartialBridgeνH; ctx::Context = default_context())
+    d = length(Po.ν[1]); out = Ref{Float64}(0.0)
+    ν0 = collect(Float64, Po.ν[1]); H0 = rowmajor(Matrix(Po.H[1])); xx = collect(Float64, x)
+    check(ccall((:bb_lptilde_nuH, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ref{Float64}),
+                ctx.h, d, ν0, H0, Po.C, xx, out))
+    out[]
+end
+"""lptilde(P°::GuidedBridge, u) = logpdfnormal(V[1] - u, H♢[1]) - traceB(tt, Pt)   (src/guip.jl:203-206)"""
+function lptilde(Po::GuidedBridge, u; ctx::Context = default_context())
+    tt = Po.tt; N = length(tt); d = length(Po.V[1]); out = Ref{Float64}(0.0)
+    tr = Float64[]
+    if isconstaux(Po.Pt)
+        push!(tr, LinearAlgebra.tr(Bridge.B(tt[1], Po.Pt)))
+    else
+        for i in 1:N-1, c in (0.0, 1/2, 3/4)      # forward Ralston stages of src/ode.jl:44-49,178-184
+            push!(tr, LinearAlgebra.tr(Bridge.B(tt[i] + c*(tt[i+1] - tt[i]), Po.Pt)))
+        end
+    end
+    V0 = collect(Float64, Po.V[1]); K0 = rowmajor(Matrix(Po.H♢[1])); uu = collect(Float64, u)
+    check(ccall((:bb_lptilde_HV, lib), Cint,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                ctx.h, N, d, tt, tr, isconstaux(Po.Pt) ? 1 : 0, V0, K0, uu, out))
+    out[]
 end
 
 # ---- per-chain parameters: the `updateparams` branch of partialbridge_bolus3.jl:248-365 (bb_theta_* of the header)
@@ -176,7 +403,7 @@ function theta_param_step!(E::PathEnsemble, rw_sd, seed::UInt64, iter::Integer; 
     sd = zeros(8); sd[1:length(rw_sd)] .= rw_sd
     check(ccall((:bb_theta_param_step, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, UInt64, UInt32, Int32, UInt32),
                 E.h, sd, seed, iter, skip, store_x ? 1 : 0))
-    acc = Ref{Int64}(0); check(ccall((:bb_theta_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, acc)); acc[]
+    a = Ref{Int64}(0); check(ccall((:bb_theta_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, a)); a[]
 end
 function theta(E::PathEnsemble)   # param(P) of every chain: 8 x P (column per chain)
     θ = Matrix{Float64}(undef, 8, E.P)

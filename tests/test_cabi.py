@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 
@@ -64,3 +65,22 @@ def test_no_cpu_fallback(lib):
     needed = subprocess.run(["readelf", "-d", os.path.join(ROOT, "bridge.jl_b200", "lib", "libbridge_b200.so")],
                             capture_output=True, text=True).stdout
     assert "oracle" not in needed and "NEEDED" in needed
+
+
+def test_julia_shim_agrees_with_the_header():
+    """julia/BridgeB200.jl cannot be executed here (no Julia): every ccall in it is checked mechanically against
+    include/bridge_b200.h (name, arity, argument classes and widths, return type) and the hand-mirrored structs against
+    gcc's sizeof / offsetof (tools/check_shim.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_shim
+    problems, ncalls, nfun, ndecl = check_shim.check()
+    assert not problems, problems
+    assert ncalls >= 50 and nfun >= 38
+    # the reference's own signatures are there (SURVEY 8a "exact reference signatures")
+    src = open(os.path.join(ROOT, "julia", "BridgeB200.jl")).read()
+    for sig in ("function solve!(s::EulerMaruyama, Y::SamplePath, u, W::SamplePath, Po::Proposal)",
+                "function llikelihood(r::LeftRule, X::SamplePath, Po::Proposal; skip = 0)",
+                "bridge!(Y::SamplePath, W::SamplePath, Po::Proposal)", "bridge!(X::SamplePath, x0, W::SamplePath, Po::Proposal)",
+                "function sample!(W::SamplePath{T}, P::Wiener{T}, y1 = W.yy[1])",
+                "function Guide(Po::GuidedBridge;", "function Guide(Po::PartialBridge;", "function Guide(Po::PartialBridgeνH;"):
+        assert sig in src, sig

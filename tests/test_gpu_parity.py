@@ -624,6 +624,41 @@ def test_config4_end_to_end_vs_reference_arithmetic(B, oracle_ref, oracle_fma):
     ens.close()
 
 
+def test_chain_backward_in_one_launch(B, oracle_ref):
+    """bb_guides_chain_nuH: the whole multi-segment backward pass in one launch, tables written in place on the device.
+    Bit-identical to the per-segment constructors (and therefore to the reference-arithmetic oracle), the forward pass on
+    its guides gives identical log-likelihoods, and update_ with other observations rewrites the same device tables."""
+    import bridge_jl_b200.configs as cfg
+    n, P = 257, 64
+    Pm, guides, x0, rho = cfg.fhn_config4(n)
+    Pm2, chain, _, _ = cfg.fhn_config4_chain(n)
+    tabs = oracle_fhn_chain(oracle_ref, cfg.fhn_segment_grids(n), cfg.FHN_OBS_V)
+    for s in range(4):
+        assert np.array_equal(chain[s].ν[:-1], guides[s].ν[:-1]) and np.array_equal(chain[s].H[:-1], guides[s].H[:-1])
+        assert np.array_equal(chain[s].ν[:-1], tabs[s][0][:-1]) and np.array_equal(chain[s].H[:-1], tabs[s][1][:-1])
+    ens = B.PathEnsemble(P, 4, n, 2, 1)
+    for s in range(4):
+        ens.set_grid(s, guides[s].tt)
+    ens.set_start(x0); ens.sample_(4, 0xFFFFFFFE)
+    ens.guided_euler_ll_(Pm, guides); ll = ens.ll; X = ens.download(B.X)
+    ens.guided_euler_ll_(Pm2, chain.segments)
+    assert np.array_equal(ens.ll, ll) and np.array_equal(ens.download(B.X), X)
+    ens.pcn_step_(Pm2, chain.segments, rho, 4, 0)
+    assert 0 < ens.acc < P
+    # other observations: the tables are rewritten in place (same device handles) and match a fresh per-segment build
+    obs2 = (-0.8, -0.2, 0.4, 0.9)
+    handles = [seg._guide.value for seg in chain]
+    cfg.fhn_config4_chain(n, obs_v=obs2, chain=chain)
+    assert [seg._guide.value for seg in chain] == handles
+    _, g2, _, _ = cfg.fhn_config4(n, obs_v=obs2)
+    for s in range(4):
+        assert np.array_equal(chain[s].ν[:-1], g2[s].ν[:-1]) and np.array_equal(chain[s].H[:-1], g2[s].H[:-1])
+    ens.guided_euler_ll_(Pm, g2); ll2 = ens.ll
+    ens.guided_euler_ll_(Pm2, chain.segments)
+    assert np.array_equal(ens.ll, ll2) and not np.array_equal(ll2, ll)
+    ens.close()
+
+
 def test_lptilde_through_the_abi(B, oracle_ref):
     """lptilde(x, P::PartialBridgeνH) (test/partialbridgenuH.jl:124) and lptilde(P::GuidedBridge, u) (src/guip.jl:206)
     on the device against the oracle, and against the closed form the reference tests compare with."""
