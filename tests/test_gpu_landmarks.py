@@ -29,6 +29,17 @@ def B():
     return B
 
 
+@pytest.fixture
+def no_dmma():
+    """The four-lane kernel WITHOUT tensor-core mat-vecs: the rounding sequence of the oracle's GPU-order build, used
+    for the bit-exact statements.  (The default guided kernel, bb_wide4m_kernel, sums the mat-vecs on the fp64 tensor
+    cores and is compared at the contract tolerance: test_landmarks_tensor_core_kernel_vs_reference_arithmetic.)"""
+    import os
+    os.environ["BB_WIDE_MMA"] = "0"
+    yield
+    os.environ.pop("BB_WIDE_MMA", None)
+
+
 def x0():
     return np.concatenate([np.concatenate([Q0[i], P0[i]]) for i in range(4)])
 
@@ -84,7 +95,7 @@ def test_landmarks_constructors_bit_exact(B, oracle_fma):
     assert np.array_equal(nul, nul_o) and np.array_equal(Hpl, Hpl_o) and C2 == C2o
 
 
-def test_landmarks_guided_euler_pcn_vs_oracle(B, oracle_fma, oracle_ref):
+def test_landmarks_guided_euler_pcn_vs_oracle(B, oracle_fma, oracle_ref, no_dmma):
     N, P, seed, rho = 97, 150, 5, 0.9
     tt, Pm, Pt, Po, om, og = setup(B, oracle_fma, N)
     ens = B.PathEnsemble(P, 1, N, 16, 8, chain_offset=300)
@@ -163,7 +174,7 @@ def test_landmarks_plain_euler_and_unsupported(B, oracle_fma):
     ens.close()
 
 
-def test_landmarks_four_lane_kernel_equals_one_thread_per_chain(B):
+def test_landmarks_four_lane_kernel_equals_one_thread_per_chain(B, no_dmma):
     """The production kernels split a chain over four lanes (one landmark each); BB_WIDE_LANES=1 selects the plain
     one-thread-per-chain kernels.  Same rounding sequence per component: results must agree bit for bit."""
     import os
@@ -190,3 +201,59 @@ def test_landmarks_four_lane_kernel_equals_one_thread_per_chain(B):
     assert len(out["4"]) == len(out["1"])
     for u, v in zip(out["4"], out["1"]):
         assert np.array_equal(u, v)
+
+
+def test_landmarks_tensor_core_kernel_vs_reference_arithmetic(B, oracle_ref):
+    """The default guided kernel of config 5 computes r = H (nu - x) and B~ x with fp64 tensor-core instructions
+    (mma.sync m8n8k4.f64, 8 chains per warp) and reduces the Girsanov sum by a butterfly: its sums round in another
+    order than the reference's, so it is held to the CONTRACT tolerance against the reference arithmetic (libm exp, no
+    fma, sequential sums): |dX| <= 1e-9 (1 + |X|), |dll| <= 1e-6 |ll| + 1e-9, same noise, accept decisions replayed
+    from the kernel's own numbers with flips against the oracle counted; and against the four-lane kernel without DMMA."""
+    import os
+    N, P, seed, rho = 129, 203, 5, 0.9
+    tt, Pm, Pt, Po, om, og = setup(B, oracle_ref, N)
+    res = {}
+    for mma in ("1", "0"):
+        os.environ["BB_WIDE_MMA"] = mma
+        try:
+            ens = B.PathEnsemble(P, 1, N, 16, 8, chain_offset=300)
+            ens.set_grid(0, tt); ens.set_start(x0()); ens.sample_(seed, 0xFFFFFFF0)
+            W = ens.download(B.W)
+            ens.guided_euler_ll_(Pm, [Po], skip=1)
+            X = ens.download(B.X); ll = ens.ll; xend = ens.xend
+            rec = [W, X, ll, xend]
+            flips = 0
+            for it in range(3):
+                llc = ens.ll; Wc = ens.download(B.W)
+                ens.pcn_step_(Pm, [Po], rho, seed, it, skip=1, store_x=(it != 1))
+                llp, logu, flags = ens.ll_prop, ens.logu, ens.accepted.astype(bool)
+                assert np.array_equal(flags, logu <= llp - llc)
+                rec += [ens.download(B.W, which=B.PROP), llp, logu]
+                if mma == "1":
+                    for p in (0, 7, 8, 100, 202):
+                        llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(om, [og], x0(), Wc[p], rho, seed, it, 300 + p, skip=1)
+                        assert lu == logu[p] and np.max(np.abs(ens.download(B.W, which=B.PROP, p0=p, np_=1)[0] - Wo)) <= 1e-12
+                        assert abs(llp[p] - llo) <= 1e-6 * abs(llo) + 1e-9, (llp[p], llo)
+                        flips += int(flags[p] != (lu <= llo - llc[p]))
+                        if it != 1:
+                            Xp = ens.download(B.X, which=B.PROP, p0=p, np_=1)[0]
+                            assert np.max(np.abs(Xp - Xo)) <= 1e-9 * (1 + np.max(np.abs(Xo)))
+            assert flips == 0
+            rec += [ens.download(B.X), ens.ll, np.array([ens.acc])]
+            res[mma] = rec
+            if mma == "1":
+                for p in (0, 7, 8, 100, 202):
+                    Xo, _ = oracle_ref.guided_euler(om, og, x0(), W[p, 0])
+                    llo = oracle_ref.llikelihood(om, og, Xo, 1)
+                    assert np.max(np.abs(X[p, 0] - Xo)) <= 1e-9 * (1 + np.max(np.abs(Xo))), np.max(np.abs(X[p, 0] - Xo))
+                    assert abs(ll[p] - llo) <= 1e-6 * abs(llo) + 1e-9
+                assert np.max(np.abs(X[:, 0, -1].reshape(P, 4, 2, 2)[:, :, 0] - QT)) < 0.15
+            ens.close()
+        finally:
+            os.environ.pop("BB_WIDE_MMA", None)
+    a, b = res["1"], res["0"]
+    assert np.array_equal(a[0], b[0])  # the noise is the same bits
+    for u, v in zip(a[1:4], b[1:4]):   # paths / ll / end points: rounding-level differences only
+        assert np.max(np.abs(u - v)) <= 1e-10 * (1 + np.max(np.abs(v)))
+    print("tensor-core vs four-lane kernel: max |dX| %.2e, max rel dll %.2e" % (
+        np.max(np.abs(a[1] - b[1])), np.max(np.abs(a[2] - b[2]) / np.abs(b[2]))))
