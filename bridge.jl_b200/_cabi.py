@@ -18,11 +18,11 @@ LIB_PATH = os.environ.get("BB_LIB") or os.path.join(_HERE, "lib", "libbridge_b20
 BB_NPAR = 32
 # status codes
 OK, ERR_LENGTH, ERR_TIMEAXIS, ERR_STARTPOINT, ERR_DIM, ERR_ASSERT_M, ERR_MODEL, ERR_ARG, ERR_CUDA, \
-    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE, ERR_COMM = (0, -1, -2, -3, -4, -5, -6, -7, -8,
-                                                                                   -9, -10, -11, -12, -13, -14)
+    ERR_NOMEM, ERR_NODEVICE, ERR_UNSUPPORTED, ERR_SINGULAR, ERR_STALE, ERR_COMM, ERR_USERSRC = (
+        0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10, -11, -12, -13, -14, -15)
 NCCL_ID_BYTES = 128
 # model ids
-WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS, BOLUS = range(10)
+WIENER, OU, LINPRO, FHN_DIAG, FHN_HYPO, INTDIFF, NCLAR3, LORENZ, LANDMARKS, BOLUS, USER = range(11)
 GUIDE_NUH, GUIDE_HV, GUIDE_LMMU = 1, 2, 3
 ODE_R3, ODE_LYAP = 0, 1
 ENS_DOUBLE_BUFFER, ENS_NO_X = 1, 2
@@ -146,6 +146,12 @@ def _load():
         "bb_theta_refresh_x": (C.c_int, [vp]),
         "bb_theta_get_acc": (C.c_int, [vp, C.POINTER(i64)]),
         "bb_theta_acc_device_ptr": (vp, [vp]),
+        "bb_user_model_create": (C.c_int, [vp, i32, i32, C.c_char_p, C.POINTER(i32), C.POINTER(C.c_char_p), pp]),
+        "bb_user_source_check": (C.c_int, [i32, i32, C.c_char_p, C.POINTER(i32), C.POINTER(C.c_char_p), i32, i32, i32, i32,
+                                           C.c_char_p, i32]),
+        "bb_user_model_handle": (i32, [vp]),
+        "bb_user_model_log": (C.c_char_p, [vp]),
+        "bb_user_model_destroy": (C.c_int, [vp]),
         "bb_comm_unique_id": (C.c_int, [vp]),
         "bb_comm_create": (C.c_int, [vp, i32, i32, vp, pp]),
         "bb_comm_adopt": (C.c_int, [vp, vp, i32, i32, pp]),

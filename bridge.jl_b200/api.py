@@ -393,6 +393,83 @@ def LandmarksTilde(a, σ, λ, qT):  # partialbridge_landmarks.jl:75-81,126-146
     return LinearAux(B, np.zeros(16), S @ S.T)
 
 
+class UserProcess(ContinuousTimeProcess):
+    """A target process whose drift and diffusion are given as CUDA C source and compiled at run time (NVRTC) into the
+    same path kernels the registry models use -- the counterpart of defining Bridge.b / Bridge.σ for an own struct
+    (src/types.jl:23,32-33, src/Bridge.jl:105-106; partialbridge_fitzhugh.jl:44-46).
+
+        drift   statements assigning o[0..d-1] from x[0..d-1] and par[...] (double precision; write fma() where a fused
+                multiply-add is wanted: nothing is contracted implicitly)
+        col     col[i] = column of the driving Wiener process entering component i, or -1
+        sigma   sigma[i] = C expression in par[] for that entry of σ (None where col[i] < 0); constant in x
+        par     parameter values (change them freely between calls: no recompilation)
+        b, σ    optional Python callables for host-side inspection (Bridge.b, Bridge.σ)"""
+    model_id = K.USER
+
+    def __init__(self, d: int, dprime: int, drift: str, col: Sequence[int], sigma: Sequence[Optional[str]], par,
+                 b: Optional[Callable] = None, σ: Optional[Callable] = None, ctx: Optional["Context"] = None):
+        self.ctx = ctx or default_context()
+        self.d, self.dprime = int(d), int(dprime)
+        self.p = [float(v) for v in par]
+        self._b, self._σ = b, σ
+        colarr = (C.c_int32 * d)(*[int(c) for c in col])
+        sigarr = (C.c_char_p * d)(*[None if s_ is None else str(s_).encode() for s_ in sigma])
+        h = C.c_void_p()
+        rc = lib.bb_user_model_create(self.ctx.h, d, dprime, drift.encode(), colarr, sigarr, C.byref(h))
+        self.h = h
+        self.log = lib.bb_user_model_log(h).decode() if h else ""
+        if rc != 0:
+            text = lib.bb_strerror(rc).decode() + ("\n" + self.log if self.log else "")
+            if h:
+                lib.bb_user_model_destroy(h)
+                self.h = None
+            raise BridgeError(rc, text)
+        self.handle = lib.bb_user_model_handle(h)
+
+    def par(self):
+        return self.p
+
+    def cmodel(self) -> K.Model:
+        m = super().cmodel()
+        m.reserved = self.handle
+        return m
+
+    def b(self, t, x):
+        if self._b is None:
+            raise NotImplementedError("no host-side b was given")
+        return self._b(t, x, self.p)
+
+    def σ(self, t, x=None):
+        if self._σ is None:
+            raise NotImplementedError("no host-side σ was given")
+        return self._σ(t, x, self.p)
+
+    sigma = σ
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib.bb_user_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def check_user_source(d, dprime, drift, col, sigma, gk=0, gm=0, auxm=1, rng=0):
+    """Compile-only check of a UserProcess definition (works without a device): -> (cubin bytes, NVRTC log); raises
+    BridgeError(ERR_USERSRC) with the log if the source does not compile."""
+    colarr = (C.c_int32 * d)(*[int(c) for c in col])
+    sigarr = (C.c_char_p * d)(*[None if s_ is None else str(s_).encode() for s_ in sigma])
+    log = C.create_string_buffer(1 << 16)
+    rc = lib.bb_user_source_check(d, dprime, drift.encode(), colarr, sigarr, gk, gm, auxm, rng, log, len(log))
+    if rc < 0:
+        raise BridgeError(rc, lib.bb_strerror(rc).decode() + "\n" + log.value.decode())
+    return rc, log.value.decode()
+
+
 class LinearAux:
     """An auxiliary process given by B(t), β(t), a(t) (constants or callables), the protocol the
     guided proposals use (Bridge.B, Bridge.β, Bridge.a; partialbridge_fitzhugh.jl:99-116)."""

@@ -36,6 +36,7 @@ extern "C" const char* bb_strerror(int status) {
     case BB_ERR_SINGULAR: return "singular matrix";
     case BB_ERR_STALE: return "X holds rejected proposals for some chains: call bb_ens_refresh_x first";
     case BB_ERR_COMM: return "NCCL error (see bb_comm_last_error)";
+    case BB_ERR_USERSRC: return "the source of the user-defined model does not compile (see bb_user_model_log)";
     default: return "unknown status";
   }
 }
@@ -268,6 +269,7 @@ static bool model_shape_ok(const bb_model* m) {
     case BB_MODEL_INTDIFF: return d == 2 && dp == 1;
     case BB_MODEL_NCLAR3: return d == 3 && dp == 1;
     case BB_MODEL_LORENZ: return d == 3 && dp == 3;
+    case BB_MODEL_USER: return d >= 1 && d <= 3 && dp >= 1 && dp <= d && bb_user_lookup(m->reserved) != nullptr;
     default: return false;
   }
 }
@@ -836,6 +838,8 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
     }
   }
   const int krng = (rs.rng == 1 && !rs.store_x) ? 3 : rs.rng; /* pCN without X° is its own instantiation */
+  bb_user_model* um = model->id == BB_MODEL_USER ? bb_user_lookup(model->reserved) : nullptr;
+  if (model->id == BB_MODEL_USER && (rs.rng == 11 || (rs.rng != 12 && rs.rng >= 10 && !guides))) return BB_ERR_UNSUPPORTED;
   bb_chain_launch_fn fn = nullptr;
   if (krng == 1 && guides && model->dprime == 1 && model->d <= 3) {
     /* a SMALL ensemble (the strong-scaling share of a GPU: fewer than two 128-chain CTAs per SM) runs the pCN
@@ -847,8 +851,8 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
     if (mode == BB_PCN_WARP_SPECIALISED || (mode == BB_PCN_AUTO && (nch + 127) / 128 < 2ll * c->sm_count))
       fn = lookup_kernel(model, gk, gm, auxc, 5);
   }
-  if (!fn) fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10) : lookup_kernel(model, gk, gm, auxc, krng);
-  if (!fn) return BB_ERR_UNSUPPORTED;
+  if (!fn && !um) fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10) : lookup_kernel(model, gk, gm, auxc, krng);
+  if (!fn && !um) return BB_ERR_UNSUPPORTED;
   if (rs.rng >= 10 && !e->X) return BB_ERR_ARG;
   if (rs.rng == 11 && !model_sigma_invertible(model)) return BB_ERR_SINGULAR;
   if (rs.rng == 1 && !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG;
@@ -871,12 +875,19 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   a.rho2 = sqrt(1 - rs.rho * rs.rho); /* sqrt(1-ρ^2)  test/partialbridgenuH.jl:178 */
   bb_prepare_model(model, &a.model);
   bb_time_begin(c);
-  cudaError_t err = fn(a, c->stream);
-  bb_time_end(c);
-  if (err != cudaSuccess) {
-    bb_set_cuda_error(err, "bb_chain_kernel launch");
-    return BB_ERR_CUDA;
+  if (um) { /* run-time compiled model: the same kernels, instantiated for the user's b and sigma (bb_user.cu) */
+    const int rcu = rs.rng == 12 ? bb_user_launch(um, 2, 0, 0, 1, 0, a, c->stream)
+                  : rs.rng >= 10 ? bb_user_launch(um, 1, gk, gm, auxc, rs.rng - 10, a, c->stream)
+                                 : bb_user_launch(um, 0, gk, gm, auxc, krng, a, c->stream);
+    if (rcu != BB_OK) return rcu;
+  } else {
+    cudaError_t err = fn(a, c->stream);
+    if (err != cudaSuccess) {
+      bb_set_cuda_error(err, "bb_chain_kernel launch");
+      return BB_ERR_CUDA;
+    }
   }
+  bb_time_end(c);
   c->launches++;
   if (rs.rng == 1) e->x_maybe_stale = true;
   else if ((rs.rng < 10 || rs.rng == 12) && rs.store_x && !rs.only_stale) e->x_maybe_stale = false;

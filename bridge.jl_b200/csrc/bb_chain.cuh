@@ -31,7 +31,9 @@
  * geometry or on how chains are sharded over GPUs.
  */
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <atomic>
+#endif
 
 #include "bb_device.cuh"
 
@@ -560,6 +562,7 @@ __global__ void __launch_bounds__(BB_THREADS, bb_min_ctas<M>()) bb_chain_kernel(
   bb_chain<M, GK, GM, AUXM, RNG>::run(a);
 }
 
+#ifndef __CUDACC_RTC__ /* host-side launch + lookup (not part of a run-time compiled user-model kernel) */
 template <class M, int GK, int GM, int AUXM, int RNG>
 static inline size_t bb_chain_smem(int S) {
   (void)S;
@@ -630,3 +633,4 @@ static bb_chain_launch_fn bb_lookup_model(int gk, int gm, int auxc, int rng) {
 }
 
 #include "bb_chain_ws.cuh" /* the warp-specialised pCN kernel (defined in terms of bb_chain) */
+#endif /* !__CUDACC_RTC__ */

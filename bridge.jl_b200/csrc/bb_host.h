@@ -76,6 +76,11 @@ void bb_theta_invalidate(bb_ens* e); /* grids or starting points changed: tables
 cudaError_t bb_pool_alloc(bb_ctx* c, size_t bytes, void** out);
 void bb_pool_release(bb_ctx* c, void* p);
 
+/* run-time compiled user models (bb_user.cu) */
+struct bb_user_model;
+bb_user_model* bb_user_lookup(int handle);
+int bb_user_launch(bb_user_model* um, int kind, int gk, int gm, int auxm, int rng, const bb_chain_args& a, cudaStream_t st);
+
 /* thread-local error text for bb_last_cuda_error */
 void bb_set_cuda_error(cudaError_t e, const char* where);
 

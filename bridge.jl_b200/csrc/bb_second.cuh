@@ -11,7 +11,7 @@
 #include "bb_chain.cuh"
 
 template <class M, int GK, int GM, int AUXM, int MODE>
-__global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_constant__ bb_chain_args a) {
+__device__ __forceinline__ void bb_second_body(const bb_chain_args& a) {
   using CH = bb_chain<M, GK, GM, AUXM, 0>;
   constexpr int D = M::D, DP = M::DP, REC = CH::REC;
   const long long P = a.P;
@@ -69,8 +69,13 @@ __global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_cons
 /* solve!(StochasticHeun(), Y, u, W, P)  src/euler.jl:178-198 for a plain target, one segment:
  *   y2 = y + b(y) dt;  y = y + 0.5 (b(y2) + b(y)) dt + sigma dw   for the steps 0 .. N-3 ("for i in 1:N-2 # fix me");
  *   yy[N-1] = endpoint(y);  yy[N] keeps its old value, as in the reference. */
+template <class M, int GK, int GM, int AUXM, int MODE>
+__global__ void __launch_bounds__(BB_THREADS) bb_second_kernel(const __grid_constant__ bb_chain_args a) {
+  bb_second_body<M, GK, GM, AUXM, MODE>(a);
+}
+
 template <class M>
-__global__ void __launch_bounds__(BB_THREADS) bb_heun_kernel(const __grid_constant__ bb_chain_args a) {
+__device__ __forceinline__ void bb_heun_body(const bb_chain_args& a) {
   constexpr int D = M::D, DP = M::DP;
   const long long P = a.P;
   const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,6 +135,11 @@ __global__ void __launch_bounds__(BB_THREADS) bb_heun_kernel(const __grid_consta
   }
 }
 template <class M>
+__global__ void __launch_bounds__(BB_THREADS) bb_heun_kernel(const __grid_constant__ bb_chain_args a) {
+  bb_heun_body<M>(a);
+}
+#ifndef __CUDACC_RTC__ /* host-side launch + lookup (not part of a run-time compiled user-model kernel) */
+template <class M>
 static cudaError_t bb_heun_launch(const bb_chain_args& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_heun_kernel<M><<<grid, BB_THREADS, 0, st>>>(a);
@@ -174,3 +184,4 @@ static bb_chain_launch_fn bb_lookup_second(int gk, int gm, int auxc, int mode) {
   }
   return nullptr;
 }
+#endif /* !__CUDACC_RTC__ */

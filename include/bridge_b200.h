@@ -64,7 +64,8 @@ typedef enum {
   BB_ERR_UNSUPPORTED = -11,/* combination not instantiated (model x guide x dims) */
   BB_ERR_SINGULAR = -12,   /* singular matrix in a backward solve / update */
   BB_ERR_STALE = -13,      /* X holds rejected proposals; bb_ens_refresh_x recomputes the current paths */
-  BB_ERR_COMM = -14        /* an NCCL call failed; see bb_comm_last_error */
+  BB_ERR_COMM = -14,       /* an NCCL call failed; see bb_comm_last_error */
+  BB_ERR_USERSRC = -15     /* the CUDA C source of a user-defined model does not compile; see bb_user_model_log */
 } bb_status;
 
 const char* bb_strerror(int status);
@@ -111,14 +112,15 @@ typedef enum {
   BB_MODEL_LORENZ = 7,
   BB_MODEL_LANDMARKS = 8,
   BB_MODEL_BOLUS = 9,
-  BB_MODEL_COUNT = 10
+  BB_MODEL_USER = 10,  /* drift and diffusion given as CUDA C source, compiled at run time: bb_user_model_create */
+  BB_MODEL_COUNT = 11
 } bb_model_id;
 
 typedef struct {
   int32_t id;       /* bb_model_id */
   int32_t d;        /* state dimension */
   int32_t dprime;   /* dimension of the driving Wiener process */
-  int32_t reserved;
+  int32_t reserved; /* BB_MODEL_USER: bb_user_model_handle(); 0 otherwise */
   double par[BB_NPAR];
 } bb_model;
 
@@ -175,6 +177,38 @@ int bb_ctx_set_arith(bb_ctx* ctx, int arith);
  * the warp-specialised kernel for small ensembles (fewer than two 128-chain CTAs per SM), where it is ~5 % faster. */
 enum { BB_PCN_AUTO = 0, BB_PCN_ONE_THREAD = 1, BB_PCN_WARP_SPECIALISED = 2 };
 int bb_ctx_set_pcn_kernel(bb_ctx* ctx, int mode);
+
+/* ------------------------------------------------------------------ user-defined target processes
+ * The reference's extension point is Julia dispatch: a user defines Bridge.b(t, x, P), Bridge.σ(t, x, P) for an own struct
+ * (src/types.jl:23,32-33, src/Bridge.jl:105-106; project_partialbridge/partialbridge_fitzhugh.jl:44-46).  Julia closures
+ * cannot run on the device, so the equivalent here is CUDA C source compiled at run time (NVRTC, bound by dlopen; the
+ * kernel headers are embedded in the library): the path kernel (sample!, solve!, guided solve! + llikelihood, pCN, the
+ * second-pass llikelihood, StochasticHeun) is instantiated for the user's model exactly as for a registry model --
+ * same TMA / cp.async staging, same arithmetic contract (-fmad=false: only explicit fma() fuses).
+ *   drift_src   statements of   void b(const double* par, const double* x, double* o)   -- o[0..d-1] = b(x; par);
+ *               autonomous (no t), double precision, e.g. the FitzHugh-Nagumo drift of partialbridge_fitzhugh.jl:44:
+ *                 "double u = x[0] - x[1]; u = fma(-(x[0]*x[0]), x[0], u); o[0] = (u + par[1]) * (1.0/par[0]);"
+ *                 "o[1] = fma(par[2], x[0], -x[1]) + par[3];"
+ *   col[i]      column of the driving Wiener process that enters component i, or -1 (each row of σ has at most one
+ *               non-zero: scalar, UniformScaling, SDiagonal or column-vector σ, as every registry model but LinPro)
+ *   sigma_src[i] expression in par[] for that entry of σ (ignored where col[i] < 0); constant in x
+ * par[] is the bb_model's parameter block, passed with every call (so parameters change without recompiling).
+ * bb_model { id = BB_MODEL_USER, d, dprime, reserved = bb_user_model_handle(um), par } then works wherever a registry
+ * model does, except innovations!, the per-chain-parameter path (bb_theta_*) and bb_pcn_step_host.  Kernels are
+ * compiled on first use of a (guide kind, mode) combination, ~1-2 s each; bb_user_model_log returns NVRTC's log. */
+typedef struct bb_user_model bb_user_model;
+int bb_user_model_create(bb_ctx* ctx, int32_t d, int32_t dprime, const char* drift_src, const int32_t* col,
+                         const char* const* sigma_src, bb_user_model** out);
+/* compile-only check (no device needed): builds the kernel of the given combination (gk: 0 or bb_guide_kind; gm: rows of L
+ * for LMMU; auxm: 1 constant / 0 tabulated / 2 non-constdiff auxiliary; rng: 0 read W, 1 pCN, 2 sample, 3 pCN without X°,
+ * 10 llikelihood, 12 StochasticHeun) and returns the cubin size (> 0) or a negative status; NVRTC's log -> log */
+int bb_user_source_check(int32_t d, int32_t dprime, const char* drift_src, const int32_t* col,
+                         const char* const* sigma_src, int32_t gk, int32_t gm, int32_t auxm, int32_t rng, char* log,
+                         int32_t log_size);
+int32_t bb_user_model_handle(bb_user_model* um);
+const char* bb_user_model_log(bb_user_model* um);
+int bb_user_model_destroy(bb_user_model* um);
+
 
 /* ------------------------------------------------------------------ ensemble
  * P chains, each a concatenation of S segments of N grid points (N-1 Euler steps);
