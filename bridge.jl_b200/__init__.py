@@ -10,7 +10,7 @@ from ._cabi import (BridgeError, CUR, PROP, W, X, SYMBOLS, LIB_PATH, ARITH_REFER
 from .api import *  # noqa: F401,F403
 from .api import (Context, default_context, PathEnsemble, SamplePath, VSamplePath, samplepath, sample, sample_,
                   seed_, solve, solve_, bridge_, llikelihood, lptilde, innovations_, pcn_, theta_mcmc_, gpupdate, gpupdate_νH,
-                  EulerMaruyama, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
+                  EulerMaruyama, EulerMaruyama_, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
                   LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde, BolusDiffusion,
                   LinearAux, UserProcess, check_user_source, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,
                   PartialBridge, GuideTables, PartialBridgeνHChain)  # noqa: F401

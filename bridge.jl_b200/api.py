@@ -100,6 +100,13 @@ class EulerMaruyama(SDESolver):  # src/euler.jl:17-21
 Euler = EulerMaruyama  # src/euler.jl:23
 
 
+class EulerMaruyama_(SDESolver):
+    """EulerMaruyama!  (src/euler.jl:62, src/sde!.jl:21-53): the in-place variant for VSamplePath (d x N matrices).  The
+    recurrence is the same -- y + b dt + σ dw, evaluated (y + b dt) + σ dw -- so it runs the same kernel; what differs is
+    the container and the checks: size(Y.yy) == (length(u), N), else "Starting point has wrong length."."""
+    inplace = True
+
+
 class StratonovichEuler(SDESolver):  # src/euler.jl:26-31
     scheme = K.SCHEME_STRATONOVICH
 
@@ -1185,6 +1192,11 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
     if len(Y) != N or (guided and N != len(P.tt)):
         raise BridgeError(K.ERR_LENGTH, lib.bb_strerror(K.ERR_LENGTH).decode())  # src/euler.jl:137,251
     u = np.atleast_1d(f64(u))
+    if getattr(method, "inplace", False):  # solve!(::EulerMaruyama!, Y::VSamplePath, u, W, P)  src/sde!.jl:21-53
+        if guided or not isinstance(Y, VSamplePath):
+            raise BridgeError(K.ERR_UNSUPPORTED, "EulerMaruyama!: solve!(EulerMaruyama!(), Y::VSamplePath, u, W, P)")
+        if Y._as2d().shape != (N, u.size) or u.size != target.d:  # size(Y.yy) != (length(y), N)  src/sde!.jl:30
+            raise BridgeError(K.ERR_STARTPOINT, lib.bb_strerror(K.ERR_STARTPOINT).decode())
     if u.size != target.d:
         raise BridgeError(K.ERR_STARTPOINT, lib.bb_strerror(K.ERR_STARTPOINT).decode())
     e = _small_ens(ctx, 1, N, target.d, target.dprime)

@@ -80,6 +80,27 @@ synchronize(ctx::Context = default_context()) = check(ccall((:bb_ctx_synchronize
 """0: reference arithmetic in the shared-table constructors (default), 1: fused multiply-adds"""
 set_arith!(a::Integer, ctx::Context = default_context()) = check(ccall((:bb_ctx_set_arith, lib), Cint, (Ptr{Cvoid}, Cint), ctx.h, a))
 
+# a model that is not in the registry: CUDA C source compiled at run time into the same kernels (bb_user_model_create)
+mutable struct UserModel
+    h::Ptr{Cvoid}; handle::Int32; d::Int; dprime::Int
+end
+"""`UserModel(d, d′, drift, col, sigma)`: `drift` = C statements assigning o[0..d-1] from x[] and par[]; col[i] = column of W
+entering component i (0-based, -1: none); sigma[i] = C expression in par[] for that entry of σ.  Then
+`BridgeB200.bbmodel(P::MyProcess) = BridgeB200.BBModel(10, d, d′, um.handle, BridgeB200.pad32(params(P)))`."""
+function UserModel(d::Integer, dprime::Integer, drift::String, col::Vector{Int32}, sigma::Vector{String}; ctx::Context = default_context())
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    sp = [col[i] >= 0 ? Base.unsafe_convert(Cstring, sigma[i]) : Cstring(C_NULL) for i in 1:d]
+    st = GC.@preserve sigma ccall((:bb_user_model_create, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Cstring, Ptr{Int32}, Ptr{Cstring}, Ref{Ptr{Cvoid}}),
+                                  ctx.h, d, dprime, drift, col, sp, r)
+    if st != 0
+        log = r[] == C_NULL ? "" : unsafe_string(ccall((:bb_user_model_log, lib), Cstring, (Ptr{Cvoid},), r[]))
+        r[] == C_NULL || ccall((:bb_user_model_destroy, lib), Cint, (Ptr{Cvoid},), r[])
+        error(unsafe_string(ccall((:bb_strerror, lib), Cstring, (Cint,), st)) * "\n" * log)
+    end
+    um = UserModel(r[], ccall((:bb_user_model_handle, lib), Int32, (Ptr{Cvoid},), r[]), d, dprime)
+    finalizer(u -> ccall((:bb_user_model_destroy, lib), Cint, (Ptr{Cvoid},), u.h), um); um
+end
+
 mutable struct PathEnsemble
     h::Ptr{Cvoid}; ctx::Context
     P::Int; S::Int; N::Int; d::Int; dprime::Int
@@ -288,6 +309,24 @@ function solve!(s::EulerMaruyama, Y::SamplePath{T}, u::T, W::SamplePath, P::Cont
         check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, w))
         check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, mr))
         check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, x))
+    end
+    Y.tt[:] = W.tt
+    Y
+end
+
+"""solve!(EulerMaruyama!(), Y::VSamplePath, u, W, P)   src/sde!.jl:21-53: d x N matrices (column = time) have the byte
+layout of the ABI's [N][d]; same recurrence, same kernel"""
+function solve!(s::Bridge.EulerMaruyama!, Y::Bridge.VSamplePath, u, W::Bridge.VSamplePath, P::ContinuousTimeProcess)
+    ondevice(P) || return invoke(solve!, Tuple{Bridge.EulerMaruyama!,Bridge.VSamplePath,Any,Any,Bridge.ProcessOrCoefficients}, s, Y, u, W, P)
+    N = length(W); N != length(Y) && error("Y and W differ in length.")
+    size(Y.yy) != (length(u), N) && error("Starting point has wrong length.")          # src/sde!.jl:30
+    m = bbmodel(P); E = small(N, Int(m.d), Int(m.dprime))
+    setgrid!(E, 1, W.tt); setstart!(E, u)
+    mr = Ref(m)
+    GC.@preserve W Y begin
+        check(ccall((:bb_ens_upload, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, 0, 1, W.yy))
+        check(ccall((:bb_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}), E.h, mr))
+        check(ccall((:bb_ens_download, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Float64}), E.h, 1, 0, 0, 1, Y.yy))
     end
     Y.tt[:] = W.tt
     Y

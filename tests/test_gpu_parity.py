@@ -1126,6 +1126,36 @@ def test_stochastic_heun_vs_oracle(B, oracle_ref, oracle_fma, name, mk, om, exac
     ens.close()
 
 
+def test_inplace_solver_on_vsamplepath(B, oracle_fma):
+    """solve!(EulerMaruyama!(), Y::VSamplePath, u, W, P) (src/sde!.jl:21-53) against solve!(EulerMaruyama(), ...) on a
+    SamplePath and the oracle: test/euler.jl:49-68 (Lorenz, d = 3; the reference asserts agreement to eps(): here the
+    two containers go through the same kernel, so it is exact), the d x N container, its DimensionMismatch and the
+    "Starting point has wrong length." check of src/sde!.jl:30."""
+    K = B.api.K
+    N = 501
+    tt = np.linspace(0.0, 5.0, N)
+    P = B.Lorenz([10.0, 28.0, 8.0 / 3.0], [3.0, 3.0, 3.0])
+    om = O.make_model(O.LORENZ, 3, 3, [10.0, 28.0, 8.0 / 3.0, 3.0, 3.0, 3.0])
+    u = np.array([1.508870, -1.531271, 25.46091])
+    B.seed_(5)
+    W = B.sample(tt.copy(), B.Wiener(3))
+    X = B.solve(B.EulerMaruyama(), u, W, P)
+    Wv = B.VSamplePath(tt.copy(), W.yy.T.copy())      # d x N, as the reference's VSamplePath
+    Yv = B.VSamplePath(tt.copy(), np.zeros((3, N)))
+    out = B.solve_(B.EulerMaruyama_(), Yv, u, Wv, P)
+    assert out is Yv and np.array_equal(Yv.yy, X.yy) and np.array_equal(Yv.tt, W.tt)
+    assert np.array_equal(X.yy, oracle_fma.euler(om, tt, u, W.yy))
+    with pytest.raises(B.BridgeError) as ei:                      # u of the wrong length
+        B.solve_(B.EulerMaruyama_(), Yv, u[:2], Wv, P)
+    assert ei.value.status == K.ERR_STARTPOINT and "Starting point has wrong length." in str(ei.value)
+    with pytest.raises(B.BridgeError) as ei:                      # DimensionMismatch of the container  src/types.jl:127
+        B.VSamplePath(tt, np.zeros((3, N - 1)))
+    assert ei.value.status == K.ERR_DIM
+    with pytest.raises(B.BridgeError) as ei:                      # Y and W differ in length
+        B.solve_(B.EulerMaruyama_(), B.VSamplePath(tt[:-1].copy(), np.zeros((3, N - 1))), u, Wv, P)
+    assert ei.value.status == K.ERR_LENGTH
+
+
 def test_schemes_through_solve(B, oracle_fma):
     """solve(StochasticHeun(), u, W, P) / solve(StratonovichEuler(), ...) on SamplePaths (P = 1 plumbing)."""
     tt = np.arange(0, 101) * 0.01

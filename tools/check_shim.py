@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "bridge_b200.h")
 SHIM = os.path.join(ROOT, "julia", "BridgeB200.jl")
 
-HANDLES = {"bb_ctx", "bb_ens", "bb_guide", "bb_comm", "void"}
+HANDLES = {"bb_ctx", "bb_ens", "bb_guide", "bb_comm", "bb_user_model", "void"}
 C_SCALARS = {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint32_t": "u32", "uint64_t": "u64", "double": "f64",
              "uint8_t": "u8"}
 JL_SCALARS = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "UInt32": "u32", "UInt64": "u64", "Float64": "f64",
@@ -63,7 +63,7 @@ def jl_class(t: str) -> str:
         return JL_SCALARS[t]
     if t == "Cstring":
         return "ptr:char"
-    if t in ("Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"):
+    if t in ("Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}", "Ptr{Cstring}"):
         return "pptr"
     if t == "Ptr{Cvoid}":
         return "ptr:handle"
