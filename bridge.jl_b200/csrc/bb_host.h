@@ -66,7 +66,7 @@ struct bb_ens {
   /* per-chain parameters and guiding tables (bb_theta.cu) */
   struct bb_theta* th = nullptr;
   /* pooled online statistics (bb_stats.cu) */
-  double *mc_sum = nullptr, *mc_sq = nullptr;
+  double *mc_sum = nullptr, *mc_sq = nullptr, *mc_pivot = nullptr;
   int64_t mc_n = 0;
 };
 

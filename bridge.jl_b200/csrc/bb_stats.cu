@@ -5,8 +5,14 @@
  * chains at once wants the same two moments over all chains and all recorded iterations without downloading
  * P paths per iteration (project_partialbridge/partialbridge_fitzhugh.jl:169-189 stores every 1000th path).
  *
- * Accumulators: sum[S][N][d], sq[S][N][d][d] (double), n.  One CTA reduces the 16 grid points of one chunk over 256
- * chains in shared memory and issues d + d*d atomic adds per grid point; X is read once (8 d bytes per path-step).
+ * Accumulators: sum[S][N][d], sq[S][N][d][d] (double), n -- of the DEVIATIONS from a pivot path c[S][N][d] (the path of
+ * chain 0 at the first update after a reset), as Welford's update in the reference works with deviations from the running
+ * mean: near a conditioned end point the variance is tiny against the mean (Σ = 1e-10 in the FitzHugh-Nagumo configs) and
+ * raw moments sum(x^2) - n mean^2 would cancel.  mean = c + sum/n, cov = (sq - n (sum/n)(sum/n)') / (n-1).
+ * One CTA reduces the 16 grid points of one chunk over 256 chains in shared memory and issues d + d*d atomic adds per
+ * grid point; X is read once (8 d bytes per path-step).  The atomic adds make the last bits depend on the order in which
+ * CTAs arrive (the only non-deterministic results of the library); the mcband semantics differ from the reference's in
+ * that moments pool P chains per call (src/mclog.jl:22-56 tracks one chain over iterations).
  */
 #include <string.h>
 
@@ -14,9 +20,20 @@
 
 #include "bb_host.h"
 
+/* pivot[s][j][a] = X of chain 0 */
+__global__ void bb_mc_pivot_kernel(const double* __restrict__ X, double* __restrict__ pivot, long long P, int S, int N, int NC,
+                                   int D) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S * N * D) return;
+  const int a = t % D, j = (t / D) % N, s = t / (D * N);
+  const int c = j / BB_TC, slot = j % BB_TC;
+  pivot[t] = X[(((long long)s * NC + c) * P) * (BB_TC * D) + slot * D + a];
+}
+
 template <int D>
-__global__ void __launch_bounds__(256) bb_mc_update_kernel(const double* __restrict__ X, double* __restrict__ sum,
-                                                           double* __restrict__ sq, long long P, int N, int NC) {
+__global__ void __launch_bounds__(256) bb_mc_update_kernel(const double* __restrict__ X, const double* __restrict__ pivot,
+                                                           double* __restrict__ sum, double* __restrict__ sq, long long P,
+                                                           int N, int NC) {
   constexpr int ROW = BB_TC * D, SUB = 64; /* chains per shared-memory tile; a CTA covers 256 chains in 4 tiles */
   constexpr int NM = BB_TC * (D + D * D);  /* moments per chunk: thread t < NM owns one of them */
   __shared__ double tile[SUB][ROW + 1];
@@ -38,7 +55,11 @@ __global__ void __launch_bounds__(256) bb_mc_update_kernel(const double* __restr
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       if (p < P) bb_ld4(X + ((long long)chunk * P + p) * ROW + 4 * q, v);
 #pragma unroll
-      for (int i = 0; i < 4; i++) tile[lc][4 * q + i] = v[i];
+      for (int i = 0; i < 4; i++) {
+        const int e = 4 * q + i, jj = c * BB_TC + e / D;
+        /* deviation from the pivot path (0 for padding and missing chains: they add nothing) */
+        tile[lc][e] = (p < P && jj < N) ? v[i] - pivot[((long long)s * N + jj) * D + e % D] : 0.0;
+      }
     }
     __syncthreads();
     if ((int)threadIdx.x < NM) {
@@ -62,11 +83,12 @@ extern "C" int bb_ens_mc_reset(bb_ens* e) {
   BB_CUDA(cudaSetDevice(e->ctx->device));
   const size_t n1 = (size_t)e->S * e->N * e->d, n2 = n1 * e->d;
   if (!e->mc_sum) {
-    BB_CUDA(cudaMalloc(&e->mc_sum, (n1 + n2) * sizeof(double)));
+    BB_CUDA(cudaMalloc(&e->mc_sum, (n1 + n2 + n1) * sizeof(double)));
     e->mc_sq = e->mc_sum + n1;
-    e->bytes += (int64_t)((n1 + n2) * sizeof(double));
+    e->mc_pivot = e->mc_sq + n2;
+    e->bytes += (int64_t)((n1 + n2 + n1) * sizeof(double));
   }
-  BB_CUDA(cudaMemsetAsync(e->mc_sum, 0, (n1 + n2) * sizeof(double), e->ctx->stream));
+  BB_CUDA(cudaMemsetAsync(e->mc_sum, 0, (n1 + n2 + n1) * sizeof(double), e->ctx->stream));
   e->mc_n = 0;
   return BB_OK;
 }
@@ -80,13 +102,18 @@ extern "C" int bb_ens_mc_update(bb_ens* e) {
   }
   bb_ctx* c = e->ctx;
   BB_CUDA(cudaSetDevice(c->device));
+  if (e->d < 1 || e->d > 3) return BB_ERR_UNSUPPORTED;
   const dim3 grid((unsigned)((e->P + 255) / 256), (unsigned)(e->S * e->NC));
   bb_time_begin(c);
+  if (e->mc_n == 0) { /* first update after a reset: the pivot is the path of chain 0 */
+    const int tot = e->S * e->N * e->d;
+    bb_mc_pivot_kernel<<<(tot + 255) / 256, 256, 0, c->stream>>>(e->X, e->mc_pivot, e->P, e->S, e->N, e->NC, e->d);
+    c->launches++;
+  }
   switch (e->d) {
-    case 1: bb_mc_update_kernel<1><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
-    case 2: bb_mc_update_kernel<2><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
-    case 3: bb_mc_update_kernel<3><<<grid, 256, 0, c->stream>>>(e->X, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
-    default: return BB_ERR_UNSUPPORTED;
+    case 1: bb_mc_update_kernel<1><<<grid, 256, 0, c->stream>>>(e->X, e->mc_pivot, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
+    case 2: bb_mc_update_kernel<2><<<grid, 256, 0, c->stream>>>(e->X, e->mc_pivot, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
+    default: bb_mc_update_kernel<3><<<grid, 256, 0, c->stream>>>(e->X, e->mc_pivot, e->mc_sum, e->mc_sq, e->P, e->N, e->NC); break;
   }
   bb_time_end(c);
   BB_CUDA(cudaGetLastError());
@@ -103,21 +130,21 @@ extern "C" int bb_ens_mc_stats(bb_ens* e, double* mean, double* cov, int64_t* n)
   BB_CUDA(cudaSetDevice(e->ctx->device));
   const int d = e->d;
   const size_t n1 = (size_t)e->S * e->N * d, n2 = n1 * d;
-  std::vector<double> h(n1 + n2);
-  BB_CUDA(cudaMemcpyAsync(h.data(), e->mc_sum, (n1 + n2) * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
+  std::vector<double> h(n1 + n2 + n1);
+  BB_CUDA(cudaMemcpyAsync(h.data(), e->mc_sum, (n1 + n2 + n1) * sizeof(double), cudaMemcpyDeviceToHost, e->ctx->stream));
   BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
   const double k = (double)e->mc_n;
   for (size_t g = 0; g < (size_t)e->S * e->N; g++) {
     double m[BB_MAXD];
     for (int a = 0; a < d; a++) {
-      m[a] = h[g * d + a] / k;
-      if (mean) mean[g * d + a] = m[a];
+      m[a] = h[g * d + a] / k; /* mean deviation from the pivot */
+      if (mean) mean[g * d + a] = h[n1 + n2 + g * d + a] + m[a];
     }
     if (cov)
       for (int a = 0; a < d; a++)
         for (int b = 0; b < d; b++) {
           double v = (h[n1 + (g * d + a) * d + b] - k * m[a] * m[b]) / (k - 1.0);
-          if (a == b && v < 0.0) v = 0.0; /* rounding of sum(x^2) - n mean^2 at (numerically) constant grid points */
+          if (a == b && v < 0.0) v = 0.0; /* rounding at (numerically) constant grid points */
           cov[(g * d + a) * d + b] = v;
         }
   }

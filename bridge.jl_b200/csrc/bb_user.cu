@@ -42,16 +42,25 @@ std::mutex g_mu;
 
 int rtc_load(std::string& err) {
   if (g_rtc.handle) return BB_OK;
-  const char* names[] = {getenv("BB_NVRTC_LIB"), "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  /* the toolkit's own NVRTC first (by path): a process that has imported torch already holds torch's bundled
+   * libnvrtc.so.12 (CUDA 12.8), which a dlopen by soname would return -- and its PTX back end rejects the 256-bit
+   * vector loads / stores the sm_100a kernels use.  Candidates older than 12.9 are skipped. */
+  const char* names[] = {getenv("BB_NVRTC_LIB"), "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                         "libnvrtc.so.12", "libnvrtc.so"};
   void* h = nullptr;
+  std::string tried;
   for (const char* n : names) {
     if (!n || !*n) continue;
-    h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
-    if (h) break;
+    void* cand = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (!cand) { tried += std::string(n) + ": " + dlerror() + "; "; continue; }
+    int (*ver)(int*, int*) = (int (*)(int*, int*))dlsym(cand, "nvrtcVersion");
+    int major = 0, minor = 0;
+    if (ver && ver(&major, &minor) == 0 && (major > 12 || (major == 12 && minor >= 9))) { h = cand; break; }
+    tried += std::string(n) + ": NVRTC " + std::to_string(major) + "." + std::to_string(minor) + " < 12.9; ";
+    dlclose(cand);
   }
   if (!h) {
-    err = std::string("NVRTC not found: ") + dlerror();
+    err = std::string("no usable NVRTC (>= 12.9): ") + tried;
     return BB_ERR_UNSUPPORTED;
   }
   nvrtc_api a;

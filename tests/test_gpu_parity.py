@@ -1075,6 +1075,10 @@ def test_pooled_online_statistics(B, oracle_fma):
     assert np.allclose(mean, Xs.mean(axis=0), rtol=1e-12, atol=1e-13)
     want = np.einsum("ksni,ksnj->snij", Xs - Xs.mean(axis=0), Xs - Xs.mean(axis=0)) / (n - 1)
     assert np.allclose(cov, want, rtol=1e-9, atol=1e-12)
+    # the conditioned end points: variance O(1e-10) (Σ = 1e-10) next to a mean O(1) -- raw moments would cancel there;
+    # the device accumulates deviations from a pivot path
+    assert np.all(want[:, -1, 0, 0] < 1e-6) and np.all(want[:, -1, 0, 0] > 0)
+    assert np.allclose(cov[:, -1, 0, 0], want[:, -1, 0, 0], rtol=1e-6, atol=0.0)
     lo, hi = ens.mc_band()
     assert np.all(lo <= mean) and np.all(mean <= hi)
     assert np.allclose(mean[0, 0], [-0.5, -0.6]) and np.allclose(cov[0, 0], 0.0, atol=1e-12)   # fixed start point
