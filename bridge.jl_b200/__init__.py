@@ -12,5 +12,5 @@ from .api import (Context, default_context, PathEnsemble, SamplePath, VSamplePat
                   seed_, solve, solve_, bridge_, llikelihood, lptilde, innovations_, pcn_, theta_mcmc_, gpupdate, gpupdate_νH,
                   EulerMaruyama, EulerMaruyama_, Euler, StratonovichEuler, StochasticHeun, StochasticRungeKutta, Mdb, LeftRule, R3, Lyap, ContinuousTimeProcess, Wiener, OrnsteinUhlenbeck,
                   LinPro, FitzHughNagumo, FitzhughDiffusion, IntegratedDiffusion, NclarDiffusion, Lorenz, Landmarks, LandmarksTilde, BolusDiffusion,
-                  LinearAux, UserProcess, check_user_source, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,
+                  LinearAux, LinearAppr, linearappr, bderiv, UserProcess, check_user_source, PartialBridgeνH, PartialBridgenuH, partialbridgeνH, partialbridgenuH, GuidedBridge,
                   PartialBridge, GuideTables, PartialBridgeνHChain)  # noqa: F401

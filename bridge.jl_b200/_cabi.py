@@ -106,6 +106,7 @@ def _load():
         "bb_ens_bytes": (i64, [vp]),
         "bb_wiener_sample": (C.c_int, [vp, u64, u32]),
         "bb_euler": (C.c_int, [vp, C.POINTER(Model)]),
+        "bb_guided_mdb": (C.c_int, [vp, C.POINTER(Model), pp]),
         "bb_sample_euler": (C.c_int, [vp, C.POINTER(Model), u64, u32]),
         "bb_solve_scheme": (C.c_int, [vp, C.POINTER(Model), i32]),
         "bb_guide_create": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, pp]),

@@ -498,6 +498,79 @@ class LinearAux:
         return np.atleast_2d(f64(self._a(t) if callable(self._a) else self._a))
 
 
+class LinearAppr:
+    """LinearAppr(tt, xx, B, b, Σ)  src/linpro.jl:181-194: a linear auxiliary process tabulated on a grid,
+        _b((i,s), x) = B[i] (x - xx[i]) + b[i],   B((i,s)) = B[i],   β((i,s)) = b[i] - B[i] xx[i],   a((i,s)) = Σ[i] Σ[i]',
+    constdiff = false.  `linearappr(Y, P)` (src/linpro.jl:196) builds it along a trajectory Y from bderiv, b, σ of P.
+    As the auxiliary process of GuidedBridge / PartialBridge / PartialBridgeνH its coefficients are needed BETWEEN grid
+    points (Ralston stages): they are interpolated linearly.  [The reference's own constructor for this auxiliary type,
+    GuidedBridge(tt, P, Pt::LinearAppr, v) -> solvebackwardi!(Heun(), ...), does not run: kerneli uses an undefined `i`
+    (src/ode.jl:98-102), so there is no reference table to match; the tables here come from the same R3 scheme as for
+    every other auxiliary process.]"""
+    is_const = False
+    constdiff = False
+
+    def __init__(self, tt, xx, B, b, Σ):
+        self.tt = f64(tt)
+        N = len(self.tt)
+        self.xx = f64(xx).reshape(N, -1)
+        self.d = self.xx.shape[1]
+        self.Bs = f64(B).reshape(N, self.d, self.d)
+        self.bs = f64(b).reshape(N, self.d)
+        Σ = f64(Σ)
+        self.Σs = Σ.reshape(N, self.d, -1)
+        self.βs = self.bs - np.einsum("nij,nj->ni", self.Bs, self.xx)
+        self.as_ = np.einsum("nik,njk->nij", self.Σs, self.Σs)
+
+    def _lerp(self, arr, t):
+        tt = self.tt
+        if t <= tt[0]:
+            return arr[0]
+        if t >= tt[-1]:
+            return arr[-1]
+        i = int(np.searchsorted(tt, t, side="right")) - 1
+        w = (t - tt[i]) / (tt[i + 1] - tt[i])
+        return (1.0 - w) * arr[i] + w * arr[i + 1]
+
+    def B(self, t):
+        """B((i,s), P) for an index-time pair (i, s) (0-based i), or the interpolated value at a plain time."""
+        return self.Bs[t[0]] if isinstance(t, tuple) else self._lerp(self.Bs, t)
+
+    def β(self, t):
+        return self.βs[t[0]] if isinstance(t, tuple) else self._lerp(self.βs, t)
+
+    def a(self, t, x=None):
+        return self.as_[t[0]] if isinstance(t, tuple) else self._lerp(self.as_, t)
+
+    def b(self, t, x):  # _b((i,s), x, P)  src/linpro.jl:189
+        i = t[0]
+        return self.Bs[i] @ (np.asarray(x) - self.xx[i]) + self.bs[i]
+
+
+def bderiv(t, x, P):
+    """Bridge.bderiv(t, x, P): the Jacobian of the drift (src/Models.jl:49-53 Lorenz, src/linpro.jl:82 LinPro; the
+    FitzHugh-Nagumo models by differentiation of src/Models.jl:18, partialbridge_fitzhugh.jl:44)."""
+    x = np.asarray(x, dtype=np.float64)
+    if isinstance(P, LinPro):
+        return P.Bm
+    if isinstance(P, Lorenz):
+        θ = P.p
+        return np.array([[-θ[0], θ[0], 0.0], [θ[1] - x[2], -1.0, -x[0]], [x[1], x[0], -θ[2]]])
+    if isinstance(P, (FitzHughNagumo, FitzhughDiffusion)):
+        ϵ, _, γ = P.p[0], P.p[1], P.p[2]
+        return np.array([[(1.0 - 3.0 * x[0] * x[0]) / ϵ, -1.0 / ϵ], [γ, -1.0]])
+    if isinstance(P, OrnsteinUhlenbeck):
+        return np.array([[-P.β]])
+    raise NotImplementedError(f"bderiv is not defined for {type(P).__name__}")
+
+
+def linearappr(Y: "SamplePath", P) -> LinearAppr:
+    """linearappr(Y, P) = LinearAppr(Y.tt, Y.yy, bderiv.(tt, yy), b.(tt, yy), σ.(tt, yy))  src/linpro.jl:196"""
+    yy = Y._as2d()
+    return LinearAppr(Y.tt, yy, [bderiv(t, x, P) for t, x in zip(Y.tt, yy)], [np.atleast_1d(P.b(t, x)) for t, x in zip(Y.tt, yy)],
+                      [np.atleast_2d(P.σ(t, x)) for t, x in zip(Y.tt, yy)])
+
+
 class _AuxC:
     """bb_aux for a backward solve on grid tt (keeps the arrays alive)."""
 
@@ -691,6 +764,12 @@ class PathEnsemble:
     def euler_(self, P: ContinuousTimeProcess):
         m = P.cmodel()
         check(lib.bb_euler(self.h, C.byref(m)))
+
+    def guided_mdb_(self, P: ContinuousTimeProcess, guides):
+        """solve!(Mdb(), Y, u, W, P°) on a guided proposal, S = 1 (bb_guided_mdb)."""
+        m = P.cmodel()
+        self._last = (P, list(guides))
+        check(lib.bb_guided_mdb(self.h, C.byref(m), self._garr(guides)))
 
     def solve_scheme_(self, P: ContinuousTimeProcess, scheme: int):
         """solve! with StratonovichEuler / StochasticHeun / StochasticRungeKutta for a plain target (bb_solve_scheme)."""
@@ -1181,9 +1260,9 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
     ctx = ctx or default_context()
     guided = _is_proposal(P)
     scheme = getattr(method, "scheme", K.SCHEME_EULER)
-    if guided and scheme not in (K.SCHEME_EULER, K.SCHEME_STRATONOVICH):
-        # guided solve! exists for Euler and StratonovichEuler only (src/euler.jl:246-306); the latter equals the
-        # former for the registry's constant σ
+    if guided and scheme not in (K.SCHEME_EULER, K.SCHEME_STRATONOVICH, K.SCHEME_MDB):
+        # guided solve! exists for Euler, StratonovichEuler (src/euler.jl:246-306; the latter equals the former for the
+        # registry's constant σ) and Mdb (src/euler.jl:308-327)
         raise BridgeError(K.ERR_UNSUPPORTED, lib.bb_strerror(K.ERR_UNSUPPORTED).decode())
     target = P.Target if guided else P
     if guided and W.tt is P.tt:
@@ -1202,7 +1281,10 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
     e = _small_ens(ctx, 1, N, target.d, target.dprime)
     e.set_start(u)
     e.upload(K.W, W._as2d())
-    if guided:
+    if guided and scheme == K.SCHEME_MDB:
+        e.guided_mdb_(target, [P])
+        Y.tt[...] = P.tt  # tt[:] = P.tt  src/euler.jl:318
+    elif guided:
         e.guided_euler_ll_(target, [P], store_x=True, ll=False)
         Y.tt[...] = P.tt  # tt[:] = P.tt  src/euler.jl:256
     else:
@@ -1216,7 +1298,7 @@ def solve_(method: SDESolver, Y: SamplePath, u, W: SamplePath, P, ctx=None):
         Y.tt[...] = W.tt
     X = e.download(K.X)
     Y.yy[...] = X.reshape(Y.yy.shape)
-    if guided:
+    if guided and scheme != K.SCHEME_MDB:  # the guided Euler method returns the end point, Mdb returns Y (src/euler.jl:326)
         return Y.yy[-1].copy()
     return Y
 

@@ -810,9 +810,10 @@ struct run_spec {
   uint32_t stream;
   bool only_stale = false;
   int64_t p_begin = 0, p_end = -1; /* chain sub-range (default: all) */
+  const double* tab1 = nullptr;    /* Mdb: per-step noise factors (device), passed as a.tab[1] (S = 1) */
 };
 
-/* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations!; 12 = StochasticHeun */
+/* rs.rng: 0/1/2 = path kernel modes; 10 = llikelihood on stored X; 11 = innovations!; 12 = StochasticHeun; 13 = Mdb */
 static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, const run_spec& rs) {
   if (!e || !model) return BB_ERR_ARG;
   bb_ctx* c = e->ctx;
@@ -858,6 +859,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   if (rs.rng == 1 && !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG;
   if (rs.store_x && !e->X) return BB_ERR_ARG;
   if (rs.skip < 0) return BB_ERR_ARG;
+  if (rs.tab1) a.tab[1] = rs.tab1;
   a.W[0] = e->W[0]; a.W[1] = e->W[1]; a.X = e->X;
   a.xstale = e->xstale; a.only = rs.only_stale ? e->xstale : nullptr;
   a.nbuf = e->nbuf;
@@ -876,7 +878,8 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   bb_prepare_model(model, &a.model);
   bb_time_begin(c);
   if (um) { /* run-time compiled model: the same kernels, instantiated for the user's b and sigma (bb_user.cu) */
-    const int rcu = rs.rng == 12 ? bb_user_launch(um, 2, 0, 0, 1, 0, a, c->stream)
+    const int rcu = rs.rng == 13 ? BB_ERR_UNSUPPORTED
+                  : rs.rng == 12 ? bb_user_launch(um, 2, 0, 0, 1, 0, a, c->stream)
                   : rs.rng >= 10 ? bb_user_launch(um, 1, gk, gm, auxc, rs.rng - 10, a, c->stream)
                                  : bb_user_launch(um, 0, gk, gm, auxc, krng, a, c->stream);
     if (rcu != BB_OK) return rcu;
@@ -890,7 +893,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
   bb_time_end(c);
   c->launches++;
   if (rs.rng == 1) e->x_maybe_stale = true;
-  else if ((rs.rng < 10 || rs.rng == 12) && rs.store_x && !rs.only_stale) e->x_maybe_stale = false;
+  else if ((rs.rng < 10 || rs.rng == 12 || rs.rng == 13) && rs.store_x && !rs.only_stale) e->x_maybe_stale = false;
   else if (rs.rng < 10 && !rs.store_x && e->X) e->x_maybe_stale = true; /* X no longer belongs to the chains' state */
   if (rs.only_stale) e->x_maybe_stale = false;
   return BB_OK;
@@ -930,6 +933,33 @@ extern "C" int bb_solve_scheme(bb_ens* e, const bb_model* model, int32_t scheme)
     case BB_SCHEME_MDB: return BB_ERR_UNSUPPORTED;
     default: return BB_ERR_ARG;
   }
+}
+/* solve!(Mdb(), Y, u, W, P°)  src/euler.jl:308-327 on a guided proposal (one segment): X_cur <- the path, xend <- yy[N] */
+extern "C" int bb_guided_mdb(bb_ens* e, const bb_model* model, bb_guide* const* guides) {
+  if (!e || !model || !guides || !guides[0]) return BB_ERR_ARG;
+  if (e->S != 1) return BB_ERR_UNSUPPORTED;
+  const bb_guide* g = guides[0];
+  if (g->N != e->N) return BB_ERR_LENGTH;
+  bb_ctx* c = e->ctx;
+  BB_CUDA(cudaSetDevice(c->device));
+  const int N = e->N;
+  std::vector<double> sc((size_t)e->NC * BB_TC, 0.0);
+  const double T = g->tt[N - 1];
+  for (int j = 1; j < N; j++) sc[j] = sqrt((T - g->tt[j]) / (T - g->tt[j - 1])); /* step j-1 -> j (i = j-1 in the reference) */
+  double* dsc = nullptr;
+  BB_CUDA(bb_pool_alloc(c, sc.size() * sizeof(double), (void**)&dsc));
+  cudaError_t ce = cudaMemcpyAsync(dsc, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  int rc = BB_ERR_CUDA;
+  if (ce == cudaSuccess) {
+    run_spec rs{13, true, false, true, 0, 0.0, 0, 0};
+    rs.tab1 = dsc;
+    rc = run_chain(e, model, guides, rs);
+  } else {
+    bb_set_cuda_error(ce, "bb_guided_mdb");
+  }
+  cudaStreamSynchronize(c->stream); /* the pageable copy above and the launch have consumed sc / dsc */
+  bb_pool_release(c, dsc);
+  return rc;
 }
 extern "C" int bb_sample_euler(bb_ens* e, const bb_model* model, uint64_t seed, uint32_t stream) {
   run_spec rs{2, true, false, true, 0, 0.0, seed, stream};

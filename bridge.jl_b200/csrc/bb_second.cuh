@@ -138,11 +138,95 @@ template <class M>
 __global__ void __launch_bounds__(BB_THREADS) bb_heun_kernel(const __grid_constant__ bb_chain_args a) {
   bb_heun_body<M>(a);
 }
+
+/* solve!(Mdb(), Y, u, W, P°)  src/euler.jl:308-327, the "modified diffusion bridge" step on a guided proposal, one segment:
+ *   y = y + _b((i, tt[i]), y, P°) dt + (σ sqrt((tt[end] - tt[i+1]) / (tt[end] - tt[i]))) dw ;  yy[N] = endpoint(y, P°)
+ * i.e. the guided Euler step with the noise damped towards the end point.  The per-step factor comes from a second
+ * table, a.tab[1][j] = sqrt((T - tt[j]) / (T - tt[j-1])) for the step j-1 -> j (0 at the last step). */
+template <class M, int GK, int GM, int AUXM>
+__device__ __forceinline__ void bb_mdb_body(const bb_chain_args& a) {
+  using CH = bb_chain<M, GK, GM, AUXM, 0>;
+  constexpr int D = M::D, DP = M::DP, REC = CH::REC;
+  const long long P = a.P;
+  const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.p_end) return;
+  const int par = a.par[p], N = a.N;
+  const double* wr = a.W[par] + p * (a.nbuf * BB_TC * DP);
+  double* xw = a.X + p * (BB_TC * D);
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+  const double* tab = a.tab[0];
+  const double* scale = a.tab[1];
+  const double* sc = a.segc[0];
+  double y[D], wprev[DP], som = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) y[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + p];
+  for (int c = 0; c < a.NC; c++) {
+    bb_rowout<D> xo;
+#pragma unroll 1
+    for (int h = 0; h < BB_TC / 4; h++) {
+      double w[4 * DP];
+#pragma unroll
+      for (int q = 0; q < DP; q++) bb_ld4(wr + 4 * h * DP + 4 * q, w + 4 * q);
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++) {
+        const int j = c * BB_TC + 4 * h + s4;
+        if (j >= 1 && j <= N - 1) {
+          const double* R = tab + (size_t)j * REC;
+          const double dt = R[0], ns = scale[j];
+          double bd[D], dw[DP];
+#pragma unroll
+          for (int k = 0; k < DP; k++) dw[k] = w[s4 * DP + k] - wprev[k];
+          CH::drift(a.model, R, sc, y, dt, false, som, bd);
+          if constexpr (M::SPARSE) {
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+              double t1 = fma(bd[i], dt, y[i]);
+              if (M::col(i) >= 0) t1 = fma(M::sig(a.model, i) * ns, dw[M::col(i) < 0 ? 0 : M::col(i)], t1);
+              y[i] = t1;
+            }
+          } else {
+            double Ss[D * DP], sd[D];
+#pragma unroll
+            for (int q = 0; q < D * DP; q++) Ss[q] = MLinPro<D>::sigma(a.model)[q] * ns;
+            bb_matvec<D, DP>(Ss, dw, sd);
+#pragma unroll
+            for (int i = 0; i < D; i++) y[i] = fma(bd[i], dt, y[i]) + sd[i];
+          }
+          if (GK == BB_GUIDE_HV && j == N - 1 && sc[D * D + D] != 0.0) { /* endpoint(y, P::GuidedBridge)  src/euler.jl:241-242 */
+#pragma unroll
+            for (int k = 0; k < D; k++) y[k] = sc[D * D + D + 1 + k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DP; k++) wprev[k] = w[s4 * DP + k];
+        xo.put(xw + 4 * h * D, s4, y, true);
+      }
+    }
+    wr += wstride;
+    xw += xstride;
+  }
+  a.xstale[p] = 0;
+  if (a.write_end) {
+#pragma unroll
+    for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = y[k];
+  }
+}
+template <class M, int GK, int GM, int AUXM>
+__global__ void __launch_bounds__(BB_THREADS) bb_mdb_kernel(const __grid_constant__ bb_chain_args a) {
+  bb_mdb_body<M, GK, GM, AUXM>(a);
+}
 #ifndef __CUDACC_RTC__ /* host-side launch + lookup (not part of a run-time compiled user-model kernel) */
 template <class M>
 static cudaError_t bb_heun_launch(const bb_chain_args& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
   bb_heun_kernel<M><<<grid, BB_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class M, int GK, int GM, int AUXM>
+static cudaError_t bb_mdb_launch(const bb_chain_args& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
+  bb_mdb_kernel<M, GK, GM, AUXM><<<grid, BB_THREADS, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -161,9 +245,11 @@ static bb_chain_launch_fn bb_lookup_second_guide(int auxm, int mode) {
     if (mode == 1) return auxm == 1 ? &bb_second_launch<M, GK, GM, 1, 1>
                                     : (auxm == 0 ? &bb_second_launch<M, GK, GM, 0, 1> : &bb_second_launch<M, GK, GM, 2, 1>);
   }
+  if (mode == 3) return auxm == 1 ? &bb_mdb_launch<M, GK, GM, 1> : (auxm == 0 ? &bb_mdb_launch<M, GK, GM, 0> : &bb_mdb_launch<M, GK, GM, 2>);
   return nullptr;
 }
-/* mode 0 = llikelihood (needs a guide), 1 = innovations (guide optional, needs d' = d), 2 = StochasticHeun (no guide) */
+/* mode 0 = llikelihood (needs a guide), 1 = innovations (guide optional, needs d' = d), 2 = StochasticHeun (no guide),
+ * 3 = Mdb on a guided proposal */
 template <class M>
 static bb_chain_launch_fn bb_lookup_second(int gk, int gm, int auxc, int mode) {
   if (gk == 0) {

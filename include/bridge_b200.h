@@ -276,10 +276,14 @@ int bb_euler(bb_ens* ens, const bb_model* model);
  *                           ½(σ(ups) - σ(y))(dw² - δ)/√δ is exactly 0 for constant σ: the Euler-Maruyama kernel, d = 1.
  *   BB_SCHEME_HEUN          solve!(StochasticHeun(), ...)     src/euler.jl:178-198: drift by Heun's rule; as in the
  *                           reference the loop stops at N-2 and yy[N] is left untouched.
- * Mdb (src/euler.jl:308-327) needs a proposal process with its own time axis (the classic BridgeProp family, out of
- * scope): BB_ERR_UNSUPPORTED. */
+ * Mdb (src/euler.jl:308-327) needs a proposal process with its own time axis: bb_guided_mdb runs it on a guided proposal;
+ * through this entry point (a plain target) it is BB_ERR_UNSUPPORTED. */
 enum { BB_SCHEME_EULER = 0, BB_SCHEME_STRATONOVICH = 1, BB_SCHEME_HEUN = 2, BB_SCHEME_SRK = 3, BB_SCHEME_MDB = 4 };
 int bb_solve_scheme(bb_ens* ens, const bb_model* model, int32_t scheme);
+/* solve!(Mdb(), Y, u, W, P°)  src/euler.jl:308-327 for a guided proposal P° (the scheme needs P.tt and the indexed drift
+ * _b((i,t), x, P), which GuidedBridge / PartialBridge / PartialBridgeνH provide), S = 1: the guided Euler step with the noise
+ * scaled by sqrt((tt[end] - tt[i+1]) / (tt[end] - tt[i])).  X_cur <- the path, BB_F_XEND <- yy[N]. */
+int bb_guided_mdb(bb_ens* ens, const bb_model* model, bb_guide* const* guides);
 /* fused sample! + solve! (W and X are both written, W is never read) */
 int bb_sample_euler(bb_ens* ens, const bb_model* model, uint64_t seed, uint32_t stream);
 

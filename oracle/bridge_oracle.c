@@ -1075,6 +1075,33 @@ void bbo_guided_euler(const bb_model* P, const bbo_guide* G, const double* u, co
   if (xend) memcpy(xend, y, sizeof(double) * d);
 }
 
+/* solve!(Mdb(), Y, u, W, P°)   src/euler.jl:308-327 with P° a guided proposal:
+ *   y = y + _b((i,tt[i]), y, P)*(tt[i+1]-tt[i]) + _scale(ww[i+1]-ww[i], σ(tt[i], y, P)*sqrt((tt[end]-tt[i+1])/(tt[end]-tt[i]))) */
+void bbo_guided_mdb(const bb_model* P, const bbo_guide* G, const double* u, const double* W, double* X, double* xend) {
+  int d = P->d, dp = P->dprime, N = G->N;
+  const double* tt = G->tt;
+  double y[DM], bo[DM], r[DM], dw[DM], S[DM2], Ss[DM2], Amat[DM2];
+  model_sigma(P, S);
+  model_a(P, Amat);
+  memcpy(y, u, sizeof(double) * d);
+  for (int i = 0; i < N - 1; i++) {
+    if (X) memcpy(X + (size_t)i * d, y, sizeof(double) * d);
+    guided_b(P, Amat, G, i, tt[i], y, bo, r);
+    for (int l = 0; l < dp; l++) dw[l] = W[(size_t)(i + 1) * dp + l] - W[(size_t)i * dp + l];
+    const double ns = sqrt((tt[N - 1] - tt[i + 1]) / (tt[N - 1] - tt[i]));
+    for (int q = 0; q < d * dp; q++) Ss[q] = S[q] * ns; /* σ*sqrt(...): exact zeros stay zero */
+    em_update(P, Ss, bo, tt[i + 1] - tt[i], dw, y);
+  }
+  if (G->kind == BB_GUIDE_HV) {
+    const double* K = G->A + (size_t)(N - 1) * d * d;
+    double n1 = 0;
+    for (int k = 0; k < d * d; k++) n1 += fabs(K[k]);
+    if (n1 < 2.220446049250313e-16) memcpy(y, G->b + (size_t)(N - 1) * d, sizeof(double) * d);
+  }
+  if (X) memcpy(X + (size_t)(N - 1) * d, y, sizeof(double) * d);
+  if (xend) memcpy(xend, y, sizeof(double) * d);
+}
+
 /* llikelihood(LeftRule(), X, P°; skip)   src/partialbridgenuH.jl:171-189, guip.jl:429-446, partialbridge.jl:67-87
  * (constdiff branch; b̃ = B̃(tt[i]) x + β̃(tt[i])) */
 double bbo_llikelihood(const bb_model* P, const bbo_guide* G, const double* X, int skip) {

@@ -213,6 +213,12 @@ class Oracle:
         self.lib.bbo_guided_euler(C.byref(model), C.byref(guide.c), _p(u), _p(W), _p(X), _p(xend))
         return X, xend
 
+    def guided_mdb(self, model, guide: GuideHolder, u, W):
+        W = _f64(W).reshape(guide.N, model.dprime); u = np.atleast_1d(_f64(u))
+        X = np.zeros((guide.N, model.d)); xend = np.zeros(model.d)
+        self.lib.bbo_guided_mdb(C.byref(model), C.byref(guide.c), _p(u), _p(W), _p(X), _p(xend))
+        return X, xend
+
     def llikelihood(self, model, guide: GuideHolder, X, skip=0):
         X = _f64(X).reshape(guide.N, model.d)
         return self.lib.bbo_llikelihood(C.byref(model), C.byref(guide.c), _p(X), C.c_int(skip))

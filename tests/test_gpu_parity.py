@@ -1160,6 +1160,83 @@ def test_inplace_solver_on_vsamplepath(B, oracle_fma):
     assert ei.value.status == K.ERR_LENGTH
 
 
+def test_linearappr_as_auxiliary_process(B, oracle_ref):
+    """Lorenz target with the auxiliary process linearised along a trajectory (linearappr, src/linpro.jl:196; the setup of
+    test/smoothing.jl:73-83): the guided proposal built from it runs on the device -- tables from the R3 backward solver
+    with the tabulated coefficients (the reference's own constructor for this type does not run), tabulated auxiliary
+    drift and the non-constdiff terms in the log-likelihood -- and agrees with the oracle fed the same tables."""
+    K = B.api.K
+    P = B.Lorenz([10.0, 28.0, 8.0 / 3.0], [3.0, 3.0, 3.0])
+    om = O.make_model(O.LORENZ, 3, 3, [10.0, 28.0, 8.0 / 3.0, 3.0, 3.0, 3.0])
+    N = 201
+    tt = np.linspace(0.0, 0.1, N)
+    u = np.array([1.508870, -1.531271, 25.46091])
+    B.seed_(9)
+    Y = B.solve(B.Euler(), u, B.sample(tt.copy(), B.Wiener(3)), P)           # a trajectory to linearise along
+    Pt = B.linearappr(Y, P)
+    v = Y.yy[-1] + np.array([0.2, -0.1, 0.3])
+    Po = B.PartialBridgeνH(tt, P, Pt, np.eye(3), v, 1e-4, 1e-2 * np.eye(3))
+    assert Po.constdiff is False
+    ens = B.PathEnsemble(16, 1, N, 3, 3, double_buffer=False)
+    ens.set_grid(0, tt); ens.set_start(u); ens.sample_(10, 0)
+    W = ens.download(B.W)
+    ens.guided_euler_ll_(P, [Po])
+    X = ens.download(B.X); ll = ens.ll
+    assert np.max(np.abs(X[:, 0, -1] - v)) < 0.35                            # the bridges approach the observation
+    Btg = np.stack([Pt.B(t) for t in tt]); btg = np.stack([Pt.β(t) for t in tt])
+    Ad = np.stack([9.0 * np.eye(3) - Pt.a(t) for t in tt])
+    og = O.GuideHolder(O.GUIDE_NUH, tt, Po.H, Po.ν, Bt=Btg, betat=btg, aux_const=False, Adiff=Ad, adiff_const=False)
+    for p in (0, 7, 15):
+        Xo, _ = oracle_ref.guided_euler(om, og, u, W[p, 0])
+        assert close_x(X[p, 0], Xo) and close_ll(ll[p], oracle_ref.llikelihood(om, og, Xo))
+    ens.close()
+
+
+def test_mdb_on_guided_proposals(B, oracle_fma, oracle_ref):
+    """solve!(Mdb(), Y, u, W, P°)  src/euler.jl:308-327 for guided proposals (they carry P.tt and the indexed drift the
+    scheme needs): device against the oracle, bit-exact in the kernels' rounding order and to tolerance against the
+    reference arithmetic; through the mirrored solve! it returns Y (not the end point), its last step is noise free."""
+    K = B.api.K
+    N, P = 201, 40
+    tt = warped(0.0, 0.5, N)
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    om = O.make_model(O.FHN_HYPO, 2, 1, FHN_PAR)
+    Bt, bt, at = fhn_aux(-1.0)
+    Po = B.PartialBridgeνH(tt, Pm, B.LinearAux(Bt, bt, at), [[1.0, 0.0]], [-1.0], 1e-3, [[1e-4]])
+    og = O.GuideHolder(O.GUIDE_NUH, tt, Po.H, Po.ν, Bt=Bt, betat=bt)
+    ens = B.PathEnsemble(P, 1, N, 2, 1, double_buffer=False)
+    ens.set_grid(0, tt); ens.set_start([-0.5, -0.6]); ens.sample_(12, 0)
+    W = ens.download(B.W)
+    ens.guided_mdb_(Pm, [Po])
+    X = ens.download(B.X); xe = ens.xend
+    for p in (0, 17, 39):
+        Xo, xo = oracle_fma.guided_mdb(om, og, [-0.5, -0.6], W[p, 0])
+        assert np.array_equal(X[p, 0], Xo) and np.array_equal(xe[p], xo)
+        Xr, _ = oracle_ref.guided_mdb(om, og, [-0.5, -0.6], W[p, 0])
+        assert close_x(X[p, 0], Xr)
+    ens.guided_euler_ll_(Pm, [Po])
+    assert not np.array_equal(ens.download(B.X), X)          # it is not the plain guided Euler path
+    ens.close()
+    # GuidedBridge (H♢, V) with the end-point rule, dense sigma, through the mirrored call
+    tt3 = np.linspace(0, 1, 101)
+    B1 = -np.array([[1.0, 0.1, 0.0], [-0.2, 1.0, 0.1], [0.0, -0.1, 1.0]])
+    sig = 0.5 * np.eye(3) + 0.05 * np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]])
+    v = np.array([0.5, 0.0, -0.5])
+    P3 = B.LinPro(B1, np.zeros(3), sig)
+    G3 = B.GuidedBridge(tt3, P3, B.LinPro(-np.eye(3), np.zeros(3), sig), v)
+    og3 = O.GuideHolder(O.GUIDE_HV, tt3, G3.Hdia, G3.V, Bt=-np.eye(3), betat=np.zeros(3))
+    B.seed_(2)
+    W3 = B.sample(tt3.copy(), B.Wiener(3))
+    Y = B.SamplePath(tt3.copy(), np.zeros((101, 3)))
+    out = B.solve_(B.Mdb(), Y, np.zeros(3), W3, G3)
+    assert out is Y and np.array_equal(Y.yy[-1], v)
+    Xo, _ = oracle_fma.guided_mdb(O.linpro_model(B1, np.zeros(3), sig), og3, np.zeros(3), W3.yy)
+    assert np.array_equal(Y.yy, Xo)
+    with pytest.raises(B.BridgeError) as ei:                 # a plain target has no time axis of its own
+        B.solve_(B.Mdb(), Y, np.zeros(3), W3, P3)
+    assert ei.value.status == K.ERR_UNSUPPORTED
+
+
 def test_schemes_through_solve(B, oracle_fma):
     """solve(StochasticHeun(), u, W, P) / solve(StratonovichEuler(), ...) on SamplePaths (P = 1 plumbing)."""
     tt = np.arange(0, 101) * 0.01

@@ -94,3 +94,30 @@ def test_solver_tags_and_sharding(B):
         with pytest.raises(B.BridgeError) as ei:
             B.sample(np.linspace(0, 1, 5), B.Wiener())
         assert ei.value.status == -10
+
+
+def test_linearappr_container_and_bderiv():
+    """LinearAppr / linearappr / bderiv (src/linpro.jl:181-196, src/Models.jl:49-53): the tabulated linearisation of a
+    target along a trajectory -- accessors at (index, time) pairs as the reference defines them, interpolation between
+    grid points for the backward solvers, and the Jacobians against finite differences."""
+    import bridge_jl_b200 as B
+    P = B.Lorenz([10.0, 28.0, 8.0 / 3.0], [3.0, 3.0, 3.0])
+    tt = np.linspace(0.0, 0.2, 21)
+    yy = np.stack([np.array([1.5, -1.5, 25.0]) + 0.1 * k * np.array([1.0, -0.5, 0.2]) for k in range(21)])
+    Y = B.SamplePath(tt, yy)
+    Pt = B.linearappr(Y, P)
+    assert Pt.constdiff is False and Pt.is_const is False and Pt.d == 3
+    for P_, x in ((P, yy[3]), (B.FitzhughDiffusion(0.1, 0.0, 1.5, 0.8, 0.3), np.array([0.3, -0.2])),
+                  (B.FitzHughNagumo(0.1, 0.0, 1.5, 0.8, 0.3, 0.3), np.array([0.3, -0.2]))):
+        J = B.bderiv(0.0, x, P_)
+        for k in range(len(x)):
+            e = np.zeros(len(x)); e[k] = 1e-6
+            fd = (np.asarray(P_.b(0.0, x + e)) - np.asarray(P_.b(0.0, x - e))) / 2e-6
+            assert np.allclose(J[:, k], fd, rtol=1e-6, atol=1e-6)
+    i = 7
+    assert np.array_equal(Pt.B((i, tt[i])), B.bderiv(tt[i], yy[i], P))
+    assert np.allclose(Pt.β((i, tt[i])), P.b(tt[i], yy[i]) - B.bderiv(tt[i], yy[i], P) @ yy[i])
+    assert np.allclose(Pt.a((i, tt[i])), 9.0 * np.eye(3))
+    assert np.allclose(Pt.b((i, tt[i]), yy[i]), P.b(tt[i], yy[i]))            # the linearisation is exact on the trajectory
+    tm = 0.5 * (tt[i] + tt[i + 1])
+    assert np.allclose(Pt.B(tm), 0.5 * (Pt.Bs[i] + Pt.Bs[i + 1])) and np.array_equal(Pt.B(-1.0), Pt.Bs[0])

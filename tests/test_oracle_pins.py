@@ -467,6 +467,30 @@ def test_pcn_bench_driver_matches_stepwise(oracle_ref):
     assert 0 <= acc <= 20 and secs >= 0
 
 
+def test_mdb_step_properties(oracle_ref):
+    """solve!(Mdb(), ...)  src/euler.jl:308-327: the noise of step i is scaled by sqrt((T - t[i+1]) / (T - t[i])), so the
+    last step is deterministic, and with W = 0 the scheme is the guided Euler scheme."""
+    tt = TT_PB[:201]
+    P = O.make_model(O.INTDIFF, 2, 1, [GAMMA])
+    G = nuH_guide(oracle_ref, tt)
+    W = oracle_ref.wiener_sample(tt, 1, 5, 0, 0)
+    X, xend = oracle_ref.guided_mdb(P, G, X0_PB, W)
+    W2 = W.copy(); W2[-1] += 7.0                       # the last increment does not matter
+    X2, _ = oracle_ref.guided_mdb(P, G, X0_PB, W2)
+    assert np.array_equal(X, X2) and np.array_equal(xend, X[-1])
+    Xe, _ = oracle_ref.guided_euler(P, G, X0_PB, W)
+    assert not np.array_equal(X, Xe)
+    Z = np.zeros_like(W)
+    assert np.array_equal(oracle_ref.guided_mdb(P, G, X0_PB, Z)[0], oracle_ref.guided_euler(P, G, X0_PB, Z)[0])
+    # one step by hand
+    i = 57
+    y = X[i]; r = G.A[i] @ (G.b[i] - y)
+    b = np.array([y[1], -(y[1] + np.sin(y[1])) + 0.5]) + AUX_PB["a"] @ r
+    s = np.sqrt((tt[-1] - tt[i + 1]) / (tt[-1] - tt[i]))
+    want = y + b * (tt[i + 1] - tt[i]) + np.array([0.0, GAMMA * s]) * (W[i + 1, 0] - W[i, 0])
+    assert np.allclose(X[i + 1], want, rtol=1e-13, atol=1e-15)
+
+
 def test_tuned_baseline_driver_is_the_same_algorithm(oracle_ref, oracle_fma):
     """bench.py's CPU baseline runs a driver specialised for the FitzHugh-Nagumo / PartialBridgeνH workload (inlined
     2-d arithmetic, batched normals, every Philox call fully used).  In the contraction-free builds it must reproduce the
