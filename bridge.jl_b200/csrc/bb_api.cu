@@ -885,6 +885,7 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
     if (rcu != BB_OK) return rcu;
   } else {
     cudaError_t err = fn(a, c->stream);
+    if (err == cudaErrorInvalidConfiguration) return BB_ERR_UNSUPPORTED; /* the staging does not fit shared memory */
     if (err != cudaSuccess) {
       bb_set_cuda_error(err, "bb_chain_kernel launch");
       return BB_ERR_CUDA;

@@ -577,6 +577,7 @@ typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   const size_t smem = bb_chain_smem<M, GK, GM, AUXM, RNG>(a.S);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration; /* d = d' = 3 with the widest step records: BB_ERR_UNSUPPORTED */
   /* per instantiation: bit i = attribute set on device i (it is per device).  Atomic: contexts of different host
    * threads launch concurrently; setting the attribute twice is harmless.  Devices >= 64 always set it. */
   static std::atomic<unsigned long long> attr_done{0};

@@ -1161,35 +1161,48 @@ def test_inplace_solver_on_vsamplepath(B, oracle_fma):
 
 
 def test_linearappr_as_auxiliary_process(B, oracle_ref):
-    """Lorenz target with the auxiliary process linearised along a trajectory (linearappr, src/linpro.jl:196; the setup of
-    test/smoothing.jl:73-83): the guided proposal built from it runs on the device -- tables from the R3 backward solver
-    with the tabulated coefficients (the reference's own constructor for this type does not run), tabulated auxiliary
-    drift and the non-constdiff terms in the log-likelihood -- and agrees with the oracle fed the same tables."""
+    """A target with the auxiliary process linearised along a trajectory (linearappr, src/linpro.jl:196; the idea of
+    test/smoothing.jl:73-83, here for the FitzHugh-Nagumo model with diagonal noise): the guided proposal built from it
+    runs on the device -- tables from the R3 backward solver with the tabulated coefficients (the reference's own
+    constructor for this type does not run), tabulated auxiliary drift and the non-constdiff terms in the
+    log-likelihood -- and agrees with the oracle fed the same tables.  (For d = d' = 3 the step records of this
+    combination do not fit the kernel's shared-memory staging: BB_ERR_UNSUPPORTED, checked below.)"""
     K = B.api.K
-    P = B.Lorenz([10.0, 28.0, 8.0 / 3.0], [3.0, 3.0, 3.0])
-    om = O.make_model(O.LORENZ, 3, 3, [10.0, 28.0, 8.0 / 3.0, 3.0, 3.0, 3.0])
+    P = B.FitzHughNagumo(0.1, 0.0, 1.5, 0.8, 0.3, 0.25)
+    om = O.make_model(O.FHN_DIAG, 2, 2, [0.1, 0.0, 1.5, 0.8, 0.3, 0.25])
     N = 201
-    tt = np.linspace(0.0, 0.1, N)
-    u = np.array([1.508870, -1.531271, 25.46091])
+    tt = warped(0.0, 0.5, N)
+    u = np.array([-0.5, -0.6])
     B.seed_(9)
-    Y = B.solve(B.Euler(), u, B.sample(tt.copy(), B.Wiener(3)), P)           # a trajectory to linearise along
+    Y = B.solve(B.Euler(), u, B.sample(tt.copy(), B.Wiener(2)), P)           # a trajectory to linearise along
     Pt = B.linearappr(Y, P)
-    v = Y.yy[-1] + np.array([0.2, -0.1, 0.3])
-    Po = B.PartialBridgeνH(tt, P, Pt, np.eye(3), v, 1e-4, 1e-2 * np.eye(3))
+    v = np.array([Y.yy[-1, 0] + 0.1])
+    Po = B.PartialBridgeνH(tt, P, Pt, [[1.0, 0.0]], v, 1e-3, [[1e-4]])
     assert Po.constdiff is False
-    ens = B.PathEnsemble(16, 1, N, 3, 3, double_buffer=False)
+    ens = B.PathEnsemble(16, 1, N, 2, 2, double_buffer=False)
     ens.set_grid(0, tt); ens.set_start(u); ens.sample_(10, 0)
     W = ens.download(B.W)
     ens.guided_euler_ll_(P, [Po])
     X = ens.download(B.X); ll = ens.ll
-    assert np.max(np.abs(X[:, 0, -1] - v)) < 0.35                            # the bridges approach the observation
+    assert np.max(np.abs(X[:, 0, -1, 0] - v[0])) < 0.05                      # the bridges hit the observation
     Btg = np.stack([Pt.B(t) for t in tt]); btg = np.stack([Pt.β(t) for t in tt])
-    Ad = np.stack([9.0 * np.eye(3) - Pt.a(t) for t in tt])
+    Ad = np.stack([np.diag([0.09, 0.0625]) - Pt.a(t) for t in tt])
     og = O.GuideHolder(O.GUIDE_NUH, tt, Po.H, Po.ν, Bt=Btg, betat=btg, aux_const=False, Adiff=Ad, adiff_const=False)
     for p in (0, 7, 15):
         Xo, _ = oracle_ref.guided_euler(om, og, u, W[p, 0])
         assert close_x(X[p, 0], Xo) and close_ll(ll[p], oracle_ref.llikelihood(om, og, Xo))
     ens.close()
+    # d = d' = 3 with tabulated auxiliary drift AND non-constdiff terms: refused cleanly
+    P3 = B.Lorenz([10.0, 28.0, 8.0 / 3.0], [3.0, 3.0, 3.0])
+    t3 = np.linspace(0.0, 0.1, 65)
+    Y3 = B.solve(B.Euler(), [1.5, -1.5, 25.0], B.sample(t3.copy(), B.Wiener(3)), P3)
+    Po3 = B.PartialBridgeνH(t3, P3, B.linearappr(Y3, P3), np.eye(3), Y3.yy[-1], 1e-4, 1e-2 * np.eye(3))
+    e3 = B.PathEnsemble(8, 1, 65, 3, 3, double_buffer=False)
+    e3.set_grid(0, t3); e3.set_start([1.5, -1.5, 25.0]); e3.sample_(1, 0)
+    with pytest.raises(B.BridgeError) as ei:
+        e3.guided_euler_ll_(P3, [Po3])
+    assert ei.value.status == K.ERR_UNSUPPORTED
+    e3.close()
 
 
 def test_mdb_on_guided_proposals(B, oracle_fma, oracle_ref):
