@@ -234,7 +234,7 @@ KERNEL_SOURCES = {  # the files whose content decides the dominant kernel's DRAM
     4: ["bb_chain.cuh", "bb_device.cuh", "bb_inst_fhn_hypo.cu", "Makefile"],
     2: ["bb_chain.cuh", "bb_device.cuh", "bb_inst_ou.cu", "Makefile"],
     3: ["bb_chain.cuh", "bb_device.cuh", "bb_inst_linpro3.cu", "Makefile"],
-    5: ["bb_wide.cuh", "bb_device.cuh", "bb_inst_landmarks.cu", "Makefile"],
+    5: ["bb_wide_mma.cuh", "bb_wide.cuh", "bb_device.cuh", "bb_inst_landmarks.cu", "Makefile"],
 }
 
 

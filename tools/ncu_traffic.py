@@ -43,7 +43,9 @@ except (OSError, ValueError):
 allrec[str(config)] = {
     "kernel": row[col["Kernel Name"]], "dram_bytes_read": rd, "dram_bytes_write": wr,
     "dram_bytes_per_launch": rd + wr, "path_steps_per_launch": units, "dram_bytes_per_unit": (rd + wr) / units,
-    "duration_ms_under_ncu": val("gpu__time_duration.sum") / 1e6 if "gpu__time_duration.sum" in col else None,
+    "duration_ms_under_ncu": (float(row[col["gpu__time_duration.sum"]].replace(",", "")) *
+                              {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[unit_row[col["gpu__time_duration.sum"]].lower()]
+                              if "gpu__time_duration.sum" in col else None),
     "src_hash": bench.kernel_source_hash(config), "source": note,
 }
 json.dump(allrec, open(path, "w"), indent=1)
