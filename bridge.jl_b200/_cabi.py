@@ -145,6 +145,8 @@ def _load():
         "bb_theta_pcn_step": (C.c_int, [vp, dbl, u64, u32, i32, u32]),
         "bb_theta_param_step": (C.c_int, [vp, vp, u64, u32, i32, u32]),
         "bb_theta_refresh_x": (C.c_int, [vp]),
+        "bb_theta_block_step": (C.c_int, [vp, i32, i32, dbl, dbl, u64, u32, i32]),
+        "bb_theta_get_block": (C.c_int, [vp, i64, i64, vp]),
         "bb_theta_get_acc": (C.c_int, [vp, C.POINTER(i64)]),
         "bb_theta_acc_device_ptr": (vp, [vp]),
         "bb_user_model_create": (C.c_int, [vp, i32, i32, C.c_char_p, C.POINTER(i32), C.POINTER(C.c_char_p), pp]),

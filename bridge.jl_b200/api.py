@@ -916,6 +916,34 @@ class PathEnsemble:
         sd = np.zeros(K.BB_NTHETA); rw = f64(rw_sd).ravel(); sd[:rw.size] = rw
         check(lib.bb_theta_param_step(self.h, ptr(sd), seed, it, skip, K.RUN_STORE_X if store_x else 0))
 
+    def theta_block_step_(self, s_lo: int, s_hi: int, ρ: float, seed: int, it: int, hzero: float = 0.1, skip: int = 0):
+        """Blocked path update of segments s_lo .. s_hi-1 (0-based) of every chain: the `updateparams == false` branch of
+        project_partialbridge/partialbridge_bolus3.jl:258-355 (ind = (kup-1):-1:klow with klow = s_lo+1, kup = s_hi+1).
+        A block that does not end the chain is conditioned on the chain's own path at its right end with H⁺ = hzero·I
+        (Hzero⁺, :234); see bb_theta_block_step in include/bridge_b200.h for the step-by-step correspondence."""
+        check(lib.bb_theta_block_step(self.h, s_lo, s_hi, ρ, hzero, seed, it, skip))
+
+    def theta_block(self):
+        """[P, 5 + 2S] numbers of the last block update: logpdfnormal start terms (current, proposal), Σ ll_temp, Σ ll°,
+        diffll, then (ll_temp[s], ll°[s]) per segment."""
+        out = np.empty((self.P, 5 + 2 * self.S))
+        check(lib.bb_theta_get_block(self.h, 0, self.P, ptr(out)))
+        return out
+
+    def theta_blocked_sweep_(self, rng, ρ: float, seed: int, it0: int, hzero: float = 0.1, skip: int = 0):
+        """One sweep of block updates over the whole chain, as the `while !finished` loop of bolus3.jl:258-362 with
+        updateparams == false runs it: klow = 1; segnum_update = sample(1:obsnum-klow) (drawn from the host generator
+        `rng`, one draw for the whole ensemble), kup = klow + segnum_update, update segments klow .. kup-1, klow = kup,
+        until klow == obsnum.  Returns the list of (s_lo, s_hi) blocks; noise stream it0 + k drives block k."""
+        obsnum = self.S + 1
+        klow, blocks = 1, []
+        while klow != obsnum:
+            kup = klow + int(rng.integers(1, obsnum - klow + 1))
+            self.theta_block_step_(klow - 1, kup - 1, ρ, seed, it0 + len(blocks), hzero, skip)
+            blocks.append((klow - 1, kup - 1))
+            klow = kup
+        return blocks
+
     @property
     def acc_theta(self) -> int:
         v = C.c_int64(0)
@@ -1366,17 +1394,22 @@ def pcn_(ens: PathEnsemble, P, guides, ρ: float, iterations: int, seed: int, fi
 
 
 def theta_mcmc_(ens: PathEnsemble, ρ: float, rw_sd, iterations: int, seed: int, first_iter: int = 0, skip: int = 0,
-                store_x: bool = True, param_prob: float = 0.5, callback: Optional[Callable] = None):
+                store_x: bool = True, param_prob: float = 0.5, callback: Optional[Callable] = None,
+                blocked: bool = False, hzero: float = 0.1):
     """The outer loop of project_partialbridge/partialbridge_bolus3.jl:248-365 for all chains of an ensemble with
     per-chain parameters (theta_attach_): every iteration is, with probability `param_prob` (`updateparams = rand(Bool)`,
-    :259), a parameter update with the innovations held fixed, otherwise a pCN update of the paths (all segments together).
+    :259), a parameter update with the innovations held fixed, otherwise a pCN update of the paths -- all segments
+    together, or with blocked = True a sweep of block updates as the script draws them (theta_blocked_sweep_).
     The coin is common to all chains (one launch per iteration) and comes from the host RNG seeded with `seed`; the two
     step kinds use disjoint Philox counters, so `it` can be shared.  Returns (accepted pCN proposals, accepted parameter
     proposals), summed over chains."""
     rng = np.random.default_rng(seed)
+    sub = 0  # noise streams of the blocks of path sweeps (blocked = True): disjoint from the iteration numbers
     for it in range(first_iter, first_iter + iterations):
         if rng.random() < param_prob:
             ens.theta_param_step_(rw_sd, seed, it, skip, store_x)
+        elif blocked:  # the script's sweep of block updates klow .. kup (:258-275, :358-359)
+            sub += len(ens.theta_blocked_sweep_(rng, ρ, seed, 0x40000000 + sub, hzero, skip))
         else:
             ens.theta_pcn_step_(ρ, seed, it, skip, store_x)
         if callback is not None:

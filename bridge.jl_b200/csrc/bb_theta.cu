@@ -51,6 +51,9 @@ struct bb_theta {
   double* tt = nullptr;                  /* [S][N] */
   double* startprop = nullptr;           /* [d][P]: x0° of the last parameter proposal (start moves only) */
   unsigned long long* acc = nullptr;
+  double* blkv = nullptr;  /* [BB_NBLK][P]: the numbers of the last blocked update (bb_theta_get_block) */
+  double* Xprop = nullptr; /* X° of a blocked update (same layout as X); committed to X for the chains that accept */
+  bool ll_stale = false; /* block updates moved W without maintaining the running ll of the whole-path steps */
   int tstate = 0; /* 0: T invalid; 1: T belongs to the current θ; 2: T belongs to the last proposal */
 };
 
@@ -83,7 +86,15 @@ struct bb_theta_args {
   double log2pi;
   double prior_c0[BB_NTHETA];
   double seg_len[BB_MAXSEG];
+  /* blocked update of segments s_lo .. s_hi-1 */
+  int blk, s_lo, s_hi;
+  double hzero;
+  double* blkv;
+  double* Xprop;
 };
+
+/* rows of blkv */
+enum { BLK_LPN = 0, BLK_LPNO = 1, BLK_LLT = 2, BLK_LLO = 3, BLK_DIFF = 4, BLK_SEG = 5, BB_NBLK = 5 + 2 * BB_MAXSEG };
 
 namespace {
 using namespace bbk;
@@ -205,9 +216,22 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
     for (int j = 0; j < D; j++) Hp[i * D + j] = (i == j) ? 1.0 / a.spec.eps : 0.0;
   }
   const int S = a.S, N = a.N;
-  if (gpupdate_dev<D, MOBS>(nu, Hp, a.spec.L, a.spec.Sigma, a.spec.v[S - 1])) bad = true;
+  /* a blocked update works on segments slo .. shi-1 (bolus3.jl:258-275) */
+  const int shi = a.blk ? a.s_hi : S, slo = a.blk ? a.s_lo : 0;
+  if (shi == S) {
+    if (gpupdate_dev<D, MOBS>(nu, Hp, a.spec.L, a.spec.Sigma, a.spec.v[S - 1])) bad = true;
+  } else {
+    /* νend = XX[ind[1]].yy[end], Hend⁺ = Hzero⁺ (:272-273): the chain's own path at the block's right end */
+    const double* xr = a.X + (((long long)(shi - 1) * a.NC + (N - 1) / BB_TC) * P + p) * (BB_TC * D) + ((N - 1) % BB_TC) * D;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      nu[i] = xr[i];
+#pragma unroll
+      for (int j = 0; j < D; j++) Hp[i * D + j] = (i == j) ? a.hzero : 0.0;
+    }
+  }
   double Cc = 0.0, trsum = 0.0;
-  for (int s = S - 1; s >= 0; s--) {
+  for (int s = shi - 1; s >= slo; s--) {
     double Bt[D * D], be[D];
     theta_aux<M, AUXK>(m, a.spec.v[s][0], 0.0, Bt, be);
     const aux_dev A{Bt, be, at, at, 1};
@@ -246,8 +270,36 @@ __global__ void __launch_bounds__(128) bb_theta_backward_kernel(const __grid_con
 #pragma unroll
     for (int i = 1; i < D; i++) tr += Bt[i * D + i];
     trsum += a.seg_len[s] * tr;
-    if (s > 0)
+    if (s > slo) /* "on the left endpoint we don't need to do gpupdate" (:288) */
       if (gpupdate_dev<D, MOBS>(nu, Hp, a.spec.L, a.spec.Sigma, a.spec.v[s - 1])) bad = true;
+  }
+  if (a.blk) {
+    /* start term of a block that contains the first segment (:311-320): x0° = x0 + (sd u) dir, always proposed */
+    double lpn = 0.0, lpno = 0.0;
+    if (slo == 0) {
+      double x[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) x[k] = xs[k] - nu[k];
+      lpn = logpdfnormal_dev<D>(x, Hp, a.log2pi);
+      lpno = lpn;
+      if (a.spec.start_sd != 0.0) {
+        float z[4];
+        bb_normal_quad(a.keys, a.stream, (uint32_t)chain, (uint32_t)(chain >> 32), 0xFFFFFFFEu, z);
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          xs[k] = xs[k] + (a.spec.start_sd * (double)z[3]) * a.spec.start_dir[k];
+          a.startprop[(long long)k * P + p] = xs[k];
+          x[k] = xs[k] - nu[k];
+        }
+        lpno = logpdfnormal_dev<D>(x, Hp, a.log2pi);
+      }
+      if (bad) lpn = lpno = nan("");
+    } else if (bad) {
+      lpno = nan("");
+    }
+    a.blkv[(long long)BLK_LPN * P + p] = lpn;
+    a.blkv[(long long)BLK_LPNO * P + p] = lpno;
+    return;
   }
   /* left end: ν(0), H⁺(0), C, logpdfnormal(x0 - ν(0), symmetrize(H⁺(0)))  (bolus3.jl:319), trace term, logπ(θ) */
   double x[D];
@@ -572,6 +624,230 @@ __global__ void __launch_bounds__(BB_THREADS, 2) bb_theta_forward_kernel(const _
   }
 }
 
+
+/* ------------------------------------------------------------------------------------------------ blocked update
+ * The path-update branch of the multi-segment sampler (partialbridge_bolus3.jl:258-355, `updateparams == false`) for
+ * the block of segments s_lo .. s_hi-1 after bb_theta_backward_kernel built the block's tables:
+ *   W°[i] = ρ W[i] + sqrt(1-ρ²) W2 (:304-305); XXtemp[i] = solve!(Euler(), xstart, W[i], Q[i]) and
+ *   XXᵒ[i] = solve!(Euler(), xstartᵒ, W°[i], Qᵒ[i]) with Qᵒ = Q (:324-325) advance side by side on the same table
+ *   rows; diffll = start term + Σ_{i in ind} (ll°[i] - ll_temp[i]) in the script's (descending) order (:331-333);
+ *   log(rand()) <= diffll (:340).  W° goes to the chain's other W buffer and X° to Xprop; the commit kernel below
+ *   moves both into place for the chains that accept (the script's swap of XX[i], WW[i] for i in ind, :342-345). */
+template <class M, int AUXK>
+__global__ void __launch_bounds__(BB_THREADS) bb_theta_block_kernel(const __grid_constant__ bb_theta_args a) {
+  using CH = bb_chain<M, BB_GUIDE_NUH, 0, 1, 0>;
+  constexpr int D = M::D, DP = M::DP, K = D + D * D, NTH = M::NTH, REC = CH::REC;
+  constexpr int NPIECE = BB_TC * DP / 4;
+  const long long P = a.P;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pc = p < P ? p : P - 1;
+  const bool act = p < P;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
+  const int S = a.S, N = a.N, NC = a.NC, slo = a.s_lo, shi = a.s_hi;
+
+  double th[NTH];
+#pragma unroll
+  for (int k = 0; k < NTH; k++) th[k] = a.theta[0][(long long)k * P + pc];
+  bb_model_dev m;
+  theta_model<M>(th, m);
+
+  const int par = a.par[pc];
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+  const double* wr = a.W[par] + pc * (a.nbuf * BB_TC * DP) + (long long)slo * NC * wstride;
+  double* ww = a.W[1 - par] + pc * (a.nbuf * BB_TC * DP) + (long long)slo * NC * wstride;
+  double* xw = a.Xprop + pc * (BB_TC * D) + (long long)slo * NC * xstride;
+
+  /* both passes start from the current path's value at the block's left end; a block that contains the first segment
+   * starts the proposal at x0° (bb_theta_backward_kernel drew it) */
+  double yt[D], yo[D];
+  if (slo == 0) {
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      yt[k] = a.start_bcast ? a.start[k] : a.start[(long long)k * P + pc];
+      yo[k] = a.spec.start_sd != 0.0 ? a.startprop[(long long)k * P + pc] : yt[k];
+    }
+  } else {
+    const double* xl = a.X + (((long long)(slo - 1) * NC + (N - 1) / BB_TC) * P + pc) * (BB_TC * D) + ((N - 1) % BB_TC) * D;
+#pragma unroll
+    for (int k = 0; k < D; k++) yt[k] = yo[k] = xl[k];
+  }
+
+  /* table rows through the shared-memory ring of bb_theta_forward_kernel */
+  extern __shared__ __align__(128) unsigned char th_smem[];
+  double* tring = reinterpret_cast<double*>(th_smem) + threadIdx.x;
+  const long long PT = a.PT;
+  const long long rowstride = (long long)K * PT;
+  const long long nrows = (long long)(shi - slo) * (N - 1);
+  const bool pair_ok = (p & ~1ll) < P;
+  long long gi = (long long)slo * N;
+  int gi_i = 0;
+  long long gi_n = 0;
+  auto t_issue = [&]() {
+    if (gi_n < nrows) {
+      double* dst = tring + (size_t)(gi_n % BB_TDEPTH) * (K * BB_THREADS);
+      if (pair_ok) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2)
+          bb_cp_async16(dst + (k + (int)(threadIdx.x & 1)) * BB_THREADS - (threadIdx.x & 1),
+                        a.T + gi * rowstride + (long long)(k + (int)(threadIdx.x & 1)) * PT + (p & ~1ll));
+      }
+      gi_n++;
+      if (++gi_i == N - 1) { gi_i = 0; gi += 2; } else { gi += 1; }
+    }
+    bb_cp_async_commit();
+  };
+#pragma unroll 1
+  for (int g = 0; g < BB_TDEPTH - 1; g++) t_issue();
+  long long rcons = 0;
+
+  double dseg[BB_MAXSEG];
+  double llt = 0.0, llo = 0.0;
+  double wq[4] = {0.0, 0.0, 0.0, 0.0}, wqo[4] = {0.0, 0.0, 0.0, 0.0};
+  double wprev_t[DP], wprev_o[DP], w2[DP];
+  for (int s = slo; s < shi; s++) {
+    const unsigned long long row = chain * (unsigned long long)S + (unsigned long long)s;
+    const uint32_t row_lo = (uint32_t)row, row_hi = (uint32_t)(row >> 32);
+    double sc[D * D + D];
+    theta_aux<M, AUXK>(m, a.spec.v[s][0], 0.0, sc, sc + D * D);
+    constexpr bool TDEP = (AUXK == BB_AUX_BOLUS);
+    const double* tts = a.tt + (long long)s * N;
+    const double* gt = a.gridtab[s];
+    double som_t = 0.0, som_o = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; k++) w2[k] = 0.0;
+    for (int c = 0; c < NC; c++) {
+      bb_rowout<D> xo;
+#pragma unroll 1
+      for (int h = 0; h < BB_TC / 4; h++) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+          const int j = c * BB_TC + 4 * h + s4;
+          double wjt[DP], wjo[DP];
+#pragma unroll
+          for (int k = 0; k < DP; k++) {
+            const int mm = s4 * DP + k;
+            if ((mm & 3) == 0) {
+              const int q = h * DP + (mm >> 2);
+              if (act) bb_ld4(wr + 4 * q, wq);
+              float z[4];
+              bb_normal_quad(a.keys, a.stream, row_lo, row_hi, (uint32_t)(NPIECE * c + q), z);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int sl = 4 * h + (mm + i) / DP, kk = (mm + i) % DP;
+                const int jj = c * BB_TC + sl;
+                const double rootdt = gt[2 * jj + 1];
+                if (jj != 0) w2[kk] = fma(rootdt, (double)z[i], w2[kk]);
+                wqo[i] = fma(a.rho2, w2[kk], a.rho * wq[i]);
+              }
+              if (act) bb_st4(ww + 4 * q, wqo[0], wqo[1], wqo[2], wqo[3]);
+            }
+            wjt[k] = wq[mm & 3];
+            wjo[k] = wqo[mm & 3];
+          }
+          if (j == 0) {
+#pragma unroll
+            for (int k = 0; k < DP; k++) { wprev_t[k] = wjt[k]; wprev_o[k] = wjo[k]; }
+          } else if (j < N) {
+            double R[REC];
+            R[0] = gt[2 * j];
+            R[1] = 0.0;
+            bb_cp_async_wait<BB_TDEPTH - 2>();
+            __syncwarp();
+            const double* Ts = tring + (size_t)(rcons % BB_TDEPTH) * (K * BB_THREADS);
+#pragma unroll
+            for (int k = 0; k < K; k++) R[2 + k] = Ts[k * BB_THREADS];
+            rcons++;
+            t_issue();
+            double dwt[DP], dwo[DP], bd[D];
+#pragma unroll
+            for (int k = 0; k < DP; k++) {
+              dwt[k] = wjt[k] - wprev_t[k];
+              dwo[k] = wjo[k] - wprev_o[k];
+              wprev_t[k] = wjt[k];
+              wprev_o[k] = wjo[k];
+            }
+            if constexpr (TDEP) {
+              m.der[1] = m.par[0] * bb_dose(tts[j - 1]);
+              sc[D * D] = m.der[1];
+            }
+            CH::drift(m, R, sc, yt, R[0], j <= a.jll, som_t, bd);
+            bb_em_update<M>(m, bd, R[0], dwt, yt);
+            CH::drift(m, R, sc, yo, R[0], j <= a.jll, som_o, bd);
+            bb_em_update<M>(m, bd, R[0], dwo, yo);
+          }
+          xo.put(xw + 4 * h * D, s4, yo, act);
+        }
+      }
+      wr += wstride;
+      ww += wstride;
+      xw += xstride;
+    }
+    dseg[s] = som_o - som_t;
+    llt += som_t;
+    llo += som_o;
+    if (act) {
+      a.blkv[(long long)(BLK_SEG + 2 * s) * P + p] = som_t;
+      a.blkv[(long long)(BLK_SEG + 2 * s + 1) * P + p] = som_o;
+    }
+  }
+
+  const double logu = bb_accept_logu(a.keys, a.stream, chain);
+  double diff = a.blkv[(long long)BLK_LPNO * P + pc] - a.blkv[(long long)BLK_LPN * P + pc];
+  for (int s = shi - 1; s >= slo; s--) diff += dseg[s];
+  const bool ok = act && (logu <= diff);
+  if (act) {
+    a.blkv[(long long)BLK_LLT * P + p] = llt;
+    a.blkv[(long long)BLK_LLO * P + p] = llo;
+    a.blkv[(long long)BLK_DIFF * P + p] = diff;
+    a.llprop[p] = llo;
+    a.logu[p] = logu;
+    a.accepted[p] = ok ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < D; k++) a.xendprop[(long long)k * P + p] = yo[k];
+  }
+  const unsigned mk = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane == 0 && mk) atomicAdd(a.acc, (unsigned long long)__popc(mk));
+}
+
+/* the accepted chains take their proposal: W°, X° of the block's segments move into the current buffers */
+template <int D, int DP>
+__global__ void __launch_bounds__(BB_THREADS) bb_theta_block_commit_kernel(const __grid_constant__ bb_theta_args a) {
+  const long long P = a.P;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P || !a.accepted[p]) return;
+  const int NC = a.NC, slo = a.s_lo, shi = a.s_hi;
+  const int par = a.par[p];
+  const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
+  const double* wsrc = a.W[1 - par] + p * (a.nbuf * BB_TC * DP) + (long long)slo * NC * wstride;
+  double* wdst = a.W[par] + p * (a.nbuf * BB_TC * DP) + (long long)slo * NC * wstride;
+  const double* xsrc = a.Xprop + p * (BB_TC * D) + (long long)slo * NC * xstride;
+  double* xdst = a.X + p * (BB_TC * D) + (long long)slo * NC * xstride;
+  for (int r = 0; r < (shi - slo) * NC; r++) {
+#pragma unroll
+    for (int q = 0; q < BB_TC * DP / 4; q++) {
+      double v[4];
+      bb_ld4(wsrc + 4 * q, v);
+      bb_st4(wdst + 4 * q, v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < BB_TC * D / 4; q++) {
+      double v[4];
+      bb_ld4(xsrc + 4 * q, v);
+      bb_st4(xdst + 4 * q, v[0], v[1], v[2], v[3]);
+    }
+    wsrc += wstride; wdst += wstride; xsrc += xstride; xdst += xstride;
+  }
+  if (slo == 0 && a.spec.start_sd != 0.0) {
+#pragma unroll
+    for (int k = 0; k < D; k++) a.start[(long long)k * P + p] = a.startprop[(long long)k * P + p];
+  }
+  if (shi == a.S) {
+#pragma unroll
+    for (int k = 0; k < D; k++) a.xend[(long long)k * P + p] = a.xendprop[(long long)k * P + p];
+  }
+}
+
 typedef void (*theta_kernel_fn)(const bb_theta_args);
 
 template <class M>
@@ -609,6 +885,17 @@ static theta_kernel_fn lookup_forward(int auxk, bool pcn) {
   }
 }
 
+template <class M>
+static theta_kernel_fn lookup_block(int auxk) {
+  if constexpr (M::ID == BB_MODEL_BOLUS) {
+    return auxk == BB_AUX_BOLUS ? &bb_theta_block_kernel<M, BB_AUX_BOLUS> : nullptr;
+  } else {
+    if (auxk == BB_AUX_FHN_MATCHING) return &bb_theta_block_kernel<M, BB_AUX_FHN_MATCHING>;
+    if (auxk == BB_AUX_FHN_LINEARISED_END) return &bb_theta_block_kernel<M, BB_AUX_FHN_LINEARISED_END>;
+    return nullptr;
+  }
+}
+
 static int fill_args(bb_ens* e, bb_theta_args& a) {
   bb_theta* t = e->th;
   memset(&a, 0, sizeof(a));
@@ -626,6 +913,7 @@ static int fill_args(bb_ens* e, bb_theta_args& a) {
   a.theta[0] = t->theta[0]; a.theta[1] = t->theta[1];
   a.T = t->T;
   a.left[0] = t->left[0]; a.left[1] = t->left[1];
+  a.blkv = t->blkv; a.Xprop = t->Xprop;
   a.spec = t->spec;
   a.log2pi = log(2 * M_PI);
   for (int k = 0; k < BB_NTHETA; k++)
@@ -646,7 +934,13 @@ static int upload_grids(bb_ens* e) {
   return BB_OK;
 }
 
-static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd, uint64_t seed, uint32_t stream) {
+struct blk_spec {
+  int s_lo, s_hi;
+  double hzero;
+};
+
+static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd, uint64_t seed, uint32_t stream,
+                        const blk_spec* blk = nullptr) {
   bb_theta* t = e->th;
   bb_ctx* c = e->ctx;
   bb_theta_args a;
@@ -656,6 +950,9 @@ static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd,
   if (rc != BB_OK) return rc;
   a.which = which;
   a.propose = propose ? 1 : 0;
+  if (blk) {
+    a.blk = 1; a.s_lo = blk->s_lo; a.s_hi = blk->s_hi; a.hzero = blk->hzero;
+  }
   if (rw_sd) memcpy(a.rw_sd, rw_sd, sizeof(a.rw_sd));
   bb_philox_key_schedule(seed, a.keys);
   a.stream = stream;
@@ -672,7 +969,45 @@ static int run_backward(bb_ens* e, int which, bool propose, const double* rw_sd,
     return BB_ERR_CUDA;
   }
   c->launches++;
-  t->tstate = which == 0 ? 1 : 2;
+  t->tstate = blk ? 0 : (which == 0 ? 1 : 2); /* a block's tables are conditioned on the chains' own paths */
+  return BB_OK;
+}
+
+static int run_block(bb_ens* e, const blk_spec& blk, int skip, double rho, uint64_t seed, uint32_t stream) {
+  bb_theta* t = e->th;
+  bb_ctx* c = e->ctx;
+  bb_theta_args a;
+  int rc = fill_args(e, a);
+  if (rc != BB_OK) return rc;
+  a.blk = 1; a.s_lo = blk.s_lo; a.s_hi = blk.s_hi; a.hzero = blk.hzero;
+  a.jll = e->N - 1 - skip;
+  a.store_x = 1;
+  a.rho = rho;
+  a.rho2 = sqrt(1 - rho * rho);
+  bb_philox_key_schedule(seed, a.keys);
+  a.stream = stream;
+  theta_kernel_fn fn = t->model.id == BB_MODEL_FHN_HYPO
+                           ? lookup_block<MFhnHypo>(t->spec.aux_kind)
+                           : (t->model.id == BB_MODEL_FHN_DIAG ? lookup_block<MFhnDiag>(t->spec.aux_kind)
+                                                               : lookup_block<MBolus>(t->spec.aux_kind));
+  if (!fn) return BB_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)((e->P + BB_THREADS - 1) / BB_THREADS);
+  const size_t smem = (size_t)BB_TDEPTH * t->K * BB_THREADS * 8;
+  BB_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<grid, BB_THREADS, smem, c->stream>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) {
+    c->launches++;
+    if (e->dp == 1) bb_theta_block_commit_kernel<2, 1><<<grid, BB_THREADS, 0, c->stream>>>(a);
+    else bb_theta_block_commit_kernel<2, 2><<<grid, BB_THREADS, 0, c->stream>>>(a);
+    err = cudaGetLastError();
+  }
+  if (err != cudaSuccess) {
+    bb_set_cuda_error(err, "bb_theta_block_kernel launch");
+    return BB_ERR_CUDA;
+  }
+  c->launches++;
+  e->x_maybe_stale = false; /* X holds the current path of every chain */
   return BB_OK;
 }
 
@@ -724,7 +1059,7 @@ void bb_theta_invalidate(bb_ens* e) {
 void bb_theta_free(bb_ens* e) {
   bb_theta* t = e->th;
   if (!t) return;
-  void* ptrs[] = {t->theta[0], t->theta[1], t->T, t->left[0], t->left[1], t->tt, t->acc, t->startprop};
+  void* ptrs[] = {t->theta[0], t->theta[1], t->T, t->left[0], t->left[1], t->tt, t->acc, t->startprop, t->blkv, t->Xprop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete t;
@@ -884,6 +1219,15 @@ static int ensure_current_tables(bb_ens* e) {
   if (e->th->tstate == 1) return BB_OK;
   return run_backward(e, 0, false, nullptr, 0, 0);
 }
+/* whole-path steps compare against the running ll of the current (W, θ) under the full backward chain; after block
+ * updates it is re-established by one forward pass (which also puts X back on that chain's guide) */
+static int ensure_running_ll(bb_ens* e, int skip) {
+  if (!e->th->ll_stale) return BB_OK;
+  int rc = ensure_current_tables(e);
+  if (rc == BB_OK) rc = run_forward(e, false, 0, 0, skip, e->X != nullptr, 0.0, 0, 0);
+  if (rc == BB_OK) e->th->ll_stale = false;
+  return rc;
+}
 
 extern "C" int bb_theta_guided_euler_ll(bb_ens* e, int32_t skip, uint32_t flags) {
   if (!e || !e->th) return BB_ERR_ARG;
@@ -891,6 +1235,7 @@ extern "C" int bb_theta_guided_euler_ll(bb_ens* e, int32_t skip, uint32_t flags)
   bb_time_begin(e->ctx);
   int rc = ensure_current_tables(e);
   if (rc == BB_OK) rc = run_forward(e, false, 0, 0, skip, (flags & BB_RUN_STORE_X) != 0, 0.0, 0, 0);
+  if (rc == BB_OK) e->th->ll_stale = false;
   bb_time_end(e->ctx);
   return rc;
 }
@@ -900,7 +1245,8 @@ extern "C" int bb_theta_pcn_step(bb_ens* e, double rho, uint64_t seed, uint32_t 
   if (!(rho >= -1.0 && rho <= 1.0)) return BB_ERR_ARG;
   BB_CUDA(cudaSetDevice(e->ctx->device));
   bb_time_begin(e->ctx);
-  int rc = ensure_current_tables(e);
+  int rc = ensure_running_ll(e, skip);
+  if (rc == BB_OK) rc = ensure_current_tables(e);
   if (rc == BB_OK) rc = run_forward(e, true, 0, 0, skip, (flags & BB_RUN_STORE_X) != 0, rho, seed, iter);
   bb_time_end(e->ctx);
   return rc;
@@ -918,9 +1264,9 @@ extern "C" int bb_theta_param_step(bb_ens* e, const double* rw_sd, uint64_t seed
   BB_CUDA(cudaSetDevice(e->ctx->device));
   if (e->th->spec.start_sd != 0.0 && e->start_bcast) return BB_ERR_STARTPOINT; /* per-chain starting points: bb_ens_set_start(..., broadcast = 0) */
   bb_time_begin(e->ctx);
-  int rc = BB_OK;
+  int rc = ensure_running_ll(e, skip);
   /* the left-end values of the current θ (logpdfnormal, trace term, prior) enter the accept test */
-  if (e->th->tstate == 0) rc = run_backward(e, 0, false, nullptr, 0, 0);
+  if (rc == BB_OK && e->th->tstate == 0) rc = run_backward(e, 0, false, nullptr, 0, 0);
   if (rc == BB_OK) rc = run_backward(e, 1, true, rw_sd, seed, iter);
   if (rc == BB_OK) rc = run_forward(e, false, 1, 2, skip, (flags & BB_RUN_STORE_X) != 0, 0.0, seed, iter);
   bb_time_end(e->ctx);
@@ -934,6 +1280,43 @@ extern "C" int bb_theta_refresh_x(bb_ens* e) {
   int rc = ensure_current_tables(e);
   if (rc == BB_OK) rc = run_forward(e, false, 0, 3, 0, true, 0.0, 0, 0);
   return rc;
+}
+
+extern "C" int bb_theta_block_step(bb_ens* e, int32_t s_lo, int32_t s_hi, double rho, double hzero, uint64_t seed,
+                                   uint32_t iter, int32_t skip) {
+  if (!e || !e->th) return BB_ERR_ARG;
+  if (s_lo < 0 || s_hi <= s_lo || s_hi > e->S || skip < 0) return BB_ERR_ARG;
+  if (!(rho >= -1.0 && rho <= 1.0) || !(hzero > 0.0)) return BB_ERR_ARG;
+  if (!e->X || !(e->flags & BB_ENS_DOUBLE_BUFFER)) return BB_ERR_ARG; /* the block is conditioned on the stored path */
+  bb_theta* t = e->th;
+  if (s_lo == 0 && t->spec.start_sd != 0.0 && e->start_bcast) return BB_ERR_STARTPOINT;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  int rc = BB_OK;
+  if (!t->blkv) rc = th_alloc(e, &t->blkv, (size_t)BB_NBLK * (size_t)e->P);
+  if (rc == BB_OK && !t->Xprop) rc = th_alloc(e, &t->Xprop, (size_t)e->S * e->NC * (size_t)e->P * BB_TC * e->d);
+  if (rc != BB_OK) return rc;
+  bb_time_begin(e->ctx);
+  if (e->x_maybe_stale) rc = bb_theta_refresh_x(e); /* rejected proposals of earlier whole-path steps */
+  const blk_spec blk{s_lo, s_hi, hzero};
+  if (rc == BB_OK) rc = run_backward(e, 0, false, nullptr, seed, iter, &blk);
+  if (rc == BB_OK) rc = run_block(e, blk, skip, rho, seed, iter);
+  if (rc == BB_OK) t->ll_stale = true;
+  bb_time_end(e->ctx);
+  return rc;
+}
+
+extern "C" int bb_theta_get_block(bb_ens* e, int64_t p0, int64_t np, double* out) {
+  if (!e || !e->th || !e->th->blkv || !out || np < 0 || p0 < 0 || p0 + np > e->P) return BB_ERR_ARG;
+  BB_CUDA(cudaSetDevice(e->ctx->device));
+  const int NB = BLK_SEG + 2 * e->S;
+  std::vector<double> h((size_t)np * NB);
+  for (int k = 0; k < NB; k++)
+    BB_CUDA(cudaMemcpyAsync(h.data() + (size_t)k * np, e->th->blkv + (size_t)k * e->P + p0, sizeof(double) * np,
+                            cudaMemcpyDeviceToHost, e->ctx->stream));
+  BB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+  for (int64_t p = 0; p < np; p++)
+    for (int k = 0; k < NB; k++) out[(size_t)p * NB + k] = h[(size_t)k * np + p];
+  return BB_OK;
 }
 
 extern "C" int bb_theta_get_acc(bb_ens* e, int64_t* acc) {

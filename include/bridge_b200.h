@@ -444,8 +444,8 @@ int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
  * T [S][N][d+d*d][P] (ν[i], H[i] per grid point, chain-minor: warp accesses are contiguous), so that no
  * θ-proposal round-trips to the host.  The auxiliary process follows from (θ, v_s) by a closed registry
  * (bb_aux_kind), for the same reason the target models do.  The script's joint random walk on the starting point
- * (:311-318) is available through start_sd / start_dir of bb_theta_spec; its blocked segment updates (klow..kup) are not:
- * all segments are updated together.
+ * (:311-318) is available through start_sd / start_dir of bb_theta_spec; its blocked segment updates (klow..kup) are
+ * bb_theta_block_step below.
  */
 #define BB_NTHETA 8
 typedef enum {
@@ -499,6 +499,38 @@ int bb_theta_param_step(bb_ens* ens, const double* rw_sd, uint64_t seed, uint32_
 /* bb_ens_refresh_x for chains with their own tables: X <- current path of the chains whose last proposal (pCN or
  * parameter) was rejected */
 int bb_theta_refresh_x(bb_ens* ens);
+/* Blocked path update: the `updateparams == false` branch of the same loop (bolus3.jl:258-275, :300-355) for ONE block
+ * of segments s_lo .. s_hi-1 (0-based; the script's ind = (kup-1):-1:klow with klow = s_lo+1, kup = s_hi+1), every
+ * chain on the same block -- the host draws the block sequence (segnum_update = sample(1:obsnum-klow), :266) and calls
+ * once per block:
+ *   right end (:272-275): the block ends the chain (s_hi == S): ν = 0, H⁺ = I/ϵ, gpupdate with v[S-1] (νrightmost,
+ *             Hrightmost⁺, :162-167); else ν = XX[s_hi-1].yy[end] -- the CHAIN'S OWN current path -- and
+ *             H⁺ = Hzero⁺ = hzero·I (:234, 0.1 in the script);
+ *   tables    for s = s_hi-1 .. s_lo: partialbridgeνH on the segment, gpupdate with v[s-1] unless s == s_lo (:281-296);
+ *   noise     W°[s] = ρ W[s] + sqrt(1-ρ²) W2, W2 ~ Wiener from noise row chain·S + s (:304-305; as bb_pcn_step);
+ *   start     s_lo == 0: x0° = x0 + (start_sd u) start_dir, ALWAYS proposed in this branch (:316-318; u = normal 3 of
+ *             Philox counter (0xFFFFFFFE, iter, chain); start_sd = 0: x0° = x0) with the start term
+ *             logpdfnormal(x0° - ν(0), symmetrize(H⁺(0))) - logpdfnormal(x0 - ν(0), ·) (:319);
+ *             s_lo > 0: both passes start at the current path's value at the block's left end, XX[s_lo-1].yy[end].
+ *             (The script reads XXtemp[i-1] / XXᵒ[i-1] there, :321-322 -- buffers of the PREVIOUS block's proposal
+ *             that, after its swap or rejection, no longer hold the current path; a chain of segments that starts
+ *             where the current path is, is what the comment on :260 describes and what is built here.  Likewise
+ *             `ind = 1:1` for a single-segment block (:268) names segment 1 whatever klow is; the caller passes the
+ *             block it means.)
+ *   passes    XXtemp = solve!(Euler(), ·, W, Q) -- the CURRENT noise re-run under the block's guide -- and
+ *             XXᵒ = solve!(Euler(), ·, W°, Q) side by side (:324-325);
+ *   diffll    start term + Σ_{s = s_hi-1 .. s_lo} (ll°[s] - ll_temp[s]) in that order (:331-333);
+ *   accept    iff log(U) <= diffll (U as bb_pcn_step): W°, X° of the block's segments (and x0°) replace the current
+ *             ones, acc += 1 (:340-353); otherwise nothing changes (XX keeps the path it had, as in the script).
+ * Needs a double-buffered ensemble with X stored (BB_ENS_DOUBLE_BUFFER, no BB_ENS_NO_X); allocates a proposal copy of X
+ * on first use.  Block updates keep no running ll (the script keeps none in this branch); the next whole-path step
+ * (bb_theta_pcn_step / bb_theta_param_step) re-establishes it with one forward pass under the full backward chain, which
+ * also re-simulates X from the chains' W under that chain's guide. */
+int bb_theta_block_step(bb_ens* ens, int32_t s_lo, int32_t s_hi, double rho, double hzero, uint64_t seed,
+                        uint32_t iter, int32_t skip);
+/* numbers of the last block update: out [np][5 + 2 S] = logpdfnormal(x0 - ν(0)), logpdfnormal(x0° - ν(0)) (0, 0 when
+ * s_lo > 0), Σ ll_temp, Σ ll°, diffll, then (ll_temp[s], ll°[s]) for s = 0 .. S-1 (entries outside the block are stale) */
+int bb_theta_get_block(bb_ens* ens, int64_t p0, int64_t np, double* out);
 /* accepted parameter proposals since attach, summed over this ensemble's chains */
 int bb_theta_get_acc(bb_ens* ens, int64_t* acc);
 void* bb_theta_acc_device_ptr(bb_ens* ens);

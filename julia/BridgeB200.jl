@@ -444,6 +444,21 @@ function theta_param_step!(E::PathEnsemble, rw_sd, seed::UInt64, iter::Integer; 
                 E.h, sd, seed, iter, skip, store_x ? 1 : 0))
     a = Ref{Int64}(0); check(ccall((:bb_theta_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, a)); a[]
 end
+# blocked path update of segments klow .. kup-1 (1-based, as ind = (kup-1):-1:klow of partialbridge_bolus3.jl:258-275);
+# Hzero⁺ = hzero*I (:234) conditions a block that does not end the chain on the chain's own path at its right end
+theta_block!(E::PathEnsemble, klow::Integer, kup::Integer, ρ, seed::UInt64, iter::Integer; hzero = 0.1, skip = 0) =
+    check(ccall((:bb_theta_block_step, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Float64, Float64, UInt64, UInt32, Int32),
+                E.h, klow - 1, kup - 1, ρ, hzero, seed, iter, skip))
+# one sweep klow = 1 .. obsnum of the `while !finished` loop (:258-362, updateparams == false); returns the blocks
+function theta_blocked_sweep!(E::PathEnsemble, ρ, seed::UInt64, iter0::Integer; hzero = 0.1, skip = 0)
+    obsnum = E.S + 1; klow = 1; blocks = Tuple{Int,Int}[]
+    while klow != obsnum
+        kup = klow + rand(1:obsnum-klow)
+        theta_block!(E, klow, kup, ρ, seed, iter0 + length(blocks); hzero = hzero, skip = skip)
+        push!(blocks, (klow, kup)); klow = kup
+    end
+    blocks
+end
 function theta(E::PathEnsemble)   # param(P) of every chain: 8 x P (column per chain)
     θ = Matrix{Float64}(undef, 8, E.P)
     check(ccall((:bb_theta_get, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), E.h, 0, 0, E.P, θ)); θ

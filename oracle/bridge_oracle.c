@@ -1187,6 +1187,26 @@ int bbo_innovations(const bb_model* P, const bbo_guide* G, int N, const double* 
   return 0;
 }
 
+/* The noise half of a pCN proposal for ONE segment (test/partialbridgenuH.jl:176-178, partialbridge_bolus3.jl:304-305):
+ * sample!(W2, Wiener()) with W2.yy[1] = 0 drawn from noise row `row`, then Wo.yy .= ρ*W.yy + sqrt(1-ρ^2)*W2.yy. */
+void bbo_pcn_combine(int N, int dp, const double* tt, const double* wc, double rho, uint64_t seed, uint32_t iter,
+                     uint64_t row, double* wo) {
+  double rho2 = sqrt(1 - rho * rho);
+  double w2[DM];
+  for (int k = 0; k < dp; k++) {
+    w2[k] = 0.0;
+    wo[k] = MA(rho2, w2[k], rho * wc[k]);
+  }
+  for (int j = 1; j < N; j++) {
+    double rootdt = sqrt(tt[j] - tt[j - 1]);
+    for (int k = 0; k < dp; k++) {
+      double xi = bbo_normal(seed, iter, row, (uint64_t)j * dp + k);
+      w2[k] = MA(rootdt, xi, w2[k]);
+      wo[j * dp + k] = MA(rho2, w2[k], rho * wc[j * dp + k]);
+    }
+  }
+}
+
 /* ======================================================================= A8: one pCN iteration of one chain
  * test/partialbridgenuH.jl:176-191; multi-segment block with one accept: bolus3.jl:300-355.
  * Wc  [S][N][dp]  current driving paths      (in)
@@ -1198,7 +1218,6 @@ double bbo_pcn_propose(const bb_model* P, const bbo_guide* const* G, int S, cons
                        uint64_t chain, int skip, double* Wo, double* Xo, double* xend,
                        double* logU) {
   int d = P->d, dp = P->dprime;
-  double rho2 = sqrt(1 - rho * rho);
   double start[DM], end[DM];
   memcpy(start, u, sizeof(double) * d);
   double ll = 0.0;
@@ -1207,21 +1226,7 @@ double bbo_pcn_propose(const bb_model* P, const bbo_guide* const* G, int S, cons
     const double* tt = G[s]->tt;
     const double* wc = Wc + (size_t)s * N * dp;
     double* wo = Wo + (size_t)s * N * dp;
-    uint64_t row = chain * (uint64_t)S + s;
-    /* sample!(W2, Wiener()) with W2.yy[1] = 0, then Wo.yy .= ρ*W.yy + sqrt(1-ρ^2)*W2.yy */
-    double w2[DM];
-    for (int k = 0; k < dp; k++) {
-      w2[k] = 0.0;
-      wo[k] = MA(rho2, w2[k], rho * wc[k]);
-    }
-    for (int j = 1; j < N; j++) {
-      double rootdt = sqrt(tt[j] - tt[j - 1]);
-      for (int k = 0; k < dp; k++) {
-        double xi = bbo_normal(seed, iter, row, (uint64_t)j * dp + k);
-        w2[k] = MA(rootdt, xi, w2[k]);
-        wo[j * dp + k] = MA(rho2, w2[k], rho * wc[j * dp + k]);
-      }
-    }
+    bbo_pcn_combine(N, dp, tt, wc, rho, seed, iter, chain * (uint64_t)S + s, wo);
     double* xo = Xo ? Xo + (size_t)s * N * d : NULL;
     double* tmp = NULL;
     if (!xo) { tmp = (double*)malloc(sizeof(double) * N * d); xo = tmp; }

@@ -322,6 +322,13 @@ class Oracle:
                                       C.c_int(skip), _p(Wo), _p(Xo), _p(xend), C.byref(logu))
         return ll, logu.value, Wo, Xo, xend
 
+    def pcn_combine(self, tt, Wc, rho, seed, it, row):
+        """W° of one segment: sample!(W2, Wiener()) from noise row `row`, W°.yy = ρ W.yy + sqrt(1-ρ²) W2.yy"""
+        tt = _f64(tt); Wc = _f64(Wc).reshape(len(tt), -1); Wo = np.zeros_like(Wc)
+        self.lib.bbo_pcn_combine(C.c_int(len(tt)), C.c_int(Wc.shape[1]), _p(tt), _p(Wc), C.c_double(rho),
+                                 C.c_uint64(seed), C.c_uint32(it), C.c_uint64(row), _p(Wo))
+        return Wo
+
     def pcn_bench(self, model, guides, P, u, rho, seed, iters, skip=0, nthreads=0):
         S = len(guides)
         garr = (C.POINTER(Guide) * S)(*[C.pointer(g.c) for g in guides])
@@ -484,3 +491,80 @@ def theta_diffll(left_c, left_o, ll_c, ll_o):
     diff += ll_o - ll_c
     diff += ((left_o["trsum"] - left_c["trsum"]) + left_o["lpri"]) - left_c["lpri"]
     return diff
+
+
+# ----------------------------------------------------------------------- blocked segment updates
+# The path-update branch (`updateparams == false`) of partialbridge_bolus3.jl:258-355 for ONE chain and ONE block of
+# segments s_lo .. s_hi-1 (0-based; the script's ind = (kup-1):-1:klow with klow = s_lo+1, kup = s_hi+1).
+def theta_block_backward(o: Oracle, model_id, par, grids, L, Sigma, eps, obs_v, aux_kind, s_lo, s_hi, x_right, hzero):
+    """Guides of the block's segments (others None) and (ν, H⁺) at the block's left end.  Right end (:272-275):
+    the right-most initialisation (ν = 0, H⁺ = I/ϵ, update with the last observation, :162-165) when the block ends
+    the chain, else ν = the chain's own path at the block's right end and H⁺ = Hzero⁺ = hzero I.  An observation update
+    follows every segment except the block's left-most one (:288-295)."""
+    S = len(grids)
+    L = np.atleast_2d(_f64(L)); d = L.shape[1]
+    if s_hi == S:
+        nu = np.zeros(d); Hp = np.eye(d) * (1.0 / eps)
+        nu, Hp = o.gpupdate_nuH(nu, Hp, L, Sigma, np.atleast_1d(obs_v[S - 1]))
+    else:
+        nu = np.array(x_right, dtype=np.float64); Hp = np.eye(d) * float(hzero)
+    guides = [None] * S
+    Cc = 0.0
+    for s in range(s_hi - 1, s_lo - 1, -1):
+        if aux_kind == AUX_BOLUS:
+            Bt, bf, at = bolus_aux(par)
+            aux = staged_aux(grids[s], lambda t: Bt, bf, lambda t: at)
+            nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], aux, nu, Hp, Cc)
+            n = len(grids[s])
+            guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=np.broadcast_to(Bt, (n, d, d)).copy(),
+                                    betat=np.stack([bf(t) for t in grids[s]]), aux_const=False)
+        else:
+            at = fhn_a(model_id, par)
+            Bt, bt = fhn_aux(aux_kind, par, float(np.atleast_1d(obs_v[s])[0]))
+            nus, Hs, nu, Hp, Cc = o.backward_nuH(ODE_LYAP, grids[s], const_aux(Bt, bt, at), nu, Hp, Cc)
+            guides[s] = GuideHolder(GUIDE_NUH, grids[s], Hs, nus, Bt=Bt, betat=bt)
+        if s > s_lo:
+            nu, Hp = o.gpupdate_nuH(nu, Hp, L, Sigma, np.atleast_1d(obs_v[s - 1]))
+    return guides, nu, Hp
+
+
+def theta_block_step(o: Oracle, model_id, dprime, par, grids, L, Sigma, eps, obs_v, aux_kind, s_lo, s_hi, hzero,
+                     x0, Xcur, Wcur, rho, seed, it, chain, start_sd=0.0, start_dir=None, skip=0):
+    """One blocked path update of one chain -> dict(Wo, Xo [block segments], x0o, lpn, lpno, llt [S], llo [S], diff,
+    logu).  Xcur [S,N,d] / Wcur [S,N,d'] are the chain's current path and driving noise.
+
+    bolus3.jl:300-345: W°[i] = ρW[i] + √(1-ρ²)W2 on the block; the CURRENT noise is re-simulated under the block's
+    guide (XXtemp) next to the proposal (XXᵒ); the block starts at the current path's value at its left end -- for
+    s_lo = 0 at x0, moved to x0° = x0 + (start_sd u) start_dir with the Gaussian start term (:311-320); diffll sums
+    the start term and then, in the script's order (i in ind, descending), ll°[i] - ll_temp[i]; log U as for pCN."""
+    S = len(grids)
+    x_right = Xcur[s_hi - 1][-1] if s_hi < S else None
+    guides, nuL, HpL = theta_block_backward(o, model_id, par, grids, L, Sigma, eps, obs_v, aux_kind, s_lo, s_hi,
+                                            x_right, hzero)
+    mdl = make_model(model_id, 2, dprime, par)
+    lpn = lpno = 0.0
+    if s_lo == 0:
+        xs = np.asarray(x0, dtype=np.float64); xso = xs
+        lpn = o.logpdfnormal(xs - nuL, HpL)
+        if start_sd != 0.0:
+            u = o.normal(seed, it, chain, 4 * Q_THETA_NORMALS + 3)
+            xso = xs + (start_sd * u) * np.asarray(start_dir, dtype=np.float64)
+            lpno = o.logpdfnormal(xso - nuL, HpL)
+        else:
+            lpno = lpn
+    else:
+        xs = xso = np.array(Xcur[s_lo - 1][-1], dtype=np.float64)
+    x0o = xso
+    llt = np.zeros(S); llo = np.zeros(S); Wo = {}; Xo = {}
+    ut, uo = xs, xso
+    for s in range(s_lo, s_hi):
+        Wo[s] = o.pcn_combine(grids[s], Wcur[s], rho, seed, it, chain * S + s)
+        Xt, ut = o.guided_euler(mdl, guides[s], ut, Wcur[s])
+        Xo[s], uo = o.guided_euler(mdl, guides[s], uo, Wo[s])
+        llt[s] = o.llikelihood(mdl, guides[s], Xt, skip)
+        llo[s] = o.llikelihood(mdl, guides[s], Xo[s], skip)
+    diff = lpno - lpn
+    for s in range(s_hi - 1, s_lo - 1, -1):
+        diff += llo[s] - llt[s]
+    return dict(Wo=Wo, Xo=Xo, x0o=x0o, lpn=lpn, lpno=lpno, llt=llt, llo=llo, diff=diff,
+                logu=o.accept_logu(seed, it, chain), nuL=nuL, HpL=HpL, guides=guides)

@@ -693,3 +693,53 @@ def test_logpdfnormal_and_gamma_prior_against_scipy(oracle_ref):
                                np.array([[1.0, 0.0]]), np.array([[1e-2]]), 0.1, [0.5], O.AUX_FHN_MATCHING,
                                {4: ("gamma", 1.0, 100.0)})
     assert left["lpri"] == -np.inf  # outside the support: never accepted
+
+
+def test_block_update_composition_properties(oracle_ref):
+    """oracle.theta_block_step (blocked segment updates, partialbridge_bolus3.jl:258-355):
+      * a block that spans the whole chain uses the tables of the full backward chain (theta_backward) and its start
+        term is that chain's logpdfnormal;
+      * with ρ = 1 and no start move the proposal IS the re-simulated current path: W° = W, diffll = 0 exactly;
+      * a block that does not end the chain is conditioned on the chain's own path: ν at the block's right end is the
+        path's value there and H⁺ = Hzero⁺, whatever the observations right of it are;
+      * the proposal's noise is the pCN combination of one segment of bbo_pcn_propose (same rows, same normals)."""
+    par = (0.1, 0.0, 1.5, 0.8, 0.3)
+    L = np.array([[1.0, 0.0]]); Sig = np.array([[1e-2]]); eps_ = 0.1
+    obs_t, obs_v = (0.5, 1.0, 1.5), (-1.0, -0.5, 0.5)
+
+    def tau(t0, t1, n):
+        s = np.linspace(0.0, t1 - t0, n)
+        return t0 + s * (2.0 - s / (t1 - t0))
+
+    S, n = 3, 31
+    grids = [tau(a, b, n) for a, b in zip((0.0,) + obs_t[:-1], obs_t)]
+    x0 = np.array([-0.5, -0.6])
+    guides, left = O.theta_backward(oracle_ref, O.FHN_HYPO, par, grids, x0, L, Sig, eps_, obs_v, O.AUX_FHN_MATCHING)
+    W = np.stack([oracle_ref.wiener_sample(g, 1, 3, 0, 10 + s) for s, g in enumerate(grids)])
+    X, ll, _ = O.theta_forward(oracle_ref, O.FHN_HYPO, 1, par, guides, x0, W)
+    args = (oracle_ref, O.FHN_HYPO, 1, par, grids, L, Sig, eps_, obs_v, O.AUX_FHN_MATCHING)
+    # whole chain
+    r = O.theta_block_step(*args, 0, S, 0.1, x0, X, W, 0.7, 5, 2, 77)
+    for s in range(S):
+        assert np.array_equal(r["guides"][s].A, guides[s].A) and np.array_equal(r["guides"][s].b, guides[s].b)
+    assert r["lpn"] == left["lpn"] and r["lpno"] == r["lpn"]
+    assert np.sum(r["llt"]) == pytest.approx(ll, rel=1e-14)  # XXtemp under the same guide is the current path
+    mdl = O.make_model(O.FHN_HYPO, 2, 1, par)
+    llo, lu, Wo, Xo, _ = oracle_ref.pcn_propose(mdl, guides, x0, W, 0.7, 5, 2, 77)
+    for s in range(S):
+        assert np.array_equal(r["Wo"][s], Wo[s]) and np.array_equal(r["Xo"][s], Xo[s])
+    assert lu == r["logu"] and np.sum(r["llo"]) == pytest.approx(llo, rel=1e-14)
+    # ρ = 1: nothing is proposed
+    r1 = O.theta_block_step(*args, 1, 3, 0.1, x0, X, W, 1.0, 5, 3, 77)
+    assert all(np.array_equal(r1["Wo"][s], W[s]) for s in (1, 2)) and r1["diff"] == 0.0
+    # interior block: conditioned on the path's own value, observations to the right do not enter
+    r2 = O.theta_block_step(*args, 0, 2, 0.1, x0, X, W, 0.7, 5, 4, 77, 0.1, [1.0, -1.0])
+    g2, nuL, HpL = O.theta_block_backward(oracle_ref, O.FHN_HYPO, par, grids, L, Sig, eps_, (-1.0, -0.5, 123.0),
+                                          O.AUX_FHN_MATCHING, 0, 2, X[1][-1], 0.1)
+    assert np.array_equal(g2[1].b[-1], X[1][-1]) and np.array_equal(r2["guides"][1].b, g2[1].b)
+    assert np.allclose(np.linalg.inv(g2[1].A[-1]), 0.1 * np.eye(2), rtol=1e-12)
+    assert np.array_equal(r2["nuL"], nuL) and g2[2] is None
+    # the start move: x0° = x0 + (0.1 u)(1, -1), and both start terms use the block's left-end (ν, H⁺)
+    u = oracle_ref.normal(5, 4, 77, 4 * O.Q_THETA_NORMALS + 3)
+    assert np.array_equal(r2["x0o"], x0 + (0.1 * u) * np.array([1.0, -1.0]))
+    assert r2["lpno"] == oracle_ref.logpdfnormal(r2["x0o"] - nuL, HpL) and np.array_equal(r2["Xo"][0][0], r2["x0o"])
