@@ -254,7 +254,7 @@ struct bb_chain {
     const int N = a.N;
     /* pipelined where the launch is memory bound (paths stored); the compute-bound pCN without X° (RNG 3) keeps the
      * noise of a group next to its own steps (measured: 4.3 ms vs 5.0 ms pipelined at 2.5e5 chains) */
-    constexpr bool PIPE = (RNG != 3);
+    constexpr bool PIPE = (RNG != 3) && (DP <= BB_PIPE_MAXDP);
     double wg[4 * DP], wn[4 * DP];
     if constexpr (PIPE) gen_group<GENERIC>(a, rec, st, wq, wrow, wout_row, c, 0, row_lo, row_hi, wact, wg);
     /* groups of 4 grid points: the body is unrolled over one group only, which bounds code size and the
@@ -482,11 +482,26 @@ struct bb_chain {
         }
         double* wrow = wslot + (size_t)(gcur % BB_WSTAGES) * BB_THREADS * WROWP;
         if constexpr (RNG != 2) {
+#if BB_WSTAGES == 1
+          /* single stage (d' >= 2: a second one would halve the chains an SM can hold): every lane has written the
+           * previous chunk's row back, the warp copies this chunk's rows -- which the lanes asked L2 for a whole
+           * chunk ago -- and waits for them; the other warps of the SM cover the L2 round trip */
+          __syncwarp();
+          w_issue(gcur);
+          bb_cp_async_wait<0>();
+          __syncwarp();
+          if (act && gcur + 1 < TW) {
+#pragma unroll
+            for (int l = 0; l < (BB_TC * DP * 8 + 127) / 128; l++)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + wstride + l * 16));
+          }
+#else
           /* rows of chunk gcur were requested a whole chunk ago: wait for them first (normally no wait at all),
            * then refill the other stage -- which every lane has finished reading -- with chunk gcur+1 */
           bb_cp_async_wait<BB_WSTAGES - 2>();
           __syncwarp();
           w_issue(gcur + BB_WSTAGES - 1);
+#endif
         }
         if ((c % BB_TSTAGE) == BB_TSTAGE - 1 || c == NC - 1) {
           /* probe the next table stage now; its result is needed only after this chunk */
@@ -555,7 +570,7 @@ struct bb_chain {
  * (a 128-register cap) bought nothing and made them spill 70-420 bytes per thread (config 3, LinPro d = 3:
  * 2.75 ms -> 0.83 ms for guided Euler + ll once the cap is lifted). */
 template <class M>
-constexpr int bb_min_ctas() { return M::DP >= 2 ? 1 : BB_MINB; }
+constexpr int bb_min_ctas() { return M::DP >= 2 ? BB_MINB_WIDE : BB_MINB; }
 
 template <class M, int GK, int GM, int AUXM, int RNG>
 __global__ void __launch_bounds__(BB_THREADS, bb_min_ctas<M>()) bb_chain_kernel(const __grid_constant__ bb_chain_args a) {
