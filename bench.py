@@ -460,26 +460,45 @@ def main():
             hostW, hostWo, hostXo, hostLL, hostAcc = bufs
             ens.download(B.W, out=hostW)
 
-            def e2e_step(itn):
-                # one call on host buffers: W up; W°, X°, ll°, accept flags down (pipelined over chain slabs)
-                ens.pcn_step_host_(Pm, guides, rho, 4, itn, hostW, hostWo, hostXo, hostLL, hostAcc)
-                return ens.acc
+            def e2e_leg(skip_rejected):
+                # one call per step on host buffers: W up; W°, X°, ll°, accept flags down (pipelined over chain slabs).
+                # skip_rejected: Wo is W itself -- the host array is updated in place for the chains that accept, which
+                # is the reference loop's swap of W and Wo, so it holds the chains' current W in every iteration
+                nonlocal it
+                ens.download(B.W, out=hostW)
+                Wo = hostW if skip_rejected else hostWo
+                ens.pcn_step_host_(Pm, guides, rho, 4, it, hostW, Wo, hostXo, hostLL, hostAcc,
+                                   skip_rejected=skip_rejected); it += 1
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                nacc = 0
+                for _ in range(args.e2e_steps):
+                    ens.pcn_step_host_(Pm, guides, rho, 4, it, hostW, Wo, hostXo, hostLL, hostAcc,
+                                       skip_rejected=skip_rejected); it += 1
+                    _ = ens.acc
+                    nacc += int(hostAcc.sum())
+                e1.record(stream)
+                barrier()
+                return allmax(e0.elapsed_time(e1)), nacc / args.e2e_steps
 
-            e2e_step(it); it += 1
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(args.e2e_steps):
-                e2e_step(it); it += 1
-            e1.record(stream)
-            barrier()
-            ems = allmax(e0.elapsed_time(e1))
+            row_bytes = int((hostWo.nbytes + hostXo.nbytes) // P)
+            ems, acc_per_step = e2e_leg(True)   # first: the chains' state is consistent with the host's W throughout
+            ems_all, _ = e2e_leg(False)
+            # the reference loop reads W°, X° only to swap them in on accept (test/partialbridgenuH.jl:184-186), so the rows
+            # of the chains that reject do not have to come back: headline = accepted rows only, all rows beside it
             e2e = {"value": steps_all * args.e2e_steps / (ems * 1e-3),
                    "unit": "path-steps/s", "h2d_bytes_per_step": int(hostW.nbytes),
-                   "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
+                   "d2h_bytes_per_step": int(acc_per_step * row_bytes + P * 9 + 8),
                    "steps": args.e2e_steps,
-                   "what": "bb_pcn_step_host on pinned host buffers: per step W up; W°, X°, ll°, accept flags down; "
-                           "H2D | kernel | D2H pipelined over chain slabs"}
+                   "what": "bb_pcn_step_host(BB_RUN_SKIP_REJECTED) on pinned host buffers: per step W of every chain up; "
+                           "ll°, accept flags of every chain and W°, X° of the chains that ACCEPT down, written straight "
+                           "into the mapped host arrays (W in place: the loop's swap); H2D | kernel | D2H pipelined over "
+                           "chain slabs",
+                   "acc_rate": acc_per_step / P,
+                   "all_rows": {"value": steps_all * args.e2e_steps / (ems_all * 1e-3), "unit": "path-steps/s",
+                                "d2h_bytes_per_step": int(hostWo.nbytes + hostXo.nbytes + P * 9 + 8),
+                                "what": "the same with W°, X° of every chain coming back (rejected proposals too)"}}
         else:
             e2e = {"value": None, "unit": "path-steps/s", "h2d_bytes_per_step": P * S * n * 8,
                    "d2h_bytes_per_step": P * S * n * 24 + P * 9 + 8,

@@ -29,7 +29,7 @@ ENS_DOUBLE_BUFFER, ENS_NO_X = 1, 2
 W, X = 0, 1
 CUR, PROP = 0, 1
 F_LL, F_LL_PROP, F_LOGU, F_XEND, F_XEND_PROP = range(5)
-RUN_STORE_X, RUN_NO_LL = 1, 2
+RUN_STORE_X, RUN_NO_LL, RUN_SKIP_REJECTED = 1, 2, 4
 ARITH_REFERENCE, ARITH_FUSED = 0, 1
 PCN_AUTO, PCN_ONE_THREAD, PCN_WARP_SPECIALISED = 0, 1, 2
 SCHEME_EULER, SCHEME_STRATONOVICH, SCHEME_HEUN, SCHEME_SRK, SCHEME_MDB = range(5)

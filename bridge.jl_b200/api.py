@@ -787,14 +787,16 @@ class PathEnsemble:
         check(lib.bb_guided_euler_ll(self.h, C.byref(m), self._garr(guides), skip, flags))
 
     def pcn_step_host_(self, P, guides, ρ: float, seed: int, it: int, W, Wo, Xo=None, llo=None, accepted=None,
-                       skip: int = 0):
+                       skip: int = 0, skip_rejected: bool = False):
         """One pCN iteration on HOST arrays (the reference loop's dataflow): W [P,S,N,d'] in; Wo, Xo, llo, accepted
-        out.  Pipelined H2D | kernel | D2H over chain slabs; use pinned arrays for full overlap."""
+        out.  Pipelined H2D | kernel | D2H over chain slabs; use pinned arrays for full overlap.  skip_rejected: rows of
+        Wo / Xo of chains that reject are left as they were (the loop only swaps proposals in on accept); with pinned,
+        device-mapped arrays the accepted rows are written straight into them and the rest never crosses the link."""
         m = P.cmodel()
         self._last = (P, list(guides))
-        check(lib.bb_pcn_step_host(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip,
-                                   K.RUN_STORE_X if Xo is not None else 0, ptr(W), ptr(Wo), ptr(Xo), ptr(llo),
-                                   ptr(accepted)))
+        flags = (K.RUN_STORE_X if Xo is not None else 0) | (K.RUN_SKIP_REJECTED if skip_rejected else 0)
+        check(lib.bb_pcn_step_host(self.h, C.byref(m), self._garr(guides), ρ, seed, it, skip, flags, ptr(W), ptr(Wo),
+                                   ptr(Xo), ptr(llo), ptr(accepted)))
 
     # ---- pooled online statistics: mcstart / mcnext! / mcstats of src/mclog.jl for the whole ensemble
     def mc_reset_(self):

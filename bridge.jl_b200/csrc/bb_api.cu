@@ -1050,6 +1050,52 @@ __global__ void __launch_bounds__(256) bb_slab_out_kernel(const double* __restri
   }
 }
 
+/* BB_RUN_SKIP_REJECTED with mapped host buffers: W°, X° of the chains that accepted go straight from the chunked device
+ * layout to the caller's host arrays ([chain][segment][N][k]; a row of 16 grid points is 128 k contiguous bytes on both
+ * sides, so the stores over the link are whole-line), chains that rejected are skipped */
+__global__ void __launch_bounds__(256) bb_slab_out_direct_kernel(const double* __restrict__ W0, const double* __restrict__ X,
+                                                                 double* __restrict__ hostW, double* __restrict__ hostX,
+                                                                 const uint8_t* __restrict__ par,
+                                                                 const uint8_t* __restrict__ accepted, long long P,
+                                                                 long long p0, long long np, int S, int N, int NC, int dp,
+                                                                 int d, int nbuf) {
+  /* one CTA per (chain, segment, W | X): the segment's N k doubles are ONE contiguous run in the host array, written
+   * front to back, 2 KB per step of the CTA, by few concurrent writers (scattered 128-byte pieces -- the order of the
+   * device layout -- reach 29 GB/s over the link, one run per warp 36 GB/s, one run per CTA 40 GB/s in this pipeline;
+   * a plain streaming kernel 48-52 GB/s, tools/pciebench.cu, profiles/r02_pciebench.txt); the reads walk the chain's chunk rows, 128 k contiguous bytes each */
+  const int lane = threadIdx.x;
+  const long long nwarp = gridDim.x;
+  const long long items = np * S * (hostX ? 2 : 1);
+  for (long long it = blockIdx.x; it < items; it += nwarp) {
+    const bool isx = it >= np * S;
+    const long long u = isx ? it - np * S : it;
+    const long long pl = u / S;
+    const int s = (int)(u - pl * S);
+    const long long p = p0 + pl;
+    if (!accepted[p]) continue;
+    const int K = isx ? d : dp;
+    const long long rowlen = (long long)BB_TC * K;
+    const double* src = isx ? X + ((long long)s * NC * P + p) * rowlen
+                            : W0 + (((long long)s * NC * P + p) * nbuf + par[p]) * rowlen; /* accepted: par has flipped */
+    const long long cstride = isx ? P * rowlen : P * nbuf * rowlen;
+    double* dst = (isx ? hostX : hostW) + (p * S + s) * (long long)N * K;
+    const int tot = N * K;
+    for (int i = lane; i < tot; i += 256) {
+      const int c = i / (int)rowlen, e = i - c * (int)rowlen;
+      dst[i] = src[(long long)c * cstride + e];
+    }
+  }
+}
+
+static double* mapped_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return at.type == cudaMemoryTypeHost ? (double*)at.devicePointer : nullptr;
+}
+
 extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* const* guides, double rho, uint64_t seed,
                                 uint32_t iter, int32_t skip, uint32_t flags, const double* W_host, double* Wo_host,
                                 double* Xo_host, double* llo_host, uint8_t* accepted_host) {
@@ -1072,6 +1118,13 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
   int64_t slab = (int64_t)((size_t)(192u << 20) / (wpc * sizeof(double)));
   slab = slab < 256 ? 256 : (slab / 256) * 256; /* whole CTAs */
   if (slab > e->P) slab = e->P;
+  /* accepted rows straight into mapped host memory (see the header) */
+  double* Wo_map = (flags & BB_RUN_SKIP_REJECTED) ? mapped_alias(Wo_host) : nullptr;
+  double* Xo_map = (flags & BB_RUN_SKIP_REJECTED) && want_x ? mapped_alias(Xo_host) : nullptr;
+  const bool direct = Wo_map && (!want_x || Xo_map);
+  /* Wo_host == W_host: the host array is updated in place for the chains that accept (the loop's swap of W and Wo);
+   * only the direct path leaves the rejecting chains' rows alone */
+  if (Wo_host == W_host && !direct) return BB_ERR_ARG;
   const size_t per_slab = (size_t)slab * (2 * wpc + (want_x ? xpc : 0));
   int rc = ctx_stage(c, 2 * per_slab * sizeof(double));
   if (rc != BB_OK) return rc;
@@ -1097,6 +1150,17 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
     rc = run_chain(e, model, guides, rs);
     if (rc != BB_OK) return rc;
     const long long tout = (long long)e->S * e->NC * n * BB_TC * (e->dp + (want_x ? e->d : 0));
+    if (direct) {
+      /* on the copy stream, so that the next slab's kernels do not wait for the link; a small grid is enough to keep
+       * the link busy and leaves the SMs to the path kernel */
+      BB_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
+      BB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+      bb_slab_out_direct_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(e->W[0], e->X, Wo_map, want_x ? Xo_map : nullptr, e->par,
+                                                               e->accepted, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->d,
+                                                               e->nbuf);
+      BB_CUDA(cudaGetLastError());
+      c->launches += 2;
+    } else {
     bb_slab_out_kernel<<<(unsigned)((tout + 255) / 256 > 148 * 16 ? 148 * 16 : (tout + 255) / 256), 256, 0, c->stream>>>(
         e->W[0], e->X, sWo, sXo, e->par, e->accepted, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->d, e->nbuf);
     BB_CUDA(cudaGetLastError());
@@ -1108,6 +1172,7 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
     if (want_x)
       BB_CUDA(cudaMemcpyAsync(Xo_host + (size_t)p0 * xpc, sXo, (size_t)n * xpc * sizeof(double), cudaMemcpyDeviceToHost,
                               c->s_d2h));
+    }
     if (llo_host)
       BB_CUDA(cudaMemcpyAsync(llo_host + p0, e->llprop + p0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
     if (accepted_host)

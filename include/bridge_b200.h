@@ -381,7 +381,7 @@ int bb_lptilde_HV(bb_ctx* ctx, int32_t N, int32_t d, const double* tt, const dou
  * X_cur <- guided Euler path driven by W_cur, ll_cur <- sum over segments of the log-likelihood,
  * xend <- yy[N] of the last segment.  guides: one table per segment.  src/euler.jl:246-268.
  */
-enum { BB_RUN_STORE_X = 1u, BB_RUN_NO_LL = 2u };
+enum { BB_RUN_STORE_X = 1u, BB_RUN_NO_LL = 2u, BB_RUN_SKIP_REJECTED = 4u /* bb_pcn_step_host only, see there */ };
 int bb_guided_euler_ll(bb_ens* ens, const bb_model* model, bb_guide* const* guides,
                        int32_t skip, uint32_t flags);
 /* llikelihood(LeftRule(), X, P°; skip) on the stored X_cur -> ll_cur  (second-pass form) */
@@ -404,7 +404,16 @@ int bb_pcn_step(bb_ens* ens, const bb_model* model, bb_guide* const* guides, dou
  * Wo_host [P][S][N][d'], Xo_host [P][S][N][d] (may be NULL), llo_host [P] (may be NULL) and accepted_host [P]
  * (may be NULL) come back.  Slabs of chains are pipelined over three streams so that both PCIe directions and
  * the GPU are busy at once; pinned host memory is needed for that overlap (pageable memory works, serially).
- * The ensemble's device state is updated exactly as by bb_pcn_step. */
+ * The ensemble's device state is updated exactly as by bb_pcn_step.
+ * flags | BB_RUN_SKIP_REJECTED: the reference loop reads Wo / Xo only to swap them in on accept (X, Xo = Xo, X;
+ * W, Wo = Wo, W, test/partialbridgenuH.jl:184-186) and overwrites them in the next iteration otherwise, so the rows of
+ * chains that REJECT need not cross the link: with the flag their rows of Wo_host / Xo_host are left as they were.  When
+ * Wo_host / Xo_host are page-locked, device-mapped memory (cudaHostAlloc / cudaHostRegister under unified addressing) the
+ * accepted rows are written straight into them by a kernel, without staging, and the device-to-host traffic drops by the
+ * rejection rate; with other memory the flag is accepted and everything is copied as without it.  On that direct path
+ * Wo_host may be W_host itself: the array is then updated in place for the chains that accept -- the loop's swap of W and
+ * Wo -- and always holds the current W of every chain (likewise Xo_host the current X once it has been initialised);
+ * aliasing without the direct path is BB_ERR_ARG. */
 int bb_pcn_step_host(bb_ens* ens, const bb_model* model, bb_guide* const* guides, double rho, uint64_t seed,
                      uint32_t iter, int32_t skip, uint32_t flags, const double* W_host, double* Wo_host,
                      double* Xo_host, double* llo_host, uint8_t* accepted_host);

@@ -970,6 +970,59 @@ def test_pcn_step_host_buffers_matches_resident(B, oracle_fma):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_pcn_step_host_skips_rejected_rows(B, oracle_fma, pinned):
+    """BB_RUN_SKIP_REJECTED: the rows of W°, X° of chains that accept are those of the plain host step, the rows of
+    chains that reject are left untouched (pinned, device-mapped arrays: written by a kernel straight into host memory;
+    pageable arrays: the flag changes nothing); ll°, flags and the device state are the same either way."""
+    import torch
+    N, P, S = 49, 900, 2
+    grids = [warped(0.0, 0.5, N), warped(0.5, 1.0, N)]
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, grids, [-1.0, -0.5])
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    enss = []
+    for _ in range(2):
+        ens = B.PathEnsemble(P, S, N, 2, 1)
+        for s in range(S):
+            ens.set_grid(s, grids[s])
+        ens.set_start([-0.5, -0.6]); ens.sample_(6, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+        enss.append(ens)
+    a, b = enss
+
+    def host(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=pinned).numpy()
+
+    Wh, Wo, Xo, llo, acc = host((P, S, N, 1)), host((P, S, N, 1)), host((P, S, N, 2)), host(P), host(P, torch.uint8)
+    Wr = np.empty((P, S, N, 1)); Xr = np.empty((P, S, N, 2)); llr = np.empty(P); accr = np.empty(P, dtype=np.uint8)
+    for it in range(3):
+        Wh[...] = a.download(B.W)
+        a.pcn_step_host_(Pm, guides, 0.8, 6, it, Wh, Wr, Xr, llr, accr)
+        Wo[...] = -7.0; Xo[...] = -7.0
+        b.pcn_step_host_(Pm, guides, 0.8, 6, it, Wh, Wo, Xo, llo, acc, skip_rejected=True)
+        f = accr.astype(bool)
+        assert 0 < f.sum() < P
+        assert np.array_equal(llo, llr) and np.array_equal(acc, accr)
+        assert np.array_equal(Wo[f], Wr[f]) and np.array_equal(Xo[f], Xr[f])
+        if pinned:
+            assert np.all(Wo[~f] == -7.0) and np.all(Xo[~f] == -7.0)
+        else:
+            assert np.array_equal(Wo, Wr) and np.array_equal(Xo, Xr)
+        assert np.array_equal(b.download(B.W), a.download(B.W)) and np.array_equal(b.ll, a.ll) and a.acc == b.acc
+    # in place: Wo aliases W, the host array follows the chains' current W through the iterations (the loop's swap)
+    Wh[...] = b.download(B.W)
+    if pinned:
+        for it in range(3, 6):
+            a.pcn_step_(Pm, guides, 0.8, 6, it)
+            b.pcn_step_host_(Pm, guides, 0.8, 6, it, Wh, Wh, Xo, llo, acc, skip_rejected=True)
+            assert np.array_equal(Wh, a.download(B.W)) and np.array_equal(acc, a.accepted) and a.acc == b.acc
+    else:
+        with pytest.raises(B.BridgeError):
+            b.pcn_step_host_(Pm, guides, 0.8, 6, 3, Wh, Wh, Xo, llo, acc, skip_rejected=True)
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("kind", ["nuH", "LMmu"])
 def test_nonconstdiff_pair(B, oracle_ref, oracle_fma, kind):
     """a != a~: the extra terms -1/2 tr((a-a~)H)dt + 1/2 r'(a-a~)r dt (src/partialbridge.jl:79-84) in the fused
