@@ -7,6 +7,11 @@ import bridge_jl_b200 as B
 import bridge_jl_b200.configs as cfg
 
 n, P = 49, 700   # ragged: N not a multiple of 16, P not a multiple of 256
+# SAN_PCN_KERNEL=1: one thread per chain everywhere (small ensembles otherwise pick the warp-specialised kernel, whose
+# warp pairs are synchronised by mbarriers only -- racecheck does not model those and reports every hand-over)
+ONE_THREAD = os.environ.get("SAN_PCN_KERNEL") == "1"
+if ONE_THREAD:
+    B.default_context().set_pcn_kernel(1)
 Pm, guides, x0, rho = cfg.fhn_config4(n, obs_t=(0.5, 1.0, 1.5), obs_v=(-1.0, -0.5, 0.5))
 ens = B.PathEnsemble(P, len(guides), n, 2, 1)
 for s, g in enumerate(guides):
@@ -66,3 +71,38 @@ eb.theta_attach_(Pb, [[0.5, 0.5]], 1e-2 * np.eye(1), 0.1, (4.0, 9.0), aux_kind=3
 eb.sample_(2, 0); eb.theta_guided_euler_ll_()
 B.theta_mcmc_(eb, 0.5, [0, 0.02, 0, 0, 0.02], 4, 3)
 print("bolus ok", eb.acc, eb.acc_theta, bool(np.all(np.isfinite(eb.download(B.X)))))
+# ---- round 2 kernels
+# warp-specialised pCN (noise warps -> dynamics warps through an mbarrier-guarded ring), ragged sizes
+ctx = B.default_context()
+if not ONE_THREAD:
+    ctx.set_pcn_kernel(2)  # BB_PCN_WARP_SPECIALISED
+    for it in range(2):
+        ens.pcn_step_(Pm, guides, rho, 1, 20 + it)
+    ctx.set_pcn_kernel(0)
+# the whole backward chain in one launch, lptilde, Mdb on a guided proposal
+Pm2, chain, x02, _ = cfg.fhn_config4_chain(n, ctx=ctx)
+cfg.fhn_config4_chain(n, ctx=ctx, chain=chain)
+e4 = B.PathEnsemble(130, len(chain.segments), n, 2, 1)
+for s, g in enumerate(chain.segments):
+    e4.set_grid(s, g.tt)
+e4.set_start(x02); e4.sample_(5, 0); e4.guided_euler_ll_(Pm2, chain.segments); e4.pcn_step_(Pm2, chain.segments, rho, 5, 1)
+print("chain ok", e4.acc, float(B.lptilde(np.array(x02), guides[0])))
+# blocked segment updates (per-chain right-end conditioning, two passes, commit of the accepted rows) and the sweep
+rngb = np.random.default_rng(0)
+eb.theta_block_step_(0, 1, 0.7, 3, 100); eb.theta_block_step_(1, 2, 0.7, 3, 101); eb.theta_block_step_(0, 2, 0.7, 3, 102)
+eb.theta_blocked_sweep_(rngb, 0.7, 3, 110)
+B.theta_mcmc_(eb, 0.5, [0, 0.02, 0, 0, 0.02], 3, 3, first_iter=50, blocked=True)
+print("blocks ok", eb.acc, bool(np.all(np.isfinite(eb.download(B.X)))))
+# tensor-core Landmarks kernel is the default wide path (above); host-buffer step with skipped rejected rows (pinned, mapped)
+import torch
+hW = torch.empty((P, len(guides), n, 1), dtype=torch.float64, pin_memory=True).numpy()
+hX = torch.empty((P, len(guides), n, 2), dtype=torch.float64, pin_memory=True).numpy()
+hl = torch.empty(P, dtype=torch.float64, pin_memory=True).numpy(); ha = torch.empty(P, dtype=torch.uint8, pin_memory=True).numpy()
+hW[...] = ens.download(B.W)
+ens.pcn_step_host_(Pm, guides, rho, 1, 30, hW, hW, hX, hl, ha, skip_rejected=True)
+print("host ok", int(ha.sum()), bool(np.array_equal(hW, ens.download(B.W))))
+# a user-defined model compiled at run time (NVRTC) through the same path kernel
+um = B.UserProcess(2, 1, "double u = x[0] - x[1]; u = fma(-(x[0]*x[0]), x[0], u); o[0] = (u + par[1]) * (1.0/par[0]);"
+                         "o[1] = fma(par[2], x[0], -x[1]) + par[3];", [-1, 0], [None, "par[4]"], cfg.FHN_PAR)
+ens.guided_euler_ll_(um, guides); ens.pcn_step_(um, guides, rho, 1, 40)
+print("user ok", ens.acc)
