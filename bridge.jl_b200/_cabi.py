@@ -31,7 +31,7 @@ CUR, PROP = 0, 1
 F_LL, F_LL_PROP, F_LOGU, F_XEND, F_XEND_PROP = range(5)
 RUN_STORE_X, RUN_NO_LL, RUN_SKIP_REJECTED = 1, 2, 4
 ARITH_REFERENCE, ARITH_FUSED = 0, 1
-PCN_AUTO, PCN_ONE_THREAD, PCN_WARP_SPECIALISED = 0, 1, 2
+PCN_AUTO, PCN_ONE_THREAD, PCN_WARP_SPECIALISED, PCN_WARP_SPECIALISED_2 = 0, 1, 2, 3
 SCHEME_EULER, SCHEME_STRATONOVICH, SCHEME_HEUN, SCHEME_SRK, SCHEME_MDB = range(5)
 
 

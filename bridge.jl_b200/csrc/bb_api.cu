@@ -126,8 +126,11 @@ extern "C" int bb_ctx_set_arith(bb_ctx* c, int arith) {
   c->arith = arith;
   return BB_OK;
 }
+#ifndef BB_AUTO_WS2
+#define BB_AUTO_WS2 0 /* automatic selection prefers the two-chains-per-dynamics-thread kernel for small ensembles */
+#endif
 extern "C" int bb_ctx_set_pcn_kernel(bb_ctx* c, int mode) {
-  if (!c || mode < BB_PCN_AUTO || mode > BB_PCN_WARP_SPECIALISED) return BB_ERR_ARG;
+  if (!c || mode < BB_PCN_AUTO || mode > BB_PCN_WARP_SPECIALISED_2) return BB_ERR_ARG;
   c->pcn_kernel = mode;
   return BB_OK;
 }
@@ -846,10 +849,17 @@ static int run_chain(bb_ens* e, const bb_model* model, bb_guide* const* guides, 
     /* a SMALL ensemble (the strong-scaling share of a GPU: fewer than two 128-chain CTAs per SM) runs the pCN
      * iteration as the warp-specialised kernel (two threads per chain, bb_chain_ws.cuh): 5 % faster there, equal at
      * full size.  Same results bit for bit.  bb_ctx_set_pcn_kernel (or BB_PCN_WS=0 / 1) forces one or the other. */
-    static const int env = []() { const char* v = getenv("BB_PCN_WS"); return v ? (v[0] == '0' ? BB_PCN_ONE_THREAD : BB_PCN_WARP_SPECIALISED) : BB_PCN_AUTO; }();
+    static const int env = []() {
+      const char* v = getenv("BB_PCN_WS");
+      return v ? (v[0] == '0' ? BB_PCN_ONE_THREAD : (v[0] == '2' ? BB_PCN_WARP_SPECIALISED_2 : BB_PCN_WARP_SPECIALISED))
+               : BB_PCN_AUTO;
+    }();
     const int mode = c->pcn_kernel != BB_PCN_AUTO ? c->pcn_kernel : env;
     const long long nch = (rs.p_end < 0 ? e->P : rs.p_end) - rs.p_begin;
-    if (mode == BB_PCN_WARP_SPECIALISED || (mode == BB_PCN_AUTO && (nch + 127) / 128 < 2ll * c->sm_count))
+    const bool small = (nch + 127) / 128 < 2ll * c->sm_count;
+    if (mode == BB_PCN_WARP_SPECIALISED_2 || (mode == BB_PCN_AUTO && small && BB_AUTO_WS2))
+      fn = lookup_kernel(model, gk, gm, auxc, 6); /* two chains per dynamics thread (d <= 2) */
+    if (!fn && (mode == BB_PCN_WARP_SPECIALISED || mode == BB_PCN_WARP_SPECIALISED_2 || (mode == BB_PCN_AUTO && small)))
       fn = lookup_kernel(model, gk, gm, auxc, 5);
   }
   if (!fn && !um) fn = rs.rng >= 10 ? lookup_second(model, gk, gm, auxc, rs.rng - 10) : lookup_kernel(model, gk, gm, auxc, krng);
@@ -1050,39 +1060,49 @@ __global__ void __launch_bounds__(256) bb_slab_out_kernel(const double* __restri
   }
 }
 
-/* BB_RUN_SKIP_REJECTED with mapped host buffers: W°, X° of the chains that accepted go straight from the chunked device
- * layout to the caller's host arrays ([chain][segment][N][k]; a row of 16 grid points is 128 k contiguous bytes on both
- * sides, so the stores over the link are whole-line), chains that rejected are skipped */
-__global__ void __launch_bounds__(256) bb_slab_out_direct_kernel(const double* __restrict__ W0, const double* __restrict__ X,
-                                                                 double* __restrict__ hostW, double* __restrict__ hostX,
-                                                                 const uint8_t* __restrict__ par,
-                                                                 const uint8_t* __restrict__ accepted, long long P,
-                                                                 long long p0, long long np, int S, int N, int NC, int dp,
-                                                                 int d, int nbuf) {
-  /* one CTA per (chain, segment, W | X): the segment's N k doubles are ONE contiguous run in the host array, written
-   * front to back, 2 KB per step of the CTA, by few concurrent writers (scattered 128-byte pieces -- the order of the
-   * device layout -- reach 29 GB/s over the link, one run per warp 36 GB/s, one run per CTA 40 GB/s in this pipeline;
-   * a plain streaming kernel 48-52 GB/s, tools/pciebench.cu, profiles/r02_pciebench.txt); the reads walk the chain's chunk rows, 128 k contiguous bytes each */
-  const int lane = threadIdx.x;
-  const long long nwarp = gridDim.x;
-  const long long items = np * S * (hostX ? 2 : 1);
-  for (long long it = blockIdx.x; it < items; it += nwarp) {
-    const bool isx = it >= np * S;
-    const long long u = isx ? it - np * S : it;
-    const long long pl = u / S;
-    const int s = (int)(u - pl * S);
-    const long long p = p0 + pl;
-    if (!accepted[p]) continue;
-    const int K = isx ? d : dp;
-    const long long rowlen = (long long)BB_TC * K;
-    const double* src = isx ? X + ((long long)s * NC * P + p) * rowlen
-                            : W0 + (((long long)s * NC * P + p) * nbuf + par[p]) * rowlen; /* accepted: par has flipped */
-    const long long cstride = isx ? P * rowlen : P * nbuf * rowlen;
-    double* dst = (isx ? hostX : hostW) + (p * S + s) * (long long)N * K;
-    const int tot = N * K;
-    for (int i = lane; i < tot; i += 256) {
-      const int c = i / (int)rowlen, e = i - c * (int)rowlen;
-      dst[i] = src[(long long)c * cstride + e];
+/* BB_RUN_SKIP_REJECTED with mapped host buffers: the rows of the chains that accepted go from the slab's staging
+ * buffer (already in the host layout [chain][segment][N][k]: bb_slab_out_kernel) straight into the caller's host arrays,
+ * one CTA per chain, front to back; chains that rejected are skipped.  Both sides stream: gathering a chain's rows from
+ * the chunked device layout inside this kernel (64 MB between consecutive chunk rows of a chain) ran at 29-40 GB/s over
+ * the link, a streaming kernel reaches the copy engine's 48-52 GB/s (tools/pciebench.cu, profiles/r02_pciebench.txt). */
+/* list of the chains of a slab that accepted (ascending), count in list[np] */
+__global__ void __launch_bounds__(1024) bb_accepted_list_kernel(const uint8_t* __restrict__ accepted, long long np,
+                                                                int* __restrict__ list) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (long long t0 = 0; t0 < np; t0 += 1024) {
+    const long long t = t0 + threadIdx.x;
+    const bool f = t < np && accepted[t] != 0;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int i = 0; i < w; i++) off += wsum[i];
+    if (f) list[off + __popc(m & ((1u << lane) - 1))] = (int)t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int i = 0; i < 32; i++) tot += wsum[i];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) list[np] = base;
+}
+__global__ void __launch_bounds__(256) bb_rows_to_host_kernel(const double* __restrict__ stage, double* __restrict__ host,
+                                                              const int* __restrict__ list, long long np, long long rowlen) {
+  /* the CTAs walk the accepted rows TOGETHER, 2 KB per CTA and step, so that the stores over the link form one dense
+   * moving window (one private row per CTA = ~600 interleaved streams reached 40 GB/s, this order the copy engine's 50) */
+  const long long ppr = (rowlen + 255) / 256; /* pieces per row */
+  const long long total = (long long)list[np] * ppr;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const long long r = t / ppr, i = (t - r * ppr) * 256 + threadIdx.x;
+    if (i < rowlen) {
+      const long long pl = list[r];
+      host[pl * rowlen + i] = stage[pl * rowlen + i];
     }
   }
 }
@@ -1126,9 +1146,12 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
    * only the direct path leaves the rejecting chains' rows alone */
   if (Wo_host == W_host && !direct) return BB_ERR_ARG;
   const size_t per_slab = (size_t)slab * (2 * wpc + (want_x ? xpc : 0));
-  int rc = ctx_stage(c, 2 * per_slab * sizeof(double));
+  const size_t list_doubles = ((size_t)slab + 1 + 1) / 2 + 16; /* an int list of accepted chains per staging buffer */
+  int rc = ctx_stage(c, (2 * per_slab + 2 * list_doubles) * sizeof(double));
   if (rc != BB_OK) return rc;
   double* st[2] = {c->stage, c->stage + per_slab};
+  int* acc_list[2] = {reinterpret_cast<int*>(c->stage + 2 * per_slab),
+                      reinterpret_cast<int*>(c->stage + 2 * per_slab + list_doubles)};
   BB_CUDA(cudaStreamSynchronize(c->stream)); /* earlier work on the context's stream is complete */
   run_spec rs{1, want_x && (flags & BB_RUN_STORE_X) != 0, true, true, skip, rho, seed, iter};
   if (want_x) rs.store_x = true;
@@ -1150,23 +1173,21 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
     rc = run_chain(e, model, guides, rs);
     if (rc != BB_OK) return rc;
     const long long tout = (long long)e->S * e->NC * n * BB_TC * (e->dp + (want_x ? e->d : 0));
-    if (direct) {
-      /* on the copy stream, so that the next slab's kernels do not wait for the link; a small grid is enough to keep
-       * the link busy and leaves the SMs to the path kernel */
-      BB_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
-      BB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
-      bb_slab_out_direct_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(e->W[0], e->X, Wo_map, want_x ? Xo_map : nullptr, e->par,
-                                                               e->accepted, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->d,
-                                                               e->nbuf);
-      BB_CUDA(cudaGetLastError());
-      c->launches += 2;
-    } else {
     bb_slab_out_kernel<<<(unsigned)((tout + 255) / 256 > 148 * 16 ? 148 * 16 : (tout + 255) / 256), 256, 0, c->stream>>>(
         e->W[0], e->X, sWo, sXo, e->par, e->accepted, e->P, p0, n, e->S, e->N, e->NC, e->dp, e->d, e->nbuf);
     BB_CUDA(cudaGetLastError());
     c->launches += 2;
     BB_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
     BB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[b], 0));
+    if (direct) {
+      /* on the copy stream (the next slab's kernels do not wait for the link); a small grid keeps the link busy */
+      bb_accepted_list_kernel<<<1, 1024, 0, c->s_d2h>>>(e->accepted + p0, n, acc_list[b]);
+      bb_rows_to_host_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(sWo, Wo_map + (size_t)p0 * wpc, acc_list[b], n, (long long)wpc);
+      if (want_x)
+        bb_rows_to_host_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(sXo, Xo_map + (size_t)p0 * xpc, acc_list[b], n, (long long)xpc);
+      BB_CUDA(cudaGetLastError());
+      c->launches += want_x ? 3 : 2;
+    } else {
     BB_CUDA(cudaMemcpyAsync(Wo_host + (size_t)p0 * wpc, sWo, (size_t)n * wpc * sizeof(double), cudaMemcpyDeviceToHost,
                             c->s_d2h));
     if (want_x)

@@ -611,6 +611,8 @@ static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
 
 template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_ws_launch(const bb_chain_args& a, cudaStream_t st); /* bb_chain_ws.cuh */
+template <class M, int GK, int GM, int AUXM>
+static cudaError_t bb_chain_ws2_launch(const bb_chain_args& a, cudaStream_t st); /* bb_chain_ws.cuh */
 
 template <class M, int GK, int GM>
 static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
@@ -624,6 +626,11 @@ static bb_chain_launch_fn bb_lookup_guide(int auxm, int rng) {
   if constexpr (M::DP == 1) {
     if (rng == 5) return auxm == 1 ? &bb_chain_ws_launch<M, GK, GM, 1, 1>
                                    : (auxm == 0 ? &bb_chain_ws_launch<M, GK, GM, 0, 1> : &bb_chain_ws_launch<M, GK, GM, 2, 1>);
+    /* 6: the same with two chains per dynamics thread (state dimension <= 2: X° through the shared-memory window) */
+    if constexpr (M::D <= 2) {
+      if (rng == 6) return auxm == 1 ? &bb_chain_ws2_launch<M, GK, GM, 1>
+                                     : (auxm == 0 ? &bb_chain_ws2_launch<M, GK, GM, 0> : &bb_chain_ws2_launch<M, GK, GM, 2>);
+    }
   }
   return nullptr;
 }

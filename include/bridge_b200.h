@@ -175,7 +175,7 @@ int bb_ctx_set_arith(bb_ctx* ctx, int arith);
 /* Which kernel runs bb_pcn_step with X° stored for scalar-noise models: one thread per chain, or the warp-specialised
  * kernel (noise warps + dynamics warps, two threads per chain).  Results are identical bit for bit; AUTO (default) takes
  * the warp-specialised kernel for small ensembles (fewer than two 128-chain CTAs per SM), where it is ~5 % faster. */
-enum { BB_PCN_AUTO = 0, BB_PCN_ONE_THREAD = 1, BB_PCN_WARP_SPECIALISED = 2 };
+enum { BB_PCN_AUTO = 0, BB_PCN_ONE_THREAD = 1, BB_PCN_WARP_SPECIALISED = 2, BB_PCN_WARP_SPECIALISED_2 = 3 /* two chains per dynamics thread */ };
 int bb_ctx_set_pcn_kernel(bb_ctx* ctx, int mode);
 
 /* ------------------------------------------------------------------ user-defined target processes

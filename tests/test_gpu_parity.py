@@ -384,8 +384,8 @@ def test_pcn_replay_bit_exact(B, oracle_fma):
 
 @pytest.mark.parametrize("model", ["fhn", "intdiff"])
 def test_pcn_kernels_agree_bit_for_bit(B, model):
-    """bb_pcn_step has two kernels for scalar-noise models with X° stored -- one thread per chain, and the
-    warp-specialised one (noise warps + dynamics warps) the library picks for small ensembles.  Same seeds, same state:
+    """bb_pcn_step has three kernels for scalar-noise models with X° stored -- one thread per chain, and the two
+    warp-specialised ones (noise warps + dynamics warps; one or two chains per dynamics thread) for small ensembles.  Same seeds, same state:
     W°, X°, ll°, log U, flags, surviving state and acceptance counter must be identical, over several iterations, for a
     ragged ensemble size, a skip and a tabulated auxiliary drift."""
     K = B.api.K
@@ -412,7 +412,7 @@ def test_pcn_kernels_agree_bit_for_bit(B, model):
         x0, skip = [2.0, 1.0], 2
     out = {}
     try:
-        for mode in (K.PCN_ONE_THREAD, K.PCN_WARP_SPECIALISED):
+        for mode in (K.PCN_ONE_THREAD, K.PCN_WARP_SPECIALISED, K.PCN_WARP_SPECIALISED_2):
             ctx.set_pcn_kernel(mode)
             ens = B.PathEnsemble(P, S, N, 2, 1, chain_offset=77)
             for s in range(S):
@@ -428,10 +428,11 @@ def test_pcn_kernels_agree_bit_for_bit(B, model):
             ens.close()
     finally:
         ctx.set_pcn_kernel(K.PCN_AUTO)
-    a, b = out[K.PCN_ONE_THREAD], out[K.PCN_WARP_SPECIALISED]
-    for ra, rb in zip(a, b):
-        for xa, xb in zip(ra, rb):
-            assert np.array_equal(xa, xb)
+    a = out[K.PCN_ONE_THREAD]
+    for other in (K.PCN_WARP_SPECIALISED, K.PCN_WARP_SPECIALISED_2):
+        for ra, rb in zip(a, out[other]):
+            for xa, xb in zip(ra, rb):
+                assert np.array_equal(xa, xb), other
     assert 0 < a[-1][2] < 4 * P
 
 
