@@ -255,6 +255,63 @@ function download_x(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Gu
     download!(Array{Float64}(undef, E.d, E.N, E.S, E.P), E, 1)   # column-major == the ABI's [P][S][N][d]
 end
 
+"""The same iteration with W, X kept in HOST arrays as the reference loop does (test/partialbridgenuH.jl:168-191):
+`W` [d′, N, S, P] goes up; `Wo`, `Xo` ([d, N, S, P]), `llo`, `accepted` come back.  `skip_rejected = true`: only the chains that
+accept write their rows; with page-locked arrays (`CUDA.Mem.pin` / `cudaHostRegister`) `Wo === W` is allowed and `W` is then
+updated in place -- the loop's `W, Wo = Wo, W`."""
+function pcn_host!(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}, ρ, seed::UInt64, iter::Integer,
+                   W::Array{Float64}, Wo::Array{Float64}, Xo::Array{Float64}, llo::Vector{Float64}, accepted::Vector{UInt8};
+                   skip = 0, skip_rejected = false)
+    m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_pcn_step_host, lib), Cint,
+        (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Float64, UInt64, UInt32, Int32, UInt32, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
+        E.h, m, hs, ρ, seed, iter, skip, 1 | (skip_rejected ? 4 : 0), W, Wo, Xo, llo, accepted))
+    acc(E)
+end
+# which kernel runs pcn!: 0 automatic, 1 one thread per chain, 2 / 3 warp-specialised (one / two chains per dynamics thread)
+set_pcn_kernel!(mode::Integer, ctx::Context = default_context()) =
+    check(ccall((:bb_ctx_set_pcn_kernel, lib), Cint, (Ptr{Cvoid}, Cint), ctx.h, mode))
+
+"""`solve!(Mdb(), Y, u, W, P°)` (src/euler.jl:308-327) for every chain of an ensemble."""
+function solve!(::Bridge.Mdb, E::PathEnsemble, u, P::ContinuousTimeProcess, guides::Vector{Guide})
+    setstart!(E, u); m = Ref(bbmodel(P)); hs = [g.h for g in guides]
+    GC.@preserve guides check(ccall((:bb_guided_mdb, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}), E.h, m, hs)); E
+end
+
+"""The backward pass of a chain of S `PartialBridgeνH` segments in ONE launch, tables written in place on the device:
+the loop of partialbridge_bolus3.jl:162-180 (νend = 0, Hend⁺ = I/ϵ, gpupdate with V.yy[end]; for i = S:-1:1
+`partialbridgeνH(tt_i, P, Pt_i, νend, Hend⁺)` and, for i > 1, `gpupdate(νend, Hend⁺, Σ, L, v_{i-1})`).
+`tts[i]`: grid of segment i; `Pts[i]`: its (constant) auxiliary process; `vs[i]`: observation at its right end.
+`guides` = the vector returned by an earlier call, to update the same device tables.  Returns (guides, ν(0), H⁺(0), C)."""
+function guides_chain_nuH(tts::Vector{Vector{Float64}}, Pts, L, Σ, vs, ϵ; guides::Vector{Guide} = Guide[], method = 1,   # 1 = BB_ODE_LYAP (as the script), 0 = BB_ODE_R3
+                          ctx::Context = default_context())
+    S = length(tts); N = length(tts[1]); m, d = size(L)
+    auxv = [AuxValues(Pts[i], tts[i]) for i in 1:S]; auxs = [bbaux(A) for A in auxv]
+    tt = reduce(vcat, tts); v = reduce(vcat, [collect(Float64, vs[i]) for i in 1:S])
+    hs = isempty(guides) ? fill(Ptr{Cvoid}(C_NULL), S) : [g.h for g in guides]
+    ν0 = zeros(d); H0 = zeros(d * d); C = Ref(0.0)
+    GC.@preserve auxv guides check(ccall((:bb_guides_chain_nuH, lib), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{BBAux}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Float64, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+        ctx.h, method, S, N, d, m, tt, auxs, rowmajor(Matrix{Float64}(L)), rowmajor(Matrix{Float64}(Σ)), v, ϵ, hs, ν0, H0, C))
+    if isempty(guides)
+        guides = [Guide(h) for h in hs]
+        foreach(g -> finalizer(x -> ccall((:bb_guide_destroy, lib), Cint, (Ptr{Cvoid},), x.h), g), guides)
+    end
+    guides, ν0, permutedims(reshape(H0, d, d)), C[]
+end
+
+# ---- mcstart / mcnext! / mcstats of src/mclog.jl:22-93 for an ensemble: moments of the current paths per grid point, pooled
+# over the chains (the reference's mcnext is per chain over iterations) and over calls
+mc_reset!(E::PathEnsemble) = check(ccall((:bb_ens_mc_reset, lib), Cint, (Ptr{Cvoid},), E.h))
+mc_update!(E::PathEnsemble) = check(ccall((:bb_ens_mc_update, lib), Cint, (Ptr{Cvoid},), E.h))   # after download_x / a refresh
+function mc_stats(E::PathEnsemble)
+    mean = Array{Float64}(undef, E.d, E.N, E.S); cov = Array{Float64}(undef, E.d, E.d, E.N, E.S); n = Ref{Int64}(0)
+    check(ccall((:bb_ens_mc_stats, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}), E.h, mean, cov, n))
+    mean, cov, n[]
+end
+
 # ---- multi-GPU: one Julia process (or task) per GPU; the acceptance counter is the only exchange (SURVEY 8e)
 mutable struct Communicator
     h::Ptr{Cvoid}
