@@ -241,6 +241,25 @@ function llikelihood(::LeftRule, E::PathEnsemble, P::ContinuousTimeProcess, guid
     GC.@preserve guides check(ccall((:bb_llikelihood, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Ptr{Ptr{Cvoid}}, Int32), E.h, m, hs, skip))
     vec(getf64(E, 0))
 end
+# solve! of an ensemble with the reference's other one-step schemes (src/euler.jl:68-88,178-198,330-356)
+scheme_id(::EulerMaruyama) = 0
+scheme_id(::Bridge.StratonovichEuler) = 1
+scheme_id(::Bridge.StochasticHeun) = 2
+scheme_id(::Bridge.StochasticRungeKutta) = 3
+function solve!(s::Union{Bridge.StratonovichEuler,Bridge.StochasticHeun,Bridge.StochasticRungeKutta}, E::PathEnsemble, u,
+                P::ContinuousTimeProcess)
+    setstart!(E, u); m = Ref(bbmodel(P))
+    check(ccall((:bb_solve_scheme, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, Int32), E.h, m, scheme_id(s))); E
+end
+"""sample!(W, Wiener()) fused with solve!(EulerMaruyama(), X, u, W, P): W and X are both written, W is never read."""
+function sample_solve!(E::PathEnsemble, u, P::ContinuousTimeProcess; seed::UInt64 = UInt64(0), stream::UInt32 = UInt32(0))
+    setstart!(E, u); m = Ref(bbmodel(P))
+    check(ccall((:bb_sample_euler, lib), Cint, (Ptr{Cvoid}, Ref{BBModel}, UInt64, UInt32), E.h, m, seed, stream)); E
+end
+# kernel time of the last call on the context (CUDA events), for benchmarking a script
+set_timing!(on::Bool, ctx::Context = default_context()) = check(ccall((:bb_ctx_set_timing, lib), Cint, (Ptr{Cvoid}, Cint), ctx.h, on ? 1 : 0))
+last_kernel_ms(ctx::Context = default_context()) = ccall((:bb_ctx_last_kernel_ms, lib), Float64, (Ptr{Cvoid},), ctx.h)
+
 """One pCN / MH update of every chain: the body of `for iter in 1:iterations` in test/partialbridgenuH.jl:176-191."""
 function pcn!(E::PathEnsemble, P::ContinuousTimeProcess, guides::Vector{Guide}, ρ, seed::UInt64, iter::Integer; skip = 0, store_x = true)
     m = Ref(bbmodel(P)); hs = [g.h for g in guides]
@@ -515,6 +534,14 @@ function theta_blocked_sweep!(E::PathEnsemble, ρ, seed::UInt64, iter0::Integer;
         push!(blocks, (klow, kup)); klow = kup
     end
     blocks
+end
+function set_theta!(E::PathEnsemble, θ::Matrix{Float64})   # 8 x P, column per chain
+    check(ccall((:bb_theta_set, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), E.h, 0, E.P, θ)); E
+end
+theta_refresh_x!(E::PathEnsemble) = check(ccall((:bb_theta_refresh_x, lib), Cint, (Ptr{Cvoid},), E.h))
+function theta_block(E::PathEnsemble)   # numbers of the last block update: (5 + 2S) x P
+    out = Matrix{Float64}(undef, 5 + 2 * E.S, E.P)
+    check(ccall((:bb_theta_get_block, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), E.h, 0, E.P, out)); out
 end
 function theta(E::PathEnsemble)   # param(P) of every chain: 8 x P (column per chain)
     θ = Matrix{Float64}(undef, 8, E.P)
