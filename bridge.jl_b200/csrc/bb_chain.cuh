@@ -32,6 +32,7 @@
  */
 #pragma once
 #ifndef __CUDACC_RTC__
+#include <stdlib.h>
 #include <atomic>
 #endif
 
@@ -59,6 +60,7 @@ struct bb_chain_args {
   int jll;                         /* steps j <= jll (1-based end index) enter the log-likelihood */
   int start_bcast, store_x, do_ll, write_end;
   int nbuf;                        /* 1, or 2 when the ensemble is double buffered */
+  int cpc;                         /* chains per CTA (<= threads that step chains; set by the launch code, see bb_pick_cpc) */
   bb_philox_keys keys;             /* Philox round keys of the seed */
   uint32_t stream;
   double rho, rho2;
@@ -346,7 +348,11 @@ struct bb_chain {
     const int NST = (NC + BB_TSTAGE - 1) / BB_TSTAGE; /* stages per segment */
     const int T = S * NST;                            /* stages this CTA walks through */
     const int lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
+    /* warps that hold no chain of this CTA (chains per CTA below the CTA size, or the ragged last CTA) leave at once:
+     * they are not counted in the consumer barriers and issue nothing */
+    const long long cta_p0 = a.p_begin + (long long)blockIdx.x * a.cpc;
+    const long long cta_n = (a.p_end - cta_p0 < a.cpc) ? a.p_end - cta_p0 : a.cpc;
+    const int nwarps = (int)((cta_n + 31) >> 5);
 
     if (threadIdx.x == 0) {
       for (int i = 0; i < BB_STAGES; i++) {
@@ -356,11 +362,12 @@ struct bb_chain {
       bb_mbar_fence_init();
     }
     __syncthreads();
+    if ((int)(threadIdx.x >> 5) >= nwarps) return;
 
     const long long P = a.P;
-    const long long p = a.p_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = a.p_begin + (long long)blockIdx.x * a.cpc + threadIdx.x;
     const long long pc = p < a.p_end ? p : a.p_end - 1;
-    const bool act = p < a.p_end && (!a.only || a.only[pc] != 0);
+    const bool act = (int)threadIdx.x < a.cpc && p < a.p_end && (!a.only || a.only[pc] != 0);
     const int par = a.par[pc];
     const int rbuf = par;                        /* where the chain's current W (and X) live */
     const int wbuf = PCN ? 1 - par : par; /* where this launch writes */
@@ -395,7 +402,7 @@ struct bb_chain {
     const int warp = threadIdx.x >> 5;
     const unsigned amask = __ballot_sync(0xFFFFFFFFu, act);
     const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
-    const long long warp_p0 = a.p_begin + (long long)blockIdx.x * blockDim.x + warp * 32;
+    const long long warp_p0 = a.p_begin + (long long)blockIdx.x * a.cpc + warp * 32;
     const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP); /* doubles between the slots of consecutive chains */
     constexpr bool COOP_FAST = (32 % NCP == 0); /* an instruction covers CPI = 32 / NCP whole chains */
     constexpr int CPI = COOP_FAST ? 32 / NCP : 1;
@@ -589,6 +596,27 @@ static inline size_t bb_chain_smem(int S) {
 /* ---- host-side launch + lookup, one translation unit per model (bb_inst_*.cu) */
 typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
 
+/* Chains per CTA.  All chains cost the same, so a launch is a number of "waves" of resident CTAs; with full CTAs the last
+ * wave is partial (2.5e5 chains = 977 CTAs of 256 on 296 slots = 3.3 waves) and its CTAs, alone on the GPU, run at their
+ * latency floor instead of the memory system's rate -- or, for one wave, some SMs hold one CTA more than others.  Slightly
+ * smaller CTAs that fill a whole number of waves keep every SM equally loaded to the end.  It pays for one or two waves
+ * (6.25e4 chains: 1.715 -> 1.549 ms, 1.25e5: 3.21 -> 3.06 ms, warp-specialised kernel at 31 250: 0.880 -> 0.856 ms); from
+ * three waves on the idle lanes cost more than the partial wave (fewer active warps per SM).  BB_CPC overrides (tuning). */
+static inline int bb_pick_cpc(long long n, int cmax, int ctas_per_sm) {
+  static const int env = []() { const char* v = getenv("BB_CPC"); return v ? atoi(v) : 0; }();
+  if (env > 0) return env < cmax ? env : cmax;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long slots = (long long)sms * ctas_per_sm;
+  const long long waves = (n + slots * cmax - 1) / (slots * cmax);
+  if (waves >= 3) return cmax; /* measured: 2.5e5 chains as 4 waves of 212 run 6.54 ms, as 3.3 waves of 256 5.89 ms */
+  long long cpc = (n + waves * slots - 1) / (waves * slots);
+  cpc = (cpc + 3) & ~3ll;
+  if (cpc < cmax / 4) cpc = cmax / 4; /* tiny ensembles: do not stream the tables for a handful of chains per CTA */
+  return (int)(cpc < cmax ? cpc : cmax);
+}
+
 template <class M, int GK, int GM, int AUXM, int RNG>
 static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
   const size_t smem = bb_chain_smem<M, GK, GM, AUXM, RNG>(a.S);
@@ -604,8 +632,10 @@ static cudaError_t bb_chain_launch(const bb_chain_args& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
   }
-  const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
-  bb_chain_kernel<M, GK, GM, AUXM, RNG><<<grid, BB_THREADS, smem, st>>>(a);
+  bb_chain_args b = a;
+  b.cpc = bb_pick_cpc(a.p_end - a.p_begin, BB_THREADS, bb_min_ctas<M>());
+  const unsigned grid = (unsigned)((a.p_end - a.p_begin + b.cpc - 1) / b.cpc);
+  bb_chain_kernel<M, GK, GM, AUXM, RNG><<<grid, BB_THREADS, smem, st>>>(b);
   return cudaGetLastError();
 }
 

@@ -98,10 +98,14 @@ struct bb_chain_ws {
     const int pair = noise ? warp - NPAIR : warp;
     const int ci = pair * 32 + lane; /* chain of this thread within the CTA */
 
+    /* warp pairs that hold no chain of this CTA (chains per CTA below 32 NPAIR, or the ragged last CTA) leave at once */
+    const long long cta_p0 = a.p_begin + (long long)blockIdx.x * a.cpc;
+    const long long cta_n = (a.p_end - cta_p0 < a.cpc) ? a.p_end - cta_p0 : a.cpc;
+    const int npair_act = (int)((cta_n + 31) >> 5);
     if (threadIdx.x == 0) {
       for (int i = 0; i < BB_STAGES; i++) {
         bb_mbar_init(&full[i], 1);
-        bb_mbar_init(&empty[i], NW);
+        bb_mbar_init(&empty[i], 2 * npair_act);
       }
       for (int i = 0; i < BB_WS_MAXPAIR * BB_WS_WST; i++) {
         bb_mbar_init(&wfull[i], 1);
@@ -110,11 +114,12 @@ struct bb_chain_ws {
       bb_mbar_fence_init();
     }
     __syncthreads();
+    if (pair >= npair_act) return;
 
     const long long P = a.P;
-    const long long p = a.p_begin + (long long)blockIdx.x * CH + ci;
+    const long long p = a.p_begin + (long long)blockIdx.x * a.cpc + ci;
     const long long pc = p < a.p_end ? p : a.p_end - 1;
-    const bool act = p < a.p_end && (!a.only || a.only[pc] != 0);
+    const bool act = ci < a.cpc && p < a.p_end && (!a.only || a.only[pc] != 0);
     const int par = a.par[pc];
     const unsigned long long chain = (unsigned long long)(a.chain_offset + pc);
     const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
@@ -173,7 +178,7 @@ struct bb_chain_ws {
       constexpr int NCP = BB_TC * DP / 2;
       const unsigned amask = __ballot_sync(0xFFFFFFFFu, act);
       const unsigned pmask = __ballot_sync(0xFFFFFFFFu, par != 0);
-      const long long warp_p0 = a.p_begin + (long long)blockIdx.x * CH + pair * 32;
+      const long long warp_p0 = a.p_begin + (long long)blockIdx.x * a.cpc + pair * 32;
       const uint32_t wrow_d = (uint32_t)(a.nbuf * BB_TC * DP);
       constexpr bool COOP_FAST = (32 % NCP == 0);
       constexpr int CPI = COOP_FAST ? 32 / NCP : 1;
@@ -432,7 +437,7 @@ struct bb_chain_ws2 {
     __syncthreads();
 
     const long long P = a.P;
-    const long long cta_p0 = a.p_begin + (long long)blockIdx.x * CH;
+    const long long cta_p0 = a.p_begin + (long long)blockIdx.x * CH; /* always full CTAs (a.cpc is not used) */
     const long long wstride = P * (a.nbuf * BB_TC * DP), xstride = P * (BB_TC * D);
     const int TW = S * NC;
 
@@ -683,7 +688,9 @@ static cudaError_t bb_chain_ws_launch(const bb_chain_args& a, cudaStream_t st) {
   }
   const long long n = a.p_end - a.p_begin;
   const int nt = (n + 127) / 128 >= 2ll * sms ? 256 : 128;
-  const unsigned grid = (unsigned)((n + nt / 2 - 1) / (nt / 2));
-  bb_chain_ws_kernel<M, GK, GM, AUXM, RNG><<<grid, nt, K::smem_bytes(nt), st>>>(a);
+  bb_chain_args b = a;
+  b.cpc = bb_pick_cpc(n, nt / 2, nt == 256 ? 2 : 4); /* resident CTAs per SM: registers (128 per thread) and shared memory */
+  const unsigned grid = (unsigned)((n + b.cpc - 1) / b.cpc);
+  bb_chain_ws_kernel<M, GK, GM, AUXM, RNG><<<grid, nt, K::smem_bytes(nt), st>>>(b);
   return cudaGetLastError();
 }

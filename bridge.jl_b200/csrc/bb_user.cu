@@ -240,7 +240,9 @@ int bb_user_launch(bb_user_model* um, int kind, int gk, int gm, int auxm, int rn
     jk.attr_set = true;
   }
   const unsigned grid = (unsigned)((a.p_end - a.p_begin + BB_THREADS - 1) / BB_THREADS);
-  void* params[] = {const_cast<bb_chain_args*>(&a)};
+  bb_chain_args b = a;
+  b.cpc = BB_THREADS; /* full CTAs */
+  void* params[] = {&b};
   BB_CUDA(cudaLaunchKernel((const void*)jk.kern, dim3(grid), dim3(BB_THREADS), params, jk.smem, st));
   return BB_OK;
 }
