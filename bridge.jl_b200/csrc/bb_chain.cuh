@@ -601,7 +601,8 @@ typedef cudaError_t (*bb_chain_launch_fn)(const bb_chain_args&, cudaStream_t);
  * latency floor instead of the memory system's rate -- or, for one wave, some SMs hold one CTA more than others.  Slightly
  * smaller CTAs that fill a whole number of waves keep every SM equally loaded to the end.  It pays for one or two waves
  * (6.25e4 chains: 1.715 -> 1.549 ms, 1.25e5: 3.21 -> 3.06 ms, warp-specialised kernel at 31 250: 0.880 -> 0.856 ms); from
- * three waves on the idle lanes cost more than the partial wave (fewer active warps per SM).  BB_CPC overrides (tuning). */
+ * three (one CTA per SM: four) waves on the idle lanes cost more than the partial wave (fewer active warps per SM).
+ * BB_CPC overrides (tuning). */
 static inline int bb_pick_cpc(long long n, int cmax, int ctas_per_sm) {
   static const int env = []() { const char* v = getenv("BB_CPC"); return v ? atoi(v) : 0; }();
   if (env > 0) return env < cmax ? env : cmax;
@@ -610,7 +611,9 @@ static inline int bb_pick_cpc(long long n, int cmax, int ctas_per_sm) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long slots = (long long)sms * ctas_per_sm;
   const long long waves = (n + slots * cmax - 1) / (slots * cmax);
-  if (waves >= 3) return cmax; /* measured: 2.5e5 chains as 4 waves of 212 run 6.54 ms, as 3.3 waves of 256 5.89 ms */
+  /* measured: 2.5e5 chains (2 CTAs per SM) as 4 waves of 212 run 6.13 ms, as 3.3 waves of 256 5.82 ms; config 3 (1e5 chains,
+   * one CTA per SM) as 3 waves of 228 0.800 ms, as 2.6 waves of 256 0.834 ms; 6.6 -> 7 waves (FHN diagonal) 8.5 -> 9.1 ms */
+  if (waves > (ctas_per_sm == 1 ? 3 : 2)) return cmax;
   long long cpc = (n + waves * slots - 1) / (waves * slots);
   cpc = (cpc + 3) & ~3ll;
   if (cpc < cmax / 4) cpc = cmax / 4; /* tiny ensembles: do not stream the tables for a handful of chains per CTA */
