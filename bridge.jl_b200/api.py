@@ -58,7 +58,8 @@ class Context:
         check(lib.bb_ctx_set_arith(self.h, arith))
 
     def set_pcn_kernel(self, mode: int):
-        """K.PCN_AUTO (default) / K.PCN_ONE_THREAD / K.PCN_WARP_SPECIALISED: which kernel runs pcn_step_ (same results)."""
+        """K.PCN_AUTO (default) / K.PCN_ONE_THREAD / K.PCN_WARP_SPECIALISED / K.PCN_WARP_SPECIALISED_2: which kernel runs
+        pcn_step_ (same results bit for bit)."""
         check(lib.bb_ctx_set_pcn_kernel(self.h, mode))
 
     @property

@@ -173,8 +173,9 @@ double bb_ctx_last_kernel_ms(bb_ctx* ctx);
 enum { BB_ARITH_REFERENCE = 0, BB_ARITH_FUSED = 1 };
 int bb_ctx_set_arith(bb_ctx* ctx, int arith);
 /* Which kernel runs bb_pcn_step with X° stored for scalar-noise models: one thread per chain, or the warp-specialised
- * kernel (noise warps + dynamics warps, two threads per chain).  Results are identical bit for bit; AUTO (default) takes
- * the warp-specialised kernel for small ensembles (fewer than two 128-chain CTAs per SM), where it is ~5 % faster. */
+ * kernel (noise warps + dynamics warps, two threads per chain), or its variant with two chains per dynamics thread
+ * (d <= 2).  Results are identical bit for bit; AUTO (default) takes the warp-specialised kernel for small ensembles
+ * (fewer than two 128-chain CTAs per SM), where it is 5-8 % faster; the variant is never chosen automatically. */
 enum { BB_PCN_AUTO = 0, BB_PCN_ONE_THREAD = 1, BB_PCN_WARP_SPECIALISED = 2, BB_PCN_WARP_SPECIALISED_2 = 3 /* two chains per dynamics thread */ };
 int bb_ctx_set_pcn_kernel(bb_ctx* ctx, int mode);
 
