@@ -47,4 +47,23 @@ for name, (fn, nbytes) in calls.items():
     print(f"{name:38s} P={P} ms={t:8.3f} steps/s={steps / t * 1e3:.3e} alg GB/s={steps * nbytes / t * 1e-6:7.0f} "
           f"({nbytes} B/step) frac={steps * nbytes / t * 1e-6 / 6549.8:.3f}", flush=True)
 print("acc_theta", ens.acc_theta, "acc", ens.acc)
+# blocked segment updates (bb_theta_block_step): per-chain backward over the block + two forward passes + commit of the
+# accepted rows.  Per path-step of the block: tables 48 written + 48 read, W 8 d' read, W° 8 d' and X° 16 written, plus the
+# commit (read + write of W° and X° for the accepting chains).  Needs per-chain starting points only for blocks with s_lo = 0.
+if os.environ.get("KBENCH_BLOCKS", "1") == "1":
+    ens.set_start(np.tile(cfg.FHN_X0, (P, 1)))
+    ens.theta_guided_euler_ll_()
+    for lo, hi in ((0, 4), (1, 3), (2, 4), (0, 1)):
+        ts = []
+        for it in range(5):
+            ens.theta_block_step_(lo, hi, cfg.FHN_RHO, 4, 2000 + it)
+            ctx.synchronize()
+            ts.append(ctx.last_kernel_ms)
+        t = float(np.median(ts[1:]))
+        bsteps = P * (hi - lo) * (n - 1)
+        rate = float(np.mean(ens.accepted))
+        nb = 96 + 2 * w + 16 + rate * 2 * (w + 16)
+        print(f"block update, segments [{lo},{hi})         P={P} ms={t:8.3f} steps/s={bsteps / t * 1e3:.3e} "
+              f"alg GB/s={bsteps * nb / t * 1e-6:7.0f} ({nb:.0f} B/step at acceptance {rate:.2f}) frac={bsteps * nb / t * 1e-6 / 6549.8:.3f}",
+              flush=True)
 ens.close()
