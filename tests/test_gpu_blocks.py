@@ -185,6 +185,51 @@ def test_blocked_sweeps_run_the_script_loop(B):
     ens.close()
 
 
+def test_block_update_size_independent_properties(B):
+    """At a size the oracle would not finish (2e4 chains x 4 segments x N = 513): with ρ = 1 and no start move the proposal
+    IS the current noise re-run under the block's guide, so ll° = ll_temp segment by segment, diffll = 0 exactly, every
+    chain accepts, W is unchanged bit for bit and X of the block becomes that re-run path (continuous inside the block and
+    at its left end); the acceptance counter is the sum of the flags; blocks that end the chain reproduce, for a chain whose
+    θ is the common one, the whole-chain tables."""
+    import bridge_jl_b200.configs as cfg
+    P, n, S = 20000, 513, 4
+    grids = cfg.fhn_segment_grids(n)
+    Pm = B.FitzhughDiffusion(*cfg.FHN_PAR)
+    ens = B.PathEnsemble(P, S, n, 2, 1)
+    for s, g in enumerate(grids):
+        ens.set_grid(s, g)
+    ens.set_start(cfg.FHN_X0)
+    ens.theta_attach_(Pm, cfg.FHN_L, 1e-2 * np.eye(1), 1e-1, cfg.FHN_OBS_V)   # start_sd = 0: no start move
+    ens.sample_(3, 0xFFFFFFF0)
+    ens.theta_guided_euler_ll_()
+    W0 = ens.download(B.W, p0=0, np_=512); X0 = ens.download(B.X, p0=0, np_=512)
+    acc0 = ens.acc
+    for it, (lo, hi) in enumerate([(1, 3), (0, 2), (0, 4)]):
+        ens.theta_block_step_(lo, hi, 1.0, 3, it)
+        blk = ens.theta_block()
+        for s in range(lo, hi):
+            assert np.array_equal(blk[:, 5 + 2 * s], blk[:, 5 + 2 * s + 1])
+        assert np.all(blk[:, 4] == 0.0) and np.all(ens.accepted == 1)
+        assert ens.acc - acc0 == P * (it + 1)
+        Wn = ens.download(B.W, p0=0, np_=512); Xn = ens.download(B.X, p0=0, np_=512)
+        assert np.array_equal(Wn, W0)
+        out = [s for s in range(S) if not (lo <= s < hi)]
+        assert np.array_equal(Xn[:, out], X0[:, out])
+        for s in range(max(lo, 1), hi):
+            assert np.array_equal(Xn[:, s, 0], Xn[:, s - 1, -1])
+        X0 = Xn
+    # the whole-chain block used the whole-chain tables: X equals a fresh solve! with the same noise
+    ens.theta_guided_euler_ll_()
+    assert np.array_equal(ens.download(B.X, p0=0, np_=512), X0)
+    # a genuine proposal at this size: decisions replay exactly, only accepting chains' block rows change
+    ens.theta_block_step_(1, 4, 0.9, 3, 10)
+    blk = ens.theta_block(); flags = ens.accepted.astype(bool)
+    assert np.array_equal(flags, ens.logu <= replay(blk, 1, 4)) and 0 < flags.sum() < P
+    Xn = ens.download(B.X, p0=0, np_=512)
+    assert np.array_equal(Xn[~flags[:512]], X0[~flags[:512]]) and np.array_equal(Xn[:, 0], X0[:, 0])
+    ens.close()
+
+
 def test_block_step_errors(B):
     ens, Pm, grids, obs_v, L = bolus_setup(B, 8, 17, 3, 0)
     ens.sample_(1, 0); ens.theta_guided_euler_ll_()
