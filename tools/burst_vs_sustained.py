@@ -48,3 +48,18 @@ for _ in range(12):
     d.append((time.perf_counter() - t2) * 1e3)
 ctx.synchronize()
 print("host time of consecutive pcn_step_ calls (ms):", " ".join(f"{x:.3f}" for x in d), flush=True)
+# does an idle pause bring the burst figure back?  (yes -> a sustained-load effect of the memory system, not of the chains' state)
+for pause in (0.0, 2.0, 0.0, 5.0):
+    time.sleep(pause)
+    ctx.set_timing(True)
+    ts = []
+    for _ in range(6):
+        ens.pcn_step_(Pm, guides, rho, 4, it); it += 1
+        ctx.synchronize(); ts.append(ctx.last_kernel_ms)
+    ctx.set_timing(False)
+    t0 = time.perf_counter()
+    for _ in range(40):
+        ens.pcn_step_(Pm, guides, rho, 4, it); it += 1
+    ctx.synchronize()
+    print(f"after a pause of {pause:.0f} s: first launches {ts[0]:.3f} {ts[1]:.3f} {ts[2]:.3f} ... median {np.median(ts):.3f} ms; "
+          f"then 40 back to back {(time.perf_counter() - t0) / 40 * 1e3:.3f} ms each", flush=True)
