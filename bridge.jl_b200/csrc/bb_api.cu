@@ -1092,17 +1092,23 @@ __global__ void __launch_bounds__(1024) bb_accepted_list_kernel(const uint8_t* _
   }
   if (threadIdx.x == 0) list[np] = base;
 }
-__global__ void __launch_bounds__(256) bb_rows_to_host_kernel(const double* __restrict__ stage, double* __restrict__ host,
-                                                              const int* __restrict__ list, long long np, long long rowlen) {
+__global__ void __launch_bounds__(256) bb_rows_to_host_kernel(const double* __restrict__ stageW, double* __restrict__ hostW,
+                                                              long long rowW, const double* __restrict__ stageX,
+                                                              double* __restrict__ hostX, long long rowX,
+                                                              const int* __restrict__ list, long long np) {
   /* the CTAs walk the accepted rows TOGETHER, 2 KB per CTA and step, so that the stores over the link form one dense
-   * moving window (one private row per CTA = ~600 interleaved streams reached 40 GB/s, this order the copy engine's 50) */
-  const long long ppr = (rowlen + 255) / 256; /* pieces per row */
-  const long long total = (long long)list[np] * ppr;
+   * moving window (one private row per CTA = ~600 interleaved streams reached 40 GB/s, this order 44-45); W rows first,
+   * then X rows (hostX may be NULL), in one launch */
+  const long long pw = (rowW + 255) / 256, px = hostX ? (rowX + 255) / 256 : 0; /* pieces per row */
+  const long long cnt = list[np], totw = cnt * pw, total = totw + cnt * px;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-    const long long r = t / ppr, i = (t - r * ppr) * 256 + threadIdx.x;
+    const bool isx = t >= totw;
+    const long long u = isx ? t - totw : t, ppr = isx ? px : pw, rowlen = isx ? rowX : rowW;
+    const long long r = u / ppr, i = (u - r * ppr) * 256 + threadIdx.x;
     if (i < rowlen) {
       const long long pl = list[r];
-      host[pl * rowlen + i] = stage[pl * rowlen + i];
+      if (isx) hostX[pl * rowlen + i] = stageX[pl * rowlen + i];
+      else hostW[pl * rowlen + i] = stageW[pl * rowlen + i];
     }
   }
 }
@@ -1135,13 +1141,15 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
     }
   }
   const size_t wpc = (size_t)e->S * e->N * e->dp, xpc = (size_t)e->S * e->N * e->d; /* doubles per chain */
-  int64_t slab = (int64_t)((size_t)(192u << 20) / (wpc * sizeof(double)));
-  slab = slab < 256 ? 256 : (slab / 256) * 256; /* whole CTAs */
-  if (slab > e->P) slab = e->P;
   /* accepted rows straight into mapped host memory (see the header) */
   double* Wo_map = (flags & BB_RUN_SKIP_REJECTED) ? mapped_alias(Wo_host) : nullptr;
   double* Xo_map = (flags & BB_RUN_SKIP_REJECTED) && want_x ? mapped_alias(Xo_host) : nullptr;
   const bool direct = Wo_map && (!want_x || Xo_map);
+  /* slab of chains per pipeline stage: 192 MB of W for the copy engine, 384 MB for the kernel write-back (measured:
+   * 2.60 / 2.65 / 2.73 / 2.55e9 path-steps/s at 96 / 192 / 384 / 768 MB; the copy-engine path prefers 96-192) */
+  int64_t slab = (int64_t)((size_t)((direct ? 384u : 192u) << 20) / (wpc * sizeof(double)));
+  slab = slab < 256 ? 256 : (slab / 256) * 256; /* whole CTAs */
+  if (slab > e->P) slab = e->P;
   /* Wo_host == W_host: the host array is updated in place for the chains that accept (the loop's swap of W and Wo);
    * only the direct path leaves the rejecting chains' rows alone */
   if (Wo_host == W_host && !direct) return BB_ERR_ARG;
@@ -1182,11 +1190,11 @@ extern "C" int bb_pcn_step_host(bb_ens* e, const bb_model* model, bb_guide* cons
     if (direct) {
       /* on the copy stream (the next slab's kernels do not wait for the link); a small grid keeps the link busy */
       bb_accepted_list_kernel<<<1, 1024, 0, c->s_d2h>>>(e->accepted + p0, n, acc_list[b]);
-      bb_rows_to_host_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(sWo, Wo_map + (size_t)p0 * wpc, acc_list[b], n, (long long)wpc);
-      if (want_x)
-        bb_rows_to_host_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(sXo, Xo_map + (size_t)p0 * xpc, acc_list[b], n, (long long)xpc);
+      bb_rows_to_host_kernel<<<148 * 4, 256, 0, c->s_d2h>>>(sWo, Wo_map + (size_t)p0 * wpc, (long long)wpc, sXo,
+                                                             want_x ? Xo_map + (size_t)p0 * xpc : nullptr, (long long)xpc,
+                                                             acc_list[b], n);
       BB_CUDA(cudaGetLastError());
-      c->launches += want_x ? 3 : 2;
+      c->launches += 2;
     } else {
     BB_CUDA(cudaMemcpyAsync(Wo_host + (size_t)p0 * wpc, sWo, (size_t)n * wpc * sizeof(double), cudaMemcpyDeviceToHost,
                             c->s_d2h));
