@@ -84,3 +84,15 @@ def test_julia_shim_agrees_with_the_header():
                 "function sample!(W::SamplePath{T}, P::Wiener{T}, y1 = W.yy[1])",
                 "function Guide(Po::GuidedBridge;", "function Guide(Po::PartialBridge;", "function Guide(Po::PartialBridgeνH;"):
         assert sig in src, sig
+
+
+def test_committed_traffic_records_belong_to_the_committed_kernels():
+    """bench.py reports `roofline.traffic` only while the hash of the kernel sources equals the one recorded with the ncu
+    capture (profiles/ncu_traffic.json); the committed records must be those of the committed sources."""
+    import json
+    import bench
+    rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    for config in (2, 3, 4, 5):
+        assert rec[str(config)]["src_hash"] == bench.kernel_source_hash(config), config
+        t, note = bench.measured_traffic(config, 1.0)
+        assert t is not None and abs(t - rec[str(config)]["dram_bytes_per_unit"]) < 1e-9, note
