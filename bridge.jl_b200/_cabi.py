@@ -133,6 +133,10 @@ def _load():
         "bb_ens_mc_reset": (C.c_int, [vp]),
         "bb_ens_mc_update": (C.c_int, [vp]),
         "bb_ens_mc_stats": (C.c_int, [vp, vp, vp, C.POINTER(i64)]),
+        "bb_ens_chain_mc_reset": (C.c_int, [vp]),
+        "bb_ens_chain_mc_update": (C.c_int, [vp]),
+        "bb_ens_chain_mc_stats": (C.c_int, [vp, i64, i64, vp, vp, C.POINTER(i64)]),
+        "bb_ens_chain_mc_band": (C.c_int, [vp, i64, i64, vp, vp]),
         "bb_pcn_step_host": (C.c_int, [vp, C.POINTER(Model), pp, dbl, u64, u32, i32, u32, vp, vp, vp, vp, vp]),
         "bb_theta_attach": (C.c_int, [vp, C.POINTER(Model), C.POINTER(ThetaSpec)]),
         "bb_theta_set": (C.c_int, [vp, i64, i64, vp]),

@@ -821,6 +821,31 @@ class PathEnsemble:
         Q = 1.959963984540054
         return mean - Q * std, mean + Q * std
 
+    # ---- the same per chain over the recorded iterations: the reference's own mcstart / mcnext! / mcstats / mcband
+    # (src/mclog.jl:22-24, 47-56, 75-93) as the scripts keep it, `mcstate = [mcnext!(mcstate[i], XX[i].yy) ...]`
+    def chain_mc_reset_(self):
+        """mcstart for every chain: m = 0, m2 = 0, k = 0 (allocates (1 + d) x the memory of X on first use)."""
+        check(lib.bb_ens_chain_mc_reset(self.h))
+
+    def chain_mc_update_(self):
+        """mcnext!(mc_p, X_p.yy) for every chain p with its CURRENT path (Welford, the reference's operation order)."""
+        self.refresh_x_()
+        check(lib.bb_ens_chain_mc_update(self.h))
+
+    def chain_mc_stats(self, p0: int = 0, np_: Optional[int] = None):
+        """mcstats per chain: (mean [np,S,N,d], cov = m2/(k-1) [np,S,N,d,d], k)."""
+        n = self.P - p0 if np_ is None else np_
+        mean = np.empty((n, self.S, self.N, self.d)); cov = np.empty((n, self.S, self.N, self.d, self.d)); k = C.c_int64(0)
+        check(lib.bb_ens_chain_mc_stats(self.h, p0, n, ptr(mean), ptr(cov), C.byref(k)))
+        return mean, cov, k.value
+
+    def chain_mc_band(self, p0: int = 0, np_: Optional[int] = None):
+        """mcband per chain: (lower, upper) [np,S,N,d] = m -/+ Q sqrt(diag(m2) (1/(k-1)))  (src/mclog.jl:75-85)."""
+        n = self.P - p0 if np_ is None else np_
+        lo = np.empty((n, self.S, self.N, self.d)); hi = np.empty_like(lo)
+        check(lib.bb_ens_chain_mc_band(self.h, p0, n, ptr(lo), ptr(hi)))
+        return lo, hi
+
     def refresh_x_(self):
         """Make X the CURRENT path of every chain again (X holds the last proposal; chains that rejected it
         get their path recomputed from W by the same guided Euler kernel).  No-op if nothing is stale."""

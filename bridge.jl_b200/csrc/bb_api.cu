@@ -370,6 +370,7 @@ extern "C" int bb_ens_destroy(bb_ens* e) {
   if (e->W[0]) cudaFree(e->W[0]);
   if (e->X) cudaFree(e->X);
   if (e->mc_sum) cudaFree(e->mc_sum);
+  if (e->cmc_m) cudaFree(e->cmc_m);
   bb_theta_free(e);
   void* ptrs[] = {e->par, e->accepted, e->xstale, e->ll, e->llprop, e->logu, e->xend, e->xendprop, e->acc, e->start};
   for (void* p : ptrs)

@@ -68,6 +68,9 @@ struct bb_ens {
   /* pooled online statistics (bb_stats.cu) */
   double *mc_sum = nullptr, *mc_sq = nullptr, *mc_pivot = nullptr;
   int64_t mc_n = 0;
+  /* per-chain online statistics (bb_stats.cu): m in the layout of X, m2 with d*d entries per grid point */
+  double *cmc_m = nullptr, *cmc_m2 = nullptr;
+  int64_t cmc_k = 0;
 };
 
 void bb_theta_free(bb_ens* e); /* bb_theta.cu */

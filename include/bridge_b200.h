@@ -433,6 +433,22 @@ int bb_ens_refresh_x(bb_ens* ens, const bb_model* model, bb_guide* const* guides
 int bb_ens_mc_reset(bb_ens* ens);
 int bb_ens_mc_update(bb_ens* ens);
 int bb_ens_mc_stats(bb_ens* ens, double* mean, double* cov, int64_t* n);
+/* The same with the reference's own semantics -- one state (m, m2, k) PER CHAIN, over the recorded iterations, as the
+ * scripts keep it: `mcstate = [mcnext!(mcstate[i], XX[i].yy) for i in ...]`, partialbridge_fitzhugh.jl:169-189:
+ *   bb_ens_chain_mc_reset   mcstart (src/mclog.jl:22-24): m = 0, m2 = 0, k = 0.  The state takes (1 + d) times the memory
+ *                           of X and is allocated on first use.
+ *   bb_ens_chain_mc_update  mcnext! (src/mclog.jl:47-56) for every chain with its CURRENT path, Welford's update in the
+ *                           reference's operation order (delta = x - m; m += delta/(k+1); m2 += delta (x - m)'): bit-identical
+ *                           to the reference recurrence, deterministic.  BB_ERR_STALE as for bb_ens_mc_update.  d <= 3.
+ *   bb_ens_chain_mc_stats   mcstats (src/mclog.jl:88-93) of chains p0 .. p0+np-1: mean [np][S][N][d], cov = m2/(k-1)
+ *                           [np][S][N][d][d] (either may be NULL); *k = number of updates.
+ *   bb_ens_chain_mc_band    mcband (src/mclog.jl:75-85): m -/+ Q sqrt(diag(m2) (1/(k-1))), Q = sqrt(2.) erfinv(0.95);
+ *                           lower, upper [np][S][N][d]. */
+#define BB_MCBAND_Q 1.9599639845400538 /* sqrt(2.) * erfinv(0.95) evaluated in double precision */
+int bb_ens_chain_mc_reset(bb_ens* ens);
+int bb_ens_chain_mc_update(bb_ens* ens);
+int bb_ens_chain_mc_stats(bb_ens* ens, int64_t p0, int64_t np, double* mean, double* cov, int64_t* k);
+int bb_ens_chain_mc_band(bb_ens* ens, int64_t p0, int64_t np, double* lower, double* upper);
 
 /* ------------------------------------------------------------------ per-chain parameters
  * Every chain p carries its own parameter vector θ_p of the target model (the leading BB_NTHETA entries of the

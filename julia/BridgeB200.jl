@@ -330,6 +330,25 @@ function mc_stats(E::PathEnsemble)
     check(ccall((:bb_ens_mc_stats, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}), E.h, mean, cov, n))
     mean, cov, n[]
 end
+# The reference's own semantics: one (m, m2, k) per chain over the recorded iterations, `mcnext!(mcstate[i], XX[i].yy)` of
+# partialbridge_fitzhugh.jl:169-189 for every chain at once (Welford in the reference's operation order, bit-identical).
+# Arrays are column-major views of the C layout: mean[a, j, s, p], cov[b, a, j, s, p] = m2[a, b]/(k - 1) of chain p.
+chain_mc_reset!(E::PathEnsemble) = check(ccall((:bb_ens_chain_mc_reset, lib), Cint, (Ptr{Cvoid},), E.h))          # mcstart
+chain_mc_update!(E::PathEnsemble) = check(ccall((:bb_ens_chain_mc_update, lib), Cint, (Ptr{Cvoid},), E.h))        # mcnext!
+function chain_mc_stats(E::PathEnsemble, chains::UnitRange{Int} = 1:E.P)                                           # mcstats
+    np = length(chains)
+    mean = Array{Float64}(undef, E.d, E.N, E.S, np); cov = Array{Float64}(undef, E.d, E.d, E.N, E.S, np); k = Ref{Int64}(0)
+    check(ccall((:bb_ens_chain_mc_stats, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+                E.h, first(chains) - 1, np, mean, cov, k))
+    mean, cov, k[]
+end
+function chain_mc_band(E::PathEnsemble, chains::UnitRange{Int} = 1:E.P)                                            # mcband
+    np = length(chains)
+    lower = Array{Float64}(undef, E.d, E.N, E.S, np); upper = similar(lower)
+    check(ccall((:bb_ens_chain_mc_band, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                E.h, first(chains) - 1, np, lower, upper))
+    lower, upper
+end
 
 # ---- multi-GPU: one Julia process (or task) per GPU; the acceptance counter is the only exchange (SURVEY 8e)
 mutable struct Communicator

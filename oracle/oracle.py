@@ -568,3 +568,40 @@ def theta_block_step(o: Oracle, model_id, dprime, par, grids, L, Sigma, eps, obs
         diff += llo[s] - llt[s]
     return dict(Wo=Wo, Xo=Xo, x0o=x0o, lpn=lpn, lpno=lpno, llt=llt, llo=llo, diff=diff,
                 logu=o.accept_logu(seed, it, chain), nuL=nuL, HpL=HpL, guides=guides)
+
+
+# ----------------------------------------------------------------------------------------------- online statistics
+# numpy restatement of src/mclog.jl (element-wise IEEE operations in the reference's order; no fused operations).
+# State mc = (m, m2, n): m has the shape of the path array [..., d], m2 = sum of outer products of deviations [..., d, d].
+MCBAND_Q = 1.9599639845400538  # sqrt(2.) * erfinv(0.95)  (src/mclog.jl:77,87), evaluated in double precision
+
+
+def mcstart(yy):
+    """mcstart(yy)  src/mclog.jl:22: zeros of the shape of yy (entries ignored), zeros of outer products, n = 0."""
+    yy = np.asarray(yy, dtype=np.float64)
+    return np.zeros(yy.shape), np.zeros(yy.shape + (yy.shape[-1],)), 0
+
+
+def mcnext(mc, x):
+    """mcnext!(mc, x::Vector{<:AbstractArray})  src/mclog.jl:47-56:
+    delta = x[i] - m[i];  m[i] += delta/(n+1);  m2[i] += outer(delta, x[i] - m[i]);  n + 1."""
+    m, m2, n = mc
+    x = np.asarray(x, dtype=np.float64)
+    delta = x - m
+    m = m + delta / float(n + 1)
+    m2 = m2 + delta[..., :, None] * (x - m)[..., None, :]
+    return m, m2, n + 1
+
+
+def mcstats(mc):
+    """mcstats(mc) = (m, m2/(k - 1))  src/mclog.jl:88-93."""
+    m, m2, k = mc
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return m, m2 / float(k - 1)
+
+
+def mcband(mc):
+    """mcband(mc)  src/mclog.jl:75-85: std = sqrt.(diag(v) * (1/(k - 1))); (m - Q std, m + Q std)."""
+    m, m2, k = mc
+    std = np.sqrt(np.einsum("...ii->...i", m2) * (1.0 / float(k - 1)))
+    return m - MCBAND_Q * std, m + MCBAND_Q * std

@@ -1139,6 +1139,55 @@ def test_pooled_online_statistics(B, oracle_fma):
     ens.close()
 
 
+def test_per_chain_online_statistics_bit_exact(B, oracle_fma):
+    """mcstart / mcnext! / mcstats / mcband with the reference's semantics (src/mclog.jl:22-24, 47-56, 75-93): one state
+    per chain over the recorded iterations, as `mcstate = [mcnext!(mcstate[i], XX[i].yy) ...]` keeps it
+    (partialbridge_fitzhugh.jl:169-189).  The device state equals the oracle's recurrence on the downloaded current paths
+    bit for bit (ragged N: the last chunk is padded; ragged P: not a multiple of the CTA size)."""
+    from oracle import oracle as O
+    N, P, S = 37, 301, 2
+    grids = [warped(0.0, 0.5, N), warped(0.5, 1.0, N)]
+    Pm = B.FitzhughDiffusion(*FHN_PAR)
+    tabs = oracle_fhn_chain(oracle_fma, grids, [-1.0, -0.5])
+    guides = [B.GuideTables(B.api.K.GUIDE_NUH, grids[s], Pm, tabs[s][1], tabs[s][0], tabs[s][2], tabs[s][3])
+              for s in range(S)]
+    ens = B.PathEnsemble(P, S, N, 2, 1)
+    for s in range(S):
+        ens.set_grid(s, grids[s])
+    ens.set_start([-0.5, -0.6]); ens.sample_(33, 0xFFFFFFFE); ens.guided_euler_ll_(Pm, guides)
+    ens.chain_mc_reset_()
+    mc = None
+    for it in range(4):
+        ens.pcn_step_(Pm, guides, 0.5, 33, it)
+        ens.chain_mc_update_()                 # refreshes the chains that rejected, then mcnext! for every chain
+        X = ens.download(B.X)                  # [P, S, N, d]
+        mc = O.mcnext(O.mcstart(X) if mc is None else mc, X)
+        if it == 0:                            # k = 1: mean = the path itself, m2 = 0, cov = 0/0
+            mean, cov, k = ens.chain_mc_stats()
+            assert k == 1 and np.array_equal(mean, X) and np.all(np.isnan(cov))
+    mean, cov, k = ens.chain_mc_stats()
+    assert k == 4
+    m_want, cov_want = O.mcstats(mc)
+    assert np.array_equal(mean, m_want)
+    assert np.array_equal(cov, cov_want)
+    assert np.any(cov[:, :, 1:, 0, 0] > 0)     # chains moved between the recorded iterations
+    lo, hi = ens.chain_mc_band()
+    lo_want, hi_want = O.mcband(mc)
+    assert np.array_equal(lo, lo_want) and np.array_equal(hi, hi_want)
+    # a sub-range of chains, and the count alone
+    m1, c1, _ = ens.chain_mc_stats(17, 5)
+    assert np.array_equal(m1, m_want[17:22]) and np.array_equal(c1, cov_want[17:22])
+    # a reset starts over
+    ens.chain_mc_reset_()
+    ens.chain_mc_update_()
+    mean, _, k = ens.chain_mc_stats()
+    assert k == 1 and np.array_equal(mean, ens.download(B.X))
+    # statistics of stale paths are refused through the raw ABI
+    ens.pcn_step_(Pm, guides, 0.5, 33, 99)
+    assert B.api.lib.bb_ens_chain_mc_update(ens.h) == -13       # BB_ERR_STALE until refreshed
+    ens.close()
+
+
 # ----------------------------------------------------------------------------------------------- rank 4: other SDE schemes
 @pytest.mark.parametrize("name,mk,om,exact", MODELS, ids=[m[0] for m in MODELS])
 def test_stochastic_heun_vs_oracle(B, oracle_ref, oracle_fma, name, mk, om, exact):

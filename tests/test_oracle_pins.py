@@ -743,3 +743,41 @@ def test_block_update_composition_properties(oracle_ref):
     u = oracle_ref.normal(5, 4, 77, 4 * O.Q_THETA_NORMALS + 3)
     assert np.array_equal(r2["x0o"], x0 + (0.1 * u) * np.array([1.0, -1.0]))
     assert r2["lpno"] == oracle_ref.logpdfnormal(r2["x0o"] - nuL, HpL) and np.array_equal(r2["Xo"][0][0], r2["x0o"])
+
+
+# --------------------------------------------------------------------------- online statistics (src/mclog.jl)
+def test_online_statistics_known_answers():
+    """test/onlinestat.jl:2-10: the running (mean, m2) of 10 random 5-vectors / 10 random scalars reproduce `mean` and
+    `cov(x, corrected = true)` / `var` to eps(100.0).  `MeanCov`'s iteration (src/mclog.jl:157-168) and `mcnext!`
+    (:47-56) are the same recurrence: delta = x - m; m += delta/(n+1); m2 += outer(delta, x - m).  Plus the worked
+    example of the reference's own comment, src/mclog.jl:270-277 (1:10 repeated over 5 entries)."""
+    rng = np.random.default_rng(0)
+    x = rng.random((10, 5))
+    mc = O.mcstart(x[0])
+    for xi in x:
+        mc = O.mcnext(mc, xi)
+    m, cov = O.mcstats(mc)
+    eps100 = np.spacing(100.0)
+    assert mc[2] == 10
+    assert np.linalg.norm(np.cov(x.T, ddof=1) - cov) < eps100
+    assert np.linalg.norm(x.mean(axis=0) - m) < eps100
+    y = rng.random(10)
+    mc = O.mcstart(y[:1])
+    for yi in y:
+        mc = O.mcnext(mc, [yi])
+    m, var = O.mcstats(mc)
+    assert abs(np.var(y, ddof=1) - var[0, 0]) < eps100 and abs(y.mean() - m[0]) < eps100
+    # S = OnlineStat(ones(5)); push!(S, i*ones(5)) for i in 2:10: mean 5.5, variance of 1:10
+    mc = O.mcstart(np.ones((5, 1)))
+    for i in range(1, 11):
+        mc = O.mcnext(mc, i * np.ones((5, 1)))
+    m, var = O.mcstats(mc)
+    assert np.all(m == 5.5) and np.allclose(var, np.var(np.arange(1, 11), ddof=1), rtol=1e-15)
+    lo, hi = O.mcband(mc)
+    assert np.allclose(hi - m, O.MCBAND_Q * np.sqrt(var[..., 0]), rtol=1e-15) and np.allclose(m - lo, hi - m, rtol=1e-15)
+    # Q = sqrt(2.) * erfinv(0.95) is the two-sided 95 % normal quantile
+    from scipy.special import erfinv
+    assert abs(O.MCBAND_Q - np.sqrt(2.0) * erfinv(0.95)) < 4e-16
+    # one observation: m2/(k-1) = 0/0, as in the reference
+    mc = O.mcnext(O.mcstart(np.ones(2)), np.ones(2))
+    assert np.all(np.isnan(O.mcstats(mc)[1]))
