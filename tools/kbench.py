@@ -29,6 +29,8 @@ calls = {
     "sample_euler": (lambda it: ens.sample_euler_(Pm, 4, it), 24),
     "euler": (lambda it: ens.euler_(Pm), 24),
     "llik": (lambda it: ens.llikelihood_(Pm, guides), 16),
+    "mc": (lambda it: ens.mc_update_(), 16),                 # pooled moments: X read once
+    "chain_mc": (lambda it: ens.chain_mc_update_(), 112),    # per-chain Welford: X read, m and m2 read + written, d = 2
 }
 for m in modes:
     fn, nbytes = calls[m]
