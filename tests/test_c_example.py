@@ -51,3 +51,21 @@ def test_c_example_matches_python_mirror(tmp_path):
     assert abs(float(np.sum(ens.ll)) - ll_c) <= 1e-10 * abs(ll_c)
     assert abs(float(np.sum(ens.xend)) - x_c) <= 1e-10 * abs(x_c)
     ens.close()
+
+
+@pytest.mark.gpu
+def test_python_example_of_the_script_loop():
+    """examples/fitzhugh_smoothing.py: the partialbridge_fitzhugh.jl:125-189 loop (pCN + per-chain mcnext!) through the host
+    mirror runs, is reproducible (same seed, same chains: bit-identical), and its statistics make sense."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fitzhugh_smoothing", os.path.join(ROOT, "examples", "fitzhugh_smoothing.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    a = ex.main(300, 65, 20, seed=5, record_from=8)
+    b = ex.main(300, 65, 20, seed=5, record_from=8)
+    assert a == b
+    assert a["k"] == 12 and 0 < a["acc"] < 20 * 300
+    lo, hi = a["band_mid"]
+    assert all(l <= m <= h for l, m, h in zip(lo, a["mean_mid"], hi)) and hi[0] > lo[0]
+    assert a["obs_fit"] < 0.05        # the chains' mean paths pass through the observations (Σ = 1e-10)
+    assert np.isfinite(a["ll_sum"])
