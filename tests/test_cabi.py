@@ -76,6 +76,20 @@ def test_julia_shim_agrees_with_the_header():
     problems, ncalls, nfun, ndecl = check_shim.check()
     assert not problems, problems
     assert ncalls >= 50 and nfun >= 38
+    # block structure (brackets, block openers vs `end`) of the Julia sources nobody can run here; the checker itself is
+    # exercised on a mutated copy so that a silent pass means something
+    assert check_shim.jl_structure() == []
+    assert check_shim.jl_structure(os.path.join(ROOT, "baseline", "julia_cpu.jl")) == []
+    shim = open(os.path.join(ROOT, "julia", "BridgeB200.jl")).read()
+    import tempfile
+    for mutated in (shim.replace("lower, upper\nend", "lower, upper\nend\nend", 1), shim.replace("similar(lower)", "similar(lower", 1)):
+        assert mutated != shim
+        with tempfile.NamedTemporaryFile("w", suffix=".jl", delete=False) as f:
+            f.write(mutated)
+        try:
+            assert check_shim.jl_structure(f.name)
+        finally:
+            os.unlink(f.name)
     # the reference's own signatures are there (SURVEY 8a "exact reference signatures")
     src = open(os.path.join(ROOT, "julia", "BridgeB200.jl")).read()
     for sig in ("function solve!(s::EulerMaruyama, Y::SamplePath, u, W::SamplePath, Po::Proposal)",

@@ -4,6 +4,7 @@
   * every `ccall((:name, lib), Ret, (ArgTypes...), args...)` names a function the header declares, with the same number
     of arguments, each Julia argument type compatible with the C parameter (scalar width and signedness, pointer vs
     scalar, pointee type), the same return type, and as many call arguments as argument types;
+  * the block structure of the file is sound: brackets close in order, every block opener has its `end` (jl_structure);
   * the structs the shim mirrors by hand (BBModel, BBAux, BBThetaSpec) have the byte layout gcc gives bb_model, bb_aux,
     bb_theta_spec (sizeof and every offsetof).
 
@@ -193,9 +194,83 @@ def c_struct_layout(cname: str):
     return list(zip(fields, nums[1:])), nums[0]
 
 
+_JL_OPENERS = {"function", "macro", "module", "baremodule", "struct", "if", "for", "while", "let", "begin", "do", "try",
+               "quote"}
+
+
+def jl_strip(src: str) -> str:
+    """Julia source with comments, strings, character literals and docstrings blanked (newlines kept)."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        c = src[i]
+        if src.startswith("#=", i):
+            j = src.find("=#", i + 2)
+            j = n if j < 0 else j + 2
+            out.append(re.sub(r"[^\n]", " ", src[i:j])); i = j
+        elif c == "#":
+            j = src.find("\n", i)
+            j = n if j < 0 else j
+            out.append(" " * (j - i)); i = j
+        elif src.startswith('"""', i):
+            j = src.find('"""', i + 3)
+            j = n if j < 0 else j + 3
+            out.append(re.sub(r"[^\n]", " ", src[i:j])); i = j
+        elif c == '"':
+            j = i + 1
+            while j < n and src[j] != '"':
+                j += 2 if src[j] == "\\" else 1
+            out.append(re.sub(r"[^\n]", " ", src[i:j + 1])); i = j + 1
+        elif c == "'" and re.match(r"'(\\.|[^'\\])'", src[i:i + 4]):
+            m = re.match(r"'(\\.|[^'\\])'", src[i:i + 4])
+            out.append(" " * m.end()); i += m.end()
+        else:
+            out.append(c); i += 1
+    return "".join(out)
+
+
+def jl_structure(path: str = SHIM):
+    """Block structure of the shim (no Julia here to parse it): every (, [, { closes in order, and outside brackets
+    (where `for` / `if` belong to comprehensions and `end` is an index) every block opener has its `end`; the file ends
+    at depth 0.  -> list of problems."""
+    src = jl_strip(open(path).read())
+    problems, brackets, blocks = [], [], []
+    pairs = {")": "(", "]": "[", "}": "{"}
+    line = 1
+    for m in re.finditer(r"\n|[()\[\]{}]|:?[A-Za-z_\u0080-\uffff][\w!\u0080-\uffff]*", src):
+        tok = m.group(0)
+        if tok == "\n":
+            line += 1
+        elif tok in "([{":
+            brackets.append((tok, line))
+        elif tok in ")]}":
+            if not brackets or brackets[-1][0] != pairs[tok]:
+                problems.append(f"line {line}: unmatched {tok}")
+                return problems
+            brackets.pop()
+        elif brackets:
+            continue
+        elif tok in _JL_OPENERS:
+            before = src[:m.start()].rstrip()
+            if tok == "struct" and before.endswith("mutable"):
+                pass
+            blocks.append((tok, line))
+        elif tok == "type" and re.search(r"\b(abstract|primitive)\s*$", src[:m.start()]):
+            blocks.append((tok, line))
+        elif tok == "end":
+            if not blocks:
+                problems.append(f"line {line}: `end` without an open block")
+                return problems
+            blocks.pop()
+    if brackets:
+        problems.append(f"line {brackets[-1][1]}: {brackets[-1][0]} never closed")
+    if blocks:
+        problems.append(f"line {blocks[-1][1]}: `{blocks[-1][0]}` without `end`")
+    return problems
+
+
 def check(verbose: bool = False):
     """-> list of problems (empty = the shim agrees with the header)"""
-    problems = []
+    problems = [f"structure: {p}" for p in jl_structure()]
     protos = header_prototypes()
     calls = shim_ccalls()
     seen = set()
