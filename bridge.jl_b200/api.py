@@ -818,8 +818,7 @@ class PathEnsemble:
         """mcband: marginal 95 % band mean -/+ Q std with Q = sqrt(2) erfinv(0.95)  (src/mclog.jl:75-85)."""
         mean, cov, _ = self.mc_stats()
         std = np.sqrt(np.einsum("snii->sni", cov))
-        Q = 1.959963984540054
-        return mean - Q * std, mean + Q * std
+        return mean - MCBAND_Q * std, mean + MCBAND_Q * std
 
     # ---- the same per chain over the recorded iterations: the reference's own mcstart / mcnext! / mcstats / mcband
     # (src/mclog.jl:22-24, 47-56, 75-93) as the scripts keep it, `mcstate = [mcnext!(mcstate[i], XX[i].yy) ...]`
@@ -1408,6 +1407,29 @@ def innovations_(method: SDESolver, W: SamplePath, Y: SamplePath, P, ctx=None) -
     W.tt[...] = Y.tt
     W.yy[...] = e.download(K.W).reshape(W.yy.shape)
     return W
+
+
+# ---- host-side readers of the online statistics (src/mclog.jl:58-111); inputs are what mc_stats / chain_mc_stats return
+MCBAND_Q = 1.9599639845400538  # sqrt(2.) * erfinv(0.95)  (BB_MCBAND_Q)
+
+
+def mcbandmean(mean, cov, k: int):
+    """mcbandmean(mc)  src/mclog.jl:63-73: band for the chain MEAN, m -/+ Q ste with ste = sqrt(diag(cov)) sqrt(1/k)."""
+    mean = np.asarray(mean, dtype=np.float64)
+    ste = np.sqrt(np.einsum("...ii->...i", np.asarray(cov, dtype=np.float64))) * np.sqrt(1.0 / k)
+    return mean - MCBAND_Q * ste, mean + MCBAND_Q * ste
+
+
+def mcmarginalstats(mean, cov):
+    """mcmarginalstats(mcstates)  src/mclog.jl:100-111 for the segments of one chain (mean [S,N,d], cov [S,N,d,d]):
+    (Xmean, Xstd) along the concatenated time axis [S (N-1) + 1, d]; the junction point of two segments is taken
+    from the right-hand segment (`pop!` before `append!`)."""
+    mean = np.asarray(mean, dtype=np.float64)
+    std = np.sqrt(np.einsum("...ii->...i", np.asarray(cov, dtype=np.float64)))
+    S = mean.shape[0]
+    Xmean = [mean[i, :-1] for i in range(S - 1)] + [mean[S - 1]]
+    Xstd = [std[i, :-1] for i in range(S - 1)] + [std[S - 1]]
+    return np.concatenate(Xmean, axis=0), np.concatenate(Xstd, axis=0)
 
 
 def pcn_(ens: PathEnsemble, P, guides, ρ: float, iterations: int, seed: int, first_iter: int = 0,

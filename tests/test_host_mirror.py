@@ -121,3 +121,24 @@ def test_linearappr_container_and_bderiv():
     assert np.allclose(Pt.b((i, tt[i]), yy[i]), P.b(tt[i], yy[i]))            # the linearisation is exact on the trajectory
     tm = 0.5 * (tt[i] + tt[i + 1])
     assert np.allclose(Pt.B(tm), 0.5 * (Pt.Bs[i] + Pt.Bs[i + 1])) and np.array_equal(Pt.B(-1.0), Pt.Bs[0])
+
+
+def test_readers_of_the_online_statistics(B):
+    """mcbandmean / mcmarginalstats (src/mclog.jl:63-73, 100-111) on the arrays chain_mc_stats returns, against the
+    oracle's restatement of the state they are derived from."""
+    rng = np.random.default_rng(3)
+    S, N, d, k = 3, 5, 2, 7
+    mc = O.mcstart(np.zeros((S, N, d)))
+    for _ in range(k):
+        mc = O.mcnext(mc, rng.normal(size=(S, N, d)))
+    mean, cov = O.mcstats(mc)
+    lo, hi = B.api.mcbandmean(mean, cov, k)
+    ste = np.sqrt(np.einsum("snii->sni", mc[1]) * (1.0 / (k - 1))) * np.sqrt(1.0 / k)     # src/mclog.jl:67
+    assert np.allclose(lo, mean - O.MCBAND_Q * ste, rtol=1e-14) and np.allclose(hi, mean + O.MCBAND_Q * ste, rtol=1e-14)
+    blo, bhi = O.mcband(mc)
+    assert np.all(blo <= lo) and np.all(hi <= bhi)            # the band of the mean lies inside the band of the chain
+    Xmean, Xstd = B.api.mcmarginalstats(mean, cov)
+    assert Xmean.shape == (S * (N - 1) + 1, d) and Xstd.shape == Xmean.shape
+    assert np.array_equal(Xmean[:N - 1], mean[0, :-1]) and np.array_equal(Xmean[N - 1], mean[1, 0])   # junction: right segment
+    assert np.array_equal(Xmean[-N:], mean[-1]) and np.allclose(Xstd[-1], np.sqrt(np.diag(cov[-1, -1])))
+    assert B.api.MCBAND_Q == O.MCBAND_Q
