@@ -135,6 +135,17 @@ function accepted(E::PathEnsemble)
     check(ccall((:bb_ens_get_accepted, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{UInt8}), E.h, 0, E.P, a)); a
 end
 acc(E::PathEnsemble) = (r = Ref{Int64}(0); check(ccall((:bb_ens_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), E.h, r)); r[])
+reset_acc!(E::PathEnsemble) = check(ccall((:bb_ens_reset_acc, lib), Cint, (Ptr{Cvoid},), E.h))
+"""`set_ll!(E, ll)`: log-likelihoods of the chains' current paths supplied by the caller (e.g. after `upload!` of W and X)."""
+set_ll!(E::PathEnsemble, ll::Vector{Float64}; p0 = 0) =
+    check(ccall((:bb_ens_set_ll, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), E.h, p0, length(ll), ll))
+device_bytes(E::PathEnsemble) = ccall((:bb_ens_bytes, lib), Int64, (Ptr{Cvoid},), E.h)
+function grid(E::PathEnsemble, seg::Integer)   # the time grid of segment `seg` (1-based) as set by set_grid!
+    tt = Vector{Float64}(undef, E.N)
+    check(ccall((:bb_ens_get_grid, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32), E.h, seg - 1, tt, E.N)); tt
+end
+abi_version() = Int(ccall((:bb_abi_version, lib), Cint, ()))
+launch_count(ctx::Context = default_context()) = ccall((:bb_ctx_launch_count, lib), Int64, (Ptr{Cvoid},), ctx.h)
 
 # ---- auxiliary process as values (bb_aux): constants, or values at the Ralston stage times of every interval
 struct BBAux
@@ -367,6 +378,11 @@ end
 """Start the all-reduce of the acceptance counter (asynchronous, NCCL on its own stream); `acc(comm)` fetches the sum."""
 allreduce_acc!(E::PathEnsemble, c::Communicator) = check(ccall((:bb_allreduce_acc, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), E.h, c.h))
 acc(c::Communicator) = (r = Ref{Int64}(0); check(ccall((:bb_comm_get_acc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), c.h, r)); r[])
+"""The same for the acceptance counter of the parameter updates (`theta_param!`)."""
+allreduce_theta_acc!(E::PathEnsemble, c::Communicator) = check(ccall((:bb_allreduce_theta_acc, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), E.h, c.h))
+synchronize(c::Communicator) = check(ccall((:bb_comm_synchronize, lib), Cint, (Ptr{Cvoid},), c.h))   # all issued all-reduces done
+Base.size(c::Communicator) = Int(ccall((:bb_comm_size, lib), Cint, (Ptr{Cvoid},), c.h))
+rank(c::Communicator) = Int(ccall((:bb_comm_rank, lib), Cint, (Ptr{Cvoid},), c.h))
 
 # ---- (1) the reference's own signatures on SamplePath: a cached one-chain ensemble per (N, d, d')
 const SMALL = Dict{NTuple{3,Int},PathEnsemble}()
